@@ -1,0 +1,523 @@
+"""CPU oracle: a functional restatement of PureSound's separator forward pass.
+
+TEST INFRASTRUCTURE — see ``oracle/__init__.py`` for who may import this.
+
+The reference (mcw519/PureSound) is pure Python on top of PyTorch, so the
+arithmetic of the path lives in a third-party dependency, ``torch`` (ATen /
+oneDNN; ``requirements.txt:3`` unpinned, the container has 2.11.0+cu128).  This
+file restates the path as *stateless functions over a reference-format
+state_dict* (same keys as SURVEY.md appendix B), calling the same
+``torch.nn.functional`` primitives at the same call sites the reference does,
+in fp32 on the CPU.  Every function cites the reference file:line it follows
+(paths relative to the reference root).
+
+Parity pinning: the reference holds NO numerical golden vectors for this path
+(only shape tests, plus SplitMerge round-trip and streaming==offline pins).  The
+oracle is therefore pinned against *outputs of the reference itself*:
+``tests/golden/make_golden.py`` imports the reference in the authoring
+container, runs it on seeded weights/inputs and commits the tensors as
+``tests/golden/*.pt``; ``tests/test_oracle_golden.py`` replays them through
+this file.  ``tests/golden/full_size_pins.json`` additionally holds reference
+outputs of the full-size BASELINE configs (sub-sampled) on seeded weights.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------- #
+# A1  learned filterbank                       puresound/nnet/lobe/encoder.py
+# --------------------------------------------------------------------------- #
+def free_encode(wav: Tensor, weight: Tensor, hop: int, relu: bool = False) -> Tensor:
+    """FreeEncDec.forward, lobe/encoder.py:71-83 (conv built at :50-56).
+
+    wav [N, L] -> feats [N, Nf, T], T = floor((L - win) / hop) + 1, no bias,
+    no padding, optional ReLU (``output_active``)."""
+    y = F.conv1d(wav.unsqueeze(1), weight, stride=hop)
+    return F.relu(y) if relu else y
+
+
+def free_decode(feats: Tensor, weight: Tensor, hop: int) -> Tensor:
+    """FreeEncDec.inverse, lobe/encoder.py:85-94 (ConvTranspose1d at :62-68).
+
+    feats [N, Nf, T] -> wav [N, (T-1)*hop + win]: plain overlap-add sum."""
+    return F.conv_transpose1d(feats, weight, stride=hop).squeeze(1)
+
+
+# --------------------------------------------------------------------------- #
+# A2/A3  conv-STFT and conv-iSTFT   lobe/encoder.py:275-456, lobe/stft.py:8-125
+# --------------------------------------------------------------------------- #
+def fourier_kernels(n_fft: int) -> Tuple[Tensor, Tensor]:
+    """create_fourier_kernels(freq_scale='no'), lobe/stft.py:91-100: unwindowed
+    sin/cos kernels [n_fft//2+1, 1, n_fft], built in float64 then cast."""
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64).view(-1, 1)
+    s = torch.arange(n_fft, dtype=torch.float64).view(1, -1)
+    ang = 2.0 * math.pi * k * s / n_fft
+    return (torch.sin(ang).float().unsqueeze(1), torch.cos(ang).float().unsqueeze(1))
+
+
+def stft_encode(wav: Tensor, wsin: Tensor, wcos: Tensor, hop: int) -> Tensor:
+    """ConvSTFT.forward (output_format='Complex'), lobe/encoder.py:358-378.
+
+    wav [N, L] -> [N, F, T, 2] with last axis (real, -imag_conv)."""
+    x = wav.unsqueeze(1)
+    im = F.conv1d(x, wsin, stride=hop)
+    re = F.conv1d(x, wcos, stride=hop)
+    return torch.stack((re, -im), dim=-1)
+
+
+def stft_decode(
+    X: Tensor, kernel_cos_inv: Tensor, kernel_sin_inv: Tensor, window_mask: Tensor, hop: int, n_fft: int
+) -> Tensor:
+    """ConvSTFT.inverse, lobe/encoder.py:393-456 with extend_fbins
+    (lobe/stft.py:118-125), overlap_add (:103-106) and torch_window_sumsquare
+    (:109-115).  X [N, F, T, 2] -> wav [N, n_fft + hop*(T-1)]."""
+    upper = X[:, 1:-1].flip(1).clone()
+    upper[..., 1] = -upper[..., 1]
+    Xf = torch.cat((X, upper), dim=1)  # [N, n_fft, T, 2]
+    a1 = F.conv2d(Xf[..., 0].unsqueeze(1), kernel_cos_inv, stride=(1, 1))
+    b2 = F.conv2d(Xf[..., 1].unsqueeze(1), kernel_sin_inv, stride=(1, 1))
+    real = (a1 - b2).squeeze(-2) * window_mask
+    real = real / n_fft
+    T = X.shape[2]
+    out_len = n_fft + hop * (T - 1)
+    real = F.fold(real, (1, out_len), kernel_size=(1, n_fft), stride=hop).flatten(1)
+    w = window_mask.flatten()
+    w_stack = (w.unsqueeze(-1).repeat(1, T) ** 2).unsqueeze(0)
+    w_sum = F.fold(w_stack, (1, out_len), kernel_size=(1, n_fft), stride=hop).flatten()
+    nz = w_sum > 1e-10
+    real[:, nz] = real[:, nz].div(w_sum[nz])
+    return real
+
+
+# --------------------------------------------------------------------------- #
+# A4  norms                                       puresound/nnet/lobe/norm.py
+# --------------------------------------------------------------------------- #
+def _gain_bias(x: Tensor, g: Tensor, b: Tensor) -> Tensor:
+    """_LayerNorm.apply_gain_and_bias, lobe/norm.py:15-17."""
+    return (g * x.transpose(1, -1) + b).transpose(1, -1)
+
+
+def norm_apply(kind: str, sd: SD, p: str, x: Tensor) -> Tensor:
+    """get_norm registry, lobe/norm.py:100-112.  x [N, C, T]."""
+    if kind == "gLN":  # GlobLN.forward, lobe/norm.py:23-34
+        dims = list(range(1, x.dim()))
+        mean = x.mean(dim=dims, keepdim=True)
+        var = torch.pow(x - mean, 2).mean(dim=dims, keepdim=True)
+        return _gain_bias((x - mean) / (var + 1e-8).sqrt(), sd[p + "gamma"], sd[p + "beta"])
+    if kind == "cLN":  # ChanLN.forward, lobe/norm.py:40-50
+        mean = torch.mean(x, dim=1, keepdim=True)
+        var = torch.var(x, dim=1, keepdim=True, unbiased=False)
+        return _gain_bias((x - mean) / (var + 1e-8).sqrt(), sd[p + "gamma"], sd[p + "beta"])
+    if kind == "gGN":  # lobe/norm.py:96  GroupNorm(1, C, 1e-8)
+        return F.group_norm(x, 1, sd[p + "weight"], sd[p + "bias"], 1e-8)
+    if kind == "bN1d":  # lobe/norm.py:94, eval mode (running statistics)
+        return F.batch_norm(
+            x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5
+        )
+    raise NameError("Could not interpret normalization identifier")
+
+
+# --------------------------------------------------------------------------- #
+# A5/A6  TCN block and Conv-TasNet stack     puresound/nnet/conv_tasnet.py
+# --------------------------------------------------------------------------- #
+def tcn_block(
+    sd: SD,
+    p: str,
+    x: Tensor,
+    embed: Optional[Tensor],
+    kernel: int,
+    dilation: int,
+    causal: bool,
+    tcn_norm: str,
+    dconv_norm: str,
+) -> Tensor:
+    """TCN.forward, conv_tasnet.py:67-90, with DepthwiseSeparableConv1d.forward
+    (lobe/cnn.py:84-106; padding rule :58-60, causal trim :100-101)."""
+    res = x
+    if embed is not None:
+        e = embed.unsqueeze(2).repeat(1, 1, x.size(2))
+        x = torch.cat([x, e], dim=1)
+    x = F.conv1d(x, sd[p + "in_conv.0.weight"])
+    x = norm_apply(tcn_norm, sd, p + "in_conv.1.", x)
+    x = F.prelu(x, sd[p + "in_conv.2.weight"])
+    d = p + "dconv.0."
+    pad = (kernel - 1) * dilation if causal else ((kernel - 1) // 2) * dilation
+    x = F.conv1d(
+        x, sd[d + "depthwise.0.weight"], sd[d + "depthwise.0.bias"], dilation=dilation, padding=pad, groups=x.size(1)
+    )
+    x = norm_apply(dconv_norm, sd, d + "depthwise.1.", x)
+    x = F.prelu(x, sd[d + "depthwise.2.weight"])
+    x = F.conv1d(x, sd[d + "pointwise.0.weight"], sd[d + "pointwise.0.bias"])
+    x = norm_apply(dconv_norm, sd, d + "pointwise.1.", x)
+    x = F.prelu(x, sd[d + "pointwise.2.weight"])
+    if causal:
+        x = x[..., :-pad]
+    x = F.conv1d(x, sd[p + "out_conv.weight"], sd[p + "out_conv.bias"])
+    return x + res
+
+
+def conv_tasnet(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tensor:
+    """ConvTasNet.forward (tcn_layer='normal'), conv_tasnet.py:338-359; dilation
+    schedule ``tcn_dilated_basic ** i`` from :290."""
+    if a["tcn_layer"].lower() != "normal":
+        raise NotImplementedError("GatedTCN is a 'next' row (SURVEY 8f)")
+    if a["embed_norm"] and dvec is not None:
+        dvec = F.normalize(dvec, p=2, dim=1)
+    for r in range(a["repeat_tcn"]):
+        for i in range(a["per_tcn_stack"]):
+            x = tcn_block(
+                sd,
+                f"{p}tcn_list.{r}.{i}.",
+                x,
+                dvec if a["tcn_with_embed"][i] else None,
+                a["tcn_kernel"],
+                a["tcn_dilated_basic"] ** i,
+                a["causal"],
+                a["tcn_norm"],
+                a["dconv_norm"],
+            )
+    return x
+
+
+# --------------------------------------------------------------------------- #
+# A7  segmentation                     lobe/trivial.py:170-241, dprnn.py:133-145
+# --------------------------------------------------------------------------- #
+def split_overlap(x: Tensor, K: int) -> Tuple[Tensor, int]:
+    """SplitMerge.split, lobe/trivial.py:178-210.  [N,C,T] -> ([N,S,K,C], rest)."""
+    s = K // 2
+    N, C, T = x.shape
+    rest = K - (s + T % K) % K
+    if rest > 0:
+        x = torch.cat([x, x.new_zeros(N, C, rest)], dim=-1)
+    z = x.new_zeros(N, C, s)
+    x = torch.cat([z, x, z], dim=-1)
+    a = x[:, :, :-s].contiguous().view(N, C, -1, K)
+    b = x[:, :, s:].contiguous().view(N, C, -1, K)
+    seg = torch.cat([a, b], dim=-1).view(N, C, -1, K)
+    return seg.permute(0, 2, 3, 1), rest
+
+
+def merge_overlap(x: Tensor, rest: int) -> Tensor:
+    """SplitMerge.merge, lobe/trivial.py:212-241.  [N,S,K,C] -> [N,C,T]."""
+    N, S, K, C = x.shape
+    s = K // 2
+    x = x.permute(0, 3, 1, 2).contiguous().view(N, C, -1, 2 * K)
+    x1 = x[:, :, :, :K].contiguous().view(N, C, -1)[:, :, s:]
+    x2 = x[:, :, :, K:].contiguous().view(N, C, -1)[:, :, :-s]
+    out = (x1 + x2) / 2
+    if rest > 0:
+        out = out[..., :-rest]
+    return out.contiguous()
+
+
+# --------------------------------------------------------------------------- #
+# A8/A9  LSTM, FiLM, DPRNN                         puresound/nnet/dprnn.py
+# --------------------------------------------------------------------------- #
+def _lstm_dir(x: Tensor, w_ih, w_hh, b_ih, b_hh, h, c, reverse: bool):
+    """One direction of torch.nn.LSTM (gate order i,f,g,o) written out step by
+    step: the published cell the reference reaches through nn.LSTM
+    (dprnn.py:67-103)."""
+    B, L, _ = x.shape
+    gx = F.linear(x, w_ih, b_ih)
+    out = x.new_empty(B, L, w_hh.shape[1])
+    steps = range(L - 1, -1, -1) if reverse else range(L)
+    for t in steps:
+        g = gx[:, t] + F.linear(h, w_hh, b_hh)
+        i, f, gg, o = g.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[:, t] = h
+    return out, h, c
+
+
+def lstm(
+    sd: SD, p: str, x: Tensor, bidirectional: bool, init: Optional[Tuple[Tensor, Tensor]] = None, fast: bool = True
+) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
+    """nn.LSTM(num_layers=1, batch_first=True) over x [B, L, C] with reference
+    keys ``weight_ih_l0[_reverse]`` etc.  ``fast`` routes through ATen's fused
+    LSTM (what the reference itself executes); ``fast=False`` is the explicit
+    cell loop above.  Tests check the two agree."""
+    D = 2 if bidirectional else 1
+    H = sd[p + "weight_hh_l0"].shape[1]
+    B = x.shape[0]
+    if init is None:
+        h0 = x.new_zeros(D, B, H)
+        c0 = x.new_zeros(D, B, H)
+    else:
+        h0, c0 = init
+    sfx = ["", "_reverse"][:D]
+    if fast:
+        flat = []
+        for s in sfx:
+            flat += [sd[p + f"weight_ih_l0{s}"], sd[p + f"weight_hh_l0{s}"], sd[p + f"bias_ih_l0{s}"], sd[p + f"bias_hh_l0{s}"]]
+        out, hn, cn = torch._VF.lstm(x, (h0, c0), flat, True, 1, 0.0, False, bidirectional, True)
+        return out, (hn, cn)
+    outs, hs, cs = [], [], []
+    for d, s in enumerate(sfx):
+        o, h, c = _lstm_dir(
+            x,
+            sd[p + f"weight_ih_l0{s}"],
+            sd[p + f"weight_hh_l0{s}"],
+            sd[p + f"bias_ih_l0{s}"],
+            sd[p + f"bias_hh_l0{s}"],
+            h0[d],
+            c0[d],
+            reverse=(d == 1),
+        )
+        outs.append(o)
+        hs.append(h)
+        cs.append(c)
+    return torch.cat(outs, dim=-1), (torch.stack(hs), torch.stack(cs))
+
+
+def film(sd: SD, p: str, x: Tensor, cond: Tensor, input_norm: bool = True) -> Tensor:
+    """FiLM.forward, lobe/trivial.py:148-167.  x [N', C, K], cond [N', E]."""
+    if input_norm:
+        C = x.shape[1]
+        x = F.layer_norm(x.transpose(1, 2), (C,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5).transpose(1, 2)
+    q = torch.cat([x, cond.unsqueeze(-1).repeat(1, 1, x.shape[-1])], dim=1)
+    return F.conv1d(q, sd[p + "cond_scale.weight"]) * x + F.conv1d(q, sd[p + "cond_bias.weight"])
+
+
+def _dprnn_segment(x: Tensor, K: int, overlap: bool) -> Tuple[Tensor, int]:
+    """dprnn.py:133-145 (and the identical :205-217)."""
+    if overlap:
+        return split_overlap(x, K)
+    N, C, T = x.shape
+    x = x.permute(0, 2, 1)
+    rest = K - T % K
+    if rest > 0:
+        x = F.pad(x, (0, 0, 0, rest))
+    return x.reshape(N, -1, K, C), rest
+
+
+def _dprnn_blocks(sd: SD, p: str, seg: Tensor, a: dict, embed, inits, collect_hidden: bool, fast_lstm: bool):
+    """The block loop shared by DPRNN.forward (dprnn.py:153-178) and
+    DPRNN._get_hidden_states (:221-244)."""
+    N, S, K, C = seg.shape
+    bi = not a["causal"]
+    out = seg
+    hidden = []
+    for i in range(a["n_blocks"]):
+        out = out.reshape(-1, K, C).contiguous()
+        if embed is not None and a["block_with_embed"] is not None and a["block_with_embed"][i]:
+            out = film(sd, f"{p}input_film.{i}.", out.transpose(1, 2), embed).transpose(1, 2)
+        y, _ = lstm(sd, f"{p}intra_rnn.{i}.", out, bi, None, fast_lstm)
+        y = F.linear(y, sd[f"{p}intra_proj.{i}.weight"], sd[f"{p}intra_proj.{i}.bias"])
+        y = F.layer_norm(y, (C,), sd[f"{p}intra_norm.{i}.weight"], sd[f"{p}intra_norm.{i}.bias"], 1e-5)
+        out = out + y
+        v = out.reshape(N, S, K, C).permute(0, 2, 1, 3).reshape(-1, S, C).contiguous()
+        y, hid = lstm(sd, f"{p}inter_rnn.{i}.", v, bi, inits[i], fast_lstm)
+        hidden.append(hid)
+        y = F.linear(y, sd[f"{p}inter_proj.{i}.weight"], sd[f"{p}inter_proj.{i}.bias"])
+        y = F.layer_norm(y, (C,), sd[f"{p}inter_norm.{i}.weight"], sd[f"{p}inter_norm.{i}.bias"], 1e-5)
+        out = v + y
+        out = out.reshape(N, K, S, C).contiguous().permute(0, 2, 1, 3)
+    return (hidden if collect_hidden else out)
+
+
+def dprnn_hidden_states(sd: SD, p: str, x: Tensor, a: dict, fast_lstm: bool = True):
+    """DPRNN._get_hidden_states, dprnn.py:193-244."""
+    seg, _ = _dprnn_segment(x, a["seg_size"], a["seg_overlap"])
+    return _dprnn_blocks(sd, p, seg, a, None, [None] * a["n_blocks"], True, fast_lstm)
+
+
+def dprnn(sd: SD, p: str, x: Tensor, embed: Optional[Tensor], a: dict, fast_lstm: bool = True) -> Tensor:
+    """DPRNN.forward, dprnn.py:111-191."""
+    if a["embedding_free_tse"]:
+        assert embed is not None and embed.dim() == 3, "embedding free tse need enrollment waveform as input."
+        inits = dprnn_hidden_states(sd, p, embed, a, fast_lstm)
+    else:
+        inits = [None] * a["n_blocks"]
+    if a["embed_norm"] and embed is not None and not a["embedding_free_tse"]:
+        embed = F.normalize(embed, p=2, dim=1)
+    N, C, T = x.shape
+    seg, rest = _dprnn_segment(x, a["seg_size"], a["seg_overlap"])
+    S = seg.shape[1]
+    film_embed = None
+    if not a["embedding_free_tse"] and embed is not None:
+        film_embed = embed.unsqueeze(1).repeat(1, S, 1).reshape(N * S, -1)
+    out = _dprnn_blocks(sd, p, seg, a, film_embed, inits, False, fast_lstm)
+    if a["seg_overlap"]:
+        out = merge_overlap(out.reshape(N, S, a["seg_size"], C), rest)
+    else:
+        out = out.reshape(N, S * a["seg_size"], C)[:, :T, :].transpose(1, 2)
+    out = F.prelu(out, sd[p + "output_fc.0.weight"])
+    return F.conv1d(out, sd[p + "output_fc.1.weight"], sd[p + "output_fc.1.bias"])
+
+
+# --------------------------------------------------------------------------- #
+# A10  speaker path            lobe/trivial.py:21-58, lobe/pooling.py:58-126
+# --------------------------------------------------------------------------- #
+def magnitude(x: Tensor, drop_first: bool = True, log1p: bool = False) -> Tensor:
+    """Magnitude.forward on the 3-D channel-cat layout, lobe/trivial.py:35-58."""
+    re, im = torch.chunk(x, 2, dim=1)
+    if drop_first:
+        re, im = re[:, 1:, :], im[:, 1:, :]
+    mag = torch.sqrt(re.pow(2) + im.pow(2) + 1e-8)
+    return torch.log1p(mag) if log1p else mag
+
+
+def asp(sd: SD, p: str, x: Tensor) -> Tensor:
+    """AttentiveStatisticsPooling.forward with lengths=None (all frames valid,
+    which is how every caller uses it), eval-mode BatchNorm,
+    lobe/pooling.py:87-126.  x [N, C, T] -> [N, 2C, 1]."""
+    a = F.conv1d(x, sd[p + "tdnn.0.weight"], sd[p + "tdnn.0.bias"])
+    a = F.relu(a)
+    a = F.batch_norm(
+        a, sd[p + "tdnn.2.running_mean"], sd[p + "tdnn.2.running_var"], sd[p + "tdnn.2.weight"], sd[p + "tdnn.2.bias"], False, 0.0, 1e-5
+    )
+    a = F.conv1d(torch.tanh(a), sd[p + "conv.weight"], sd[p + "conv.bias"])
+    w = F.softmax(a, dim=2)
+    mean = (w * x).sum(2)
+    std = torch.sqrt((w * (x - mean.unsqueeze(2)).pow(2)).sum(2).clamp(1e-12))
+    return torch.cat((mean, std), dim=1).unsqueeze(2)
+
+
+def speaker_net(sd: SD, p: str, layers: Sequence[dict], x: Tensor) -> Tensor:
+    """The ModuleList speaker nets of the TSE recipes (egs/tse/model.py:118-135),
+    applied layer by layer as base_nn.py:699-705 does.  Returns [N, E]."""
+    for j, l in enumerate(layers):
+        q = f"{p}{j}."
+        t = l["type"]
+        if t == "Magnitude":
+            x = magnitude(x, l["drop_first"], l["log1p"])
+        elif t == "TCN":
+            x = tcn_block(sd, q, x, None, l["kernel"], l["dilation"], l["causal"], l["tcn_norm"], l["dconv_norm"])
+        elif t == "AttentiveStatisticsPooling":
+            x = asp(sd, q, x)
+        elif t == "Conv1d":
+            x = F.conv1d(x, sd[q + "weight"], sd.get(q + "bias"))
+        else:
+            raise NotImplementedError(t)
+    return x.squeeze(-1)
+
+
+# --------------------------------------------------------------------------- #
+# A6/A11/A12  task wrapper                       puresound/nnet/base_nn.py
+# --------------------------------------------------------------------------- #
+def get_mask(mask: Tensor, constraint: str) -> Tensor:
+    """EncDecMaskerBaseModel.get_mask, base_nn.py:81-95."""
+    c = constraint.lower()
+    if c == "linear":
+        return mask
+    if c == "relu":
+        return torch.relu(mask)
+    if c == "sigmoid":
+        return torch.sigmoid(mask)
+    raise NotImplementedError
+
+
+def apply_tf_masks(tf: Tensor, m: Tensor, mask_type: str, f_type: str) -> Tensor:
+    """apply_tf_masks, base_nn.py:41-79 — the two working combinations
+    (real/real :146-159 and complex/complex :97-112); output re-laid as the
+    channel-cat [N, 2F, T] that _get_waveform re-stacks (:381-383)."""
+    mt, ft = mask_type.lower(), f_type.lower()
+    if mt == "real" and ft == "real":
+        return tf * m
+    if mt == "complex" and ft == "complex":
+        a, b = torch.chunk(tf, 2, dim=1)
+        c, d = torch.chunk(m, 2, dim=1)
+        return torch.cat([a * c - b * d, a * d + b * c], dim=1)
+    if (mt, ft) in (("real", "complex"), ("polar", "polar")):
+        raise NotImplementedError("broken upstream (base_nn.py:127, :75); not targeted")
+    raise NameError
+
+
+def _encode(sd: SD, p: str, e: dict, wav: Tensor, drop_first_bin: bool) -> Tensor:
+    """SoTaskWrapModule._get_feature for one input, base_nn.py:335-345."""
+    if e["type"] == "FreeEncDec":
+        return free_encode(wav, sd[p + "encoder.weight"], e["hop_length"], e["output_active"])
+    if e["type"] == "ConvEncDec":
+        X = stft_encode(wav, sd[p + "encoder.wsin"], sd[p + "encoder.wcos"], e["hop_length"])
+        re, im = X[..., 0], X[..., 1]
+        if drop_first_bin:
+            re, im = re[:, 1:, :], im[:, 1:, :]
+        return torch.cat([re, im], dim=1)
+    raise NotImplementedError(e["type"])
+
+
+def _decode(sd: SD, p: str, e: dict, feats: Tensor, drop_first_bin: bool) -> Tensor:
+    """SoTaskWrapModule._get_waveform, base_nn.py:379-396."""
+    if e["type"] == "FreeEncDec":
+        return free_decode(feats, sd[p + "decoder.weight"], e["hop_length"])
+    re, im = torch.chunk(feats, 2, dim=1)
+    if drop_first_bin:
+        z = re.new_zeros(re.shape[0], 1, re.shape[2])
+        re, im = torch.cat([z, re], dim=1), torch.cat([z, im], dim=1)
+    X = torch.stack([re, im], dim=-1)
+    return stft_decode(
+        X, sd[p + "encoder.kernel_cos_inv"], sd[p + "encoder.kernel_sin_inv"], sd[p + "encoder.window_mask"], e["hop_length"], e["fft_length"]
+    )
+
+
+def wav_constrain(wav: Tensor, mode: str) -> Tensor:
+    """_wav_output_constrain, base_nn.py:414-424."""
+    m = mode.lower()
+    if m == "linear":
+        return torch.clamp(wav, min=-1, max=1)
+    if m == "sigmoid":
+        return torch.sigmoid(wav)
+    raise NameError("Non support type.")
+
+
+def masker_forward(sd: SD, p: str, mcfg: dict, x: Tensor, dvec: Optional[Tensor], fast_lstm: bool = True) -> Tensor:
+    if mcfg["type"] == "ConvTasNet":
+        return conv_tasnet(sd, p, x, dvec, mcfg)
+    if mcfg["type"] == "DPRNN":
+        return dprnn(sd, p, x, dvec, mcfg, fast_lstm)
+    raise NotImplementedError(mcfg["type"])
+
+
+def tse_embedding(sd: SD, cfg: dict, enroll: Tensor) -> Tensor:
+    """SoTaskWrapModule.inference_tse_embedding, base_nn.py:724-738 (returns the
+    un-squeezed speaker-net output, as the reference does)."""
+    if cfg.get("encoder_spk") is not None:
+        f = _encode(sd, "encoder_spk.", cfg["encoder_spk"], enroll, cfg["drop_first_bin"])
+    else:
+        f = _encode(sd, "encoder.", cfg["encoder"], enroll, cfg["drop_first_bin"])
+    return speaker_net(sd, "speaker_net.", cfg["speaker_net"], f).unsqueeze(-1)
+
+
+def inference(
+    sd: SD, cfg: dict, noisy: Tensor, enroll: Optional[Tensor] = None, pre_clamp: bool = False, fast_lstm: bool = True
+) -> Tensor:
+    """SoTaskWrapModule.inference, base_nn.py:690-722.  ``pre_clamp`` returns the
+    waveform before _wav_output_constrain (parity is also checked
+    there because the clamp can hide errors)."""
+    with torch.no_grad():
+        feats = _encode(sd, "encoder.", cfg["encoder"], noisy, cfg["drop_first_bin"])
+        dvec = None
+        if enroll is not None:
+            if cfg.get("encoder_spk") is not None:
+                dvec = _encode(sd, "encoder_spk.", cfg["encoder_spk"], enroll, cfg["drop_first_bin"])
+            else:
+                dvec = _encode(sd, "encoder.", cfg["encoder"], enroll, cfg["drop_first_bin"])
+            if not cfg["embedding_free_tse"]:
+                dvec = speaker_net(sd, "speaker_net.", cfg["speaker_net"], dvec)
+        mask = masker_forward(sd, "masker.", cfg["masker"], feats, dvec, fast_lstm)
+        mask = get_mask(mask, cfg["mask_constraint"])
+        enh = apply_tf_masks(feats, mask, cfg["mask_type"], cfg["f_type"])
+        wav = _decode(sd, "encoder.", cfg["encoder"], enh, cfg["drop_first_bin"])
+        return wav if pre_clamp else wav_constrain(wav, cfg["output_constraint"])
+
+
+# --------------------------------------------------------------------------- #
+# acceptance metric                     puresound/nnet/loss/sdr.py:263-299
+# --------------------------------------------------------------------------- #
+def si_snr(est: Tensor, ref: Tensor, eps: float = 1e-8) -> Tensor:
+    """si_snr(reduction=False): zero-mean, project, 10*log10 power ratio."""
+    est = est - est.mean(-1, keepdim=True)
+    ref = ref - ref.mean(-1, keepdim=True)
+    dot = (est * ref).sum(-1, keepdim=True)
+    tgt = dot / ((ref * ref).sum(-1, keepdim=True) + eps) * ref
+    err = est - tgt
+    return 10 * torch.log10((tgt * tgt).sum(-1) / ((err * err).sum(-1) + eps) + eps)

@@ -1,0 +1,296 @@
+"""Generate the golden vectors under tests/golden/ from the REFERENCE itself.
+
+Run in the authoring container only (it imports /root/reference, which does not
+exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Small cases (``small_*.pt``): reference modules with tiny dimensions, seeded
+'perturbed' weights (puresound_b200.testing.perturb_), seeded inputs; each file
+stores cfg + state_dict + inputs + the reference's outputs.
+
+Full-size pins (``full_size_pins.json``): the BASELINE.json configurations
+built under torch.manual_seed(0) (+ perturb seed 1), run through the reference's
+``SoTaskWrapModule.inference`` on the seeded synthetic inputs; stores a weight
+checksum and a strided sub-sample of the output so that a GPU-box test can
+rebuild identical weights from the seed and compare against the reference's own
+numbers without the reference being present.
+"""
+from __future__ import annotations
+
+import importlib.util
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+REF = os.environ.get("PURESOUND_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+from puresound.nnet.base_nn import SoTaskWrapModule  # noqa: E402
+from puresound.nnet.conv_tasnet import TCN, ConvTasNet  # noqa: E402
+from puresound.nnet.dprnn import DPRNN  # noqa: E402
+from puresound.nnet.lobe.encoder import ConvEncDec, FreeEncDec  # noqa: E402
+from puresound.nnet.lobe.pooling import AttentiveStatisticsPooling  # noqa: E402
+from puresound.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge  # noqa: E402
+
+from oracle import describe as D  # noqa: E402
+from puresound_b200 import testing as T  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def quiet(fn, *a, **k):
+    with redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return scale * (2 * torch.rand(*shape, generator=g) - 1)
+
+
+def sd_of(m):
+    return {k: v.clone() for k, v in m.state_dict().items()}
+
+
+@torch.no_grad()
+def small_cases():
+    # ---- lobes ----
+    torch.manual_seed(10)
+    enc = FreeEncDec(win_length=32, laten_length=24, hop_length=16, output_active=True)
+    x = rnd(2, 400, seed=1)
+    f = enc(x)
+    save("small_free_encdec.pt", {"cfg": D.describe_encoder(enc), "sd": sd_of(enc), "wav": x, "feats": f, "inv": enc.inverse(f)})
+
+    torch.manual_seed(11)
+    stft = ConvEncDec(fft_length=64, win_type="hann", win_length=64, hop_length=16, trainable=True, output_format="Complex")
+    x = rnd(2, 64 + 16 * 9, seed=2)
+    X = stft(x)
+    save("small_conv_stft.pt", {"cfg": D.describe_encoder(stft), "sd": sd_of(stft), "wav": x, "spec": X, "inv": stft.inverse(X.clone())})
+
+    cases = {}
+    for tag, kw in {
+        "gln": dict(causal=False, tcn_norm="gLN", dconv_norm="gGN", emb_dim=0, dilation=2),
+        "gln_emb": dict(causal=False, tcn_norm="gLN", dconv_norm="gGN", emb_dim=6, dilation=4),
+        "cln_causal": dict(causal=True, tcn_norm="cLN", dconv_norm="cLN", emb_dim=0, dilation=2),
+        "bn_causal": dict(causal=True, tcn_norm="bN1d", dconv_norm="bN1d", emb_dim=0, dilation=1),
+    }.items():
+        torch.manual_seed(12)
+        m = T.perturb_(TCN(16, 24, 3, **kw).eval(), seed=3)
+        x = rnd(2, 16, 50, seed=4)
+        e = rnd(2, 6, seed=5) if kw["emb_dim"] else None
+        cases[tag] = {"cfg": D.describe_tcn(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e) if e is not None else m(x)}
+    save("small_tcn.pt", cases)
+
+    torch.manual_seed(13)
+    m = T.perturb_(ConvTasNet(16, 8, True, tcn_dim=24, per_tcn_stack=3, repeat_tcn=2, tcn_with_embed=[1, 0, 1]).eval(), seed=6)
+    x, dv = rnd(2, 16, 70, seed=7), rnd(2, 8, seed=8)
+    save("small_conv_tasnet.pt", {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "dvec": dv, "y": m(x, dv)})
+
+    x = rnd(3, 8, 103, seed=9)
+    seg, rest = SplitMerge.split(x, 10)
+    save("small_splitmerge.pt", {"x": x, "K": 10, "seg": seg, "rest": rest, "merged": SplitMerge.merge(seg, rest)})
+
+    torch.manual_seed(14)
+    fm = T.perturb_(FiLM(16, 6, input_norm=True).eval(), seed=10)
+    x, c = rnd(4, 16, 10, seed=11), rnd(4, 6, seed=12)
+    save("small_film.pt", {"sd": sd_of(fm), "x": x, "cond": c, "y": fm(x, c)})
+
+    cases = {}
+    for tag, kw in {
+        "overlap_bi": dict(n_blocks=2, seg_size=10, seg_overlap=True, causal=False),
+        "nooverlap_causal": dict(n_blocks=2, seg_size=10, seg_overlap=False, causal=True),
+        "nooverlap_exact": dict(n_blocks=1, seg_size=10, seg_overlap=False, causal=True),  # T % K == 0 quirk
+        "film": dict(n_blocks=3, seg_size=8, seg_overlap=True, causal=True, embed_dim=6, embed_norm=True, block_with_embed=[0, 1, 1]),
+    }.items():
+        torch.manual_seed(15)
+        m = T.perturb_(DPRNN(16, 12, 16, **kw).eval(), seed=13)
+        Tn = 60 if tag == "nooverlap_exact" else 57
+        x = rnd(2, 16, Tn, seed=14)
+        e = rnd(2, 6, seed=15) if kw.get("embed_dim") else None
+        cases[tag] = {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e)}
+    torch.manual_seed(16)
+    m = T.perturb_(
+        DPRNN(16, 12, 16, n_blocks=2, seg_size=10, seg_overlap=False, causal=True, block_with_embed=(False, False), embedding_free_tse=True).eval(),
+        seed=16,
+    )
+    x, e = rnd(2, 16, 57, seed=17), rnd(2, 16, 83, seed=18)
+    cases["embedding_free"] = {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e)}
+    save("small_dprnn.pt", cases)
+
+    torch.manual_seed(17)
+    pool = T.perturb_(AttentiveStatisticsPooling(16, 8).eval(), seed=19)
+    x = rnd(2, 16, 41, seed=20)
+    mg = Magnitude(drop_first=False)
+    save("small_speaker.pt", {"sd": sd_of(pool), "x": x, "asp": pool(x), "mag": mg(x), "mag_drop": Magnitude(drop_first=True)(x)})
+
+    # ---- wrappers ----
+    cases = {}
+    torch.manual_seed(18)
+    ns = quiet(
+        SoTaskWrapModule,
+        encoder=FreeEncDec(32, 32, 16),
+        masker=ConvTasNet(32, 0, False, tcn_dim=48, per_tcn_stack=4, repeat_tcn=2, tcn_with_embed=[0] * 4),
+        mask_constraint="ReLU",
+        verbose=False,
+    ).eval()
+    T.perturb_(ns, seed=21)
+    x = T.white(2, 1600, amp=0.1, seed=22)
+    cases["ns"] = {"cfg": D.describe(ns), "sd": sd_of(ns), "noisy": x, "enroll": None, "y": ns.inference(x)}
+
+    torch.manual_seed(19)
+    tse = quiet(
+        SoTaskWrapModule,
+        encoder=ConvEncDec(64, "hann", 64, hop_length=16, trainable=True, output_format="Complex"),
+        masker=ConvTasNet(64, 12, True, tcn_dim=24, per_tcn_stack=3, repeat_tcn=2, tcn_with_embed=[1, 0, 0]),
+        speaker_net=nn.ModuleList(
+            [Magnitude(drop_first=False)] + [TCN(32, 24, 3, dilation=2 ** i) for i in range(2)] + [AttentiveStatisticsPooling(32, 8), nn.Conv1d(64, 12, 1, bias=False)]
+        ),
+        f_type="complex",
+        mask_type="complex",
+        mask_constraint="linear",
+        drop_first_bin=True,
+        verbose=False,
+    ).eval()
+    T.perturb_(tse, seed=23)
+    x, e = T.white(2, 64 + 16 * 30, amp=0.1, seed=24), T.white(2, 64 + 16 * 44, amp=0.1, seed=25)
+    cases["tse_stft"] = {
+        "cfg": D.describe(tse), "sd": sd_of(tse), "noisy": x, "enroll": e, "y": tse.inference(x, e), "dvec": tse.inference_tse_embedding(e),
+    }
+
+    torch.manual_seed(20)
+    tse2 = quiet(
+        SoTaskWrapModule,
+        encoder=FreeEncDec(32, 32, 16),
+        masker=ConvTasNet(32, 12, True, tcn_dim=24, per_tcn_stack=3, repeat_tcn=2, tcn_with_embed=[1, 0, 0], tcn_norm="bN1d", dconv_norm="bN1d", causal=True),
+        speaker_net=nn.ModuleList([TCN(32, 24, 3, dilation=2 ** i) for i in range(2)] + [AttentiveStatisticsPooling(32, 8), nn.Conv1d(64, 12, 1, bias=False)]),
+        mask_constraint="ReLU",
+        verbose=False,
+    ).eval()
+    T.perturb_(tse2, seed=26)
+    x, e = T.white(2, 1200, amp=0.1, seed=27), T.white(2, 1700, amp=0.1, seed=28)
+    cases["tse_free_causal"] = {"cfg": D.describe(tse2), "sd": sd_of(tse2), "noisy": x, "enroll": e, "y": tse2.inference(x, e)}
+
+    torch.manual_seed(21)
+    veve = quiet(
+        SoTaskWrapModule,
+        encoder=FreeEncDec(32, 16, 16, output_active=True),
+        masker=DPRNN(16, 12, 16, n_blocks=2, seg_size=10, seg_overlap=False, causal=True, block_with_embed=(False, False), embedding_free_tse=True),
+        mask_constraint="ReLU",
+        embedding_free_tse=True,
+        verbose=False,
+    ).eval()
+    T.perturb_(veve, seed=29)
+    x, e = T.white(2, 1500, amp=0.1, seed=30), T.white(2, 1100, amp=0.1, seed=31)
+    cases["veve_dprnn"] = {"cfg": D.describe(veve), "sd": sd_of(veve), "noisy": x, "enroll": e, "y": veve.inference(x, e)}
+    save("small_wrappers.pt", cases)
+
+
+def full_cfgs():
+    """SURVEY 8d constructors.  name -> (builder, noisy_len, enroll_len, batch)."""
+    def cfg1():
+        return quiet(
+            SoTaskWrapModule,
+            encoder=FreeEncDec(32, 512, 16),
+            masker=ConvTasNet(512, 0, False, tcn_kernel=3, tcn_dim=512, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8, tcn_with_embed=[0] * 8, tcn_norm="gLN", dconv_norm="gGN", causal=False, tcn_layer="normal"),
+            mask_constraint="ReLU",
+            verbose=False,
+        )
+
+    def cfg3():
+        return quiet(
+            SoTaskWrapModule,
+            encoder=FreeEncDec(32, 128, 16, output_active=True),
+            masker=DPRNN(128, 128, 128, n_blocks=6, seg_size=100, seg_overlap=True, causal=False),
+            mask_constraint="ReLU",
+            verbose=False,
+        )
+
+    def cfg4():
+        return quiet(
+            SoTaskWrapModule,
+            encoder=ConvEncDec(512, "hann", 512, hop_length=128, trainable=True, output_format="Complex"),
+            masker=ConvTasNet(512, 192, True, tcn_dim=256, repeat_tcn=3, per_tcn_stack=8, tcn_with_embed=[1, 0, 0, 0, 0, 0, 0, 0]),
+            speaker_net=nn.ModuleList(
+                [Magnitude(drop_first=False)] + [TCN(256, 256, 3, dilation=2 ** i) for i in range(5)] + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(512, 192, 1, bias=False)]
+            ),
+            mask_constraint="linear",
+            drop_first_bin=True,
+            verbose=False,
+        )
+
+    def cfg5():
+        return quiet(
+            SoTaskWrapModule,
+            encoder=FreeEncDec(320, 512, 160),
+            masker=ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN", dconv_norm="cLN", causal=True),
+            mask_constraint="ReLU",
+            verbose=False,
+        )
+
+    def veve():
+        spec = importlib.util.spec_from_file_location("ref_tse_model", os.path.join(REF, "egs/tse/model.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return quiet(mod.init_model, "veve_dprnn_v0_causal", None, None, verbose=False)
+
+    return {
+        "cfg1": (cfg1, 64000, None, 2),
+        "cfg3": (cfg3, 160000, None, 1),
+        "cfg4": (cfg4, 64000, 96000, 2),
+        "cfg5_offline": (cfg5, 32000, None, 1),
+        "veve_dprnn_v0_causal": (veve, 64000, 96000, 1),
+    }
+
+
+@torch.no_grad()
+def full_pins():
+    pins = {}
+    for name, (build, L, Le, n) in full_cfgs().items():
+        torch.manual_seed(0)
+        m = build().eval()
+        T.perturb_(m, seed=1)
+        mix, _ = T.noisy_speech(n, L, seed=1234)
+        enr = T.noisy_speech(n, Le, seed=4321)[0] if Le else None
+        y = m.inference(mix, enr)
+        stride = 997
+        pins[name] = {
+            "params": sum(p.numel() for p in m.parameters()),
+            "state_checksum": T.state_checksum(m.state_dict()),
+            "batch": n,
+            "length": L,
+            "enroll_length": Le,
+            "input_seed": 1234,
+            "enroll_seed": 4321,
+            "stride": stride,
+            "out_len": y.shape[-1],
+            "out_abs_mean": float(y.abs().mean()),
+            "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+            "samples": [[float(v) for v in row[::stride]] for row in y],
+        }
+        print(name, pins[name]["params"], pins[name]["state_checksum"], pins[name]["out_abs_mean"], pins[name]["out_clamped_frac"])
+    with open(os.path.join(HERE, "full_size_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "small"):
+        small_cases()
+    if which in ("all", "full"):
+        full_pins()
