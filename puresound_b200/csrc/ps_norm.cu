@@ -1,0 +1,154 @@
+// Normalisation kernels: gLN/gGN statistics merge, bN1d fold, cLN / LayerNorm rows.
+#include "ps_common.cuh"
+
+namespace ps {
+
+// One CTA per batch item: Chan-merge the (count, mean, M2) partials in a fixed
+// (deterministic) order in fp64, then emit the folded per-channel affine.
+__global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __restrict__ partials, int64_t slots,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int64_t C,
+                                                             float* __restrict__ scale, float* __restrict__ shift,
+                                                             float* __restrict__ meanvar) {
+  __shared__ double sn[256], sm[256], s2[256];
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const float* p = partials + b * slots * 3;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int64_t i = tid; i < slots; i += 256) {
+    double bn = p[i * 3], bm = p[i * 3 + 1], b2 = p[i * 3 + 2];
+    if (bn > 0.0) {
+      double nn = n + bn, dlt = bm - mean;
+      mean += dlt * (bn / nn);
+      m2 += b2 + dlt * dlt * n * (bn / nn);
+      n = nn;
+    }
+  }
+  sn[tid] = n; sm[tid] = mean; s2[tid] = m2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      double an = sn[tid], am = sm[tid], a2 = s2[tid];
+      double bn = sn[tid + o], bm = sm[tid + o], b2 = s2[tid + o];
+      if (bn > 0.0) {
+        double nn = an + bn, dlt = bm - am;
+        am += dlt * (bn / nn);
+        a2 += b2 + dlt * dlt * an * (bn / nn);
+        an = nn;
+      }
+      sn[tid] = an; sm[tid] = am; s2[tid] = a2;
+    }
+    __syncthreads();
+  }
+  const double cnt = sn[0];
+  const double mu = sm[0];
+  const double var = cnt > 0.0 ? s2[0] / cnt : 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float muf = (float)mu;
+  for (int64_t c = tid; c < C; c += 256) {
+    const float g = gamma ? gamma[c] : 1.f;
+    const float bt = beta ? beta[c] : 0.f;
+    const float sc = g * rstd;
+    scale[b * C + c] = sc;
+    shift[b * C + c] = fmaf(-muf, sc, bt);
+  }
+  if (meanvar && tid == 0) {
+    meanvar[b * 2] = muf;
+    meanvar[b * 2 + 1] = (float)var;
+  }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float eps, int64_t C, float* __restrict__ scale,
+                               float* __restrict__ shift) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc = (w ? w[c] : 1.f) / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = fmaf(-rm[c], sc, b ? b[c] : 0.f);
+}
+
+// one warp per row: two-pass mean / biased variance, exactly as torch computes them
+__device__ __forceinline__ void row_mean_rstd(const float* __restrict__ x, int64_t C, float eps, int lane, float& mean,
+                                              float& rstd) {
+  float s = 0.f;
+  for (int64_t c = lane; c < C; c += 32) s += x[c];
+  mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int64_t c = lane; c < C; c += 32) {
+    float dlt = x[c] - mean;
+    q = fmaf(dlt, dlt, q);
+  }
+  rstd = 1.f / sqrtf(warp_sum(q) / (float)C + eps);
+}
+
+__global__ void __launch_bounds__(256) rowstats_kernel(const float* __restrict__ x, int64_t rows, int64_t C,
+                                                       int64_t row_stride, float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float mean, rstd;
+  row_mean_rstd(x + r * row_stride, C, eps, lane, mean, rstd);
+  if (lane == 0) {
+    out[r * 2] = mean;
+    out[r * 2 + 1] = rstd;
+  }
+}
+
+__global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                      float* __restrict__ y, int64_t rows, int64_t C,
+                                                      const float* __restrict__ w, const float* __restrict__ b,
+                                                      float eps, int act, const float* __restrict__ slope_p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float slope = slope_p ? __ldg(slope_p) : 0.f;
+  const float* xr = x + r * C;
+  float mean, rstd;
+  row_mean_rstd(xr, C, eps, lane, mean, rstd);
+  for (int64_t c = lane; c < C; c += 32) {
+    float v = (xr[c] - mean) * rstd;
+    v = fmaf(v, w ? w[c] : 1.f, b ? b[c] : 0.f);
+    v = apply_act(v, act, slope);
+    if (res) v += res[r * C + c];
+    y[r * C + c] = v;
+  }
+}
+
+}  // namespace ps
+
+extern "C" int ps_stats_finalize(const float* partials, int64_t batch, int64_t slots, const float* gamma,
+                                 const float* beta, float eps, int64_t C, float* scale, float* shift, float* meanvar,
+                                 void* stream) {
+  PS_REQUIRE(partials && scale && shift && batch > 0 && slots > 0 && C > 0);
+  ps::stats_finalize_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(partials, slots, gamma, beta, eps, C,
+                                                                               scale, shift, meanvar);
+  PS_CHECK_LAUNCH("stats_finalize_kernel");
+  return PS_OK;
+}
+
+extern "C" int ps_bn_fold(const float* weight, const float* bias, const float* running_mean, const float* running_var,
+                          float eps, int64_t C, float* scale, float* shift, void* stream) {
+  PS_REQUIRE(running_mean && running_var && scale && shift && C > 0);
+  ps::bn_fold_kernel<<<(unsigned)ps::cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(weight, bias, running_mean,
+                                                                                  running_var, eps, C, scale, shift);
+  PS_CHECK_LAUNCH("bn_fold_kernel");
+  return PS_OK;
+}
+
+extern "C" int ps_rowstats(const float* x, int64_t rows, int64_t C, int64_t row_stride, float eps, float* out,
+                           void* stream) {
+  PS_REQUIRE(x && out && rows > 0 && C > 0 && row_stride >= C);
+  ps::rowstats_kernel<<<(unsigned)ps::cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, C, row_stride, eps, out);
+  PS_CHECK_LAUNCH("rowstats_kernel");
+  return PS_OK;
+}
+
+extern "C" int ps_rownorm(const float* x, const float* res, float* y, int64_t rows, int64_t C, const float* w,
+                          const float* b, float eps, int32_t act, const float* slope, void* stream) {
+  PS_REQUIRE(x && y && rows > 0 && C > 0);
+  ps::rownorm_kernel<<<(unsigned)ps::cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, res, y, rows, C, w, b, eps, act,
+                                                                                   slope);
+  PS_CHECK_LAUNCH("rownorm_kernel");
+  return PS_OK;
+}

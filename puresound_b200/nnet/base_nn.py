@@ -1,0 +1,212 @@
+"""Task wrapper on the B200 engine: drop-in for the *inference* surface of
+``puresound.nnet.base_nn.SoTaskWrapModule`` (base_nn.py:193-777).
+
+Same constructor signature, attribute names (hence state-dict prefixes
+``encoder.``, ``encoder_spk.``, ``masker.``, ``speaker_net.{j}.``) and the same
+``inference(noisy, enroll)`` / ``inference_tse_embedding(enroll)`` contracts.  The
+whole waveform-in -> waveform-out path stays frames-major on the device: encoder
+GEMM -> [speaker net] -> masker -> mask activation+apply (fused into the decoder
+GEMM's operand load for real masks) -> synthesis GEMM -> overlap-add with the
+output constraint fused.  Training (``forward(**kw)`` -> loss) is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_RELU, ACT_SIGMOID
+from .lobe.encoder import ConvEncDec, FreeEncDec
+
+_MASK_ACT = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
+_OUT_CONSTRAINT = {"linear": 1, "sigmoid": 2}
+
+
+class SoTaskWrapModule(nn.Module):
+    def __init__(
+        self,
+        encoder: nn.Module,
+        masker: nn.Module,
+        embedding_free_tse: bool = False,
+        encoder_spk: Optional[nn.Module] = None,
+        speaker_net: Optional[nn.Module] = None,
+        loss_func_wav: Optional[nn.Module] = None,
+        loss_func_spk: Optional[nn.Module] = None,
+        loss_func_others: Optional[nn.Module] = None,
+        f_type: str = "real",
+        mask_type: str = "real",
+        mask_constraint: str = "linear",
+        output_constraint: str = "linear",
+        drop_first_bin: bool = False,
+        verbose: bool = True,
+    ) -> None:
+        super().__init__()
+        self.f_type, self.mask_type = f_type, mask_type
+        self.encoder, self.masker = encoder, masker
+        self.embedding_free_tse = embedding_free_tse
+        self.encoder_spk, self.speaker_net = encoder_spk, speaker_net
+        self.loss_func_wav, self.loss_func_spk, self.loss_func_others = loss_func_wav, loss_func_spk, loss_func_others
+        self.mask_constraint, self.output_constraint = mask_constraint, output_constraint
+        self.drop_first_bin = drop_first_bin
+        self.task = self.check_task()
+        if verbose:
+            self._verbose()
+
+    # ------------------------------------------------------------------ bookkeeping
+    def check_task(self):
+        """Task label as the reference derives it (base_nn.py:263-317): 0 SE/BSS, 1 TSE multi-task,
+        4 embedding-free TSE, None inference-only TSE."""
+        if self.speaker_net is None:
+            return 4 if self.embedding_free_tse else 0
+        if self.loss_func_wav is None and self.loss_func_spk is None:
+            return None
+        if self.loss_func_spk is not None and self.loss_func_wav is None:
+            return 2
+        if self.loss_func_spk is not None and self.loss_func_others is not None:
+            return 3
+        return 1
+
+    @property
+    def overall_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    @property
+    def overall_trainable_parameters(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def get_state_dict(self):
+        return self.state_dict()
+
+    def forward(self, **kwargs):
+        raise NotImplementedError("the B200 engine implements inference(); training losses are out of scope (SURVEY.md 8)")
+
+    # ------------------------------------------------------------------ engine path
+    def _encode_cl(self, enc: nn.Module, wav: torch.Tensor) -> torch.Tensor:
+        if isinstance(enc, ConvEncDec):
+            return enc.encode_cl(wav, self.drop_first_bin)
+        if isinstance(enc, FreeEncDec):
+            return enc.encode_cl(wav)
+        raise NotImplementedError(f"encoder {type(enc).__name__} is outside the separator hot path")
+
+    def _speaker_net_cl(self, feats: torch.Tensor) -> torch.Tensor:
+        """Apply the speaker net layer by layer (base_nn.py:699-705) on frames-major features -> dvec [N, E]."""
+        layers = list(self.speaker_net) if isinstance(self.speaker_net, (nn.ModuleList, nn.Sequential)) else [self.speaker_net]
+        x = feats
+        for layer in layers:
+            if hasattr(layer, "forward_cl"):
+                x = layer.forward_cl(x)
+            elif isinstance(layer, nn.Conv1d) and layer.kernel_size == (1,) and layer.groups == 1:
+                if x.dim() == 2:
+                    x = x.unsqueeze(1)
+                x, _ = ops.linear(x.contiguous(), layer.weight.view(layer.out_channels, layer.in_channels), bias=layer.bias)
+            else:
+                raise NotImplementedError(f"speaker-net layer {type(layer).__name__} is outside the separator hot path")
+        if x.dim() == 3:
+            if x.shape[1] != 1:
+                raise ValueError("speaker net must pool over time (output [N, E, 1] in the reference layout)")
+            x = x[:, 0, :]
+        return x.contiguous()
+
+    def _to_device(self, t: Optional[torch.Tensor]):
+        if t is None:
+            return None
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("puresound_b200 modules run on a CUDA device only: call model.to('cuda') (no CPU fallback)")
+        return t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def _inference_cl(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor], constrain: bool = True) -> torch.Tensor:
+        mask_act = _MASK_ACT.get(self.mask_constraint.lower())
+        if mask_act is None:
+            raise NotImplementedError
+        if constrain:
+            constraint = _OUT_CONSTRAINT.get(self.output_constraint.lower())
+            if constraint is None:
+                raise NameError("Non support type.")
+        else:
+            constraint = 0
+        mt, ft = self.mask_type.lower(), self.f_type.lower()
+        if (mt, ft) not in (("real", "real"), ("complex", "complex")):
+            if (mt, ft) in (("real", "complex"), ("polar", "polar")):
+                raise NotImplementedError("this mask/feature combination is broken upstream (base_nn.py:127, :75)")
+            raise NameError
+
+        feats = self._encode_cl(self.encoder, noisy)
+        dvec = None
+        if enroll is not None:
+            enc = self.encoder if self.encoder_spk is None else self.encoder_spk
+            dvec = self._encode_cl(enc, enroll)
+            if not self.embedding_free_tse:
+                dvec = self._speaker_net_cl(dvec)
+        mask = self.masker.forward_cl(feats, dvec) if dvec is not None else self.masker.forward_cl(feats)
+
+        if isinstance(self.encoder, ConvEncDec):
+            enh = ops.mask_apply(feats, mask, mask_act, mt == "complex")
+            return self.encoder.decode_cl(enh, self.drop_first_bin, constraint)
+        if mt == "complex":
+            enh = ops.mask_apply(feats, mask, mask_act, True)
+            return self.encoder.decode_cl(enh, None, ACT_NONE, constraint)
+        return self.encoder.decode_cl(feats, mask, mask_act, constraint)
+
+    # ------------------------------------------------------------------ reference API
+    @torch.no_grad()
+    def inference(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """noisy [N, L], enroll [N, Le] -> enhanced waveform [N, L'] on the caller's device.
+
+        Host tensors are accepted: they are copied to the model's GPU, and the result is copied back."""
+        ops.require_device()
+        on_host = not noisy.is_cuda
+        y = self._inference_cl(self._to_device(noisy), self._to_device(enroll))
+        return y.cpu() if on_host else y
+
+    @torch.no_grad()
+    def inference_pre_constraint(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The waveform before ``_wav_output_constrain`` (parity is also checked here: the clamp hides errors)."""
+        ops.require_device()
+        on_host = not noisy.is_cuda
+        y = self._inference_cl(self._to_device(noisy), self._to_device(enroll), constrain=False)
+        return y.cpu() if on_host else y
+
+    @torch.no_grad()
+    def inference_tse_embedding(self, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Speaker embedding of an enrollment utterance, [N, E, 1] (base_nn.py:724-738)."""
+        ops.require_device()
+        on_host = not enroll.is_cuda
+        enc = self.encoder if self.encoder_spk is None else self.encoder_spk
+        dvec = self._speaker_net_cl(self._encode_cl(enc, self._to_device(enroll))).unsqueeze(-1)
+        return dvec.cpu() if on_host else dvec
+
+    def _verbose(self):
+        """Same probe as the reference (base_nn.py:740-777): half the input is +inf and the first/last NaN in
+        the output gives look-ahead / receptive field, so kernels must propagate NaN/Inf.  Leaves the model in
+        train mode like the reference does."""
+        import numpy as np
+
+        print("---------------Verbose logging---------------")
+        self.eval()
+        print(f"Current training mode is: {self.training}")
+        print(f"Total params: {self.overall_parameters}")
+        if next(self.parameters()).is_cuda:
+            x = torch.rand(1, 10 * 16000)
+            x[..., 5 * 16000:] = np.inf
+            x_spk = torch.rand(1, 10 * 16000)
+            needs_enroll = self.speaker_net is not None or self.embedding_free_tse
+            y = self.inference(x, x_spk if needs_enroll else None).detach()
+            nan_idx = np.where(np.isnan(y.numpy()))[-1]
+            lookahead = nan_idx[0]
+            print("Lookahead(samples): infinite" if lookahead == 0 else f"Lookahead(samples): {80000 - lookahead}")
+            x = torch.rand(1, 10 * 16000)
+            x[..., : -5 * 16000] = np.inf
+            y = self.inference(x, x_spk if needs_enroll else None).detach()
+            receptive = np.where(np.isnan(y.numpy()))[-1][-1]
+            if receptive - (80000 - 1) == 80000:
+                print("Receptive Fields(samples): infinite")
+            else:
+                print(f"Receptive Fields(samples): {receptive - (80000 - 1)}")
+        else:
+            print("(look-ahead / receptive-field probe needs the model on a CUDA device; skipped)")
+        self.train()
+        print(f"Current training mode is: {self.training}")
+        print("---------------Verbose logging---------------")

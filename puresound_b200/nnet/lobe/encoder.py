@@ -1,0 +1,218 @@
+"""Encoders / decoders of the separator path on the B200 engine.
+
+Drop-ins for ``puresound.nnet.lobe.encoder.FreeEncDec`` and ``ConvEncDec``
+(constructor signatures, attribute names and state-dict keys preserved).
+
+Both analysis transforms are *framed GEMMs*: the waveform is read in place as an
+overlapping-row matrix (row stride = hop < K = window), so no im2col buffer is
+ever materialised; the output is written frames-major ``[N, T, C]`` in exactly
+the channel-cat layout the masker consumes.  Both synthesis transforms are a GEMM
+to per-frame windows followed by a gather-form overlap-add with the output
+constraint fused.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...ops import ACT_NONE, ACT_RELU, GEMM_SIMT, PRO_MASK, Prologue
+from .._fuse import ParamCache
+
+
+def _check_wav(x: torch.Tensor, win: int) -> None:
+    if x.dim() != 2:
+        raise ValueError(f"expected a waveform batch [N, L], got shape {tuple(x.shape)}")
+    if x.shape[1] < win:
+        # F.conv1d in the reference raises RuntimeError here (kernel larger than input)
+        raise RuntimeError(f"Kernel size can't be greater than actual input size: L={x.shape[1]} < win={win}")
+
+
+class FreeEncDec(nn.Module):
+    """Learned Conv1d / ConvTranspose1d filterbank (reference lobe/encoder.py:16-94)."""
+
+    def __init__(self, win_length: int = 512, laten_length: int = 512, hop_length: int = 128, output_active: bool = False):
+        super().__init__()
+        self.win_length = win_length
+        self.hop_length = hop_length
+        self.output_active = output_active
+        # parameter holders under the reference's keys: encoder.weight (Nf,1,win), decoder.weight (Nf,1,win)
+        self.encoder = nn.Conv1d(1, laten_length, kernel_size=win_length, stride=hop_length, bias=False)
+        self.decoder = nn.ConvTranspose1d(laten_length, 1, kernel_size=win_length, stride=hop_length, bias=False)
+        self._cache = ParamCache()
+
+    # ---- engine path ----
+    def encode_cl(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [N, L] -> feats [N, T, Nf], T = (L - win)//hop + 1."""
+        _check_wav(wav, self.win_length)
+        N, L = wav.shape
+        Nf, win, hop = self.encoder.out_channels, self.win_length, self.hop_length
+        T = (L - win) // hop + 1
+        y, _ = ops.gemm(wav.contiguous(), self.encoder.weight.view(Nf, win), batch=N, rows=T, M=Nf, K=win,
+                        x_batch_stride=L, x_row_stride=hop, w_row_stride=win,
+                        epi_act=ACT_RELU if self.output_active else ACT_NONE)
+        return y
+
+    def decode_cl(self, feats: torch.Tensor, mask: Optional[torch.Tensor] = None, mask_act: int = ACT_NONE,
+                  constraint: int = 0) -> torch.Tensor:
+        """feats [N, T, Nf] (optionally multiplied by act(mask) on load) -> wav [N, (T-1)*hop + win]."""
+        Nf, win = self.decoder.in_channels, self.win_length
+        w_t = self._cache.get("dec_t", [self.decoder.weight], lambda: self.decoder.weight.view(Nf, win).t().contiguous())
+        pro = Prologue(PRO_MASK, mask_act, x2=mask) if mask is not None else ops.NO_PRO
+        frames, _ = ops.linear(feats, w_t, pro=pro)
+        return ops.ola(frames, self.hop_length, None, constraint)
+
+    # ---- reference-layout API ----
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, L] -> [N, C, T]"""
+        return ops.transpose(self.encode_cl(x))
+
+    @torch.no_grad()
+    def inverse(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, C, T] -> [N, L']"""
+        return self.decode_cl(ops.transpose(x))
+
+
+class ConvSTFT(nn.Module):
+    """Holder of the conv-STFT kernels under the reference's keys
+    (lobe/encoder.py:275-356): ``wsin``/``wcos`` (Parameters iff trainable) and the
+    iSTFT buffers ``kernel_sin_inv``/``kernel_cos_inv``/``window_mask``."""
+
+    def __init__(self, window: torch.Tensor, n_fft: int, hop_length: int, iSTFT: bool, trainable: bool):
+        super().__init__()
+        self.n_fft, self.stride, self.trainable, self.iSTFT = n_fft, hop_length, trainable, iSTFT
+        if len(window) != n_fft:
+            raise TypeError("only support window length == n_fft")
+        # float64 Fourier kernels cast to fp32, bins 0..n_fft/2 (lobe/stft.py:91-100, freq_scale='no')
+        s = np.arange(0, n_fft, 1.0)
+        bins = n_fft // 2 + 1
+        ksin = np.empty((bins, 1, n_fft))
+        kcos = np.empty((bins, 1, n_fft))
+        for k in range(bins):
+            ksin[k, 0, :] = np.sin(2 * np.pi * k * s / n_fft)
+            kcos[k, 0, :] = np.cos(2 * np.pi * k * s / n_fft)
+        ksin = torch.tensor(ksin.astype(np.float32), dtype=torch.float)
+        kcos = torch.tensor(kcos.astype(np.float32), dtype=torch.float)
+        if iSTFT:
+            self.register_buffer("kernel_sin_inv", torch.cat((ksin, -ksin[1:-1].flip(0)), 0).unsqueeze(-1))
+            self.register_buffer("kernel_cos_inv", torch.cat((kcos, kcos[1:-1].flip(0)), 0).unsqueeze(-1))
+        wsin, wcos = ksin * window, kcos * window
+        if trainable:
+            self.wsin = nn.Parameter(wsin)
+            self.wcos = nn.Parameter(wcos)
+        else:
+            self.register_buffer("wsin", wsin)
+            self.register_buffer("wcos", wcos)
+        self.register_buffer("window_mask", window.unsqueeze(0).unsqueeze(-1))
+
+
+class ConvEncDec(nn.Module):
+    """Conv-STFT encoder / conv-iSTFT decoder (reference lobe/encoder.py:97-183)."""
+
+    def __init__(
+        self,
+        fft_length: int = 512,
+        win_type: str = "hann",
+        win_length: int = 512,
+        freq_bins: int = None,
+        hop_length: int = 128,
+        freq_scale: str = "no",
+        iSTFT: bool = True,
+        fmin: int = 0,
+        fmax: int = 8000,
+        sr: int = 16000,
+        trainable: bool = True,
+        output_format: str = "Complex",
+    ):
+        super().__init__()
+        if freq_scale != "no" or freq_bins is not None:
+            raise NotImplementedError("only the linear full-band STFT (freq_scale='no') is on the separator path")
+        if output_format != "Complex":
+            raise NotImplementedError("only output_format='Complex' feeds the maskers")
+        self.n_fft, self.win_length, self.freq_bins, self.hop_length = fft_length, win_length, freq_bins, hop_length
+        self.freq_scale, self.iSTFT, self.fmin, self.fmax, self.sr = freq_scale, iSTFT, fmin, fmax, sr
+        self.trainable, self.output_format = trainable, output_format
+        if win_type.lower() != "hann":
+            raise NotImplementedError("window type not support")
+        self.window = torch.hann_window(win_length)
+        self.encoder = ConvSTFT(self.window, fft_length, hop_length, iSTFT, trainable)
+        self._cache = ParamCache()
+        self._wsum = {}
+
+    @property
+    def bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+    # ---- engine path ----
+    def encode_cl(self, wav: torch.Tensor, drop_first_bin: bool) -> torch.Tensor:
+        """wav [N, L] -> [N, T, 2F'] = cat(Re[s:], Im[s:]) on channels (base_nn.py:337-345 layout), Im = -conv(wsin)."""
+        _check_wav(wav, self.n_fft)
+        e = self.encoder
+        s = 1 if drop_first_bin else 0
+        w = self._cache.get(f"ana{s}", [e.wsin, e.wcos], lambda: torch.cat([e.wcos[s:, 0, :], -e.wsin[s:, 0, :]], 0).contiguous())
+        N, L = wav.shape
+        T = (L - self.n_fft) // self.hop_length + 1
+        y, _ = ops.gemm(wav.contiguous(), w, batch=N, rows=T, M=w.shape[0], K=self.n_fft, x_batch_stride=L,
+                        x_row_stride=self.hop_length, w_row_stride=self.n_fft)
+        return y
+
+    def _synthesis_weight(self, s: int) -> torch.Tensor:
+        """[n_fft (sample k), 2F'] such that frame[k] = sum_f Re[f] Wre[k,f] + Im[f] Wim[k,f] equals the reference's
+        Hermitian-extended conv2d pair, window and 1/n_fft included (lobe/encoder.py:419-438, lobe/stft.py:118-125)."""
+        e = self.encoder
+        F = self.bins
+
+        def build():
+            kc = e.kernel_cos_inv[:F, 0, :, 0].double()  # [F, n_fft]
+            ks = e.kernel_sin_inv[:F, 0, :, 0].double()
+            coef = torch.full((F, 1), 2.0, dtype=torch.float64, device=kc.device)
+            coef[0] = 1.0
+            coef[F - 1] = 1.0
+            win = e.window_mask.flatten().double() / self.n_fft
+            wre = (coef * kc * win)[s:]
+            wim = (-coef * ks * win)[s:]
+            return torch.cat([wre, wim], 0).t().contiguous().float()
+
+        return self._cache.get(f"syn{s}", [e.kernel_cos_inv, e.kernel_sin_inv, e.window_mask], build)
+
+    def _window_sumsquare(self, T: int, device) -> torch.Tensor:
+        """sum_t window^2[j - t*hop] (lobe/stft.py:109-115); constant per frame count, cached."""
+        key = (T, str(device), self.encoder.window_mask._version)
+        if key not in self._wsum:
+            w2 = (self.encoder.window_mask.detach().flatten().cpu() ** 2)
+            out_len = self.n_fft + self.hop_length * (T - 1)
+            stack = w2.unsqueeze(-1).repeat(1, T).unsqueeze(0)
+            ws = torch.nn.functional.fold(stack, (1, out_len), kernel_size=(1, self.n_fft), stride=self.hop_length).flatten()
+            self._wsum = {key: ws.to(device)}
+        return self._wsum[key]
+
+    def decode_cl(self, feats: torch.Tensor, drop_first_bin: bool, constraint: int = 0) -> torch.Tensor:
+        """[N, T, 2F'] channel-cat spectrum -> wav [N, n_fft + hop*(T-1)].  The synthesis GEMM and the
+        overlap-add stay in true fp32: the division by the window sum-square amplifies rounding ~2.6e4x at
+        the first/last hop."""
+        if not self.iSTFT:
+            raise NameError("Please activate the iSTFT module by setting `iSTFT=True` if you want to use `inverse`")
+        s = 1 if drop_first_bin else 0
+        w = self._synthesis_weight(s)
+        frames, _ = ops.linear(feats, w, backend=GEMM_SIMT)
+        return ops.ola(frames, self.hop_length, self._window_sumsquare(feats.shape[1], feats.device), constraint)
+
+    # ---- reference-layout API ----
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, L] -> [N, F, T, 2] (real, imag)"""
+        y = ops.transpose(self.encode_cl(x, False))  # [N, 2F, T]
+        N, _, T = y.shape
+        return y.view(N, 2, self.bins, T).permute(0, 2, 3, 1).contiguous()
+
+    @torch.no_grad()
+    def inverse(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, F, T, 2] -> [N, L']"""
+        assert x.dim() == 4, "Inverse iSTFT only works for complex number, shape (batch, freq_bins, timesteps, 2)"
+        N, F, T, _ = x.shape
+        cl = x.permute(0, 2, 3, 1).reshape(N, T, 2 * F).contiguous()
+        return self.decode_cl(cl, False)

@@ -1,0 +1,300 @@
+"""Thin host-side wrappers: torch CUDA tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory, streams); every arithmetic step of the
+separator forward is a kernel in ``libpuresound_b200.so``.  Activations are
+frames-major ``[batch, rows, channels]`` fp32 contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_PRELU, ACT_RELU, ACT_SIGMOID, ACT_TANH, GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05,  # noqa: F401
+                   PRO_AFFINE, PRO_MASK, PRO_NONE, PRO_ROWNORM)
+
+Tensor = torch.Tensor
+
+#: kernels launched through this module since the last reset (bench.py's gpu_launches)
+launch_count = 0
+#: force a GEMM back end for every call (tests / A-B runs); None = per-call choice
+force_gemm_backend: Optional[int] = None
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: Tensor, what: str) -> Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{what}: expected a CUDA float32 tensor, got {t.device} {t.dtype} (no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{what}: expected a contiguous tensor")
+    return t
+
+
+def _dev(t: Tensor, what: str) -> Tensor:
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{what}: expected a CUDA float32 tensor, got {t.device} {t.dtype} (no CPU fallback)")
+    return t
+
+
+def _launched(n: int = 1):
+    global launch_count
+    launch_count += n
+
+
+def require_device() -> None:
+    """Fail loudly unless a B200-class device and the built library are present."""
+    lib = _lib.load()
+    if not torch.cuda.is_available():
+        raise _lib.EngineMissing("puresound_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    ok = lib.ps_device_ok()
+    if ok != 1:
+        raise _lib.EngineMissing(f"puresound_b200 kernels are built for sm_100a only (device check returned {ok})")
+
+
+@dataclass
+class Prologue:
+    """What a consumer kernel applies to its input on load."""
+    mode: int = PRO_NONE
+    act: int = ACT_NONE
+    a: Optional[Tensor] = None          # AFFINE scale [B or 1, K] / ROWNORM gamma [K]
+    b: Optional[Tensor] = None
+    batch_stride: int = 0
+    rowstats: Optional[Tensor] = None   # [B, rows, 2]
+    slope: Optional[Tensor] = None      # PReLU weight (1,)
+    x2: Optional[Tensor] = None         # MASK operand
+
+
+NO_PRO = Prologue()
+
+
+def gemm(
+    X: Tensor, W: Tensor, *, batch: int, rows: int, M: int, K: int,
+    x_batch_stride: int, x_row_stride: int, w_row_stride: int,
+    pro: Prologue = NO_PRO, bias: Optional[Tensor] = None, bias_batch: Optional[Tensor] = None,
+    epi_act: int = ACT_NONE, epi_slope: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+    want_stats: bool = False, out: Optional[Tensor] = None, backend: int = GEMM_AUTO,
+    w_packed: Optional[Tensor] = None,
+) -> Tuple[Tensor, Optional[Tensor]]:
+    """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None)."""
+    lib = _lib.load()
+    _req(X, "gemm X")
+    _dev(W, "gemm W")  # may be a row-strided view (embedding columns of in_conv)
+    Y = out if out is not None else torch.empty(batch, rows, M, device=X.device, dtype=torch.float32)
+    partials = None
+    if want_stats:
+        slots = lib.ps_gemm_stats_slots(rows, M)
+        partials = torch.empty(batch, slots, 3, device=X.device, dtype=torch.float32)
+    d = _lib.GemmDesc()
+    d.batch, d.rows, d.M, d.K = batch, rows, M, K
+    d.X, d.x_batch_stride, d.x_row_stride = X.data_ptr(), x_batch_stride, x_row_stride
+    d.W, d.w_row_stride = W.data_ptr(), w_row_stride
+    d.Y, d.y_batch_stride, d.y_row_stride = Y.data_ptr(), rows * M, M
+    d.pro_mode, d.pro_act = pro.mode, pro.act
+    d.pro_a, d.pro_b, d.pro_batch_stride = _p(pro.a), _p(pro.b), pro.batch_stride
+    d.pro_rowstats, d.pro_slope, d.X2 = _p(pro.rowstats), _p(pro.slope), _p(pro.x2)
+    d.bias, d.bias_batch = _p(bias), _p(bias_batch)
+    d.epi_act = epi_act
+    d.backend = force_gemm_backend if force_gemm_backend is not None else backend
+    d.epi_slope = _p(epi_slope)
+    if residual is not None:
+        d.residual, d.res_batch_stride, d.res_row_stride = residual.data_ptr(), rows * M, M
+    d.stats_partials = _p(partials)
+    d.W_packed = _p(w_packed)
+    _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
+    _launched()
+    return Y, partials
+
+
+def linear(x: Tensor, W: Tensor, K: Optional[int] = None, w_row_stride: Optional[int] = None, **kw):
+    """GEMM over a contiguous frames-major activation x [B, R, K]; W [M, >=K] row-major."""
+    B, R, Kx = x.shape
+    K = Kx if K is None else K
+    return gemm(x, W, batch=B, rows=R, M=W.shape[0], K=K, x_batch_stride=R * Kx, x_row_stride=Kx,
+                w_row_stride=W.stride(0) if w_row_stride is None else w_row_stride, **kw)
+
+
+def stats_finalize(partials: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float, Cn: int):
+    """gLN/gGN: merge Welford partials -> folded per-item affine (scale, shift) [B, C]."""
+    lib = _lib.load()
+    B, slots, _ = partials.shape
+    scale = torch.empty(B, Cn, device=partials.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    _lib.check(lib.ps_stats_finalize(partials.data_ptr(), B, slots, _p(gamma), _p(beta), eps, Cn, scale.data_ptr(),
+                                     shift.data_ptr(), None, _stream()), "ps_stats_finalize")
+    _launched()
+    return scale, shift
+
+
+def bn_fold(weight, bias, running_mean, running_var, eps: float):
+    lib = _lib.load()
+    Cn = running_mean.numel()
+    scale = torch.empty(Cn, device=running_mean.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    _lib.check(lib.ps_bn_fold(_p(weight), _p(bias), running_mean.data_ptr(), running_var.data_ptr(), eps, Cn,
+                              scale.data_ptr(), shift.data_ptr(), _stream()), "ps_bn_fold")
+    _launched()
+    return scale, shift
+
+
+def rowstats(x: Tensor, eps: float) -> Tensor:
+    """x [..., C] contiguous -> [..., 2] (mean, rstd) per row."""
+    lib = _lib.load()
+    Cn = x.shape[-1]
+    rows = x.numel() // Cn
+    out = torch.empty(*x.shape[:-1], 2, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_rowstats(_req(x, "rowstats").data_ptr(), rows, Cn, Cn, eps, out.data_ptr(), _stream()), "ps_rowstats")
+    _launched()
+    return out
+
+
+def dwconv(x: Tensor, w: Tensor, bias: Optional[Tensor], P: int, dilation: int, causal: bool, pro: Prologue = NO_PRO,
+           want_stats: bool = False):
+    """x [B, T, C] -> (y [B, T, C], partials)."""
+    lib = _lib.load()
+    B, T, Cn = _req(x, "dwconv x").shape
+    y = torch.empty_like(x)
+    partials = None
+    if want_stats:
+        partials = torch.empty(B, lib.ps_dwconv_stats_slots(T, Cn), 3, device=x.device, dtype=torch.float32)
+    d = _lib.DwconvDesc()
+    d.batch, d.T, d.C, d.P, d.dilation, d.causal = B, T, Cn, P, dilation, int(causal)
+    d.x, d.y, d.w, d.bias = x.data_ptr(), y.data_ptr(), w.data_ptr(), _p(bias)
+    d.pro_mode, d.pro_act = pro.mode, pro.act
+    d.pro_a, d.pro_b, d.pro_batch_stride = _p(pro.a), _p(pro.b), pro.batch_stride
+    d.pro_rowstats, d.pro_slope = _p(pro.rowstats), _p(pro.slope)
+    d.stats_partials = _p(partials)
+    _lib.check(lib.ps_dwconv(C.byref(d), _stream()), "ps_dwconv")
+    _launched()
+    return y, partials
+
+
+def rownorm(x: Tensor, w: Optional[Tensor], b: Optional[Tensor], eps: float, res: Optional[Tensor] = None,
+            act: int = ACT_NONE, slope: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    lib = _lib.load()
+    Cn = x.shape[-1]
+    rows = x.numel() // Cn
+    y = out if out is not None else torch.empty_like(x)
+    _lib.check(lib.ps_rownorm(_req(x, "rownorm").data_ptr(), _p(res), y.data_ptr(), rows, Cn, _p(w), _p(b), eps, act,
+                              _p(slope), _stream()), "ps_rownorm")
+    _launched()
+    return y
+
+
+def ola(frames: Tensor, hop: int, wsum: Optional[Tensor], constraint: int) -> Tensor:
+    """frames [B, T, win] -> wav [B, (T-1)*hop + win]; constraint 0 none / 1 clamp / 2 sigmoid."""
+    lib = _lib.load()
+    B, T, win = _req(frames, "ola").shape
+    y = torch.empty(B, (T - 1) * hop + win, device=frames.device, dtype=torch.float32)
+    _lib.check(lib.ps_ola(frames.data_ptr(), B, T, win, hop, _p(wsum), constraint, y.data_ptr(), _stream()), "ps_ola")
+    _launched()
+    return y
+
+
+def mask_apply(feats: Tensor, mask: Tensor, act: int, is_complex: bool) -> Tensor:
+    lib = _lib.load()
+    Cn = feats.shape[-1]
+    y = torch.empty_like(feats)
+    _lib.check(lib.ps_mask_apply(_req(feats, "mask feats").data_ptr(), _req(mask, "mask").data_ptr(), y.data_ptr(),
+                                 feats.numel() // Cn, Cn, act, int(is_complex), _stream()), "ps_mask_apply")
+    _launched()
+    return y
+
+
+def magnitude(x: Tensor, drop_first: bool, log1p: bool) -> Tensor:
+    lib = _lib.load()
+    F2 = x.shape[-1]
+    F = F2 // 2
+    y = torch.empty(*x.shape[:-1], F - int(drop_first), device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_magnitude(_req(x, "magnitude").data_ptr(), y.data_ptr(), x.numel() // F2, F, int(drop_first),
+                                int(log1p), _stream()), "ps_magnitude")
+    _launched()
+    return y
+
+
+def asp_pool(x: Tensor, logits: Tensor) -> Tensor:
+    lib = _lib.load()
+    B, T, Cn = _req(x, "asp x").shape
+    out = torch.empty(B, 2 * Cn, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_asp_pool(x.data_ptr(), _req(logits, "asp logits").data_ptr(), B, T, Cn, out.data_ptr(), _stream()),
+               "ps_asp_pool")
+    _launched()
+    return out
+
+
+def l2normalize(x: Tensor) -> Tensor:
+    lib = _lib.load()
+    rows, E = _req(x, "l2normalize").shape
+    y = torch.empty_like(x)
+    _lib.check(lib.ps_l2normalize(x.data_ptr(), y.data_ptr(), rows, E, _stream()), "ps_l2normalize")
+    _launched()
+    return y
+
+
+def segment(x: Tensor, K: int, S: int, overlap: bool) -> Tensor:
+    lib = _lib.load()
+    B, T, Cn = _req(x, "segment").shape
+    seg = torch.empty(B, S, K, Cn, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_segment(x.data_ptr(), seg.data_ptr(), B, T, Cn, K, S, int(overlap), _stream()), "ps_segment")
+    _launched()
+    return seg
+
+
+def merge(seg: Tensor, T: int, overlap: bool) -> Tensor:
+    lib = _lib.load()
+    B, S, K, Cn = _req(seg, "merge").shape
+    y = torch.empty(B, T, Cn, device=seg.device, dtype=torch.float32)
+    _lib.check(lib.ps_merge(seg.data_ptr(), y.data_ptr(), B, T, Cn, K, S, int(overlap), _stream()), "ps_merge")
+    _launched()
+    return y
+
+
+def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inner: int, outer_stride: int,
+         inner_stride: int, step_stride: int, h0: Optional[Tensor] = None, c0: Optional[Tensor] = None,
+         want_state: bool = False):
+    """gx [positions, D*4H] -> out [positions, D*H] (+ (hn, cn) [D, n_seq, H])."""
+    lib = _lib.load()
+    positions = gx.shape[0]
+    out = torch.empty(positions, D * H, device=gx.device, dtype=torch.float32)
+    hn = cn = None
+    if want_state:
+        hn = torch.empty(D, n_seq, H, device=gx.device, dtype=torch.float32)
+        cn = torch.empty_like(hn)
+    d = _lib.LstmDesc()
+    d.n_seq, d.L, d.H, d.D = n_seq, L, H, D
+    d.inner, d.outer_stride, d.inner_stride, d.step_stride = inner, outer_stride, inner_stride, step_stride
+    d.gx, d.w_hh_t, d.h0, d.c0 = _req(gx, "lstm gx").data_ptr(), w_hh_t.data_ptr(), _p(h0), _p(c0)
+    d.out, d.hn, d.cn = out.data_ptr(), _p(hn), _p(cn)
+    _lib.check(lib.ps_lstm(C.byref(d), _stream()), "ps_lstm")
+    _launched()
+    return out, ((hn, cn) if want_state else None)
+
+
+def film_combine(sb: Tensor, xn: Tensor) -> Tensor:
+    lib = _lib.load()
+    Cn = xn.shape[-1]
+    y = torch.empty_like(xn)
+    _lib.check(lib.ps_film_combine(_req(sb, "film sb").data_ptr(), xn.data_ptr(), y.data_ptr(), xn.numel() // Cn, Cn,
+                                   _stream()), "ps_film_combine")
+    _launched()
+    return y
+
+
+def transpose(x: Tensor) -> Tensor:
+    """[B, R, C] -> [B, C, R] (the reference's [N,C,T] <-> frames-major [N,T,C])."""
+    lib = _lib.load()
+    x = x.contiguous()
+    B, R, Cn = _req(x, "transpose").shape
+    y = torch.empty(B, Cn, R, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_transpose(x.data_ptr(), y.data_ptr(), B, R, Cn, _stream()), "ps_transpose")
+    _launched()
+    return y

@@ -1,0 +1,77 @@
+"""Model registry: the reference's recipe constructors (egs/tse/model.py:89-182,
+608-637) and the BASELINE.json configurations, built from this
+package's drop-in modules.  The constructor arguments *are* the configuration —
+the reference has no other config system on this path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch.nn as nn
+
+from .nnet.base_nn import SoTaskWrapModule
+from .nnet.conv_tasnet import TCN, ConvTasNet
+from .nnet.dprnn import DPRNN
+from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
+from .nnet.lobe.pooling import AttentiveStatisticsPooling
+from .nnet.lobe.trivial import Magnitude
+
+
+def _td_speaker_net():
+    return nn.ModuleList(
+        [TCN(512, 256, 3, dilation=2 ** i, causal=False, tcn_norm="gLN", dconv_norm="gGN") for i in range(5)]
+        + [AttentiveStatisticsPooling(512, 128), nn.Conv1d(512 * 2, 192, 1, bias=False)]
+    )
+
+
+def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Optional[nn.Module] = None, **kwargs):
+    """Same names and argument meaning as the reference's ``init_model`` (egs/tse/model.py:89-94);
+    unknown names raise NameError like the reference (:639-640)."""
+    if name in ("td_tse_conv_tasnet_v0", "td_tse_conv_tasnet_v0_causal"):
+        causal = name.endswith("_causal")
+        norm = "bN1d" if causal else "gLN"
+        dnorm = "bN1d" if causal else "gGN"
+        return SoTaskWrapModule(
+            encoder=FreeEncDec(win_length=32, hop_length=16, laten_length=512),
+            masker=ConvTasNet(512, 192, True, tcn_kernel=3, tcn_dim=256, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8,
+                              tcn_with_embed=[1, 0, 0, 0, 0, 0, 0, 0], tcn_norm=norm, dconv_norm=dnorm, causal=causal, tcn_layer="normal"),
+            speaker_net=_td_speaker_net(),
+            loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", **kwargs)
+    if name == "veve_dprnn_v0_causal":
+        return SoTaskWrapModule(
+            encoder=FreeEncDec(win_length=32, hop_length=16, laten_length=128, output_active=True),
+            masker=DPRNN(input_size=128, hidden_size=64, output_size=128, n_blocks=6, seg_size=20, seg_overlap=False, causal=True,
+                         embed_dim=0, embed_norm=False, block_with_embed=(False,) * 6, embedding_free_tse=True),
+            speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", embedding_free_tse=True, **kwargs)
+    raise NameError
+
+
+def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
+    """The five BASELINE.json configurations as SURVEY.md 8d maps them onto reference constructors."""
+    if name in ("cfg1", "cfg2"):
+        return SoTaskWrapModule(
+            FreeEncDec(32, 512, 16),
+            ConvTasNet(512, 0, False, tcn_kernel=3, tcn_dim=512, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8,
+                       tcn_with_embed=[0] * 8, tcn_norm="gLN", dconv_norm="gGN", causal=False, tcn_layer="normal"),
+            mask_constraint="ReLU", verbose=verbose)
+    if name == "cfg3":
+        return SoTaskWrapModule(
+            FreeEncDec(32, 128, 16, output_active=True),
+            DPRNN(128, 128, 128, n_blocks=6, seg_size=100, seg_overlap=True, causal=False),
+            mask_constraint="ReLU", verbose=verbose)
+    if name == "cfg4":
+        return SoTaskWrapModule(
+            ConvEncDec(512, "hann", 512, hop_length=128, trainable=True, output_format="Complex"),
+            ConvTasNet(512, 192, True, tcn_dim=256, repeat_tcn=3, per_tcn_stack=8, tcn_with_embed=[1, 0, 0, 0, 0, 0, 0, 0]),
+            speaker_net=nn.ModuleList([Magnitude(drop_first=False)] + [TCN(256, 256, 3, dilation=2 ** i) for i in range(5)]
+                                      + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(512, 192, 1, bias=False)]),
+            mask_constraint="linear", drop_first_bin=True, verbose=verbose)
+    if name in ("cfg5", "cfg5_offline"):
+        return SoTaskWrapModule(
+            FreeEncDec(320, 512, 160),
+            ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN",
+                       dconv_norm="cLN", causal=True),
+            mask_constraint="ReLU", verbose=verbose)
+    if name == "veve_dprnn_v0_causal":
+        return init_model(name, None, None, verbose=verbose)
+    raise NameError(name)

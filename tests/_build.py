@@ -1,0 +1,64 @@
+"""Build this repo's drop-in modules from the plain-dict configs stored in the golden files."""
+import torch.nn as nn
+
+from puresound_b200.nnet.base_nn import SoTaskWrapModule
+from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet
+from puresound_b200.nnet.dprnn import DPRNN
+from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
+from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
+from puresound_b200.nnet.lobe.trivial import Magnitude
+
+
+def tcn(c):
+    return TCN(c["in_channels"], c["hid_channels"], c["kernel"], c["dilation"], emb_dim=c["emb_dim"], causal=c["causal"],
+               tcn_norm=c["tcn_norm"], dconv_norm=c["dconv_norm"])
+
+
+def encoder(c):
+    if c["type"] == "FreeEncDec":
+        return FreeEncDec(c["win_length"], c["laten_length"], c["hop_length"], c["output_active"])
+    return ConvEncDec(c["fft_length"], "hann", c["win_length"], hop_length=c["hop_length"], trainable=True, output_format="Complex")
+
+
+def masker(c):
+    c = dict(c)
+    t = c.pop("type")
+    if t == "ConvTasNet":
+        return ConvTasNet(**c)
+    out = c.pop("output_size", c["input_size"])
+    return DPRNN(c["input_size"], c["hidden_size"], out, n_blocks=c["n_blocks"], seg_size=c["seg_size"], seg_overlap=c["seg_overlap"],
+                 causal=c["causal"], embed_dim=c["embed_dim"], embed_norm=c["embed_norm"], block_with_embed=c["block_with_embed"],
+                 embedding_free_tse=c["embedding_free_tse"])
+
+
+def speaker_net(layers):
+    mods = []
+    for l in layers:
+        t = l["type"]
+        if t == "Magnitude":
+            mods.append(Magnitude(l["drop_first"], l["log1p"]))
+        elif t == "TCN":
+            mods.append(tcn(l))
+        elif t == "AttentiveStatisticsPooling":
+            mods.append(AttentiveStatisticsPooling(l["channels"], l["attention_channels"]))
+        elif t == "Conv1d":
+            mods.append(None)  # sized from the state dict by the caller
+    return mods
+
+
+def wrapper(cfg, sd):
+    spk = None
+    if cfg["speaker_net"] is not None:
+        mods = speaker_net(cfg["speaker_net"])
+        for j, m in enumerate(mods):
+            if m is None:
+                w = sd[f"speaker_net.{j}.weight"]
+                mods[j] = nn.Conv1d(w.shape[1], w.shape[0], 1, bias=f"speaker_net.{j}.bias" in sd)
+        spk = nn.ModuleList(mods)
+    m = SoTaskWrapModule(
+        encoder(cfg["encoder"]), masker(cfg["masker"]), embedding_free_tse=cfg["embedding_free_tse"],
+        encoder_spk=None if cfg["encoder_spk"] is None else encoder(cfg["encoder_spk"]), speaker_net=spk,
+        f_type=cfg["f_type"], mask_type=cfg["mask_type"], mask_constraint=cfg["mask_constraint"],
+        output_constraint=cfg["output_constraint"], drop_first_bin=cfg["drop_first_bin"], verbose=False)
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
