@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds per second of the separator forward on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic 16 kHz audio.
+The workload is BASELINE.json configs[1] (cfg2: Conv-TasNet N=512,H=512,P=3,X=8,R=3,
+batch 64 x 4 s) per GPU; utterances are independent, so ranks shard them with no
+data-path collective (weak scaling: 64 utterances on every rank).  One JSON line is
+printed by rank 0 (see README / DESIGN.md for the keys).
+
+`--impl reference` times the reference's CPU forward of the same path on the host
+cores: the oracle port (oracle/separator_ref.py, which issues the same ATen calls
+the reference does) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+WORKLOADS = {
+    # name: (config, batch per GPU, samples, enroll samples, description)
+    "cfg1": ("cfg1", 1, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) 1 x 4 s @16 kHz"),
+    "cfg2": ("cfg2", 64, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) batch 64 x 4 s @16 kHz per GPU"),
+    "cfg3": ("cfg3", 32, 160000, None, "DPRNN-LSTM (chunk 100, 6 blocks, H=128 bi) batch 32 x 10 s @16 kHz per GPU"),
+    "cfg4": ("cfg4", 64, 64000, 96000, "TSE: STFT 512/128 + TCN (H=256, dvec 192) + speaker net, 64 x (4 s mix + 6 s enroll) per GPU"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(workload: str, rank: int, batch=None):
+    from puresound_b200 import testing
+
+    cfg, n, L, Le, _ = WORKLOADS[workload]
+    n = batch or n
+    mix, _ = testing.noisy_speech(n, L, seed=1234 + rank)
+    enr = testing.noisy_speech(n, Le, seed=4321 + rank)[0] if Le else None
+    return mix, enr
+
+
+def build_model(workload: str):
+    from puresound_b200 import recipes, testing
+
+    torch.manual_seed(0)
+    m = recipes.baseline_config(WORKLOADS[workload][0]).eval()
+    testing.perturb_(m, seed=1)
+    return m
+
+
+def gemm_flops_bytes(model, workload):
+    """Algorithmic FLOPs (2*MAC) and fp32 bytes of ONE launch of the dominant kernel: a 1x1-conv GEMM of the
+    TCN stack, [batch*T, K] x [M, K]^T (reads X and W once, writes Y once; +residual for out_conv)."""
+    _, n, L, _, _ = WORKLOADS[workload]
+    enc = model.encoder
+    T = (L - enc.win_length) // enc.hop_length + 1
+    mk = model.masker
+    if not hasattr(mk, "tcn_dim"):
+        return None
+    M, K = mk.tcn_dim, mk.input_dim
+    rows = n * T
+    return {"flops": 2.0 * rows * M * K, "bytes": 4.0 * (rows * K + rows * M + M * K), "rows": rows, "M": M, "K": K}
+
+
+def cpu_reference_run(workload: str, sample_batch: int, steps: int, warmup: int, threads: int):
+    """The reference's CPU forward of the path (oracle port: same ATen calls as puresound's nn.Modules)."""
+    from oracle import describe as D
+    from oracle import separator_ref as R
+
+    torch.set_num_threads(threads)
+    m = build_model(workload)
+    sd, cfg = m.state_dict(), D.describe(m)
+    mix, enr = build_inputs(workload, 0, sample_batch)
+    for _ in range(warmup):
+        R.inference(sd, cfg, mix, enr)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        R.inference(sd, cfg, mix, enr)
+        times.append(time.perf_counter() - t0)
+    audio_s = sample_batch * mix.shape[1] / SR
+    return audio_s, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-batch", type=int, default=0, help="utterances in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg_name, batch, L, Le, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8}[args.workload]
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
+        audio_s, times = cpu_reference_run(args.workload, sample_batch, steps, warm, cores)
+        t = sum(times) / len(times)
+        v = audio_s / t
+        sample = f"{sample_batch} x {L / SR:.0f} s utterances of the {batch}-utterance batch per step, {cores} torch threads"
+        print(json.dumps({
+            "impl": "reference", "metric": "audio-sec/sec", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (B200)
+    from puresound_b200 import ops
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    ops.require_device()
+    if args.gemm_backend != "auto":
+        ops.force_gemm_backend = {"simt": ops.GEMM_SIMT, "tcgen05": ops.GEMM_TCGEN05}[args.gemm_backend]
+
+    model = build_model(args.workload).to(dev)
+    mix_h, enr_h = build_inputs(args.workload, rank)
+    mix_h = mix_h.pin_memory()
+    enr_h = enr_h.pin_memory() if enr_h is not None else None
+    mix_d = mix_h.to(dev)
+    enr_d = enr_h.to(dev) if enr_h is not None else None
+    audio_s_rank = batch * L / SR
+
+    def step_resident():
+        return model._inference_cl(mix_d, enr_d)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            y = step_resident()
+        barrier()
+        # ---- value: inputs resident in HBM, device-timed, per-GEMM events for the roofline ----
+        ops.gemm_events = []
+        launches0 = ops.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for _ in range(args.steps):
+                y = step_resident()
+            e1.record()
+            barrier()
+        launches = ops.launch_count - launches0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        gemm_ev, ops.gemm_events = ops.gemm_events, None
+        # ---- e2e: the public API with HOST buffers; H2D of the inputs and D2H of the result inside the timed region ----
+        for _ in range(2):
+            yh = model.inference(mix_h, enr_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            yh = model.inference(mix_h, enr_h)
+        torch.cuda.synchronize()
+        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    assert torch.isfinite(yh).all()
+
+    value = world * audio_s_rank * args.steps / (ms / 1e3)
+    e2e_value = world * audio_s_rank * args.steps / (e2e_ms / 1e3)
+    h2d = mix_h.numel() * 4 + (enr_h.numel() * 4 if enr_h is not None else 0)
+    d2h = yh.numel() * 4
+
+    hbm_peak, tf_peak, peak_kind = peaks()
+    roof = None
+    fb = gemm_flops_bytes(model, args.workload)
+    if fb is not None and gemm_ev:
+        # dominant kernel = the dense 1x1-conv GEMM of the TCN blocks (same shape for pointwise / out_conv when C == H)
+        durs = [a.elapsed_time(b) for (a, b, shape) in gemm_ev if shape == (fb["rows"], fb["M"], fb["K"])]
+        if durs:
+            avg_ms = sum(durs) / len(durs)
+            achieved = fb["flops"] / (avg_ms / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": "ps_gemm (1x1 conv, %d x %d x %d)" % (fb["rows"], fb["M"], fb["K"]),
+                    "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                    "peak_source": f"{peak_kind} bf16 sustained", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
+                    "share_of_step": sum(durs) / ms, "hbm_frac_if_memory_bound": fb["bytes"] / (avg_ms / 1e3) / 1e9 / hbm_peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        audio_s, times = cpu_reference_run(args.workload, sample_batch, 2, 1, cores)
+        cpu = {"value": audio_s / min(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": f"{sample_batch} x {L / SR:.0f} s utterances of the {batch}-utterance batch, best of 2 after 1 warm-up"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "l2": "activations (524 MB per tensor at cfg2) exceed the 126 MB L2",
+                                            "gemm_backend": args.gemm_backend, "accumulate": "fp32"},
+            "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                           "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -20,6 +20,8 @@ Tensor = torch.Tensor
 
 #: kernels launched through this module since the last reset (bench.py's gpu_launches)
 launch_count = 0
+#: when a list, every ps_gemm launch appends (start_event, end_event, (batch*rows, M, K)) — bench.py's live roofline timing
+gemm_events = None
 #: force a GEMM back end for every call (tests / A-B runs); None = per-call choice
 force_gemm_backend: Optional[int] = None
 
@@ -110,7 +112,14 @@ def gemm(
         d.residual, d.res_batch_stride, d.res_row_stride = residual.data_ptr(), rows * M, M
     d.stats_partials = _p(partials)
     d.W_packed = _p(w_packed)
+    ev = None
+    if gemm_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
+    if ev is not None:
+        ev[1].record()
+        gemm_events.append((ev[0], ev[1], (batch * rows, M, K)))
     _launched()
     return Y, partials
 

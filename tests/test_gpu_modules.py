@@ -1,0 +1,102 @@
+"""Drop-in modules on the B200 against the REFERENCE's own outputs (tests/golden/*.pt) on identical weights and
+inputs, called through the reference's API ([N,C,T] tensors, inference(noisy, enroll))."""
+import pytest
+import torch
+
+import _build
+from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
+from puresound_b200.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2e-5  # exact-fp32 kernels: summation-order noise only
+
+
+def close(a, b, tol=TOL):
+    a, b = a.cpu(), b.cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    assert err <= tol * max(1.0, b.abs().max().item()), err
+
+
+def cu(t):
+    return None if t is None else t.to(DEV)
+
+
+def test_free_encdec(golden):
+    g = golden("small_free_encdec.pt")
+    m = _build.encoder(g["cfg"]).to(DEV)
+    m.load_state_dict(g["sd"])
+    f = m(cu(g["wav"]))
+    close(f, g["feats"])
+    close(m.inverse(f), g["inv"])
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 8, device=DEV))
+
+
+def test_conv_stft(golden):
+    g = golden("small_conv_stft.pt")
+    m = _build.encoder(g["cfg"]).to(DEV)
+    m.load_state_dict(g["sd"])
+    X = m(cu(g["wav"]))
+    close(X, g["spec"])
+    y = m.inverse(X)
+    close(y, g["inv"], 1e-4)  # window-sumsquare division amplifies rounding at the edges
+    assert y[:, 0].abs().max().item() == 0.0
+
+
+def test_tcn_variants(golden):
+    for tag, g in golden("small_tcn.pt").items():
+        m = _build.tcn(g["cfg"]).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        y = m(cu(g["x"]), cu(g["embed"])) if g["embed"] is not None else m(cu(g["x"]))
+        close(y, g["y"])
+
+
+def test_conv_tasnet(golden):
+    g = golden("small_conv_tasnet.pt")
+    m = _build.masker(g["cfg"]).to(DEV).eval()
+    m.load_state_dict(g["sd"])
+    close(m(cu(g["x"]), cu(g["dvec"])), g["y"])
+
+
+def test_splitmerge_film_speaker(golden):
+    g = golden("small_splitmerge.pt")
+    seg, rest = SplitMerge.split(cu(g["x"]), g["K"])
+    assert rest == g["rest"] and torch.equal(seg.cpu(), g["seg"])
+    assert torch.equal(SplitMerge.merge(seg, rest).cpu(), g["merged"])
+    g = golden("small_film.pt")
+    fm = FiLM(16, 6).to(DEV)
+    fm.load_state_dict(g["sd"])
+    close(fm(cu(g["x"]), cu(g["cond"])), g["y"])
+    g = golden("small_speaker.pt")
+    pool = AttentiveStatisticsPooling(16, 8).to(DEV).eval()
+    pool.load_state_dict(g["sd"])
+    close(pool(cu(g["x"])), g["asp"])
+    close(Magnitude(drop_first=False)(cu(g["x"])), g["mag"])
+    close(Magnitude(drop_first=True)(cu(g["x"])), g["mag_drop"])
+    with pytest.raises(NotImplementedError):
+        pool.train()(cu(g["x"]))
+
+
+def test_dprnn_variants(golden):
+    for tag, g in golden("small_dprnn.pt").items():
+        c = dict(g["cfg"])
+        c["output_size"] = g["sd"]["output_fc.1.weight"].shape[0]
+        m = _build.masker(c).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        y = m(cu(g["x"]), cu(g["embed"])) if g["embed"] is not None else m(cu(g["x"]))
+        close(y, g["y"], 5e-5)
+
+
+def test_wrappers_inference(golden):
+    for tag, g in golden("small_wrappers.pt").items():
+        m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)
+        y = m.inference(cu(g["noisy"]), cu(g["enroll"]))
+        close(y, g["y"], 1e-4)
+        # host-buffer API: same numbers, result back on the host
+        yh = m.inference(g["noisy"], g["enroll"])
+        assert not yh.is_cuda
+        close(yh, g["y"], 1e-4)
+        if "dvec" in g:
+            close(m.inference_tse_embedding(cu(g["enroll"])), g["dvec"], 5e-5)
