@@ -153,7 +153,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="utterances in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gemm-backend", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--gemm-backend", default="auto", choices=["auto", "simt"],
+                    help="auto: tcgen05 3xBF16 GEMM where eligible, exact-fp32 CUDA-core GEMM elsewhere; simt: CUDA-core everywhere")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +194,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device()
     if args.gemm_backend != "auto":
-        ops.force_gemm_backend = {"simt": ops.GEMM_SIMT, "tcgen05": ops.GEMM_TCGEN05}[args.gemm_backend]
+        ops.force_gemm_backend = ops.GEMM_SIMT
 
     model = build_model(args.workload).to(dev)
     mix_h, enr_h = build_inputs(args.workload, rank)
@@ -206,18 +207,13 @@ def main():
     def step_resident():
         return model._inference_cl(mix_d, enr_d)
 
+    from puresound_b200 import sharding
+
     def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sharding.barrier(dev)
 
     def max_over_ranks(ms: float) -> float:
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(ms, dev)
 
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):

@@ -52,6 +52,11 @@ class TCN(nn.Module):
         self.out_conv = nn.Conv1d(hid_channels, in_channels, kernel_size=1, stride=1)
         self.in_channels, self.hid_channels, self.emb_dim = in_channels, hid_channels, emb_dim
         self.kernel, self.dilation, self.causal = kernel, dilation, causal
+        self._cache = ParamCache()
+
+    def _packed(self, tag: str, w: torch.Tensor, M: int, K: int, ld: int):
+        """bf16 hi/lo split + swizzled tile image of a 1x1-conv weight for the tcgen05 GEMM (None if not eligible)."""
+        return self._cache.get(tag, [w], lambda: ops.pack_weights(w, M, K, ld))
 
     # ---- engine path: frames-major ----
     def forward_cl(self, x: torch.Tensor, embed: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -72,16 +77,19 @@ class TCN(nn.Module):
         elif E != 0:
             raise ValueError("this TCN block expects a conditioning embedding")
         n1, n2, n3 = self.in_conv[1], dsc.depthwise[1], dsc.pointwise[1]
-        u1, p1 = ops.linear(x, w_in, K=C, w_row_stride=C + E, bias_batch=bias_item, want_stats=needs_stats(norm_kind(n1)))
+        u1, p1 = ops.linear(x, w_in, K=C, w_row_stride=C + E, bias_batch=bias_item, want_stats=needs_stats(norm_kind(n1)),
+                            w_packed=self._packed("in", self.in_conv[0].weight, H, C, C + E))
         pro1 = norm_prologue(n1, u1, p1, prelu_slope(self.in_conv[2]))
         dw = dsc.depthwise[0]
         u2, p2 = ops.dwconv(u1, dw.weight.view(H, self.kernel), dw.bias, self.kernel, self.dilation, self.causal, pro1,
                             want_stats=needs_stats(norm_kind(n2)))
         pro2 = norm_prologue(n2, u2, p2, prelu_slope(dsc.depthwise[2]))
         pw = dsc.pointwise[0]
-        u3, p3 = ops.linear(u2, pw.weight.view(H, H), pro=pro2, bias=pw.bias, want_stats=needs_stats(norm_kind(n3)))
+        u3, p3 = ops.linear(u2, pw.weight.view(H, H), pro=pro2, bias=pw.bias, want_stats=needs_stats(norm_kind(n3)),
+                            w_packed=self._packed("pw", pw.weight, H, H, H))
         pro3 = norm_prologue(n3, u3, p3, prelu_slope(dsc.pointwise[2]))
-        y, _ = ops.linear(u3, self.out_conv.weight.view(C, H), pro=pro3, bias=self.out_conv.bias, residual=x)
+        y, _ = ops.linear(u3, self.out_conv.weight.view(C, H), pro=pro3, bias=self.out_conv.bias, residual=x,
+                          w_packed=self._packed("out", self.out_conv.weight, C, H, H))
         return y
 
     # ---- reference-layout API ----

@@ -124,6 +124,20 @@ def gemm(
     return Y, partials
 
 
+def pack_weights(W: Tensor, M: int, K: int, w_row_stride: int) -> Optional[Tensor]:
+    """Pre-split (bf16 hi/lo) and pre-swizzle W[:M, :K] into the tcgen05 kernel's shared-memory tile image.
+    Returns None when the shape is not eligible for the tensor-core back end (M % 256, K % 64)."""
+    lib = _lib.load()
+    nbytes = lib.ps_gemm_packed_bytes(M, K)
+    if nbytes == 0:
+        return None
+    out = torch.empty(nbytes, device=W.device, dtype=torch.uint8)
+    _lib.check(lib.ps_gemm_pack_weights(_dev(W, "pack W").data_ptr(), w_row_stride, M, K, out.data_ptr(), _stream()),
+               "ps_gemm_pack_weights")
+    _launched()
+    return out
+
+
 def linear(x: Tensor, W: Tensor, K: Optional[int] = None, w_row_stride: Optional[int] = None, **kw):
     """GEMM over a contiguous frames-major activation x [B, R, K]; W [M, >=K] row-major."""
     B, R, Kx = x.shape

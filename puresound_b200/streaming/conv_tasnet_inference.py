@@ -1,0 +1,236 @@
+"""Frame-by-frame causal Conv-TasNet on the B200 engine.
+
+The reference ships one streaming wrapper, ``StreamingSkiM``
+(puresound/streaming/skim_inference.py:10-252), whose surface is ``init_status()``
+and ``step_frame(x, embed) -> [., C, 1]`` with the carried state kept on the
+module.  A streaming Conv-TasNet does not exist upstream; this one follows the same
+API pattern, and — exactly like the reference tests its streaming model
+(test/test_streaming.py:62-116) — its oracle is the *offline* causal forward
+``ConvTasNet(causal=True, tcn_norm/dconv_norm in {cLN, bN1d})`` of the same weights.
+
+Differences by design: S concurrent streams advance together (x is ``[S, C, 1]``);
+all state lives on the device (one dilation-history ring ``[S, (P-1)*d+1, H]`` per
+block plus a step counter), so one hop is a fixed chain of kernels that is captured
+once in a CUDA graph and replayed (``StreamingSeparator(use_graph=True)``).
+
+Per block and hop: GEMM(W_in) -> one fused kernel (norm1+PReLU, ring push, causal
+dilated depthwise taps from the ring, norm2+PReLU) -> GEMM(W_pw) -> [cLN+PReLU row
+kernel | bN1d folded into the next GEMM's prologue] -> GEMM(W_out)+residual.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..nnet._fuse import norm_kind, prelu_slope
+from ..nnet.conv_tasnet import ConvTasNet
+from ..nnet.lobe.encoder import FreeEncDec
+from ..ops import ACT_NONE, ACT_PRELU, ACT_RELU, ACT_SIGMOID, PRO_AFFINE, PRO_MASK, Prologue
+
+
+class StreamingConvTasNet(ConvTasNet):
+    """Same constructor as ``ConvTasNet``; requires ``causal=True`` and per-frame norms (cLN or bN1d)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not self.causal:
+            raise AssertionError("streaming needs causal=True")
+        if self.tcn_norm not in ("cLN", "bN1d") or self.dconv_norm not in ("cLN", "bN1d") or self.tcn_norm != self.dconv_norm:
+            raise AssertionError("streaming needs per-frame norms: tcn_norm == dconv_norm in {cLN, bN1d} "
+                                 "(a global gLN silently breaks causality, SURVEY.md section 7)")
+        self._state = None
+
+    # ------------------------------------------------------------------ state
+    @torch.no_grad()
+    def init_status(self, n_streams: int = 1):
+        """(Re)start ``n_streams`` streams: zero history rings and step counter (reference: skim_inference.py:142-167)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("StreamingConvTasNet runs on a CUDA device only (no CPU fallback)")
+        rings, folded = [], []
+        for stack in self.tcn_list:
+            for blk in stack:
+                rl = (blk.kernel - 1) * blk.dilation + 1
+                rings.append(torch.zeros(n_streams, rl, blk.hid_channels, device=dev))
+                if self.tcn_norm == "bN1d":
+                    dsc = blk.dconv[0]
+                    norms = (blk.in_conv[1], dsc.depthwise[1], dsc.pointwise[1])
+                    if any(n.training for n in norms):
+                        raise NotImplementedError("train-mode BatchNorm: call .eval() first")
+                    folded.append([ops.bn_fold(n.weight, n.bias, n.running_mean, n.running_var, n.eps) for n in norms])
+                else:
+                    folded.append(None)
+        self._state = {"S": n_streams, "rings": rings, "folded": folded, "step": torch.zeros(1, dtype=torch.int64, device=dev)}
+        self.frames_counter = 0
+
+    # ------------------------------------------------------------------ one hop
+    def _block_step(self, blk, j: int, x: torch.Tensor, embed_bias: Optional[torch.Tensor]) -> torch.Tensor:
+        st = self._state
+        S = st["S"]
+        Cc, H, E = blk.in_channels, blk.hid_channels, blk.emb_dim
+        dsc = blk.dconv[0]
+        n1, n2, n3 = blk.in_conv[1], dsc.depthwise[1], dsc.pointwise[1]
+        kind = 0 if self.tcn_norm == "cLN" else 1
+        if embed_bias is not None or E != 0:
+            raise NotImplementedError("conditioned streaming blocks are a 'next' row (SURVEY.md 8f)")
+        xin = x.view(1, S, Cc)
+        u1, _ = ops.linear(xin, blk.in_conv[0].weight.view(H, Cc), K=Cc, w_row_stride=Cc)
+        u2 = torch.empty(S, H, device=x.device, dtype=torch.float32)
+        d = _lib.StreamDwDesc()
+        d.streams, d.C, d.P, d.dilation = S, H, blk.kernel, blk.dilation
+        d.u, d.y, d.ring, d.step = u1.data_ptr(), u2.data_ptr(), st["rings"][j].data_ptr(), st["step"].data_ptr()
+        dw = dsc.depthwise[0]
+        d.w, d.bias = dw.weight.data_ptr(), dw.bias.data_ptr()
+        d.norm_kind = kind
+        if kind == 0:
+            d.eps = n1.eps
+            d.n1_a, d.n1_b, d.n2_a, d.n2_b = n1.gamma.data_ptr(), n1.beta.data_ptr(), n2.gamma.data_ptr(), n2.beta.data_ptr()
+        else:
+            f = st["folded"][j]
+            d.eps = 0.0
+            d.n1_a, d.n1_b, d.n2_a, d.n2_b = f[0][0].data_ptr(), f[0][1].data_ptr(), f[1][0].data_ptr(), f[1][1].data_ptr()
+        d.slope1, d.slope2 = prelu_slope(blk.in_conv[2]).data_ptr(), prelu_slope(dsc.depthwise[2]).data_ptr()
+        _lib.check(_lib.load().ps_stream_dwconv_step(C.byref(d), torch.cuda.current_stream().cuda_stream), "ps_stream_dwconv_step")
+        ops._launched()
+        pw = dsc.pointwise[0]
+        u3, _ = ops.linear(u2.view(1, S, H), pw.weight.view(H, H), bias=pw.bias)
+        slope3 = prelu_slope(dsc.pointwise[2])
+        if kind == 0:
+            u3n = ops.rownorm(u3, n3.gamma, n3.beta, n3.eps, act=ACT_PRELU, slope=slope3)
+            pro = ops.NO_PRO
+        else:
+            u3n = u3
+            f = st["folded"][j]
+            pro = Prologue(PRO_AFFINE, ACT_PRELU, f[2][0], f[2][1], 0, None, slope3)
+        y, _ = ops.linear(u3n, blk.out_conv.weight.view(Cc, H), pro=pro, bias=blk.out_conv.bias, residual=xin)
+        return y.view(S, Cc)
+
+    def step_frame_cl(self, x: torch.Tensor, embed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [S, C] (one frame per stream) -> mask logits [S, C]; advances every stream by one frame."""
+        if self._state is None:
+            raise RuntimeError("call init_status(n_streams) first")
+        if embed is not None or any(self.tcn_with_embed):
+            raise NotImplementedError("speaker-conditioned streaming is a 'next' row (SURVEY.md 8f)")
+        if x.shape[0] != self._state["S"]:
+            raise ValueError(f"expected {self._state['S']} streams, got {x.shape[0]}")
+        j = 0
+        for stack in self.tcn_list:
+            for blk in stack:
+                x = self._block_step(blk, j, x, None)
+                j += 1
+        _lib.check(_lib.load().ps_stream_advance(self._state["step"].data_ptr(), torch.cuda.current_stream().cuda_stream), "ps_stream_advance")
+        ops._launched()
+        return x
+
+    @torch.no_grad()
+    def step_frame(self, x: torch.Tensor, embed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [S, C, 1] -> [S, C, 1] (reference pattern: skim_inference.py:176-218)."""
+        ops.require_device()
+        self.frames_counter += 1
+        return self.step_frame_cl(x.reshape(x.shape[0], -1).contiguous(), embed).unsqueeze(-1)
+
+
+class StreamingSeparator(nn.Module):
+    """Waveform-in / waveform-out streaming around a task wrapper whose encoder is a ``FreeEncDec`` and whose
+    masker is a ``StreamingConvTasNet`` (caller pattern: egs/tse/demo/utils.py:78-118).
+
+    ``step_wave(chunk[S, hop]) -> [S, hop]``: every call consumes one hop of new samples per stream and emits the
+    hop of output whose overlap-add is complete.  Unlike the demo's *averaging* overlap-add (utils.py:121-128) the
+    emitted samples are the offline decoder's *sum* (ConvTranspose1d), so the concatenated output equals
+    ``SoTaskWrapModule.inference`` on the whole signal, delayed by ``win - hop`` samples of priming.
+    """
+
+    def __init__(self, model: nn.Module, use_graph: bool = True):
+        super().__init__()
+        if not isinstance(model.encoder, FreeEncDec) or not isinstance(model.masker, StreamingConvTasNet):
+            raise NotImplementedError("StreamingSeparator needs FreeEncDec + StreamingConvTasNet")
+        if model.speaker_net is not None or model.embedding_free_tse:
+            raise NotImplementedError("speaker-conditioned streaming is a 'next' row (SURVEY.md 8f)")
+        if model.mask_type.lower() != "real" or model.f_type.lower() != "real":
+            raise NotImplementedError
+        self.model = model
+        self.use_graph = use_graph
+        self._mask_act = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}[model.mask_constraint.lower()]
+        self._constraint = {"linear": 1, "sigmoid": 2}[model.output_constraint.lower()]
+        self._st = None
+
+    @property
+    def hop(self) -> int:
+        return self.model.encoder.hop_length
+
+    @property
+    def win(self) -> int:
+        return self.model.encoder.win_length
+
+    @torch.no_grad()
+    def init_status(self, n_streams: int = 1):
+        ops.require_device()
+        enc = self.model.encoder
+        dev = next(self.model.parameters()).device
+        if enc.win_length % enc.hop_length != 0:
+            raise NotImplementedError("streaming needs win_length to be a multiple of hop_length")
+        S, win, hop = n_streams, enc.win_length, enc.hop_length
+        self.model.masker.init_status(S)
+        self._st = {
+            "S": S, "chunks": 0, "prime": win // hop - 1,
+            "hist": torch.zeros(S, max(win - hop, 1), device=dev), "frame": torch.zeros(S, win, device=dev),
+            "acc": torch.zeros(S, win, device=dev), "chunk": torch.zeros(S, hop, device=dev), "out": torch.zeros(S, hop, device=dev),
+            "graph": None,
+        }
+        # decoder weight transposed once (cache) before any graph capture
+        Nf = enc.decoder.in_channels
+        self._w_dec_t = enc._cache.get("dec_t", [enc.decoder.weight], lambda: enc.decoder.weight.view(Nf, win).t().contiguous())
+
+    def _push(self):
+        st = self._st
+        lib = _lib.load()
+        _lib.check(lib.ps_stream_push(st["chunk"].data_ptr(), st["hist"].data_ptr(), st["frame"].data_ptr(), st["S"], self.win, self.hop,
+                                      torch.cuda.current_stream().cuda_stream), "ps_stream_push")
+        ops._launched()
+
+    def _compute(self):
+        """encoder GEMM -> masker step -> mask-apply + decoder GEMM -> overlap-add emit, all on static buffers."""
+        st = self._st
+        enc = self.model.encoder
+        S, win, hop = st["S"], self.win, self.hop
+        Nf = enc.encoder.out_channels
+        feats, _ = ops.linear(st["frame"].view(1, S, win), enc.encoder.weight.view(Nf, win), epi_act=ACT_RELU if enc.output_active else ACT_NONE)
+        mask = self.model.masker.step_frame_cl(feats.view(S, Nf))
+        fr, _ = ops.linear(feats, self._w_dec_t, pro=Prologue(PRO_MASK, self._mask_act, x2=mask.view(1, S, Nf)))
+        lib = _lib.load()
+        _lib.check(lib.ps_stream_ola(fr.data_ptr(), st["acc"].data_ptr(), st["out"].data_ptr(), S, win, hop, self._constraint,
+                                     torch.cuda.current_stream().cuda_stream), "ps_stream_ola")
+        ops._launched()
+
+    @torch.no_grad()
+    def step_wave(self, chunk: torch.Tensor) -> torch.Tensor:
+        """chunk [S, hop] (host or device) -> [S, hop] on the same device."""
+        st = self._st
+        if st is None:
+            raise RuntimeError("call init_status(n_streams) first")
+        if tuple(chunk.shape) != (st["S"], self.hop):
+            raise ValueError(f"expected a chunk of shape {(st['S'], self.hop)}, got {tuple(chunk.shape)}")
+        on_host = not chunk.is_cuda
+        st["chunk"].copy_(chunk, non_blocking=True)
+        self._push()
+        st["chunks"] += 1
+        if st["chunks"] <= st["prime"]:
+            out = torch.zeros_like(st["out"])  # the first complete window has not arrived yet
+            return out.cpu() if on_host else out
+        first = st["chunks"] == st["prime"] + 1
+        if not self.use_graph or first:
+            self._compute()  # the first hop runs eagerly: it loads the kernels and fills the weight caches
+        else:
+            if st["graph"] is None:
+                # capture the fixed kernel chain of one hop (capture records, it does not execute) ...
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._compute()
+                st["graph"] = g
+            st["graph"].replay()  # ... and replay it for this and every later hop
+        out = st["out"].clone()
+        return out.cpu() if on_host else out

@@ -21,8 +21,18 @@ WAVE_TOL = 1e-3
 SISNR_TOL_DB = 0.05
 
 
+@pytest.fixture(params=["auto", "simt"])
+def backend(request):
+    """auto = tcgen05 3xBF16 GEMM wherever eligible; simt = exact-fp32 CUDA-core GEMM everywhere."""
+    from puresound_b200 import ops
+
+    ops.force_gemm_backend = ops.GEMM_SIMT if request.param == "simt" else None
+    yield request.param
+    ops.force_gemm_backend = None
+
+
 @pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal"])
-def test_full_size_parity(name):
+def test_full_size_parity(name, backend):
     with open(os.path.join(GOLDEN, "full_size_pins.json")) as fh:
         pin = json.load(fh)[name]
     torch.manual_seed(0)
@@ -47,7 +57,7 @@ def test_full_size_parity(name):
     err_pre = ((pre - pre_ref).abs() / pre_ref.abs().clamp(min=1.0)).max().item()
     L = y.shape[-1]
     s_ours, s_ref = R.si_snr(y, clean[:, :L]), R.si_snr(y_ref, clean[:, :L])
-    print(f"{name}: max|dy|={err:.3e} pre-clamp={err_pre:.3e} SI-SNR(ours,ref)={R.si_snr(y, y_ref).min():.1f} dB "
+    print(f"{name}[{backend}]: max|dy|={err:.3e} pre-clamp={err_pre:.3e} SI-SNR(ours,ref)={R.si_snr(y, y_ref).min():.1f} dB "
           f"dSI-SNR={float((s_ours - s_ref).abs().max()):.2e} dB")
     assert err <= WAVE_TOL and err_pre <= WAVE_TOL
     assert float((s_ours - s_ref).abs().max()) <= SISNR_TOL_DB

@@ -1,0 +1,94 @@
+"""tcgen05/TMEM GEMM (3xBF16 split, fp32 TMEM accumulate) against an fp64 reference and against the exact-fp32
+CUDA-core kernel.  Tolerance: ~2^-17 relative per product (hi*hi + hi*lo + lo*hi), i.e. 5e-5 of the output scale —
+30x tighter than TF32 would give; end-to-end waveform parity (1e-3) is checked in test_gpu_full.py."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 5e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from puresound_b200 import ops as o
+
+    o.require_device()
+    return o
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * (2 * torch.rand(*shape, generator=g) - 1)).to(DEV)
+
+
+def check(y, ref64, tol=TOL):
+    err = (y.double() - ref64).abs().max().item()
+    scale = max(1.0, ref64.abs().max().item())
+    assert err <= tol * scale, f"max abs err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(1, 128, 256, 64), (2, 300, 512, 512), (3, 129, 256, 128), (1, 1000, 512, 256), (5, 77, 512, 64)])
+def test_tc_plain(ops, B, Rr, M, K):
+    x, w = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1)
+    pk = ops.pack_weights(w, M, K, K)
+    assert pk is not None and pk.numel() == M * K * 4
+    y, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    check(y, x.double() @ w.double().t())
+    y2, _ = ops.linear(x, w, backend=ops.GEMM_SIMT)
+    check(y2, x.double() @ w.double().t(), 1e-5)
+
+
+def test_tc_fused_prologue_epilogue_stats(ops):
+    B, Rr, M, K = 3, 413, 512, 512
+    x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
+    sc, sh, slope = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4), torch.tensor([0.2], device=DEV)
+    bias, bb, res = rnd(M, seed=5), rnd(B, M, seed=6), rnd(B, Rr, M, seed=7)
+    pk = ops.pack_weights(w, M, K, K)
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+    y, part = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    xin = F.prelu((x * sc.unsqueeze(1) + sh.unsqueeze(1)), slope).double()
+    ref = xin @ w.double().t() + bias.double() + bb.double().unsqueeze(1) + res.double()
+    check(y, ref)
+    # Welford partials of the tile outputs -> same folded affine as torch's mean / biased var
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, M)
+    mu = ref.mean(dim=(1, 2))
+    rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
+    assert (shift[:, 0].double() + mu * rstd).abs().max() <= 5e-5
+    # and the two back ends agree with each other
+    y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
+    check(y, y2.double())
+
+
+def test_tc_weight_columns_view_and_relu(ops):
+    """in_conv of a conditioned block: the packed image is built from the first C columns of a [H, C+E] weight."""
+    H, Cc, E = 256, 512, 192
+    w_full, x = rnd(H, Cc + E, seed=1, scale=0.05), rnd(2, 200, Cc, seed=2)
+    pk = ops.pack_weights(w_full, H, Cc, Cc + E)
+    y, _ = ops.linear(x, w_full, K=Cc, w_row_stride=Cc + E, epi_act=ops.ACT_RELU, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    check(y, torch.relu(x.double() @ w_full[:, :Cc].double().t()))
+
+
+def test_tc_many_tiles_persistent(ops):
+    """more tiles than SMs: every CTA walks several tiles through both TMEM accumulator buffers"""
+    B, Rr, M, K = 8, 3999, 512, 128
+    x, w = rnd(B, Rr, K, seed=1), rnd(M, K, seed=2, scale=0.1)
+    pk = ops.pack_weights(w, M, K, K)
+    y, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    check(y, x.double() @ w.double().t())
+
+
+def test_tc_nan_inf_rows_stay_local(ops):
+    x, w = rnd(1, 256, 64, seed=1), rnd(256, 64, seed=2)
+    x[0, 100:, :] = float("inf")
+    y, _ = ops.linear(x, w, w_packed=ops.pack_weights(w, 256, 64, 64), backend=ops.GEMM_TCGEN05)
+    assert torch.isfinite(y[0, :100]).all() and not torch.isfinite(y[0, 100:]).any()
+
+
+def test_tc_ineligible_shapes_are_refused(ops):
+    x, w = rnd(1, 10, 60, seed=1), rnd(130, 60, seed=2)
+    assert ops.pack_weights(w, 130, 60, 60) is None
+    with pytest.raises(NotImplementedError):
+        ops.linear(x, w, backend=ops.GEMM_TCGEN05)

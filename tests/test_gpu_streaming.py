@@ -1,0 +1,83 @@
+"""Streaming == offline, the equivalence the reference pins for its own streaming model (test/test_streaming.py:62-116).
+Oracle: the offline causal forward (oracle.inference) of the same weights on the whole signal."""
+import pytest
+import torch
+
+from oracle import describe as D
+from oracle import separator_ref as R
+from puresound_b200 import testing
+from puresound_b200.nnet.base_nn import SoTaskWrapModule
+from puresound_b200.nnet.lobe.encoder import FreeEncDec
+from puresound_b200.streaming.conv_tasnet_inference import StreamingConvTasNet, StreamingSeparator
+
+pytestmark = pytest.mark.gpu
+
+
+def build(norm, win, hop, nf, hid, X, Rp, seed):
+    torch.manual_seed(seed)
+    m = SoTaskWrapModule(
+        FreeEncDec(win, nf, hop),
+        StreamingConvTasNet(nf, 0, False, tcn_dim=hid, per_tcn_stack=X, repeat_tcn=Rp, tcn_with_embed=[0] * X, tcn_norm=norm, dconv_norm=norm, causal=True),
+        mask_constraint="ReLU", verbose=False).eval()
+    testing.perturb_(m, seed=seed + 1)
+    return m
+
+
+def run_stream(m, wav, use_graph):
+    S, L = wav.shape
+    sep = StreamingSeparator(m, use_graph=use_graph)
+    sep.init_status(S)
+    hop, win = sep.hop, sep.win
+    outs = []
+    for j in range(L // hop):
+        outs.append(sep.step_wave(wav[:, j * hop:(j + 1) * hop].cuda()))
+    y = torch.cat(outs, dim=1).cpu()
+    return y[:, (win // hop - 1) * hop:]  # drop the priming hops
+
+
+@pytest.mark.parametrize("norm,win,hop", [("cLN", 32, 16), ("bN1d", 32, 16), ("cLN", 48, 16)])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_streaming_equals_offline_small(norm, win, hop, use_graph):
+    m = build(norm, win, hop, 24, 40, 4, 2, seed=3)
+    wav = testing.white(3, hop * 90, amp=0.1, seed=5)
+    ref = R.inference(m.state_dict(), D.describe(m), wav)
+    y = run_stream(m.cuda(), wav, use_graph)
+    n = y.shape[1]
+    assert n >= ref.shape[1] - win
+    err = (y - ref[:, :n]).abs().max().item()
+    assert err <= 2e-5, err
+    # and the offline engine path of the same module agrees too
+    off = m.inference(wav)
+    assert (off - ref).abs().max().item() <= 2e-5
+
+
+def test_streaming_cfg5_full_width():
+    """cfg-5 architecture (N=512, H=512, X=8, R=3, cLN, 10 ms hop): 8 streams x 40 hops against the offline oracle."""
+    from puresound_b200 import recipes
+
+    torch.manual_seed(0)
+    ref_model = recipes.baseline_config("cfg5").eval()
+    testing.perturb_(ref_model, seed=1)
+    m = build("cLN", 320, 160, 512, 512, 8, 3, seed=0)
+    m.load_state_dict(ref_model.state_dict())
+    wav = testing.noisy_speech(8, 160 * 41, seed=11)[0]
+    ref = R.inference(m.state_dict(), D.describe(m), wav)
+    y = run_stream(m.cuda(), wav, True)
+    n = y.shape[1]
+    err = (y - ref[:, :n]).abs().max().item()
+    print(f"cfg5 streaming vs offline oracle: max|err|={err:.3e} over {n} samples x 8 streams")
+    assert err <= 1e-3
+
+
+def test_streaming_guards():
+    with pytest.raises(AssertionError):
+        StreamingConvTasNet(16, 0, tcn_dim=8, per_tcn_stack=1, repeat_tcn=1, tcn_with_embed=[0], causal=False)
+    with pytest.raises(AssertionError):
+        StreamingConvTasNet(16, 0, tcn_dim=8, per_tcn_stack=1, repeat_tcn=1, tcn_with_embed=[0], causal=True, tcn_norm="gLN", dconv_norm="cLN")
+    m = build("cLN", 32, 16, 16, 16, 1, 1, seed=1).cuda()
+    sep = StreamingSeparator(m)
+    with pytest.raises(RuntimeError):
+        sep.step_wave(torch.zeros(1, 16))
+    sep.init_status(2)
+    with pytest.raises(ValueError):
+        sep.step_wave(torch.zeros(1, 16))
