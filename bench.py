@@ -36,6 +36,8 @@ WORKLOADS = {
     "cfg2": ("cfg2", 64, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) batch 64 x 4 s @16 kHz per GPU"),
     "cfg3": ("cfg3", 32, 160000, None, "DPRNN-LSTM (chunk 100, 6 blocks, H=128 bi) batch 32 x 10 s @16 kHz per GPU"),
     "cfg4": ("cfg4", 64, 64000, 96000, "TSE: STFT 512/128 + TCN (H=256, dvec 192) + speaker net, 64 x (4 s mix + 6 s enroll) per GPU"),
+    # streaming: a step is one 10 ms hop of every stream (batch = concurrent streams, samples = hop)
+    "cfg5": ("cfg5", 256, 160, None, "causal cLN Conv-TasNet (N=512,H=512,X=8,R=3), 10 ms hop, 256 concurrent streams per GPU, frame-by-frame"),
 }
 
 
@@ -124,6 +126,78 @@ def gemm_flops_bytes(model, workload):
     return {"flops": 2.0 * rows * M * K, "bytes": 4.0 * (rows * K + rows * M + M * K), "rows": rows, "M": M, "K": K}
 
 
+def streaming_bench(args, rank, world, local_rank):
+    """cfg5: frame-by-frame streaming.  value = audio-s/s over all streams; also per-hop latency p50/p99 at S=256 and S=1."""
+    from puresound_b200 import ops, recipes, sharding, testing
+    from puresound_b200.streaming.conv_tasnet_inference import StreamingConvTasNet, StreamingSeparator
+    from puresound_b200.nnet.base_nn import SoTaskWrapModule
+    from puresound_b200.nnet.lobe.encoder import FreeEncDec
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    ops.require_device()
+    torch.manual_seed(0)
+    m = SoTaskWrapModule(FreeEncDec(320, 512, 160),
+                         StreamingConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8,
+                                             tcn_norm="cLN", dconv_norm="cLN", causal=True), mask_constraint="ReLU", verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    m = m.to(dev)
+    _, S, hop, _, desc = WORKLOADS["cfg5"]
+
+    def run(n_streams, steps, warm):
+        sep = StreamingSeparator(m, use_graph=True)
+        sep.init_status(n_streams)
+        chunk_h = testing.white(n_streams, hop, amp=0.1, seed=99 + rank).pin_memory()
+        chunk_d = chunk_h.to(dev)
+        for _ in range(warm + 2):
+            sep.step_wave(chunk_d)
+        torch.cuda.synchronize()
+        lat = []
+        l0 = ops.launch_count
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sep.step_wave(chunk_d)
+            e1.record()
+            e1.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        launches = ops.launch_count - l0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = sep.step_wave(chunk_h)  # host chunk in, host chunk out
+        e2e = (time.perf_counter() - t0) * 1e3 / steps
+        lat.sort()
+        return lat, e2e, launches, out
+
+    steps = max(args.steps, 50)
+    sharding.barrier(dev)
+    with ClockSampler(local_rank) as clk:
+        lat256, e2e256, launches, out = run(S, steps, max(args.warmup, 3))
+    lat1, e2e1, _, _ = run(1, steps, max(args.warmup, 3))
+    ms = sharding.max_over_ranks(sum(lat256) / len(lat256), dev)
+    e2e_ms = sharding.max_over_ranks(e2e256, dev)
+    audio_s = S * hop / SR
+    if rank == 0:
+        pct = lambda v, q: v[min(len(v) - 1, int(q * len(v)))]
+        print(json.dumps({
+            "metric": "audio-sec/sec", "value": world * audio_s / (ms / 1e3), "unit": "audio-s/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"cfg5: {desc}", "graph": "one CUDA graph replay per hop", "hop_budget_ms": 10.0,
+                                            "l2": "per-hop state touch (815 MB of ring buffers at S=256) exceeds L2"},
+            "latency_ms": {"S=256": {"p50": pct(lat256, 0.5), "p99": pct(lat256, 0.99)}, "S=1": {"p50": pct(lat1, 0.5), "p99": pct(lat1, 0.99)},
+                           "e2e_host_S=1": e2e1},
+            "clocks": clk.summary(),
+            "e2e": {"value": world * audio_s / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": S * hop * 4, "d2h_bytes_per_step": S * hop * 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+        }))
+    return 0
+
+
 def cpu_reference_run(workload: str, sample_batch: int, steps: int, warmup: int, threads: int):
     """The reference's CPU forward of the path (oracle port: same ATen calls as puresound's nn.Modules)."""
     from oracle import describe as D
@@ -162,11 +236,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name, batch, L, Le, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8}[args.workload]
+    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg5": 1}[args.workload]
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
+            return 0
+        if args.workload == "cfg5":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has no streaming Conv-TasNet (SURVEY.md section 0.3); see cfg2"}))
             return 0
         steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
         audio_s, times = cpu_reference_run(args.workload, sample_batch, steps, warm, cores)
@@ -181,6 +258,9 @@ def main():
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
+
+    if args.workload == "cfg5":
+        return streaming_bench(args, rank, world, local_rank)
 
     # ------------------------------------------------------------------ our arm (B200)
     from puresound_b200 import ops

@@ -137,6 +137,7 @@ typedef struct {
   const float* pro_a; const float* pro_b; int64_t pro_batch_stride;
   const float* pro_rowstats; const float* pro_slope;
   float* stats_partials;             /* NULL or [batch, ps_dwconv_stats_slots, 3] */
+  int64_t stats_slots;               /* set by the library: row pitch of stats_partials (callers leave 0) */
 } ps_dwconv_t;
 PS_API int ps_dwconv(const ps_dwconv_t* d, void* stream);
 PS_API int64_t ps_dwconv_stats_slots(int64_t T, int64_t C);

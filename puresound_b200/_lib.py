@@ -44,7 +44,7 @@ class DwconvDesc(C.Structure):
         ("pro_mode", I32), ("pro_act", I32),
         ("pro_a", P), ("pro_b", P), ("pro_batch_stride", I64),
         ("pro_rowstats", P), ("pro_slope", P),
-        ("stats_partials", P),
+        ("stats_partials", P), ("stats_slots", I64),
     ]
 
 

@@ -30,14 +30,15 @@ void set_cuda_error(cudaError_t e, const char* where);
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// if-chain with the hot cases first (PReLU, none): a switch here becomes an indirect branch (BRX) per element
+// once it is inlined into unrolled loops, which measured 4x more instructions in the GEMM producers
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
-  switch (act) {
-    case PS_ACT_PRELU: return v > 0.f ? v : v * slope;  // NaN stays NaN: (NaN > 0) is false, NaN*slope = NaN
-    case PS_ACT_RELU: return (v != v) ? v : fmaxf(v, 0.f);  // torch.relu propagates NaN
-    case PS_ACT_TANH: return tanhf(v);
-    case PS_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-    default: return v;
-  }
+  if (act == PS_ACT_PRELU) return v > 0.f ? v : v * slope;  // NaN stays NaN: (NaN > 0) is false, NaN*slope = NaN
+  if (act == PS_ACT_NONE) return v;
+  if (act == PS_ACT_RELU) return (v != v) ? v : fmaxf(v, 0.f);  // torch.relu propagates NaN
+  if (act == PS_ACT_TANH) return tanhf(v);
+  if (act == PS_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
 }
 
 // ---- Welford / Chan partials: (count, mean, M2) --------------------------------

@@ -6,6 +6,8 @@
 // whole 2 KB frame rows at C=512), so compulsory traffic is one read and one
 // write of the tensor.  Threads run along channels (float4 per thread), so every
 // global access is a fully coalesced 512 B warp request.
+#include <stdlib.h>
+
 #include "ps_common.cuh"
 
 namespace ps {
@@ -131,11 +133,164 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const ps_dwconv_t d,
     Wf tot = wf_block_reduce(st.finish(), red);
     if (threadIdx.x == 0) {
       const int64_t slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-      const int64_t slots = (int64_t)gridDim.x * gridDim.y;
-      float* o = d.stats_partials + (b * slots + slot) * 3;
+      float* o = d.stats_partials + (b * d.stats_slots + slot) * 3;
       o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Tiled variant (the one used for the TCN shapes).  The streaming kernel above reads every input element
+// P times; with dilations up to 128 those re-reads are L2 hits but still cost L2->SM bandwidth (measured:
+// 44 % of HBM peak, L2-bound).  Here a CTA owns TC frames x 32 channels of one item, stages the tile plus
+// its (P-1)*d halo in shared memory ONCE — already transformed by the norm+PReLU prologue, so the
+// transform is also done once instead of P times — and computes all taps from shared memory.
+// Read amplification drops from P to (TC + (P-1)d)/TC (1.25x averaged over d = 1..128 at TC = 256).
+// ---------------------------------------------------------------------------------------------------
+constexpr int DT_THREADS = 256;
+constexpr int DT_CG = 32;  // channels per CTA: one 128-byte row segment
+
+static inline int dt_chunk(int P, int dilation) { return ((P - 1) * dilation <= 128) ? 256 : 512; }
+
+// PT: compile-time taps (3) or 0 = runtime (<= 8).  PRO: 0 none, 1 folded affine + PReLU, 2 row-norm (cLN) + PReLU;
+// "no activation" runs as PReLU with slope 1.  Everything per-element is compile-time selected: with runtime
+// mode/activation dispatch inside the unrolled loops this kernel executed 65 instructions per element and was
+// issue-bound at 27 % of HBM peak (ncu, round 1 run 5).
+template <int PT, int PRO>
+__global__ void __launch_bounds__(DT_THREADS) dwconv_tile_kernel(const ps_dwconv_t d, const int TC) {
+  extern __shared__ __align__(16) float tile[];  // [(TC + halo) rows][32 channels]
+  __shared__ Wf red[DT_THREADS / 32];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int64_t b = blockIdx.z;
+  const int c0 = blockIdx.y * DT_CG + tx * 4;
+  const int t0 = blockIdx.x * TC;
+  const int T = (int)d.T, C = (int)d.C;
+  const int P = PT ? PT : d.P;
+  const int dil = d.dilation;
+  const int halo = (P - 1) * dil;
+  const int halo_l = d.causal ? halo : halo / 2;
+  const int rows_total = TC + halo;
+  const bool c_ok = c0 < C;  // C % 4 == 0, so the whole float4 is in range
+  const float slope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;
+
+  float pa[4] = {1.f, 1.f, 1.f, 1.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f};
+  float w[PT ? PT : 1][4];
+  if (c_ok) {
+    if constexpr (PRO == 1) {
+      ldv<4>(d.pro_a + b * d.pro_batch_stride + c0, pa);
+      ldv<4>(d.pro_b + b * d.pro_batch_stride + c0, pb);
+    } else if constexpr (PRO == 2) {
+      ldv<4>(d.pro_a + c0, pa);
+      ldv<4>(d.pro_b + c0, pb);
+    }
+    if (d.bias) ldv<4>(d.bias + c0, bias);
+    if constexpr (PT > 0) {
+#pragma unroll
+      for (int p = 0; p < PT; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[p][i] = __ldg(d.w + (c0 + i) * PT + p);
+    }
+  }
+  const float* xb = d.x + b * d.T * d.C + c0;
+
+  // ---- stage: 8 independent 128-bit loads per thread in flight, transform once, store to shared memory ----
+  for (int base = 0; base < rows_total; base += 32 * 8) {
+    float4 v[8];
+    float2 rs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int rr = base + u * 32 + ty;
+      const int t = t0 - halo_l + rr;
+      const bool ok = c_ok && rr < rows_total && t >= 0 && t < T;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      rs[u] = make_float2(0.f, 1.f);
+      if (ok) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)t * C));
+        if constexpr (PRO == 2) rs[u] = __ldg(reinterpret_cast<const float2*>(d.pro_rowstats + (b * d.T + t) * 2));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int rr = base + u * 32 + ty;
+      if (rr >= rows_total) continue;
+      const int t = t0 - halo_l + rr;
+      const bool ok = c_ok && t >= 0 && t < T;
+      float o[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      if constexpr (PRO != 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float z = o[i];
+          if constexpr (PRO == 2) z = (z - rs[u].x) * rs[u].y;
+          z = fmaf(z, pa[i], pb[i]);
+          z = z > 0.f ? z : z * slope;
+          o[i] = ok ? z : 0.f;  // zero padding applies AFTER the prologue: the reference pads the activated tensor
+        }
+      }
+      *reinterpret_cast<float4*>(tile + rr * DT_CG + tx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- taps from shared memory; statistics as shifted sums about a per-thread pivot (count known analytically) ----
+  float piv = 0.f, ssum = 0.f, ssq = 0.f;
+  int nout = 0;
+  float* yb = d.y + b * d.T * d.C + c0;
+  if (c_ok) {
+    const int jmax = (T - t0) < TC ? (T - t0) : TC;
+    for (int j = ty; j < jmax; j += 32) {
+      float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
+#pragma unroll
+      for (int p = 0; p < (PT ? PT : 8); ++p) {
+        if (p >= P) break;
+        const float4 u4 = *reinterpret_cast<const float4*>(tile + (j + p * dil) * DT_CG + tx * 4);
+        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float wv;
+          if constexpr (PT > 0) wv = w[p][i];
+          else wv = __ldg(d.w + (c0 + i) * P + p);
+          acc[i] = fmaf(wv, uu[i], acc[i]);
+        }
+      }
+      *reinterpret_cast<float4*>(yb + (int64_t)(t0 + j) * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      if (nout == 0) piv = acc[0];
+      ++nout;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float dv = acc[i] - piv;
+        ssum += dv;
+        ssq = fmaf(dv, dv, ssq);
+      }
+    }
+  }
+  if (d.stats_partials) {
+    Wf mine;
+    mine.n = (float)(nout * 4);
+    mine.mean = 0.f; mine.m2 = 0.f;
+    if (nout > 0) {
+      const float md = ssum / mine.n;
+      mine.mean = piv + md;
+      mine.m2 = fmaxf(ssq - ssum * md, 0.f);
+    }
+    Wf tot = wf_block_reduce(mine, red);
+    if (threadIdx.x == 0) {
+      const int64_t slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+      float* o = d.stats_partials + (b * d.stats_slots + slot) * 3;
+      o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
+    }
+  }
+}
+
+template <int PT, int PRO>
+static int launch_tile(const ps_dwconv_t& dd, int TC, size_t smem, dim3 grid, cudaStream_t s, bool set_attr) {
+  if (set_attr) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<PT, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(dwconv_tile_kernel)"); return PS_ERR_CUDA; }
+  }
+  dwconv_tile_kernel<PT, PRO><<<grid, DT_THREADS, smem, s>>>(dd, TC);
+  PS_CHECK_LAUNCH("dwconv_tile_kernel");
+  return PS_OK;
 }
 
 }  // namespace ps
@@ -143,7 +298,9 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const ps_dwconv_t d,
 extern "C" int64_t ps_dwconv_stats_slots(int64_t T, int64_t C) {
   if (T <= 0 || C <= 0) return 0;
   ps::DwGeom g = ps::dw_geom(C);
-  return ps::cdiv(T, ps::DW_TT) * ps::cdiv(C, g.chan_per_block);
+  const int64_t a = ps::cdiv(T, ps::DW_TT) * ps::cdiv(C, g.chan_per_block);  // streaming kernel
+  const int64_t t = ps::cdiv(T, 256) * ps::cdiv(C, ps::DT_CG);               // tiled kernel (its largest grid)
+  return a > t ? a : t;
 }
 
 extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
@@ -162,14 +319,42 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
     PS_REQUIRE(al(d.x) && al(d.y) && (!d.bias || al(d.bias)) && (d.pro_mode == PS_PRO_NONE || (al(d.pro_a) && al(d.pro_b))));
     if (d.pro_mode == PS_PRO_AFFINE) PS_REQUIRE(d.pro_batch_stride % 4 == 0);
   }
-  dim3 grid((unsigned)ps::cdiv(d.T, ps::DW_TT), (unsigned)ps::cdiv(d.C, g.chan_per_block), (unsigned)d.batch);
   cudaStream_t s = (cudaStream_t)stream;
+  ps_dwconv_t dd = d;
+  dd.stats_slots = ps_dwconv_stats_slots(d.T, d.C);
+  if (d.stats_partials) {
+    // both kernels fill a prefix of the slot array; the rest must read as empty (count 0) partials
+    cudaError_t e = cudaMemsetAsync(d.stats_partials, 0, (size_t)d.batch * dd.stats_slots * 3 * sizeof(float), s);
+    if (e != cudaSuccess) { ps::set_cuda_error(e, "cudaMemsetAsync(stats_partials)"); return PS_ERR_CUDA; }
+  }
+  const int halo = (d.P - 1) * d.dilation;
+  const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
+  if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {
+    static bool attr_set[64][6] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int TC = ps::dt_chunk(d.P, d.dilation);
+    const size_t smem = (size_t)(TC + halo) * ps::DT_CG * sizeof(float);
+    const int which = (d.P == 3 ? 3 : 0) + d.pro_mode;
+    bool set_attr = false;
+    if (dev >= 0 && dev < 64 && !attr_set[dev][which]) { set_attr = true; attr_set[dev][which] = true; }
+    dim3 tgrid((unsigned)ps::cdiv(d.T, TC), (unsigned)ps::cdiv(d.C, ps::DT_CG), (unsigned)d.batch);
+    switch (which) {
+      case 0: return ps::launch_tile<0, 0>(dd, TC, smem, tgrid, s, set_attr);
+      case 1: return ps::launch_tile<0, 1>(dd, TC, smem, tgrid, s, set_attr);
+      case 2: return ps::launch_tile<0, 2>(dd, TC, smem, tgrid, s, set_attr);
+      case 3: return ps::launch_tile<3, 0>(dd, TC, smem, tgrid, s, set_attr);
+      case 4: return ps::launch_tile<3, 1>(dd, TC, smem, tgrid, s, set_attr);
+      default: return ps::launch_tile<3, 2>(dd, TC, smem, tgrid, s, set_attr);
+    }
+  }
+  dim3 grid((unsigned)ps::cdiv(d.T, ps::DW_TT), (unsigned)ps::cdiv(d.C, g.chan_per_block), (unsigned)d.batch);
   if (g.vec == 4) {
-    if (d.P == 3) ps::dwconv_kernel<4, 3><<<grid, ps::DW_THREADS, 0, s>>>(d, g.threads_c, g.rows_par);
-    else ps::dwconv_kernel<4, 0><<<grid, ps::DW_THREADS, 0, s>>>(d, g.threads_c, g.rows_par);
+    if (d.P == 3) ps::dwconv_kernel<4, 3><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
+    else ps::dwconv_kernel<4, 0><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
   } else {
-    if (d.P == 3) ps::dwconv_kernel<1, 3><<<grid, ps::DW_THREADS, 0, s>>>(d, g.threads_c, g.rows_par);
-    else ps::dwconv_kernel<1, 0><<<grid, ps::DW_THREADS, 0, s>>>(d, g.threads_c, g.rows_par);
+    if (d.P == 3) ps::dwconv_kernel<1, 3><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
+    else ps::dwconv_kernel<1, 0><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
   }
   PS_CHECK_LAUNCH("dwconv_kernel");
   return PS_OK;

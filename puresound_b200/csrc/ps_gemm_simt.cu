@@ -24,21 +24,22 @@ struct XLoadCtx {
   float mean, rstd, slope;
 };
 
+// PRO is a template parameter: dispatching on d.pro_mode per loaded element costs an indirect branch each time
+template <int PRO>
 __device__ __forceinline__ float pro_apply(const ps_gemm_t& d, float x, float x2, int64_t b, int64_t k, const XLoadCtx& c) {
-  switch (d.pro_mode) {
-    case PS_PRO_AFFINE: {
-      int64_t o = b * d.pro_batch_stride + k;
-      return apply_act(fmaf(x, __ldg(d.pro_a + o), __ldg(d.pro_b + o)), d.pro_act, c.slope);
-    }
-    case PS_PRO_ROWNORM:
-      return apply_act(fmaf((x - c.mean) * c.rstd, __ldg(d.pro_a + k), __ldg(d.pro_b + k)), d.pro_act, c.slope);
-    case PS_PRO_MASK:
-      return x * apply_act(x2, d.pro_act, c.slope);
-    default:
-      return x;
+  if constexpr (PRO == PS_PRO_AFFINE) {
+    int64_t o = b * d.pro_batch_stride + k;
+    return apply_act(fmaf(x, __ldg(d.pro_a + o), __ldg(d.pro_b + o)), d.pro_act, c.slope);
+  } else if constexpr (PRO == PS_PRO_ROWNORM) {
+    return apply_act(fmaf((x - c.mean) * c.rstd, __ldg(d.pro_a + k), __ldg(d.pro_b + k)), d.pro_act, c.slope);
+  } else if constexpr (PRO == PS_PRO_MASK) {
+    return x * apply_act(x2, d.pro_act, c.slope);
+  } else {
+    return x;
   }
 }
 
+template <int PRO>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const int x_vec, const int w_vec) {
   __shared__ __align__(16) float Xs[BK][LDS];
   __shared__ __align__(16) float Ws[BK][LDS];
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
   XLoadCtx ctx;
   ctx.mean = 0.f; ctx.rstd = 1.f;
   ctx.slope = (d.pro_slope != nullptr) ? __ldg(d.pro_slope) : 0.f;
-  if (d.pro_mode == PS_PRO_ROWNORM && xr_ok) {
+  if (PRO == PS_PRO_ROWNORM && xr_ok) {
     const float* rs = d.pro_rowstats + (b * d.rows + xr) * 2;
     ctx.mean = __ldg(rs);
     ctx.rstd = __ldg(rs + 1);
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool ok = xr_ok && (k + i < d.K);
-        xreg[h * 4 + i] = ok ? pro_apply(d, xv[i], x2v[i], b, k + i, ctx) : 0.f;
+        xreg[h * 4 + i] = ok ? pro_apply<PRO>(d, xv[i], x2v[i], b, k + i, ctx) : 0.f;
         wreg[h * 4 + i] = wv[i];
       }
     }
@@ -232,7 +233,12 @@ int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s) {
                     ((reinterpret_cast<uintptr_t>(d.X) & 15) == 0) &&
                     (!d.X2 || (reinterpret_cast<uintptr_t>(d.X2) & 15) == 0);
   const int w_vec = ((d.w_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
-  gemm_simt_kernel<<<grid, NT, 0, s>>>(d, x_vec, w_vec);
+  switch (d.pro_mode) {
+    case PS_PRO_AFFINE: gemm_simt_kernel<PS_PRO_AFFINE><<<grid, NT, 0, s>>>(d, x_vec, w_vec); break;
+    case PS_PRO_ROWNORM: gemm_simt_kernel<PS_PRO_ROWNORM><<<grid, NT, 0, s>>>(d, x_vec, w_vec); break;
+    case PS_PRO_MASK: gemm_simt_kernel<PS_PRO_MASK><<<grid, NT, 0, s>>>(d, x_vec, w_vec); break;
+    default: gemm_simt_kernel<PS_PRO_NONE><<<grid, NT, 0, s>>>(d, x_vec, w_vec); break;
+  }
   PS_CHECK_LAUNCH("gemm_simt_kernel");
   return PS_OK;
 }

@@ -24,20 +24,42 @@
 //               memory.  The normalised tensor never exists in HBM.
 // Pipelines: smem stages full/empty (producers+TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "ps_common.cuh"
 
 namespace ps {
 
-constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64, TC_STAGES = 2;
-constexpr int TC_A_PART = TC_BM * 128;  // bytes of one bf16 [128 x 64] tile
-constexpr int TC_B_PART = TC_BN * 128;  // bytes of one bf16 [256 x 64] tile
-constexpr int TC_STAGE_BYTES = 2 * TC_A_PART + 2 * TC_B_PART;
+constexpr int TC_BM = 128, TC_BN = 256;
 constexpr int TC_PRODUCERS = 256, TC_EPI = 128;
 constexpr int TC_THREADS = 64 + TC_EPI + TC_PRODUCERS;
 constexpr int TC_EPI_PITCH = 36;                                  // floats per staged row: 16 B aligned, conflict-free for 128-bit access
 constexpr int TC_EPI_STAGE = 4 * 32 * TC_EPI_PITCH * 4;            // one 32x32 fp32 transpose buffer per epilogue warp
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_MAXK = 1024;                                      // affine prologue: K <= 1024 (scale|shift staged in smem)
+constexpr int TC_AFF_BYTES = 2 * TC_MAXK * 4;
+constexpr int TC_PF_DIST = 4;                                      // L2 prefetch distance of the activation stream, in 64-k blocks
+
+// Pipeline geometry.  BK = k extent of one shared-memory stage: 64 (128-byte swizzle rows, 2 stages of 96 KB) or
+// 32 (64-byte swizzle rows, 4 stages of 48 KB).  Same bytes in flight, but the deeper ring lets the weight copies
+// and the activation producers run three MMA-stages ahead instead of one.
+template <int BK>
+struct TcCfg {
+  static constexpr int kBK = BK;
+  static constexpr int kRowBytes = BK * 2;                   // bf16 row of one operand tile = swizzle span
+  static constexpr int kStages = BK == 64 ? 2 : 4;
+  static constexpr int kAPart = TC_BM * kRowBytes;
+  static constexpr int kBPart = TC_BN * kRowBytes;
+  static constexpr int kStageBytes = 2 * kAPart + 2 * kBPart;
+  static constexpr int kSub = 64 / BK;                       // stages filled by one producer iteration (64 k)
+  static constexpr int kChunks = kRowBytes / 16;             // 16-byte chunks per row: 8 or 4
+  static constexpr uint32_t kSBO = 8 * kRowBytes;            // byte distance between 8-row swizzle atoms
+  static constexpr uint64_t kLayout = BK == 64 ? 2 : 4;      // UMMA LayoutType: SWIZZLE_128B / SWIZZLE_64B
+  static constexpr int kSmem = kStages * kStageBytes + TC_EPI_STAGE + TC_AFF_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // byte offset of 16-byte chunk c of row r inside a tile (Swizzle<3,4,3> resp. Swizzle<2,4,3>)
+  __host__ __device__ static constexpr uint32_t swz(uint32_t r, uint32_t c) {
+    return r * kRowBytes + ((BK == 64 ? (c ^ (r & 7u)) : (c ^ ((r >> 1) & 3u))) << 4);
+  }
+};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +89,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// same, for waiters that are not on the critical path (epilogue waiting for an accumulator, the weight loader waiting
+// for a free stage): back off between polls so the spin does not eat the issue slots the producer warps need
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -120,14 +152,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: K-major, 128B swizzle, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+// shared-memory matrix descriptor: K-major, swizzled rows, 8-row atoms kSBO bytes apart (cute::UMMA::SmemDescriptor)
+template <class Cfg>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);      // start address      [0,14)
   d |= (uint64_t)1 << 16;                      // leading byte off.  [16,30) (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset [32,46)
+  d |= (uint64_t)(Cfg::kSBO >> 4) << 32;       // stride byte offset [32,46): next 8-row atom
   d |= (uint64_t)1 << 46;                      // descriptor version [46,48) = 1 on sm_100
-  d |= (uint64_t)2 << 61;                      // layout type        [61,64) = SWIZZLE_128B
+  d |= (uint64_t)Cfg::kLayout << 61;           // layout type        [61,64)
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=256
@@ -158,29 +191,34 @@ __device__ __forceinline__ float epi_act(float x, float slope) {
   return x;
 }
 
-template <bool kAffine>
+template <bool kAffine, int BK>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh,
                                                                 const int64_t n_tiles) {
+  using Cfg = TcCfg<BK>;
+  constexpr int TC_STAGES = Cfg::kStages, TC_STAGE_BYTES = Cfg::kStageBytes, TC_A_PART = Cfg::kAPart, TC_B_PART = Cfg::kBPart;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;       // 128B swizzle atoms need 1024 B alignment
   uint8_t* sm = smem_raw + (base - raw);
   float* epi_stage = reinterpret_cast<float*>(sm + TC_STAGES * TC_STAGE_BYTES);
-  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE;
-  // barrier map (8 B each): full[0..1] empty[0..1] tfull[0..1] tempty[0..1], then tmem ptr, then stats scratch
-  const uint32_t bar_full = bars, bar_empty = bars + 16, bar_tfull = bars + 32, bar_tempty = bars + 48;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + 64);
-  Wf* wf_s = reinterpret_cast<Wf*>(sm + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + 80);
+  float* aff_s = reinterpret_cast<float*>(sm + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE);  // [scale K | shift K] of the current item
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + TC_AFF_BYTES;
+  // barrier map (8 B each): full[0..3] empty[0..3] tfull[0..1] tempty[0..1], then tmem ptr, then stats scratch
+  const uint32_t bar_full = bars, bar_empty = bars + 32, bar_tfull = bars + 64, bar_tempty = bars + 80;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + TC_AFF_BYTES + 128);
+  Wf* wf_s = reinterpret_cast<Wf*>(sm + TC_STAGES * TC_STAGE_BYTES + TC_EPI_STAGE + TC_AFF_BYTES + 144);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int KB = (int)(d.K / TC_BK);
+  const int KB = (int)(d.K / BK);  // shared-memory stages per tile
 
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, TC_PRODUCERS + 1);
+      mbar_init(bar_full + 8 * s, TC_PRODUCERS / Cfg::kSub + 1);  // the producer threads that own this stage + the weight copy
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_tfull + 8 * s, 1);
-      mbar_init(bar_tempty + 8 * s, TC_EPI);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, TC_EPI);
     }
     fence_barrier_init();
   }
@@ -225,10 +263,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = base + s * TC_STAGE_BYTES;
-          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + TC_A_PART);
-          const uint64_t b_hi = make_sw128_desc(sa + 2 * TC_A_PART), b_lo = make_sw128_desc(sa + 2 * TC_A_PART + TC_B_PART);
+          const uint64_t a_hi = make_smem_desc<Cfg>(sa), a_lo = make_smem_desc<Cfg>(sa + TC_A_PART);
+          const uint64_t b_hi = make_smem_desc<Cfg>(sa + 2 * TC_A_PART), b_lo = make_smem_desc<Cfg>(sa + 2 * TC_A_PART + TC_B_PART);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ko = (uint64_t)((k * 32) >> 4);  // +32 B per K=16 step inside the swizzle row
             // small cross terms first, the dominant hi*hi last
             umma_bf16(tmem_d, a_lo + ko, b_hi + ko, TC_IDESC, (kb | k) != 0);
@@ -256,16 +294,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
       const TileCoord tc = tile_coord(t, n_rt, n_nh);
       const int a = (int)(it & 1);
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
-      mbar_wait(bar_tfull + 8 * a, aph);
-      tc_fence_after();
       const int64_t row0 = tc.rt * TC_BM + q * 32;
       const int64_t n0 = tc.nh * TC_BN;
       float* yb = d.Y + tc.b * d.y_batch_stride + n0 + c4;
       const float* rb = d.residual ? d.residual + tc.b * d.res_batch_stride + n0 + c4 : nullptr;
+      if (rb && row0 + lane < d.rows) {
+        // this tile's MMAs are still in flight: pull the residual rows (1 KB each) into L2 now, so the epilogue's
+        // loads below are L2 hits instead of 64 serial HBM round trips per tile
+        const char* pr = reinterpret_cast<const char*>(d.residual + tc.b * d.res_batch_stride + (row0 + lane) * d.res_row_stride + n0);
+#pragma unroll
+        for (int l = 0; l < TC_BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + l * 128));
+      }
+      mbar_wait_relaxed(bar_tfull + 8 * a, aph);
+      tc_fence_after();
       const float* bp = d.bias ? d.bias + n0 + c4 : nullptr;
       const float* bbp = d.bias_batch ? d.bias_batch + tc.b * d.M + n0 + c4 : nullptr;
-      WfAcc st;
-      st.init();
+      // statistics: shifted sums about a per-thread pivot (its first output of the tile); the count is known
+      // analytically, so the hot loop pays 3 flops per element instead of a full Welford update
+      const int nvalid = (int)((d.rows - row0) < 32 ? (d.rows - row0) : 32);  // valid rows of this warp's quarter (may be <= 0)
+      float piv = 0.f, ssum = 0.f, ssq = 0.f;
+      bool have_piv = false;
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
         float v[32];
@@ -280,11 +328,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
           const float4 b2 = __ldg(reinterpret_cast<const float4*>(bbp + c * 32));
           bs.x += b2.x; bs.y += b2.y; bs.z += b2.z; bs.w += b2.w;
         }
+        float4 res4[8];
+        if (rb) {  // all eight residual loads of this chunk in flight together
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            res4[i] = rr < nvalid ? __ldg(reinterpret_cast<const float4*>(rb + (row0 + rr) * d.res_row_stride + c * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + rsub;
           const int64_t row = row0 + rr;
-          if (row < d.rows) {
+          if (rr < nvalid) {
             const float4 x4 = *reinterpret_cast<const float4*>(stg + rr * TC_EPI_PITCH + c4);
             float o[4] = {x4.x + bs.x, x4.y + bs.y, x4.z + bs.z, x4.w + bs.w};
             if (d.epi_act == PS_ACT_RELU) {
@@ -294,12 +350,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
 #pragma unroll
               for (int e = 0; e < 4; ++e) o[e] = epi_act<PS_ACT_PRELU>(o[e], eslope);
             }
-            if (rb) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rb + row * d.res_row_stride + c * 32));
-              o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
-            }
+            if (rb) { o[0] += res4[i].x; o[1] += res4[i].y; o[2] += res4[i].z; o[3] += res4[i].w; }
             *reinterpret_cast<float4*>(yb + row * d.y_row_stride + c * 32) = make_float4(o[0], o[1], o[2], o[3]);
-            st.add(o[0]); st.add(o[1]); st.add(o[2]); st.add(o[3]);
+            if (!have_piv) { piv = o[0]; have_piv = true; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float dv = o[e] - piv;
+              ssum += dv;
+              ssq = fmaf(dv, dv, ssq);
+            }
           }
         }
         __syncwarp();
@@ -308,7 +367,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * a);
       if (d.stats_partials) {
-        Wf w = wf_warp_reduce(st.finish());
+        // rows rsub, rsub+4, ... below nvalid, 4 columns x 8 chunks each
+        const int nrows_t = nvalid > rsub ? (nvalid - rsub + 3) / 4 : 0;
+        Wf mine;
+        mine.n = (float)(nrows_t * 4 * (TC_BN / 32));
+        mine.mean = 0.f; mine.m2 = 0.f;
+        if (mine.n > 0.f) {
+          const float md = ssum / mine.n;
+          mine.mean = piv + md;
+          mine.m2 = fmaxf(ssq - ssum * md, 0.f);
+        }
+        Wf w = wf_warp_reduce(mine);
         if (lane == 0) wf_s[q] = w;
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory");
         if (et == 0) {
@@ -325,9 +394,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
     }
   } else {
     // ===================== activation producers (warps 6..13) =====================
+    // A producer iteration covers 64 k = one stage (BK=64) or two consecutive stages (BK=32).  Thread mapping: 8
+    // threads cover the 64 k of a row (coalesced 256 B), 32 rows per pass, 4 passes.
     const int pt = tid - 192;
-    const int kc = pt & 7;   // 16-byte chunk of the 128-byte swizzle row: k = kc*8 .. kc*8+7
-    const int r0 = pt >> 3;  // 0..31
+    const int kc = pt & 7;                          // k = kc*8 .. kc*8+7 of the 64-k block
+    const int r0 = pt >> 3;                         // 0..31
+    const int sub = kc / Cfg::kChunks;              // which of the iteration's stages this thread fills
+    const uint32_t cch = (uint32_t)(kc % Cfg::kChunks);  // 16-byte chunk inside that stage's row
+    const int KB64 = (int)(d.K / 64);
+    const int K = (int)d.K;
     // AFFINE with no activation is PReLU with slope 1
     const float pslope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;
     int s = 0;
@@ -337,41 +412,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
     // HBM latency hides behind the transform of the previous block and the wait for a free stage
     auto issue = [&](float4(&x)[4][2], int64_t t, int kb) {
       const TileCoord tc = tile_coord(t, n_rt, n_nh);
-      const float* xb = d.X + tc.b * d.x_batch_stride + (int64_t)kb * TC_BK + kc * 8;
+      const float* xb = d.X + tc.b * d.x_batch_stride + (int64_t)kb * 64 + kc * 8;
       const int64_t row_base = tc.rt * TC_BM + r0;
+      const int64_t last = d.rows - 1;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const int64_t row = row_base + p * 32;
-        if (row < d.rows) {
-          const float4* src = reinterpret_cast<const float4*>(xb + row * d.x_row_stride);
-          x[p][0] = __ldg(src);
-          x[p][1] = __ldg(src + 1);
-        } else {
-          x[p][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-          x[p][1] = x[p][0];
-        }
+        // rows past the end of the item re-read its last row: their accumulator rows are computed but never stored
+        // (and never enter the statistics), which is cheaper than predicating the whole transform
+        int64_t row = row_base + p * 32;
+        row = row < last ? row : last;
+        const float4* src = reinterpret_cast<const float4*>(xb + row * d.x_row_stride);
+        x[p][0] = __ldg(src);
+        x[p][1] = __ldg(src + 1);
       }
     };
     // transform + bf16 hi/lo split + swizzled store of one k-block into stage s
     auto process = [&](const float4(&x)[4][2], int64_t t, int kb) {
-      const TileCoord tc = tile_coord(t, n_rt, n_nh);
       float sc[8], sh[8];
       if constexpr (kAffine) {
-        const int64_t k0 = (int64_t)kb * TC_BK + kc * 8;
-        const float4* ap = reinterpret_cast<const float4*>(d.pro_a + tc.b * d.pro_batch_stride + k0);
-        const float4* bp = reinterpret_cast<const float4*>(d.pro_b + tc.b * d.pro_batch_stride + k0);
-        const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1), b0 = __ldg(bp), b1 = __ldg(bp + 1);
+        // the folded norm affine of this item was staged in shared memory at the tile boundary (see below): two
+        // 29-cycle LDS.128 pairs instead of L2-latency global loads in the dependency chain of every block
+        const int k0 = kb * 64 + kc * 8;
+        const float4 a0 = *reinterpret_cast<const float4*>(aff_s + k0), a1 = *reinterpret_cast<const float4*>(aff_s + k0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(aff_s + K + k0), b1 = *reinterpret_cast<const float4*>(aff_s + K + k0 + 4);
         sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
         sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
       }
-      const int64_t row_base = tc.rt * TC_BM;
-      mbar_wait(bar_empty + 8 * s, ph ^ 1);
-      uint8_t* a_hi = sm + s * TC_STAGE_BYTES;
+      const int my_s = s + sub;
+      mbar_wait(bar_empty + 8 * my_s, ph ^ 1);
+      uint8_t* a_hi = sm + my_s * TC_STAGE_BYTES;
       uint8_t* a_lo = a_hi + TC_A_PART;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int r = p * 32 + r0;
-        const bool ok = row_base + r < d.rows;
         const float v[8] = {x[p][0].x, x[p][0].y, x[p][0].z, x[p][0].w, x[p][1].x, x[p][1].y, x[p][1].z, x[p][1].w};
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -382,7 +455,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
             u1 = fmaf(u1, sc[i + 1], sh[i + 1]);
             u0 = u0 > 0.f ? u0 : u0 * pslope;
             u1 = u1 > 0.f ? u1 : u1 * pslope;
-            if (!ok) { u0 = 0.f; u1 = 0.f; }  // rows past the end must not see the shift term
           }
           // packed conversions (one F2FP per pair) keep the slow XU pipe out of the loop
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(u0, u1);
@@ -393,22 +465,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
           hi[i >> 1] = hb;
           lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
         }
-        const uint32_t off = (uint32_t)r * 128u + ((uint32_t)(kc ^ (r & 7)) << 4);
+        const uint32_t off = Cfg::swz((uint32_t)r, cch);
         *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(bar_full + 8 * s);
-      if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+      mbar_arrive(bar_full + 8 * my_s);
+      s += Cfg::kSub;
+      if (s == TC_STAGES) { s = 0; ph ^= 1; }
     };
     auto next = [&](int64_t& t, int& kb) {
-      if (++kb == KB) { kb = 0; t += gridDim.x; }
+      if (++kb == KB64) { kb = 0; t += gridDim.x; }
+    };
+
+    int64_t staged_b = -1;
+    // when a block belongs to another batch item than the staged one, (re)load that item's scale|shift rows
+    auto stage_affine = [&](int64_t t) {
+      if constexpr (kAffine) {
+        const int64_t b = tile_coord(t, n_rt, n_nh).b;
+        if (b != staged_b) {
+          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");  // every producer is done reading the old rows
+          const float* pa = d.pro_a + b * d.pro_batch_stride;
+          const float* pb = d.pro_b + b * d.pro_batch_stride;
+          for (int k = pt * 4; k < K; k += TC_PRODUCERS * 4) {
+            *reinterpret_cast<float4*>(aff_s + k) = __ldg(reinterpret_cast<const float4*>(pa + k));
+            *reinterpret_cast<float4*>(aff_s + K + k) = __ldg(reinterpret_cast<const float4*>(pb + k));
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");
+          staged_b = b;
+        }
+      }
+    };
+    // software prefetch into L2, TC_PF_DIST blocks ahead of the register loads: one 128-byte line per 4 threads
+    auto prefetch = [&](int64_t t, int kb) {
+      if ((kc & 3) == 0) {
+        const TileCoord tc = tile_coord(t, n_rt, n_nh);
+        const float* xb = d.X + tc.b * d.x_batch_stride + (int64_t)kb * 64 + kc * 8;
+        const int64_t row_base = tc.rt * TC_BM + r0;
+        const int64_t last = d.rows - 1;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          int64_t row = row_base + p * 32;
+          row = row < last ? row : last;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + row * d.x_row_stride));
+        }
+      }
     };
 
     float4 xa[4][2], xb2[4][2];
     int64_t t = blockIdx.x;
     int kb = 0;
     bool have = t < n_tiles;
+    int64_t tp = t;  // prefetch cursor
+    int kbp = kb;
+    for (int i = 0; i < TC_PF_DIST && tp < n_tiles; ++i) {
+      if (i > 0) prefetch(tp, kbp);
+      next(tp, kbp);
+    }
     if (have) issue(xa, t, kb);
     while (have) {
       int64_t t2 = t;
@@ -416,6 +529,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
       next(t2, kb2);
       const bool have2 = t2 < n_tiles;
       if (have2) issue(xb2, t2, kb2);
+      if (tp < n_tiles) { prefetch(tp, kbp); next(tp, kbp); }
+      stage_affine(t);
       process(xa, t, kb);
       if (!have2) break;
       int64_t t3 = t2;
@@ -423,6 +538,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
       next(t3, kb3);
       const bool have3 = t3 < n_tiles;
       if (have3) issue(xa, t3, kb3);
+      if (tp < n_tiles) { prefetch(tp, kbp); next(tp, kbp); }
+      stage_affine(t2);
       process(xb2, t2, kb2);
       t = t3; kb = kb3; have = have3;
     }
@@ -437,75 +554,99 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
 }
 
 // ---------------------------------------------------------------- weight packing
-// W [M, K] fp32 -> per (n-half, k-block): [hi 256x64 bf16 | lo 256x64 bf16], each already in the
-// K-major 128B-swizzled shared-memory image, so the GEMM loads it with a plain bulk copy.
+// W [M, K] fp32 -> per (n-half, stage k-block): [hi 256xBK bf16 | lo 256xBK bf16], each already in the K-major
+// swizzled shared-memory image of the chosen stage geometry, so the GEMM loads it with a plain bulk copy.
+template <int BK>
 __global__ void pack_weights_kernel(const float* __restrict__ W, int64_t ldw, int64_t M, int64_t K, uint8_t* __restrict__ out) {
+  using Cfg = TcCfg<BK>;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * K) return;
   const int64_t n = i / K, k = i % K;
-  const int64_t nh = n / TC_BN, r = n % TC_BN, kb = k / TC_BK, kk = k % TC_BK;
-  const int64_t KB = K / TC_BK;
+  const int64_t nh = n / TC_BN, r = n % TC_BN, kb = k / BK, kk = k % BK;
+  const int64_t KB = K / BK;
   const float w = W[n * ldw + k];
   const __nv_bfloat16 h = __float2bfloat16_rn(w);
   const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
-  const size_t tile = ((size_t)(nh * KB + kb) * 2) * TC_B_PART;
-  const size_t off = (size_t)r * 128 + (size_t)((((kk >> 3) ^ (r & 7))) << 4) + (size_t)(kk & 7) * 2;
+  const size_t tile = ((size_t)(nh * KB + kb) * 2) * Cfg::kBPart;
+  const size_t off = (size_t)Cfg::swz((uint32_t)r, (uint32_t)(kk >> 3)) + (size_t)(kk & 7) * 2;
   *reinterpret_cast<__nv_bfloat16*>(out + tile + off) = h;
-  *reinterpret_cast<__nv_bfloat16*>(out + tile + TC_B_PART + off) = l;
+  *reinterpret_cast<__nv_bfloat16*>(out + tile + Cfg::kBPart + off) = l;
 }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// stage geometry, fixed per process (the packed weight image depends on it): PS_TC_BK=64|32
+int tc_bk() {
+  static int bk = 0;
+  if (bk == 0) {
+    const char* e = getenv("PS_TC_BK");
+    bk = (e && atoi(e) == 64) ? 64 : 32;
+  }
+  return bk;
+}
+
 bool gemm_tc_eligible(const ps_gemm_t& d) {
   if (!d.W_packed) return false;
-  if (d.M % TC_BN != 0 || d.K % TC_BK != 0) return false;
+  if (d.M % TC_BN != 0 || d.K % 64 != 0) return false;
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE)) return false;
   if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU)) return false;
   if (!(d.epi_act == PS_ACT_NONE || d.epi_act == PS_ACT_RELU || d.epi_act == PS_ACT_PRELU)) return false;
   if ((d.bias && !al16(d.bias)) || (d.bias_batch && !al16(d.bias_batch))) return false;
   if ((d.x_row_stride & 3) || (d.x_batch_stride & 3) || !al16(d.X) || d.x_row_stride < d.K) return false;
   if ((d.y_row_stride & 3) || (d.y_batch_stride & 3) || !al16(d.Y)) return false;
-  if (d.pro_mode == PS_PRO_AFFINE && ((d.pro_batch_stride & 3) || !al16(d.pro_a) || !al16(d.pro_b))) return false;
+  if (d.pro_mode == PS_PRO_AFFINE && ((d.pro_batch_stride & 3) || !al16(d.pro_a) || !al16(d.pro_b) || d.K > TC_MAXK)) return false;
   if (d.residual && ((d.res_row_stride & 3) || (d.res_batch_stride & 3) || !al16(d.residual))) return false;
   if (!al16(d.W_packed)) return false;
   return true;
 }
 
+template <bool kAffine, int BK>
+static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
+  if (set_attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kAffine, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BK>::kSmem);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)"); return PS_ERR_CUDA; }
+  }
+  gemm_tc_kernel<kAffine, BK><<<(unsigned)grid, TC_THREADS, TcCfg<BK>::kSmem, s>>>(d, n_rt, n_nh, n_tiles);
+  PS_CHECK_LAUNCH("gemm_tc_kernel");
+  return PS_OK;
+}
+
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
   static int sm_count[64] = {0};
-  static bool attr_set[64] = {false};
+  static bool attr_set[64][2] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
-  if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)"); return PS_ERR_CUDA; }
+  if (sm_count[dev] == 0) {
     e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
-    attr_set[dev] = true;
   }
+  const bool affine = d.pro_mode == PS_PRO_AFFINE;
+  const bool set_attr = !attr_set[dev][affine];
+  attr_set[dev][affine] = true;
   const int64_t n_rt = cdiv(d.rows, TC_BM), n_nh = d.M / TC_BN;
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   const int64_t grid = n_tiles < sm_count[dev] ? n_tiles : sm_count[dev];
-  if (d.pro_mode == PS_PRO_AFFINE) gemm_tc_kernel<true><<<(unsigned)grid, TC_THREADS, TC_SMEM, s>>>(d, n_rt, n_nh, n_tiles);
-  else gemm_tc_kernel<false><<<(unsigned)grid, TC_THREADS, TC_SMEM, s>>>(d, n_rt, n_nh, n_tiles);
-  PS_CHECK_LAUNCH("gemm_tc_kernel");
-  return PS_OK;
+  if (tc_bk() == 64)
+    return affine ? launch_variant<true, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_variant<false, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  return affine ? launch_variant<true, 32>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_variant<false, 32>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
 }
 
 }  // namespace ps
 
 extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
-  if (M <= 0 || K <= 0 || M % ps::TC_BN != 0 || K % ps::TC_BK != 0) return 0;
+  if (M <= 0 || K <= 0 || M % ps::TC_BN != 0 || K % 64 != 0) return 0;
   return M * K * 4;  // bf16 hi + bf16 lo
 }
 
 extern "C" int ps_gemm_pack_weights(const float* W, int64_t w_row_stride, int64_t M, int64_t K, void* packed, void* stream) {
   PS_REQUIRE(W && packed && w_row_stride >= K);
   if (ps_gemm_packed_bytes(M, K) == 0) return PS_ERR_UNSUPPORTED;
-  ps::pack_weights_kernel<<<(unsigned)ps::cdiv(M * K, 256), 256, 0, (cudaStream_t)stream>>>(W, w_row_stride, M, K,
-                                                                                          reinterpret_cast<uint8_t*>(packed));
+  const unsigned blocks = (unsigned)ps::cdiv(M * K, 256);
+  if (ps::tc_bk() == 64)
+    ps::pack_weights_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, w_row_stride, M, K, reinterpret_cast<uint8_t*>(packed));
+  else
+    ps::pack_weights_kernel<32><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, w_row_stride, M, K, reinterpret_cast<uint8_t*>(packed));
   PS_CHECK_LAUNCH("pack_weights_kernel");
   return PS_OK;
 }

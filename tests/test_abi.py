@@ -46,7 +46,7 @@ def test_version_and_struct_mirrors(lib):
 def test_slot_counts(lib):
     assert lib.ps_gemm_stats_slots(3999, 512) == 32 * 4
     assert lib.ps_gemm_stats_slots(1, 1) == 1
-    assert lib.ps_dwconv_stats_slots(3999, 512) == 250
+    assert lib.ps_dwconv_stats_slots(3999, 512) == 256  # max(streaming 250, tiled 16 x 16)
     assert lib.ps_dwconv_stats_slots(50, 24) == 4
 
 
