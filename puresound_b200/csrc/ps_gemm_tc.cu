@@ -173,12 +173,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 struct TileCoord {
   int64_t b, rt, nh;
 };
+// 32-bit decode (tile counts are < 2^31, checked at launch): 64-bit div/mod costs ~100 instructions each and this
+// used to run four times per k-block in the producer warps
 __device__ __forceinline__ TileCoord tile_coord(int64_t t, int64_t n_rt, int64_t n_nh) {
+  const uint32_t tt = (uint32_t)t, nrt = (uint32_t)n_rt, nnh = (uint32_t)n_nh;
+  const uint32_t q = tt / nnh;
   TileCoord c;
-  c.nh = t % n_nh;
-  const int64_t q = t / n_nh;
-  c.rt = q % n_rt;
-  c.b = q / n_rt;
+  c.nh = tt - q * nnh;
+  const uint32_t bb = q / nrt;
+  c.rt = q - bb * nrt;
+  c.b = bb;
   return c;
 }
 
@@ -408,30 +412,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
     int s = 0;
     uint32_t ph = 0;
 
+    // A cursor walks this CTA's (tile, 64-k block) sequence; the tile is decoded once per tile, not per block.
+    struct Cur {
+      int64_t t;
+      int kb;
+      const float* x0;   // &X[b][rt*128 + r0][kc*8]  (row clamped per pass below)
+      int64_t row_base;  // rt*128 + r0
+      int64_t b;
+    };
+    const int64_t last_row = d.rows - 1;
+    auto decode = [&](Cur& c) {
+      if (c.t < n_tiles) {
+        const TileCoord tc = tile_coord(c.t, n_rt, n_nh);
+        c.b = tc.b;
+        c.row_base = tc.rt * TC_BM + r0;
+        c.x0 = d.X + tc.b * d.x_batch_stride + kc * 8;
+      }
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.kb == KB64) {
+        c.kb = 0;
+        c.t += gridDim.x;
+        decode(c);
+      }
+    };
     // global loads of one (tile, k-block): 8 x LDG.128 per thread, issued one k-block AHEAD of their use so the
-    // HBM latency hides behind the transform of the previous block and the wait for a free stage
-    auto issue = [&](float4(&x)[4][2], int64_t t, int kb) {
-      const TileCoord tc = tile_coord(t, n_rt, n_nh);
-      const float* xb = d.X + tc.b * d.x_batch_stride + (int64_t)kb * 64 + kc * 8;
-      const int64_t row_base = tc.rt * TC_BM + r0;
-      const int64_t last = d.rows - 1;
+    // HBM latency hides behind the transform of the previous block and the wait for a free stage.  Rows past the end
+    // of the item re-read its last row: their accumulator rows are computed but never stored (and never enter the
+    // statistics), which is cheaper than predicating the whole transform.
+    auto issue = [&](float4(&x)[4][2], const Cur& c) {
+      const float* xb = c.x0 + c.kb * 64;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        // rows past the end of the item re-read its last row: their accumulator rows are computed but never stored
-        // (and never enter the statistics), which is cheaper than predicating the whole transform
-        int64_t row = row_base + p * 32;
-        row = row < last ? row : last;
+        int64_t row = c.row_base + p * 32;
+        row = row < last_row ? row : last_row;
         const float4* src = reinterpret_cast<const float4*>(xb + row * d.x_row_stride);
         x[p][0] = __ldg(src);
         x[p][1] = __ldg(src + 1);
       }
     };
-    // transform + bf16 hi/lo split + swizzled store of one k-block into stage s
-    auto process = [&](const float4(&x)[4][2], int64_t t, int kb) {
+    // software prefetch into L2, TC_PF_DIST blocks ahead of the register loads: one 128-byte line per 4 threads
+    auto prefetch = [&](const Cur& c) {
+      if ((kc & 3) == 0) {
+        const float* xb = c.x0 + c.kb * 64;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          int64_t row = c.row_base + p * 32;
+          row = row < last_row ? row : last_row;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + row * d.x_row_stride));
+        }
+      }
+    };
+    int64_t staged_b = -1;
+    // when a block belongs to another batch item than the staged one, (re)load that item's scale|shift rows
+    auto stage_affine = [&](int64_t b) {
+      if constexpr (kAffine) {
+        if (b != staged_b) {
+          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");  // every producer is done reading the old rows
+          const float* pa = d.pro_a + b * d.pro_batch_stride;
+          const float* pb = d.pro_b + b * d.pro_batch_stride;
+          for (int k = pt * 4; k < K; k += TC_PRODUCERS * 4) {
+            *reinterpret_cast<float4*>(aff_s + k) = __ldg(reinterpret_cast<const float4*>(pa + k));
+            *reinterpret_cast<float4*>(aff_s + K + k) = __ldg(reinterpret_cast<const float4*>(pb + k));
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");
+          staged_b = b;
+        }
+      }
+    };
+    // transform + bf16 hi/lo split + swizzled store of one k-block into stage s (+ s+1 for the 32-k geometry)
+    auto process = [&](const float4(&x)[4][2], int kb) {
       float sc[8], sh[8];
       if constexpr (kAffine) {
-        // the folded norm affine of this item was staged in shared memory at the tile boundary (see below): two
-        // 29-cycle LDS.128 pairs instead of L2-latency global loads in the dependency chain of every block
+        // the folded norm affine of this item was staged in shared memory at the item boundary: two 29-cycle LDS.128
+        // pairs instead of L2-latency global loads in the dependency chain of every block
         const int k0 = kb * 64 + kc * 8;
         const float4 a0 = *reinterpret_cast<const float4*>(aff_s + k0), a1 = *reinterpret_cast<const float4*>(aff_s + k0 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(aff_s + K + k0), b1 = *reinterpret_cast<const float4*>(aff_s + K + k0 + 4);
@@ -474,74 +528,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const ps_gemm_t 
       s += Cfg::kSub;
       if (s == TC_STAGES) { s = 0; ph ^= 1; }
     };
-    auto next = [&](int64_t& t, int& kb) {
-      if (++kb == KB64) { kb = 0; t += gridDim.x; }
-    };
-
-    int64_t staged_b = -1;
-    // when a block belongs to another batch item than the staged one, (re)load that item's scale|shift rows
-    auto stage_affine = [&](int64_t t) {
-      if constexpr (kAffine) {
-        const int64_t b = tile_coord(t, n_rt, n_nh).b;
-        if (b != staged_b) {
-          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");  // every producer is done reading the old rows
-          const float* pa = d.pro_a + b * d.pro_batch_stride;
-          const float* pb = d.pro_b + b * d.pro_batch_stride;
-          for (int k = pt * 4; k < K; k += TC_PRODUCERS * 4) {
-            *reinterpret_cast<float4*>(aff_s + k) = __ldg(reinterpret_cast<const float4*>(pa + k));
-            *reinterpret_cast<float4*>(aff_s + K + k) = __ldg(reinterpret_cast<const float4*>(pb + k));
-          }
-          asm volatile("bar.sync 2, %0;" ::"n"(TC_PRODUCERS) : "memory");
-          staged_b = b;
-        }
-      }
-    };
-    // software prefetch into L2, TC_PF_DIST blocks ahead of the register loads: one 128-byte line per 4 threads
-    auto prefetch = [&](int64_t t, int kb) {
-      if ((kc & 3) == 0) {
-        const TileCoord tc = tile_coord(t, n_rt, n_nh);
-        const float* xb = d.X + tc.b * d.x_batch_stride + (int64_t)kb * 64 + kc * 8;
-        const int64_t row_base = tc.rt * TC_BM + r0;
-        const int64_t last = d.rows - 1;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          int64_t row = row_base + p * 32;
-          row = row < last ? row : last;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(xb + row * d.x_row_stride));
-        }
-      }
-    };
 
     float4 xa[4][2], xb2[4][2];
-    int64_t t = blockIdx.x;
-    int kb = 0;
-    bool have = t < n_tiles;
-    int64_t tp = t;  // prefetch cursor
-    int kbp = kb;
-    for (int i = 0; i < TC_PF_DIST && tp < n_tiles; ++i) {
-      if (i > 0) prefetch(tp, kbp);
-      next(tp, kbp);
+    Cur cur, nxt, pf;            // block being transformed, block being loaded, block being prefetched
+    cur.t = blockIdx.x; cur.kb = 0;
+    decode(cur);
+    pf = cur;
+    for (int i = 0; i < TC_PF_DIST && pf.t < n_tiles; ++i) {
+      if (i > 0) prefetch(pf);
+      advance(pf);
     }
-    if (have) issue(xa, t, kb);
-    while (have) {
-      int64_t t2 = t;
-      int kb2 = kb;
-      next(t2, kb2);
-      const bool have2 = t2 < n_tiles;
-      if (have2) issue(xb2, t2, kb2);
-      if (tp < n_tiles) { prefetch(tp, kbp); next(tp, kbp); }
-      stage_affine(t);
-      process(xa, t, kb);
-      if (!have2) break;
-      int64_t t3 = t2;
-      int kb3 = kb2;
-      next(t3, kb3);
-      const bool have3 = t3 < n_tiles;
-      if (have3) issue(xa, t3, kb3);
-      if (tp < n_tiles) { prefetch(tp, kbp); next(tp, kbp); }
-      stage_affine(t2);
-      process(xb2, t2, kb2);
-      t = t3; kb = kb3; have = have3;
+    if (cur.t < n_tiles) issue(xa, cur);
+    while (cur.t < n_tiles) {
+      nxt = cur;
+      advance(nxt);
+      if (nxt.t < n_tiles) issue(xb2, nxt);
+      if (pf.t < n_tiles) { prefetch(pf); advance(pf); }
+      stage_affine(cur.b);
+      process(xa, cur.kb);
+      if (nxt.t >= n_tiles) break;
+      cur = nxt;
+      advance(cur);
+      if (cur.t < n_tiles) issue(xa, cur);
+      if (pf.t < n_tiles) { prefetch(pf); advance(pf); }
+      stage_affine(nxt.b);
+      process(xb2, nxt.kb);
     }
   }
 
@@ -626,6 +637,7 @@ int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
   attr_set[dev][affine] = true;
   const int64_t n_rt = cdiv(d.rows, TC_BM), n_nh = d.M / TC_BN;
   const int64_t n_tiles = d.batch * n_rt * n_nh;
+  if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
   const int64_t grid = n_tiles < sm_count[dev] ? n_tiles : sm_count[dev];
   if (tc_bk() == 64)
     return affine ? launch_variant<true, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_variant<false, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
