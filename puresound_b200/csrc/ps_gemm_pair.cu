@@ -1,0 +1,566 @@
+// CTA-pair tcgen05 / TMEM GEMM for the 1x1 convolutions of the TCN stack (sm_100a, cta_group::2).
+//
+//   Y[b,f,c] = epi( sum_k pro(X[b,f,k]) * W[c,k] ),  fp32 in HBM, fp32-grade result (3xBF16 split, see ps_gemm_tc.cu).
+//
+// Why a second kernel.  ncu on the single-CTA kernel (profiles/r01_tc_gemm_ncu_notes.md) showed the tensor pipe 48 %
+// busy and the MMA thread waiting for the activation producers: with a 128-frame x 256-channel tile every activation
+// tile is loaded and transformed (norm affine + PReLU + bf16 hi/lo split) once per 256-channel half, and the LSU data
+// pipe (71 %) carries that twice plus an epilogue transpose through shared memory.  Here the operand roles are
+// swapped and two SMs share one tile:
+//
+//   * A (M side, TMEM lanes)   = weights: 256 channels per MMA, 128 from each CTA of the pair;
+//   * B (N side, TMEM columns) = activations: 128 frames per MMA, 64 transformed by each CTA - the tensor core reads
+//     the other half straight from the peer's shared memory, so every activation element is transformed ONCE for all
+//     (up to 512) output channels of the tile;
+//   * D: each CTA holds [128 channels x 128 frames] per 256-channel block; two blocks (512 channels) use 256 TMEM
+//     columns, so two tiles ping-pong in the 512 columns and the epilogue of one overlaps the MMAs of the next;
+//   * the epilogue needs no transpose: a TMEM lane is a channel, a column is a frame, so for one frame a warp's 32
+//     lanes are 32 consecutive channels = one coalesced 128-byte store (and residual load) into the [frames, channels]
+//     tensor.
+//
+// Warp roles per CTA (576 threads): warp 0 weight loader (cp.async.bulk of the pre-packed, pre-swizzled image),
+// warp 1 MMA issuer (leader CTA) / stage relay (peer CTA), warps 2-9 epilogue (two per TMEM lane quarter), warps
+// 10-17 activation producers.
+// Pipelines: 4 shared-memory stages of 32 k (full / peer-full / empty), 2 TMEM accumulator sets (tfull / tempty).
+// The leader's MMA thread issues for both SMs; tcgen05.commit multicasts the stage-free and accumulator-ready
+// arrivals to both CTAs; the peer reports its filled stages and drained accumulators with remote mbarrier arrives.
+#include <stdlib.h>
+#include <string.h>
+
+#include "ps_tc_ptx.cuh"
+
+namespace ps {
+
+constexpr int PR_FRAMES = 128;      // frames per pair tile (MMA N)
+constexpr int PR_FR_CTA = 64;       // frames staged by each CTA
+constexpr int PR_BK = 32;           // k per shared-memory stage (64-byte swizzle rows)
+#ifndef PR_STAGES
+#define PR_STAGES 4                 // shared-memory ring depth (4 x 40 KB at 512 channels; 5 measured no faster)
+#endif
+constexpr int PR_XPART = PR_FR_CTA * PR_BK * 2;   // 4 KB: activation hi (or lo) of one stage
+constexpr int PR_WBLK = 128 * PR_BK * 2;          // 8 KB: one 128-channel weight block, hi (or lo), of one stage
+#ifndef PR_EPI_WARPS
+#define PR_EPI_WARPS 8              // 4 or 8: warps draining TMEM (one or two per lane quarter)
+#endif
+constexpr int PR_PRODUCERS = 256, PR_EPI = PR_EPI_WARPS * 32;
+constexpr int PR_THREADS = 64 + PR_EPI + PR_PRODUCERS;
+constexpr int PR_MAXK = 1024;
+constexpr int PR_AFF_BYTES = 2 * PR_MAXK * 4;
+constexpr int PR_CW = 16;           // frames (TMEM columns) per epilogue chunk
+
+template <int NB>
+struct PairCfg {
+  static constexpr int kStageBytes = 2 * PR_XPART + 2 * NB * PR_WBLK;       // NB=2: 40 KB, NB=1: 24 KB
+  static constexpr int kWBytes = 2 * NB * PR_WBLK;                          // weight bytes per stage per CTA
+  static constexpr int kAccCols = NB * PR_FRAMES;                           // TMEM columns of one accumulator set
+  static constexpr int kSmem = PR_STAGES * kStageBytes + PR_AFF_BYTES + 1024 /*align*/ + 512 /*barriers, scratch*/;
+};
+
+// byte offset of 16-byte chunk c of row r in a [rows x 32 k] bf16 tile, 64-byte swizzle (Swizzle<2,4,3>)
+__host__ __device__ constexpr uint32_t pr_swz(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
+
+// K-major, SWIZZLE_64B, 8-row atoms 512 B apart
+__device__ __forceinline__ uint64_t pr_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// D=f32, A=B=bf16, K-major both, M=256 (pair), N=128
+constexpr uint32_t PR_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PR_FRAMES >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+struct PairTile {
+  uint32_t b, rt, nh;
+};
+__device__ __forceinline__ PairTile pr_tile(int64_t t, int64_t n_rt, int64_t n_nh) {
+  const uint32_t tt = (uint32_t)t, nrt = (uint32_t)n_rt, nnh = (uint32_t)n_nh;
+  const uint32_t q = tt / nnh;
+  PairTile c;
+  c.nh = tt - q * nnh;
+  c.b = q / nrt;
+  c.rt = q - c.b * nrt;
+  return c;
+}
+
+// Epilogue of one PR_CW-frame chunk of one channel (thread): out = act(acc + bias) (+ residual), strided scalar stores that
+// are coalesced across the warp's 32 channels, and shifted sums about a pivot for the gLN statistics.  ACT = -1 takes
+// the activation at run time (uniform branch per element); kFull = all frames of the chunk valid, no predication.
+template <int ACT, bool kRes, bool kFull>
+__device__ __forceinline__ void epi_chunk(const float (&v)[PR_CW], float bsum, float eslope, float* yp, int64_t ystride, const float* rp,
+                                          int64_t rstride, int nj, bool first, float& piv, float& ssum, float& ssq, int act = ACT) {
+  float r[PR_CW];
+  if constexpr (kRes) {  // all residual loads of the chunk in flight together
+    const float* p = rp;
+#pragma unroll
+    for (int j = 0; j < PR_CW; ++j) {
+      r[j] = (kFull || j < nj) ? __ldg(p) : 0.f;
+      p += rstride;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PR_CW; ++j) {
+    float o = v[j] + bsum;
+    if (ACT == PS_ACT_NONE) {
+    } else if (act == PS_ACT_PRELU) o = o > 0.f ? o : o * eslope;
+    else if (act == PS_ACT_RELU) o = (o != o) ? o : fmaxf(o, 0.f);
+    if constexpr (kRes) o += r[j];
+    if (j == 0 && first) piv = o;  // statistics pivot: this thread's first output of the block
+    if (kFull || j < nj) {
+      *yp = o;
+      const float dv = o - piv;
+      ssum += dv;
+      ssq = fmaf(dv, dv, ssq);
+    }
+    yp += ystride;
+  }
+}
+
+template <bool kAffine, int NB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
+    gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
+  using Cfg = PairCfg<NB>;
+  constexpr int STAGE = Cfg::kStageBytes;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float* aff_s = reinterpret_cast<float*>(sm + PR_STAGES * STAGE);
+  const uint32_t bars = base + PR_STAGES * STAGE + PR_AFF_BYTES;
+  // barrier map (8 B each, room for 8 stages): full @0, empty @64, pfull @128, tfull[0..1] @192, tempty[0..1] @208
+  static_assert(PR_STAGES <= 8, "barrier map holds 8 stages");
+  const uint32_t bar_full = bars, bar_empty = bars + 64, bar_pfull = bars + 128, bar_tfull = bars + 192, bar_tempty = bars + 208;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 224);
+  Wf* wf_s = reinterpret_cast<Wf*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 240);  // [NB][epilogue warps]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int KB = (int)(d.K / PR_BK);
+
+  if (tid == 0) {
+    for (int s = 0; s < PR_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, PR_PRODUCERS / 64 + 1);  // the 4 producer warps of this stage + the weight copy
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_pfull + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * PR_EPI_WARPS);  // one arrival per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32((const void*)tmem_ptr_s), 512);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== weight loader =====================
+    // (whole warp walks the loop so every value stays warp-uniform; one elected lane issues)
+    int s = 0;
+    uint32_t ph = 0;
+    const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.W_packed);
+    for (int64_t t = pair; t < n_tiles; t += n_pairs) {
+      const PairTile tc = pr_tile(t, n_rt, n_nh);
+      const uint8_t* src = wp + (size_t)(tc.nh * 2 + rank) * KB * Cfg::kWBytes;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kWBytes);
+          if (dbg & 1) {  // experiment: no weight traffic (results are garbage)
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"((uint32_t)Cfg::kWBytes) : "memory");
+          } else if (dbg & 32) {  // experiment: four smaller copies
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              bulk_g2s(base + s * STAGE + 2 * PR_XPART + i * (Cfg::kWBytes / 4), src + (size_t)kb * Cfg::kWBytes + i * (Cfg::kWBytes / 4), Cfg::kWBytes / 4, bar_full + 8 * s);
+          } else
+            bulk_g2s(base + s * STAGE + 2 * PR_XPART, src + (size_t)kb * Cfg::kWBytes, Cfg::kWBytes, bar_full + 8 * s);
+        }
+        __syncwarp();
+        if (++s == PR_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int s = 0;
+    uint32_t ph = 0;
+    if (rank == 0) {
+      // ===================== MMA issuer (leader) =====================
+      int64_t it = 0;
+      for (int64_t t = pair; t < n_tiles; t += n_pairs, ++it) {
+        const int a = (int)(it & 1);
+        const uint32_t aph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(bar_tempty + 8 * a, aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * Cfg::kAccCols);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);   // this CTA's stage: producers + weight copy
+          mbar_wait(bar_pfull + 8 * s, ph);  // the peer's stage (relayed)
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = base + s * STAGE;
+            const uint64_t x_hi = pr_desc(sa), x_lo = pr_desc(sa + PR_XPART);
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb) {
+              const uint64_t w_hi = pr_desc(sa + 2 * PR_XPART + mb * PR_WBLK);
+              const uint64_t w_lo = pr_desc(sa + 2 * PR_XPART + (NB + mb) * PR_WBLK);
+#pragma unroll
+              for (int k = 0; k < PR_BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)((k * 32) >> 4);
+                const uint32_t dd = tmem_d + (uint32_t)(mb * PR_FRAMES);
+                // small cross terms first, the dominant hi*hi last
+                umma_bf16_pair(dd, w_lo + ko, x_hi + ko, PR_IDESC, (kb | k) != 0);
+                umma_bf16_pair(dd, w_hi + ko, x_lo + ko, PR_IDESC, 1);
+                umma_bf16_pair(dd, w_hi + ko, x_hi + ko, PR_IDESC, 1);
+              }
+            }
+            umma_commit_pair(bar_empty + 8 * s);                  // frees this stage in both CTAs when the MMAs retire
+            if (kb == KB - 1) umma_commit_pair(bar_tfull + 8 * a);  // accumulators complete -> both epilogues
+          }
+          __syncwarp();
+          if (++s == PR_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else {
+      // ===================== stage relay (peer) =====================
+      // tells the leader that this CTA's half of a stage (its 64 activation frames and its weight blocks) landed
+      for (int64_t t = pair; t < n_tiles; t += n_pairs) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          if (elect_one()) mbar_arrive_remote(bar_pfull + 8 * s, 0);
+          __syncwarp();
+          if (++s == PR_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 2 + PR_EPI_WARPS) {
+    // ===================== epilogue (warps 2..2+EW) =====================
+    // Work unit = (256-channel block mb, 32-frame chunk c); warp group g = (warp-2)/4 takes the units u = mb*4+c with
+    // u % G == g, so with 8 epilogue warps two warps drain each TMEM lane quarter concurrently.
+    constexpr int G = PR_EPI_WARPS / 4;
+    constexpr int NCH = PR_FRAMES / PR_CW;  // chunks per 256-channel block
+    const int q = warp & 3;            // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+    const int g = (warp - 2) >> 2;
+    const int cl = q * 32 + lane;      // channel within this CTA's 128-channel block = TMEM lane
+    const int et = tid - 64;
+    const float eslope = d.epi_slope ? __ldg(d.epi_slope) : 0.f;
+    const int epi_act = d.epi_act;
+    const int64_t ystride = d.y_row_stride, rstride = d.res_row_stride;
+    const float* const bias = d.bias;
+    const float* const bias_batch = d.bias_batch;
+    const bool want_stats = d.stats_partials != nullptr;
+    int64_t it = 0;
+    for (int64_t t = pair; t < n_tiles; t += n_pairs, ++it) {
+      const PairTile tc = pr_tile(t, n_rt, n_nh);
+      const int a = (int)(it & 1);
+      const uint32_t aph = (uint32_t)((it >> 1) & 1);
+      const int64_t frame0 = (int64_t)tc.rt * PR_FRAMES;
+      const int nvalid = (int)((d.rows - frame0) < PR_FRAMES ? (d.rows - frame0) : PR_FRAMES);
+      const int64_t ch0 = (int64_t)tc.nh * (256 * NB) + rank * 128;  // + mb*256 + cl
+      float* yb = d.Y + tc.b * d.y_batch_stride + frame0 * ystride + ch0 + cl;
+      const float* rb = d.residual ? d.residual + tc.b * d.res_batch_stride + frame0 * rstride + ch0 + cl : nullptr;
+      if (rb) {
+        // this tile's MMAs are still in flight: pull the residual lines of this warp's chunks (32 channels = 128 B per
+        // frame) into L2, one frame per lane
+#pragma unroll
+        for (int u = 0; u < NB * 4; ++u) {
+          if (u % G != g) continue;
+          const int mb = u >> 2, f = (u & 3) * 32 + lane;
+          if (f < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb - lane + f * rstride + mb * 256));
+        }
+        // (32-frame granularity: the two PR_CW-frame chunks a warp group drains back to back)
+      }
+      mbar_wait_relaxed(bar_tfull + 8 * a, aph);
+      tc_fence_after();
+      float piv[NB], ssum[NB], ssq[NB], cnt[NB];
+#pragma unroll
+      for (int mb = 0; mb < NB; ++mb) { piv[mb] = 0.f; ssum[mb] = 0.f; ssq[mb] = 0.f; cnt[mb] = 0.f; }
+#pragma unroll
+      for (int mb = 0; mb < NB; ++mb) {
+        const int64_t ch = ch0 + mb * 256 + cl;
+        float bsum = bias ? __ldg(bias + ch) : 0.f;
+        if (bias_batch) bsum += __ldg(bias_batch + tc.b * d.M + ch);
+        // real loops (not unrolled): the chunk body exists once per variant, which keeps the kernel inside the
+        // instruction cache (the fully unrolled version stalled 4 warps per issue on instruction fetch)
+#pragma unroll 1
+        for (int c = g * (32 / PR_CW); c < NCH; c += (c % (32 / PR_CW) == 32 / PR_CW - 1) ? (G - 1) * (32 / PR_CW) + 1 : 1) {
+          const int nj = nvalid - c * PR_CW;  // valid frames of this chunk (warp-uniform)
+          if (nj <= 0) break;
+          float v[PR_CW];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::kAccCols + mb * PR_FRAMES + c * PR_CW), v);
+          float* yp = yb + (int64_t)(c * PR_CW) * ystride + mb * 256;
+          const float* rp = rb ? rb + (int64_t)(c * PR_CW) * rstride + mb * 256 : nullptr;
+          const bool first = cnt[mb] == 0.f;
+          cnt[mb] += (float)(nj < PR_CW ? nj : PR_CW);
+          if (dbg & 4) continue;
+          if (nj >= PR_CW) {
+            if (rp) {
+              if (epi_act == PS_ACT_NONE) epi_chunk<PS_ACT_NONE, true, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb]);
+              else epi_chunk<-1, true, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb], epi_act);
+            } else {
+              if (epi_act == PS_ACT_NONE) epi_chunk<PS_ACT_NONE, false, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb]);
+              else epi_chunk<-1, false, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb], epi_act);
+            }
+          } else {
+            if (rp) epi_chunk<-1, true, false>(v, bsum, eslope, yp, ystride, rp, rstride, nj, first, piv[mb], ssum[mb], ssq[mb], epi_act);
+            else epi_chunk<-1, false, false>(v, bsum, eslope, yp, ystride, rp, rstride, nj, first, piv[mb], ssum[mb], ssq[mb], epi_act);
+          }
+        }
+      }
+      // all TMEM reads of this accumulator set are complete (tcgen05.wait::ld): hand it back to the leader's MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(bar_tempty + 8 * a, 0);
+      if (want_stats) {
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+          Wf mine;
+          mine.n = cnt[mb]; mine.mean = 0.f; mine.m2 = 0.f;
+          if (mine.n > 0.f) {
+            const float md = ssum[mb] / mine.n;
+            mine.mean = piv[mb] + md;
+            mine.m2 = fmaxf(ssq[mb] - ssum[mb] * md, 0.f);
+          }
+          Wf w = wf_warp_reduce(mine);
+          if (lane == 0) wf_s[mb * PR_EPI_WARPS + (warp - 2)] = w;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+        if (et < NB) {
+          // fixed merge order over the epilogue warps -> deterministic
+          const int mb = et;
+          Wf tot = wf_s[mb * PR_EPI_WARPS];
+#pragma unroll
+          for (int w = 1; w < PR_EPI_WARPS; ++w) tot = wf_merge(tot, wf_s[mb * PR_EPI_WARPS + w]);
+          const int64_t slots_m = (d.M + 127) / 128;
+          const int64_t slots = n_rt * slots_m;
+          float* o = d.stats_partials + (tc.b * slots + tc.rt * slots_m + tc.nh * (2 * NB) + mb * 2 + rank) * 3;
+          o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+      }
+    }
+  } else {
+    // ===================== activation producers (last 8 warps) =====================
+    // One iteration covers 64 k of this CTA's 64 frames = two stages: threads 0..127 fill stage s (k 0..31), threads
+    // 128..255 stage s+1 (k 32..63).  Within a half, 4 threads cover the 32 k of a frame (coalesced 128 B) and a
+    // warp covers 8 consecutive frames, so each 8-lane phase of a 128-bit shared store lands on two consecutive swizzle
+    // rows = 32 distinct banks.  Every thread handles its chunk for frames r and r+32, so the affine is read once
+    // per 16 elements.
+    const int pt = tid - (64 + PR_EPI);
+    const int half = pt >> 7;
+    const int u = pt & 127;
+    const uint32_t chunk = (uint32_t)(u & 3);
+    const int r0 = u >> 2;  // 0..31
+    const int kofs = half * 32 + (int)chunk * 8;
+    const int KB64 = (int)(d.K / 64);
+    const int K = (int)d.K;
+    const float pslope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;  // AFFINE w/o act = slope 1
+    int s = half;  // this thread's stage: half 0 walks stages 0,2,4,.., half 1 walks 1,3,5,.. (mod the ring depth)
+    uint32_t ph = 0;
+
+    struct Cur {
+      int64_t t;
+      int kb;
+      const float* x0;   // &X[b][0][kofs]
+      int64_t row_base;  // rt*128 + rank*64 + r0
+      int64_t b;
+    };
+    const int64_t last_row = d.rows - 1;
+    auto decode = [&](Cur& c) {
+      if (c.t < n_tiles) {
+        const PairTile tc = pr_tile(c.t, n_rt, n_nh);
+        c.b = tc.b;
+        c.row_base = (int64_t)((dbg & 64) ? 0 : tc.rt) * PR_FRAMES + rank * PR_FR_CTA + r0;
+        c.x0 = d.X + ((dbg & 64) ? 0 : tc.b) * d.x_batch_stride + kofs;  // (64: experiment, every tile reads tile 0)
+      }
+    };
+    auto advance = [&](Cur& c) {
+      if (++c.kb == KB64) {
+        c.kb = 0;
+        c.t += n_pairs;
+        decode(c);
+      }
+    };
+    // frames past the end of the item re-read its last frame: their accumulator columns are never stored
+    auto issue = [&](float4(&x)[2][2], const Cur& c) {
+      if (dbg & 2) return;  // experiment: no activation loads
+      const float* xb = c.x0 + c.kb * 64;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        int64_t row = c.row_base + p * 32;
+        row = row < last_row ? row : last_row;
+        const float4* src = reinterpret_cast<const float4*>(xb + row * d.x_row_stride);
+        x[p][0] = __ldg(src);
+        x[p][1] = __ldg(src + 1);
+      }
+    };
+    int64_t staged_b = -1;
+    auto stage_affine = [&](int64_t b) {
+      if constexpr (kAffine) {
+        if (b != staged_b) {
+          asm volatile("bar.sync 2, %0;" ::"n"(PR_PRODUCERS) : "memory");  // every producer is done with the old rows
+          const float* pa = d.pro_a + b * d.pro_batch_stride;
+          const float* pb = d.pro_b + b * d.pro_batch_stride;
+          for (int k = pt * 4; k < K; k += PR_PRODUCERS * 4) {
+            *reinterpret_cast<float4*>(aff_s + k) = __ldg(reinterpret_cast<const float4*>(pa + k));
+            *reinterpret_cast<float4*>(aff_s + K + k) = __ldg(reinterpret_cast<const float4*>(pb + k));
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(PR_PRODUCERS) : "memory");
+          staged_b = b;
+        }
+      }
+    };
+    auto process = [&](const float4(&x)[2][2], int kb) {
+      float sc[8], sh[8];
+      if constexpr (kAffine) {
+        const int k0 = kb * 64 + kofs;
+        const float4 a0 = *reinterpret_cast<const float4*>(aff_s + k0), a1 = *reinterpret_cast<const float4*>(aff_s + k0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(aff_s + K + k0), b1 = *reinterpret_cast<const float4*>(aff_s + K + k0 + 4);
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+      }
+      const int my_s = s;
+      mbar_wait(bar_empty + 8 * my_s, ph ^ 1);
+      uint8_t* x_hi = sm + my_s * STAGE;
+      uint8_t* x_lo = x_hi + PR_XPART;
+#pragma unroll
+      for (int p = 0; p < 2 && !(dbg & 8); ++p) {
+        const int r = p * 32 + r0;
+        const float v[8] = {x[p][0].x, x[p][0].y, x[p][0].z, x[p][0].w, x[p][1].x, x[p][1].y, x[p][1].z, x[p][1].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float u0 = v[i], u1 = v[i + 1];
+          if constexpr (kAffine) {
+            u0 = fmaf(u0, sc[i], sh[i]);
+            u1 = fmaf(u1, sc[i + 1], sh[i + 1]);
+            u0 = u0 > 0.f ? u0 : u0 * pslope;
+            u1 = u1 > 0.f ? u1 : u1 * pslope;
+          }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(u0, u1);
+          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+          const float r0f = u0 - __uint_as_float(hb << 16);
+          const float r1f = u1 - __uint_as_float(hb & 0xFFFF0000u);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0f, r1f);
+          hi[i >> 1] = hb;
+          lo[i >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        const uint32_t off = pr_swz((uint32_t)r, chunk);
+        *reinterpret_cast<uint4*>(x_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(x_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor cores of both SMs (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * my_s);  // one arrival per warp (a warp lies entirely in one half)
+      s += 2;
+      if (s >= PR_STAGES) { s -= PR_STAGES; ph ^= 1; }
+    };
+
+    // Register double buffer: the loads of block n+1 are in flight while block n is transformed.  (Measured: a third
+    // buffer and an L2 software prefetch 4 blocks ahead were both SLOWER - the stream is not latency-bound.)
+    float4 x0[2][2], x1[2][2];
+    Cur pr, ld;
+    pr.t = pair; pr.kb = 0;
+    decode(pr);
+    ld = pr;
+    auto ld_next = [&](float4(&x)[2][2]) {
+      if (ld.t < n_tiles) {
+        issue(x, ld);
+        advance(ld);
+      }
+    };
+    auto pr_next = [&](const float4(&x)[2][2]) -> bool {
+      if (pr.t >= n_tiles) return false;
+      stage_affine(pr.b);
+      process(x, pr.kb);
+      advance(pr);
+      return true;
+    };
+    ld_next(x0);
+    while (true) {
+      ld_next(x1);
+      if (!pr_next(x0)) break;
+      ld_next(x0);
+      if (!pr_next(x1)) break;
+    }
+  }
+
+  // nobody leaves while the pair's MMAs may still read this CTA's shared memory or write its TMEM
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------- weight packing
+// W [M, K] fp32 -> per (512-channel group nh, pair rank, 32-k stage): [hi block 0 .. hi block NB-1 | lo block 0 ..],
+// each block = 128 channels x 32 k bf16 in the K-major 64-byte-swizzled shared-memory image.  Channel of (nh, mb,
+// rank, r) = nh*256*NB + mb*256 + rank*128 + r.
+__global__ void pack_weights_pair_kernel(const float* __restrict__ W, int64_t ldw, int64_t M, int64_t K, int NB, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * K) return;
+  const int64_t n = i / K, k = i % K;
+  const int64_t grp = 256 * NB;
+  const int64_t nh = n / grp, w = n % grp, mb = w / 256, rank = (w % 256) / 128, r = w % 128;
+  const int64_t kb = k / PR_BK, kk = k % PR_BK, KB = K / PR_BK;
+  const float x = W[n * ldw + k];
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  const size_t stage = ((size_t)(nh * 2 + rank) * KB + kb) * (size_t)(2 * NB * PR_WBLK);
+  const size_t off = (size_t)pr_swz((uint32_t)r, (uint32_t)(kk >> 3)) + (size_t)(kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(out + stage + mb * PR_WBLK + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(out + stage + (NB + mb) * PR_WBLK + off) = l;
+}
+
+static inline int pair_nb(int64_t M) { return (M % 512 == 0) ? 2 : 1; }
+
+int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s) {
+  const unsigned blocks = (unsigned)cdiv(M * K, 256);
+  pack_weights_pair_kernel<<<blocks, 256, 0, s>>>(W, ldw, M, K, pair_nb(M), reinterpret_cast<uint8_t*>(packed));
+  PS_CHECK_LAUNCH("pack_weights_pair_kernel");
+  return PS_OK;
+}
+
+template <bool kAffine, int NB>
+static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
+  if (set_attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<kAffine, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_pair_kernel)"); return PS_ERR_CUDA; }
+  }
+  static int dbg = -1;  // PS_PAIR_DBG: bottleneck experiments only (1 no weight copies, 2 no activation loads, 4 no epilogue, 8 no transform)
+  if (dbg < 0) { const char* e = getenv("PS_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
+  gemm_pair_kernel<kAffine, NB><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
+  PS_CHECK_LAUNCH("gemm_pair_kernel");
+  return PS_OK;
+}
+
+int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
+  static int sm_count[64] = {0};
+  static bool attr_set[64][2][2] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
+  if (sm_count[dev] == 0) {
+    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
+  }
+  const bool affine = d.pro_mode == PS_PRO_AFFINE;
+  const int nb = pair_nb(d.M);
+  const bool set_attr = !attr_set[dev][affine][nb - 1];
+  attr_set[dev][affine][nb - 1] = true;
+  const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = d.M / (256 * nb);
+  const int64_t n_tiles = d.batch * n_rt * n_nh;
+  if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
+  const int64_t max_pairs = sm_count[dev] / 2;
+  const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+  if (nb == 2)
+    return affine ? launch_pair<true, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_pair<false, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  return affine ? launch_pair<true, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_pair<false, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+}
+
+}  // namespace ps

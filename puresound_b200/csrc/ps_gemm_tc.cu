@@ -23,10 +23,9 @@
 //               split to bf16 hi/lo and write both into the swizzled UMMA layout in shared
 //               memory.  The normalised tensor never exists in HBM.
 // Pipelines: smem stages full/empty (producers+TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
-#include "ps_common.cuh"
+#include "ps_tc_ptx.cuh"
 
 namespace ps {
 
@@ -60,97 +59,6 @@ struct TcCfg {
     return r * kRowBytes + ((BK == 64 ? (c ^ (r & 7u)) : (c ^ ((r >> 1) & 3u))) << 4);
   }
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-// same, for waiters that are not on the critical path (epilogue waiting for an accumulator, the weight loader waiting
-// for a free stage): back off between polls so the spin does not eat the issue slots the producer warps need
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once every previously issued tcgen05.mma has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // shared-memory matrix descriptor: K-major, swizzled rows, 8-row atoms kSBO bytes apart (cute::UMMA::SmemDescriptor)
 template <class Cfg>
@@ -596,6 +504,19 @@ int tc_bk() {
   return bk;
 }
 
+// which tcgen05 kernel serves eligible shapes, fixed per process (the packed weight image depends on it):
+// PS_TC_KERNEL=pair (default; CTA-pair kernel of ps_gemm_pair.cu) | single (the one-CTA kernel of this file)
+int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s);
+int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s);
+bool tc_pair() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("PS_TC_KERNEL");
+    mode = (e && e[0] == 's') ? 0 : 1;
+  }
+  return mode == 1;
+}
+
 bool gemm_tc_eligible(const ps_gemm_t& d) {
   if (!d.W_packed) return false;
   if (d.M % TC_BN != 0 || d.K % 64 != 0) return false;
@@ -623,6 +544,7 @@ static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int6
 }
 
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
+  if (tc_pair()) return gemm_pair_launch(d, s);
   static int sm_count[64] = {0};
   static bool attr_set[64][2] = {};
   int dev = 0;
@@ -654,6 +576,7 @@ extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
 extern "C" int ps_gemm_pack_weights(const float* W, int64_t w_row_stride, int64_t M, int64_t K, void* packed, void* stream) {
   PS_REQUIRE(W && packed && w_row_stride >= K);
   if (ps_gemm_packed_bytes(M, K) == 0) return PS_ERR_UNSUPPORTED;
+  if (ps::tc_pair()) return ps::gemm_pair_pack(W, w_row_stride, M, K, packed, (cudaStream_t)stream);
   const unsigned blocks = (unsigned)ps::cdiv(M * K, 256);
   if (ps::tc_bk() == 64)
     ps::pack_weights_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, w_row_stride, M, K, reinterpret_cast<uint8_t*>(packed));
