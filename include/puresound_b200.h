@@ -194,8 +194,14 @@ typedef struct {
   const float* gx; const float* w_hh_t;
   const float* h0; const float* c0;
   float* out; float* hn; float* cn;
+  /* tensor-core path (H = 128): image built by ps_lstm_pack_weights from w_hh_t, else NULL (exact-fp32 CUDA-core path) */
+  const void* w_packed;
 } ps_lstm_t;
 PS_API int ps_lstm(const ps_lstm_t* d, void* stream);
+/* bytes of the packed recurrent-weight image (0 if H is not served by the tensor-core path) */
+PS_API int64_t ps_lstm_packed_bytes(int64_t H, int32_t D);
+/* w_hh_t [D, H, 4H] -> per direction: W_hh as bf16 hi (shared-memory tile image) | bf16 lo (row-major, goes to TMEM) */
+PS_API int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void* packed, void* stream);
 
 /* FiLM combine (lobe/trivial.py:163-165): y = sb[:, :C] * xn + sb[:, C:]; sb [rows, 2C] */
 PS_API int ps_film_combine(const float* sb, const float* xn, float* y, int64_t rows, int64_t C, void* stream);

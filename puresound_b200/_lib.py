@@ -54,6 +54,7 @@ class LstmDesc(C.Structure):
         ("inner", I64), ("outer_stride", I64), ("inner_stride", I64), ("step_stride", I64),
         ("gx", P), ("w_hh_t", P), ("h0", P), ("c0", P),
         ("out", P), ("hn", P), ("cn", P),
+        ("w_packed", P),
     ]
 
 
@@ -94,6 +95,8 @@ SIGNATURES = {
     "ps_segment": (C.c_int, [P, P, I64, I64, I64, I64, I64, I32, P]),
     "ps_merge": (C.c_int, [P, P, I64, I64, I64, I64, I64, I32, P]),
     "ps_lstm": (C.c_int, [C.POINTER(LstmDesc), P]),
+    "ps_lstm_packed_bytes": (I64, [I64, I32]),
+    "ps_lstm_pack_weights": (C.c_int, [P, I64, I32, P, P]),
     "ps_film_combine": (C.c_int, [P, P, P, I64, I64, P]),
     "ps_transpose": (C.c_int, [P, P, I64, I64, I64, P]),
     "ps_stream_dwconv_step": (C.c_int, [C.POINTER(StreamDwDesc), P]),

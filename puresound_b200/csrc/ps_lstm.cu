@@ -105,6 +105,9 @@ __global__ void lstm_kernel(const ps_lstm_t d, const int BG) {
   }
 }
 
+bool lstm_tc_eligible(const ps_lstm_t& d);
+int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s);
+
 }  // namespace ps
 
 extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
@@ -112,6 +115,7 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
   const ps_lstm_t& d = *dp;
   PS_REQUIRE(d.gx && d.w_hh_t && d.out && d.n_seq > 0 && d.L > 0 && d.H > 0 && (d.D == 1 || d.D == 2));
   PS_REQUIRE(d.inner > 0 && (d.h0 == nullptr) == (d.c0 == nullptr));
+  if (ps::lstm_tc_eligible(d)) return ps::lstm_tc_launch(d, (cudaStream_t)stream);
   if (d.H > 256) return PS_ERR_UNSUPPORTED;  // 140 regs x (H*BG) threads must fit the register file
   int BG = (int)(256 / d.H);
   if (BG < 1) BG = 1;

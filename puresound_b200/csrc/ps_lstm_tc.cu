@@ -1,0 +1,333 @@
+// Tensor-core LSTM recurrence for H = 128 (DPRNN intra- / inter-chunk passes; reference dprnn.py:67-103 via nn.LSTM,
+// gate order i,f,g,o).  One CTA per SM owns 64 sequences of one direction for all L steps; the recurrent matrix never
+// leaves the SM:
+//
+//   * W_hh (512 x 128 fp32 = 256 KB) does not fit the 227 KB of shared memory, so it is kept as a bf16 hi/lo split
+//     (the 3xBF16 scheme of ps_gemm_tc.cu: hi*hi + hi*lo + lo*hi in the fp32 accumulator, ~2^-17 per product) with
+//     W_hi (128 KB) resident in SHARED MEMORY and W_lo (128 KB) resident in TENSOR MEMORY, where tcgen05.mma takes it
+//     as its A operand (TS form);
+//   * per step the gate pre-activations  G[512 x 64] = W_hh[512 x 128] * h_{t-1}^T[128 x 64]  are 96 tcgen05.mma
+//     (M=128 = one gate of all 128 units, N=64 sequences, K=16; 4 gates x 8 k-steps x 3 split passes) into the other
+//     256 TMEM columns; B = h_{t-1} as bf16 hi/lo, K-major 64-byte-swizzled tiles in shared memory;
+//   * TMEM lane = hidden unit, column = sequence, one 64-column block per gate: a thread reads i,f,g,o of ITS unit for
+//     a sequence from the four blocks, so the cell update is thread-local (c in registers), and writes h_t back as
+//     the next step's B operand (bf16 hi/lo) and to the output tensor (a warp = 32 consecutive units = one coalesced
+//     128-byte store per sequence);
+//   * gx = W_ih x + b (ps_gemm) is read in its native [position, D*4H] layout: for one gate and sequence a warp reads
+//     128 contiguous bytes; next step's lines are prefetched into L2 while this step computes.
+//
+// Warps: 0 = MMA issuer (+ TMEM allocation), 4..11 = gate warps (two per TMEM lane quarter, 32 sequences each).
+// Barriers: mma_done (tcgen05.commit -> gate warps), h_ready (gate warps -> MMA issuer).
+// The strided position function of ps_lstm_t is honoured, so one [N,S,K,*] tensor serves both passes without a permute.
+#include <stdlib.h>
+
+#include "ps_tc_ptx.cuh"
+
+namespace ps {
+
+constexpr int LT_H = 128, LT_N = 64;           // hidden units, sequences per CTA
+constexpr int LT_THREADS = 384;                // 12 warps: 0 MMA, 1-3 idle, 4-11 gates
+constexpr int LT_WTILE = 128 * 64;             // one [128 rows x 32 k] bf16 tile, 64-byte swizzle: 8 KB
+constexpr int LT_WHI_BYTES = 4 * 4 * LT_WTILE; // 4 gates x 4 k-tiles = 128 KB
+constexpr int LT_HTILE = LT_N * 64;            // [64 seqs x 32 k] bf16: 4 KB
+constexpr int LT_H_BYTES = 2 * 4 * LT_HTILE;   // hi | lo, 4 k-tiles each = 32 KB
+constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_N * 8 /*base positions*/ + 64 /*barriers*/ + 1024 /*align*/;
+constexpr uint32_t LT_ACC_COL = 256;           // TMEM: W_lo in columns [0,256), accumulators in [256,512)
+// D=f32, A=B=bf16, K-major, M=128, N=64
+constexpr uint32_t LT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__host__ __device__ constexpr uint32_t lt_swz(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
+
+__device__ __forceinline__ uint64_t lt_desc(uint32_t saddr) {  // K-major, SWIZZLE_64B, 8-row atoms 512 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// accurate to a few ulp (MUFU ex2 + rcp), saturates cleanly: exp(+big) = inf -> 1/inf = 0
+__device__ __forceinline__ float lt_sigmoid(float x) { return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, __frcp_rn(1.f + exp2f(-2.8853900817779268f * x)), -1.f); }
+
+__global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  uint8_t* h_sm = sm + LT_WHI_BYTES;                       // [hi: 4 tiles][lo: 4 tiles]
+  int64_t* pos_s = reinterpret_cast<int64_t*>(sm + LT_WHI_BYTES + LT_H_BYTES);
+  const uint32_t bars = base + LT_WHI_BYTES + LT_H_BYTES + LT_N * 8;
+  const uint32_t bar_w = bars, bar_mma = bars + 8, bar_h = bars + 16;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_N * 8 + 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int64_t q0 = (int64_t)blockIdx.x * LT_N;
+  const int64_t G = (int64_t)d.D * 4 * LT_H, OW = (int64_t)d.D * LT_H;
+  const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)dir * (2 * LT_WHI_BYTES);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init(bar_h, 8);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32((const void*)tmem_ptr_s), 512);
+  if (tid < LT_N) {
+    int64_t q = q0 + tid;
+    if (q >= d.n_seq) q = d.n_seq - 1;  // tail sequences shadow the last real one; their results are never stored
+    pos_s[tid] = (q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    // ===================== W_hi -> shared memory, then the MMA issue loop =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_w, LT_WHI_BYTES);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bulk_g2s(base + i * (LT_WHI_BYTES / 4), wimg + (size_t)i * (LT_WHI_BYTES / 4), LT_WHI_BYTES / 4, bar_w);
+    }
+    __syncwarp();
+    mbar_wait(bar_w, 0);
+    for (int64_t step = 0; step < d.L; ++step) {
+      // h_{t-1} (and, for step 0, h0 and W_lo in TMEM) are in place; the previous step's accumulators have been read
+      mbar_wait(bar_h, (uint32_t)(step & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t hs = base + LT_WHI_BYTES;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
+            const int kt = k >> 1;
+            const uint64_t ko = (uint64_t)(((k & 1) * 32) >> 4);
+            const uint64_t h_hi = lt_desc(hs + kt * LT_HTILE) + ko, h_lo = lt_desc(hs + (4 + kt) * LT_HTILE) + ko;
+            const uint64_t w_hi = lt_desc(base + (g * 4 + kt) * LT_WTILE) + ko;
+            const uint32_t w_lo = tmem_base + (uint32_t)(g * 64 + k * 8);  // 8 columns = 16 packed bf16
+            umma_bf16_ts(dd, w_lo, h_hi, LT_IDESC, k != 0);
+            umma_bf16(dd, w_hi, h_lo, LT_IDESC, 1);
+            umma_bf16(dd, w_hi, h_hi, LT_IDESC, 1);
+          }
+        }
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================== gate warps =====================
+    const int q = warp & 3;              // TMEM lane quarter
+    const int half = (warp - 4) >> 2;    // sequences [32*half, 32*half + 32)
+    const int u = q * 32 + lane;         // hidden unit = TMEM lane
+    const int s0 = half * 32;
+    // ---- one-time: W_lo rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
+    if (half == 0) {
+      const uint32_t* wlo = reinterpret_cast<const uint32_t*>(wimg + LT_WHI_BYTES);  // [512 rows][64 words]
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[16];
+          const uint4* src = reinterpret_cast<const uint4*>(wlo + (size_t)(g * LT_H + u) * 64 + c * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 t4 = __ldg(src + i);
+            r[4 * i] = t4.x; r[4 * i + 1] = t4.y; r[4 * i + 2] = t4.z; r[4 * i + 3] = t4.w;
+          }
+          tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c * 16), r);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // ---- initial state: c in registers, h0 into the B-operand tiles
+    float c[32];
+    const uint32_t hoff_k = (uint32_t)(q * LT_HTILE);                       // k-tile of this warp's 32 units = q
+    const uint32_t hchunk = (uint32_t)(lane >> 3), helem = (uint32_t)(lane & 7) * 2;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t qq = q0 + s0 + j;
+      const bool valid = qq < d.n_seq;
+      const int64_t so = ((int64_t)dir * d.n_seq + qq) * LT_H + u;
+      c[j] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
+      const float h = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
+      const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+      const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
+      const uint32_t off = hoff_k + lt_swz((uint32_t)(s0 + j), hchunk) + helem;
+      *reinterpret_cast<__nv_bfloat16*>(h_sm + off) = hh;
+      *reinterpret_cast<__nv_bfloat16*>(h_sm + 4 * LT_HTILE + off) = hl;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_h);
+
+    const float* gxu = d.gx + (int64_t)dir * 4 * LT_H + u;
+    float* outu = d.out + (int64_t)dir * LT_H + u;
+    for (int64_t step = 0; step < d.L; ++step) {
+      const int64_t t = dir ? d.L - 1 - step : step;
+      const int64_t toff = t * d.step_stride;
+      const bool last = step + 1 == d.L;
+      // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
+      if (step + 1 < d.L) {
+        const int64_t tn = dir ? t - 1 : t + 1;
+        const float* pn = d.gx + (pos_s[s0 + lane] + tn * d.step_stride) * G + (int64_t)dir * 4 * LT_H + q * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * LT_H));
+      }
+      // gx of the first 8 sequences is requested before the wait on the tensor core
+      float gxa[4][8], gxb[4][8];
+      auto load_gx = [&](float(&gx)[4][8], int j0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float* p = gxu + (pos_s[s0 + j0 + j] + toff) * G;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * LT_H);
+        }
+      };
+      load_gx(gxa, 0);
+      mbar_wait(bar_mma, (uint32_t)(step & 1));
+      tc_fence_after();
+      auto chunk = [&](const float(&gx)[4][8], int j0) {
+        float a[4][8];
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + LT_ACC_COL + (uint32_t)(s0 + j0);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld8(tb + (uint32_t)(g * LT_N), a[g]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float ig = lt_sigmoid(a[0][j] + gx[0][j]);
+          const float fg = lt_sigmoid(a[1][j] + gx[1][j]);
+          const float gg = lt_tanh(a[2][j] + gx[2][j]);
+          const float og = lt_sigmoid(a[3][j] + gx[3][j]);
+          const float cn = fmaf(fg, c[j0 + j], ig * gg);
+          c[j0 + j] = cn;
+          const float h = og * lt_tanh(cn);
+          const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+          const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
+          const uint32_t off = hoff_k + lt_swz((uint32_t)(s0 + j0 + j), hchunk) + helem;
+          *reinterpret_cast<__nv_bfloat16*>(h_sm + off) = hh;
+          *reinterpret_cast<__nv_bfloat16*>(h_sm + 4 * LT_HTILE + off) = hl;
+          if (q0 + s0 + j0 + j < d.n_seq) {
+            outu[(pos_s[s0 + j0 + j] + toff) * OW] = h;
+            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + q0 + s0 + j0 + j) * LT_H + u] = h;
+          }
+        }
+      };
+      load_gx(gxb, 8);
+      chunk(gxa, 0);
+      load_gx(gxa, 16);
+      chunk(gxb, 8);
+      load_gx(gxb, 24);
+      chunk(gxa, 16);
+      chunk(gxb, 24);
+      // h_t is in shared memory for the tensor core (async proxy) and this step's accumulators have been read
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t qq = q0 + s0 + j;
+      if (qq >= d.n_seq) continue;
+      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * LT_H + u] = c[j];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// w_hh_t [D, H, 4H] (W_hh transposed, the layout ps_lstm takes) -> per direction [W_hi shared-memory image 128 KB |
+// W_lo row-major bf16 [4H][H] 128 KB]
+__global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int D, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)D * 4 * LT_H * LT_H) return;
+  const int dir = (int)(i / (4 * LT_H * LT_H));
+  const int r = (int)((i / LT_H) % (4 * LT_H)), k = (int)(i % LT_H);  // W_hh[r][k] = w_hh_t[dir][k][r]
+  const float w = w_hh_t[((int64_t)dir * LT_H + k) * 4 * LT_H + r];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  uint8_t* o = out + (size_t)dir * (2 * LT_WHI_BYTES);
+  const int g = r / LT_H, row = r % LT_H, kt = k / 32, kk = k % 32;
+  const size_t off = (size_t)(g * 4 + kt) * LT_WTILE + lt_swz((uint32_t)row, (uint32_t)(kk >> 3)) + (size_t)(kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(o + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(o + LT_WHI_BYTES + ((size_t)r * LT_H + k) * 2) = l;
+}
+
+bool lstm_tc_eligible(const ps_lstm_t& d) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("PS_LSTM"); off = (e && e[0] == 's') ? 1 : 0; }  // PS_LSTM=simt forces the fp32 kernel
+  return !off && d.w_packed != nullptr && d.H == LT_H && (reinterpret_cast<uintptr_t>(d.w_packed) & 15) == 0;
+}
+
+int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
+  if (!attr_set[dev]) {
+    e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(lstm_tc_kernel)"); return PS_ERR_CUDA; }
+    attr_set[dev] = true;
+  }
+  const int64_t nblk = cdiv(d.n_seq, LT_N);
+  if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)nblk, (unsigned)d.D);
+  lstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM, s>>>(d);
+  PS_CHECK_LAUNCH("lstm_tc_kernel");
+  return PS_OK;
+}
+
+}  // namespace ps
+
+extern "C" int64_t ps_lstm_packed_bytes(int64_t H, int32_t D) {
+  if (H != ps::LT_H || (D != 1 && D != 2)) return 0;
+  return (int64_t)D * 2 * ps::LT_WHI_BYTES;
+}
+
+extern "C" int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void* packed, void* stream) {
+  PS_REQUIRE(w_hh_t && packed);
+  if (ps_lstm_packed_bytes(H, D) == 0) return PS_ERR_UNSUPPORTED;
+  const int64_t n = (int64_t)D * 4 * H * H;
+  ps::lstm_pack_kernel<<<(unsigned)ps::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh_t, D, reinterpret_cast<uint8_t*>(packed));
+  PS_CHECK_LAUNCH("lstm_pack_kernel");
+  return PS_OK;
+}

@@ -76,7 +76,10 @@ class DPRNN(nn.Module):
             w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
             b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
             w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
-            return w_ih, b, w_hh_t
+            # resident image for the tensor-core recurrence (None unless H == 128), tcgen05 image of W_ih for the projections
+            w_hh_pk = ops.lstm_pack_weights(w_hh_t, self.hidden_size, len(sfx))
+            w_ih_pk = ops.pack_weights(w_ih, w_ih.shape[0], w_ih.shape[1], w_ih.shape[1])
+            return w_ih, b, w_hh_t, w_hh_pk, w_ih_pk
 
         return self._cache.get(tag, srcs, build)
 
@@ -94,10 +97,10 @@ class DPRNN(nn.Module):
         """One intra- or inter-chunk pass on out [N, S, K, C]: out + LN(Linear(LSTM(out)))."""
         N, S, K, Cn = out.shape
         H, D = self.hidden_size, (2 if self.bi_direct else 1)
-        w_ih, b, w_hh_t = self._lstm_weights(tag, rnn)
+        w_ih, b, w_hh_t, w_hh_pk, w_ih_pk = self._lstm_weights(tag, rnn)
         P = N * S * K
         flat = out.view(1, P, Cn)
-        gx, _ = ops.linear(flat, w_ih, bias=b)  # [1, P, D*4H]
+        gx, _ = ops.linear(flat, w_ih, bias=b, w_packed=w_ih_pk)  # [1, P, D*4H]
         if inter:
             geo = dict(n_seq=N * K, L=S, inner=K, outer_stride=S * K, inner_stride=1, step_stride=K)
         else:
@@ -105,7 +108,7 @@ class DPRNN(nn.Module):
         h0 = c0 = None
         if init is not None:
             h0, c0 = init[0].contiguous(), init[1].contiguous()
-        h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, **geo)
+        h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk, **geo)
         y, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias)
         new = ops.rownorm(y.view(N, S, K, Cn), norm.weight, norm.bias, norm.eps, res=out)
         return new, state

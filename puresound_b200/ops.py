@@ -283,7 +283,7 @@ def merge(seg: Tensor, T: int, overlap: bool) -> Tensor:
 
 def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inner: int, outer_stride: int,
          inner_stride: int, step_stride: int, h0: Optional[Tensor] = None, c0: Optional[Tensor] = None,
-         want_state: bool = False):
+         want_state: bool = False, w_packed: Optional[Tensor] = None):
     """gx [positions, D*4H] -> out [positions, D*H] (+ (hn, cn) [D, n_seq, H])."""
     lib = _lib.load()
     positions = gx.shape[0]
@@ -297,9 +297,23 @@ def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inne
     d.inner, d.outer_stride, d.inner_stride, d.step_stride = inner, outer_stride, inner_stride, step_stride
     d.gx, d.w_hh_t, d.h0, d.c0 = _req(gx, "lstm gx").data_ptr(), w_hh_t.data_ptr(), _p(h0), _p(c0)
     d.out, d.hn, d.cn = out.data_ptr(), _p(hn), _p(cn)
+    d.w_packed = _p(w_packed)
     _lib.check(lib.ps_lstm(C.byref(d), _stream()), "ps_lstm")
     _launched()
     return out, ((hn, cn) if want_state else None)
+
+
+def lstm_pack_weights(w_hh_t: Tensor, H: int, D: int) -> Optional[Tensor]:
+    """Recurrent weights [D, H, 4H] -> the tensor-core LSTM's resident image (bf16 hi for shared memory, bf16 lo for
+    tensor memory); None when H is not served by that kernel (it handles H = 128)."""
+    lib = _lib.load()
+    nbytes = lib.ps_lstm_packed_bytes(H, D)
+    if nbytes == 0:
+        return None
+    out = torch.empty(nbytes, device=w_hh_t.device, dtype=torch.uint8)
+    _lib.check(lib.ps_lstm_pack_weights(_req(w_hh_t, "lstm w_hh_t").data_ptr(), H, D, out.data_ptr(), _stream()), "ps_lstm_pack_weights")
+    _launched()
+    return out
 
 
 def film_combine(sb: Tensor, xn: Tensor) -> Tensor:

@@ -200,6 +200,46 @@ def test_segment_merge_bit_exact(ops, T, K):
     assert torch.equal(ops.merge(seg2, T, False), x)
 
 
+@pytest.mark.parametrize("D", [1, 2])
+def test_lstm_tensor_core_path(ops, D):
+    """H = 128: W_hh resident as bf16 hi (shared memory) + lo (tensor memory), gates on tcgen05 with the 3xBF16 split.
+    Same oracle (step-by-step LSTM cell, dprnn.py:67-103 via nn.LSTM) as the exact-fp32 kernel; ragged last CTA
+    (n_seq % 64 != 0), both addressing modes, initial and final state."""
+    H, N, S, K, C = 128, 2, 37, 50, 16
+    sd = {}
+    for s in ["", "_reverse"][:D]:
+        sd[f"weight_ih_l0{s}"], sd[f"weight_hh_l0{s}"] = rnd(4 * H, C, seed=1, scale=0.3).cpu(), rnd(4 * H, H, seed=2, scale=0.15).cpu()
+        sd[f"bias_ih_l0{s}"], sd[f"bias_hh_l0{s}"] = rnd(4 * H, seed=3, scale=0.3).cpu(), rnd(4 * H, seed=4, scale=0.3).cpu()
+    sfx = ["", "_reverse"][:D]
+    w_ih = torch.cat([sd[f"weight_ih_l0{s}"] for s in sfx]).to(DEV)
+    b = torch.cat([sd[f"bias_ih_l0{s}"] + sd[f"bias_hh_l0{s}"] for s in sfx]).to(DEV)
+    w_hh_t = torch.stack([sd[f"weight_hh_l0{s}"].t().contiguous() for s in sfx]).to(DEV)
+    pk = ops.lstm_pack_weights(w_hh_t, H, D)
+    assert pk is not None and pk.numel() == D * 4 * H * H * 4
+    x = rnd(N, S, K, C, seed=5)
+    P = N * S * K
+    gx, _ = ops.linear(x.view(1, P, C), w_ih, bias=b)
+    gx = gx.view(P, D * 4 * H)
+    out, st = ops.lstm(gx, w_hh_t, n_seq=N * S, L=K, H=H, D=D, inner=1, outer_stride=K, inner_stride=0, step_stride=1,
+                       want_state=True, w_packed=pk)
+    ref, (hn, cn) = R.lstm(sd, "", x.cpu().view(N * S, K, C), D == 2, None, fast=True)
+    close(out.view(N * S, K, D * H).cpu(), ref, 5e-5)
+    close(st[0].cpu(), hn, 5e-5)
+    close(st[1].cpu(), cn, 2e-4)
+    # and it agrees with the exact-fp32 CUDA-core kernel
+    out32, _ = ops.lstm(gx, w_hh_t, n_seq=N * S, L=K, H=H, D=D, inner=1, outer_stride=K, inner_stride=0, step_stride=1)
+    close(out, out32, 5e-5)
+    h0, c0 = rnd(D, N * K, H, seed=6), rnd(D, N * K, H, seed=7)
+    out, st = ops.lstm(gx, w_hh_t, n_seq=N * K, L=S, H=H, D=D, inner=K, outer_stride=S * K, inner_stride=1, step_stride=K,
+                       h0=h0, c0=c0, want_state=True, w_packed=pk)
+    xi = x.cpu().permute(0, 2, 1, 3).reshape(N * K, S, C)
+    ref, (hn, cn) = R.lstm(sd, "", xi, D == 2, (h0.cpu(), c0.cpu()), fast=True)
+    got = out.view(N, S, K, D * H).permute(0, 2, 1, 3).reshape(N * K, S, D * H).cpu()
+    close(got, ref, 5e-5)
+    close(st[0].cpu(), hn, 5e-5)
+    close(st[1].cpu(), cn, 2e-4)
+
+
 @pytest.mark.parametrize("H,D", [(12, 1), (12, 2), (64, 1), (128, 2), (256, 1)])
 def test_lstm_intra_and_inter_addressing(ops, H, D):
     N, S, K, C = 2, 5, 7, 16
