@@ -269,7 +269,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
         for (int u = 0; u < NB * 4; ++u) {
           if (u % G != g) continue;
           const int mb = u >> 2, f = (u & 3) * 32 + lane;
-          if (f < nvalid) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb - lane + f * rstride + mb * 256));
+          if (f < nvalid && ch0 + mb * 256 < d.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(rb - lane + f * rstride + mb * 256));
         }
         // (32-frame granularity: the two PR_CW-frame chunks a warp group drains back to back)
       }
@@ -281,6 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 #pragma unroll
       for (int mb = 0; mb < NB; ++mb) {
         const int64_t ch = ch0 + mb * 256 + cl;
+        if (ch0 + mb * 256 >= d.M) continue;  // zero-padded block (M = 128: the peer CTA's rows): nothing to store
         float bsum = bias ? __ldg(bias + ch) : 0.f;
         if (bias_batch) bsum += __ldg(bias_batch + tc.b * d.M + ch);
         // real loops (not unrolled): the chunk body exists once per variant, which keeps the kernel inside the
@@ -328,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
           if (lane == 0) wf_s[mb * PR_EPI_WARPS + (warp - 2)] = w;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
-        if (et < NB) {
+        if (et < NB && ch0 + et * 256 < d.M) {
           // fixed merge order over the epilogue warps -> deterministic
           const int mb = et;
           Wf tot = wf_s[mb * PR_EPI_WARPS];
@@ -503,12 +504,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 // rank, r) = nh*256*NB + mb*256 + rank*128 + r.
 __global__ void pack_weights_pair_kernel(const float* __restrict__ W, int64_t ldw, int64_t M, int64_t K, int NB, uint8_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * K) return;
+  const int64_t Mp = (M + 255) / 256 * 256;  // channels are padded with zero rows to whole 256-channel blocks
+  if (i >= Mp * K) return;
   const int64_t n = i / K, k = i % K;
   const int64_t grp = 256 * NB;
   const int64_t nh = n / grp, w = n % grp, mb = w / 256, rank = (w % 256) / 128, r = w % 128;
   const int64_t kb = k / PR_BK, kk = k % PR_BK, KB = K / PR_BK;
-  const float x = W[n * ldw + k];
+  const float x = n < M ? W[n * ldw + k] : 0.f;
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
   const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
   const size_t stage = ((size_t)(nh * 2 + rank) * KB + kb) * (size_t)(2 * NB * PR_WBLK);
@@ -517,10 +519,10 @@ __global__ void pack_weights_pair_kernel(const float* __restrict__ W, int64_t ld
   *reinterpret_cast<__nv_bfloat16*>(out + stage + (NB + mb) * PR_WBLK + off) = l;
 }
 
-static inline int pair_nb(int64_t M) { return (M % 512 == 0) ? 2 : 1; }
+static inline int pair_nb(int64_t M) { return (((M + 255) / 256 * 256) % 512 == 0) ? 2 : 1; }
 
 int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s) {
-  const unsigned blocks = (unsigned)cdiv(M * K, 256);
+  const unsigned blocks = (unsigned)cdiv((M + 255) / 256 * 256 * K, 256);
   pack_weights_pair_kernel<<<blocks, 256, 0, s>>>(W, ldw, M, K, pair_nb(M), reinterpret_cast<uint8_t*>(packed));
   PS_CHECK_LAUNCH("pack_weights_pair_kernel");
   return PS_OK;
@@ -553,7 +555,7 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   const int nb = pair_nb(d.M);
   const bool set_attr = !attr_set[dev][affine][nb - 1];
   attr_set[dev][affine][nb - 1] = true;
-  const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = d.M / (256 * nb);
+  const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
   const int64_t max_pairs = sm_count[dev] / 2;

@@ -519,7 +519,7 @@ bool tc_pair() {
 
 bool gemm_tc_eligible(const ps_gemm_t& d) {
   if (!d.W_packed) return false;
-  if (d.M % TC_BN != 0 || d.K % 64 != 0) return false;
+  if (d.M % (tc_pair() ? 128 : TC_BN) != 0 || d.K % 64 != 0) return false;  // the pair kernel zero-pads to 256 channels
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE)) return false;
   if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU)) return false;
   if (!(d.epi_act == PS_ACT_NONE || d.epi_act == PS_ACT_RELU || d.epi_act == PS_ACT_PRELU)) return false;
@@ -569,7 +569,9 @@ int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
 }  // namespace ps
 
 extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
-  if (M <= 0 || K <= 0 || M % ps::TC_BN != 0 || K % 64 != 0) return 0;
+  if (M <= 0 || K <= 0 || K % 64 != 0) return 0;
+  if (ps::tc_pair()) return M % 128 == 0 ? (M + 255) / 256 * 256 * K * 4 : 0;  // padded to whole 256-channel blocks
+  if (M % ps::TC_BN != 0) return 0;
   return M * K * 4;  // bf16 hi + bf16 lo
 }
 

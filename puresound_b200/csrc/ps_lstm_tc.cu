@@ -75,9 +75,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// accurate to a few ulp (MUFU ex2 + rcp), saturates cleanly: exp(+big) = inf -> 1/inf = 0
-__device__ __forceinline__ float lt_sigmoid(float x) { return __frcp_rn(1.f + exp2f(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, __frcp_rn(1.f + exp2f(-2.8853900817779268f * x)), -1.f); }
+// One MUFU.EX2 + one MUFU.RCP per activation (2^-22 / 1 ulp), ~1e-7 absolute on the gate; saturates cleanly
+// (ex2(+big) = inf -> rcp(inf) = 0) and propagates NaN.  The IEEE-rounded __frcp_rn / exp2f forms cost ~25 instructions
+// per activation and made the gate phase 90 % of the step (ncu, profiles/).
+__device__ __forceinline__ float lt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lt_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.f + lt_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, lt_rcp(1.f + lt_ex2(-2.8853900817779268f * x)), -1.f); }
 
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d) {
   extern __shared__ uint8_t smem_raw[];

@@ -109,7 +109,9 @@ class DPRNN(nn.Module):
         if init is not None:
             h0, c0 = init[0].contiguous(), init[1].contiguous()
         h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk, **geo)
-        y, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias)
+        proj_pk = self._cache.get(tag + "_proj", [proj.weight],
+                                  lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
+        y, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk)
         new = ops.rownorm(y.view(N, S, K, Cn), norm.weight, norm.bias, norm.eps, res=out)
         return new, state
 
@@ -153,7 +155,8 @@ class DPRNN(nn.Module):
         ones, zeros = self._cache.get("fc_id", [self.output_fc[1].weight],
                                       lambda: (torch.ones(Cn, device=x.device), torch.zeros(Cn, device=x.device)))
         fc = self.output_fc[1]
-        y, _ = ops.linear(merged, fc.weight.view(fc.out_channels, Cn),
+        fc_pk = self._cache.get("fc_pk", [fc.weight], lambda: ops.pack_weights(fc.weight.view(fc.out_channels, Cn), fc.out_channels, Cn, Cn))
+        y, _ = ops.linear(merged, fc.weight.view(fc.out_channels, Cn), w_packed=fc_pk,
                           pro=Prologue(PRO_AFFINE, ACT_PRELU, ones, zeros, 0, None, prelu_slope(self.output_fc[0])), bias=fc.bias)
         return y
 

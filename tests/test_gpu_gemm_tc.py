@@ -40,6 +40,21 @@ def test_tc_plain(ops, B, Rr, M, K):
     check(y2, x.double() @ w.double().t(), 1e-5)
 
 
+@pytest.mark.parametrize("B,Rr,M,K", [(2, 300, 128, 256), (1, 200, 384, 64), (1, 150, 640, 128)])
+def test_tc_channel_counts_padded_to_256(ops, B, Rr, M, K):
+    """M = 128 (the DPRNN projections), 384, 640: the CTA-pair kernel works on whole 256-channel blocks; the packed image
+    pads the missing rows with zeros and the epilogue skips them (output, bias, statistics)."""
+    x, w, bias = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1), rnd(M, seed=3)
+    pk = ops.pack_weights(w, M, K, K)
+    assert pk is not None
+    y, part = ops.linear(x, w, bias=bias, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    ref = x.double() @ w.double().t() + bias.double()
+    check(y, ref)
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, M)
+    rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
+
+
 def test_tc_fused_prologue_epilogue_stats(ops):
     B, Rr, M, K = 3, 413, 512, 512
     x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
