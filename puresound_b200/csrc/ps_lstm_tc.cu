@@ -16,8 +16,10 @@
 //   * gx = W_ih x + b (ps_gemm) is read in its native [position, D*4H] layout: for one gate and sequence a warp reads
 //     128 contiguous bytes; next step's lines are prefetched into L2 while this step computes.
 //
-// Warps: 0 = MMA issuer (+ TMEM allocation), 4..11 = gate warps (two per TMEM lane quarter, 32 sequences each).
-// Barriers: mma_done (tcgen05.commit -> gate warps), h_ready (gate warps -> MMA issuer).
+// Warps: 0 = MMA issuer (+ TMEM allocation), 4..19 = gate warps (per half-batch two per TMEM lane quarter, 16
+// sequences each).
+// Barriers, one pair per half-batch of 32 sequences: mma_done (tcgen05.commit -> gate warps), h_ready (gate warps ->
+// MMA issuer); the halves run in antiphase, so the tensor core works on one while the other's gates are computed.
 // The strided position function of ps_lstm_t is honoured, so one [N,S,K,*] tensor serves both passes without a permute.
 #include <stdlib.h>
 
@@ -26,15 +28,18 @@
 namespace ps {
 
 constexpr int LT_H = 128, LT_N = 64;           // hidden units, sequences per CTA
-constexpr int LT_THREADS = 384;                // 12 warps: 0 MMA, 1-3 idle, 4-11 gates
+constexpr int LT_GWQ = 2;                      // gate warps per (half-batch, TMEM lane quarter)
+constexpr int LT_THREADS = (4 + 8 * LT_GWQ) * 32;  // warp 0 MMA, 1-3 idle, then 8*GWQ gate warps
 constexpr int LT_WTILE = 128 * 64;             // one [128 rows x 32 k] bf16 tile, 64-byte swizzle: 8 KB
 constexpr int LT_WHI_BYTES = 4 * 4 * LT_WTILE; // 4 gates x 4 k-tiles = 128 KB
 constexpr int LT_HTILE = LT_N * 64;            // [64 seqs x 32 k] bf16: 4 KB
 constexpr int LT_H_BYTES = 2 * 4 * LT_HTILE;   // hi | lo, 4 k-tiles each = 32 KB
-constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_N * 8 /*base positions*/ + 64 /*barriers*/ + 1024 /*align*/;
+constexpr int LT_POS_BYTES = 2 * LT_N * 8;     // per sequence: element offset of its rows in gx and in out
+constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 64 /*barriers*/ + 1024 /*align*/;
 constexpr uint32_t LT_ACC_COL = 256;           // TMEM: W_lo in columns [0,256), accumulators in [256,512)
-// D=f32, A=B=bf16, K-major, M=128, N=64
-constexpr uint32_t LT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// D=f32, A=B=bf16, K-major, M=128, N=32 (one half-batch of sequences per MMA)
+constexpr int LT_NH = LT_N / 2;
+constexpr uint32_t LT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_NH >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __host__ __device__ constexpr uint32_t lt_swz(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
 
@@ -73,6 +78,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One MUFU.EX2 + one MUFU.RCP per activation (2^-22 / 1 ulp), ~1e-7 absolute on the gate; saturates cleanly
@@ -97,10 +111,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   uint8_t* h_sm = sm + LT_WHI_BYTES;                       // [hi: 4 tiles][lo: 4 tiles]
-  int64_t* pos_s = reinterpret_cast<int64_t*>(sm + LT_WHI_BYTES + LT_H_BYTES);
-  const uint32_t bars = base + LT_WHI_BYTES + LT_H_BYTES + LT_N * 8;
-  const uint32_t bar_w = bars, bar_mma = bars + 8, bar_h = bars + 16;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_N * 8 + 32);
+  int64_t* posg_s = reinterpret_cast<int64_t*>(sm + LT_WHI_BYTES + LT_H_BYTES);  // base position * gx row width
+  int64_t* poso_s = posg_s + LT_N;                                                 // base position * out row width
+  const uint32_t bars = base + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES;
+  const uint32_t bar_w = bars, bar_mma = bars + 8 /*[2]*/, bar_h = bars + 24 /*[2]*/;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 48);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
@@ -110,15 +125,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
-    mbar_init(bar_h, 8);
+    for (int hf = 0; hf < 2; ++hf) {
+      mbar_init(bar_mma + 8 * hf, 1);
+      mbar_init(bar_h + 8 * hf, 4 * LT_GWQ);  // the gate warps of a half-batch
+    }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)tmem_ptr_s), 512);
   if (tid < LT_N) {
     int64_t q = q0 + tid;
     if (q >= d.n_seq) q = d.n_seq - 1;  // tail sequences shadow the last real one; their results are never stored
-    pos_s[tid] = (q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride;
+    const int64_t pos = (q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride;
+    posg_s[tid] = pos * G;
+    poso_s[tid] = pos * OW;
   }
   tc_fence_before();
   __syncthreads();
@@ -134,39 +153,48 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     }
     __syncwarp();
     mbar_wait(bar_w, 0);
+    // The 64 sequences run as two independent half-batches of 32 (own barriers, own accumulator columns): while the
+    // gate warps of one half compute its cell update, the tensor core is already busy with the other half's step.
     for (int64_t step = 0; step < d.L; ++step) {
-      // h_{t-1} (and, for step 0, h0 and W_lo in TMEM) are in place; the previous step's accumulators have been read
-      mbar_wait(bar_h, (uint32_t)(step & 1));
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t hs = base + LT_WHI_BYTES;
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        // h_{t-1} of this half (and, for step 0, h0 and W_lo in TMEM) is in place; its accumulators have been read
+        mbar_wait(bar_h + 8 * hf, (uint32_t)(step & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t hs = base + LT_WHI_BYTES + (uint32_t)(hf * LT_NH * 64);  // rows [32*hf, 32*hf+32) of every h tile
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N);
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N + hf * LT_NH);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
-            const int kt = k >> 1;
-            const uint64_t ko = (uint64_t)(((k & 1) * 32) >> 4);
-            const uint64_t h_hi = lt_desc(hs + kt * LT_HTILE) + ko, h_lo = lt_desc(hs + (4 + kt) * LT_HTILE) + ko;
-            const uint64_t w_hi = lt_desc(base + (g * 4 + kt) * LT_WTILE) + ko;
-            const uint32_t w_lo = tmem_base + (uint32_t)(g * 64 + k * 8);  // 8 columns = 16 packed bf16
-            umma_bf16_ts(dd, w_lo, h_hi, LT_IDESC, k != 0);
-            umma_bf16(dd, w_hi, h_lo, LT_IDESC, 1);
-            umma_bf16(dd, w_hi, h_hi, LT_IDESC, 1);
+            for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
+              const int kt = k >> 1;
+              const uint64_t ko = (uint64_t)(((k & 1) * 32) >> 4);
+              const uint64_t h_hi = lt_desc(hs + kt * LT_HTILE) + ko, h_lo = lt_desc(hs + (4 + kt) * LT_HTILE) + ko;
+              const uint64_t w_hi = lt_desc(base + (g * 4 + kt) * LT_WTILE) + ko;
+              const uint32_t w_lo = tmem_base + (uint32_t)(g * 64 + k * 8);  // 8 columns = 16 packed bf16
+              umma_bf16_ts(dd, w_lo, h_hi, LT_IDESC, k != 0);
+              umma_bf16(dd, w_hi, h_lo, LT_IDESC, 1);
+              umma_bf16(dd, w_hi, h_hi, LT_IDESC, 1);
+            }
           }
+          umma_commit(bar_mma + 8 * hf);
         }
-        umma_commit(bar_mma);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================== gate warps =====================
-    const int q = warp & 3;              // TMEM lane quarter
-    const int half = (warp - 4) >> 2;    // sequences [32*half, 32*half + 32)
+    // warp = 4 + half*4*GWQ + wq*4 + q: q = TMEM lane quarter (hardware rule: warp id % 4), half = half-batch,
+    // wq = which SPT-sequence slice of the half this warp owns
+    constexpr int GWQ = LT_GWQ, SPT = LT_NH / GWQ, CH = 4;
+    const int q = warp & 3;
+    const int half = (warp - 4) / (4 * GWQ);
+    const int wq = ((warp - 4) >> 2) % GWQ;
     const int u = q * 32 + lane;         // hidden unit = TMEM lane
-    const int s0 = half * 32;
+    const int s0 = half * LT_NH + wq * SPT;
     // ---- one-time: W_lo rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
-    if (half == 0) {
+    if (half == 0 && wq == 0) {
       const uint32_t* wlo = reinterpret_cast<const uint32_t*>(wimg + LT_WHI_BYTES);  // [512 rows][64 words]
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -185,94 +213,106 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
     // ---- initial state: c in registers, h0 into the B-operand tiles
-    float c[32];
+    float c[SPT];
     const uint32_t hoff_k = (uint32_t)(q * LT_HTILE);                       // k-tile of this warp's 32 units = q
     const uint32_t hchunk = (uint32_t)(lane >> 3), helem = (uint32_t)(lane & 7) * 2;
+    // bf16 hi/lo split of two values with packed conversions (F2FP on the ALU pipe; the scalar F2F.BF16 runs on the
+    // XU pipe, which the ex2/rcp of the gates already saturate) and 16-bit stores into the swizzled h tiles
+    auto store_h2 = [&](float ha, float hb, int sa) {
+      const __nv_bfloat162 ph = __floats2bfloat162_rn(ha, hb);
+      const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&ph);
+      const __nv_bfloat162 pl = __floats2bfloat162_rn(ha - __uint_as_float(hbits << 16), hb - __uint_as_float(hbits & 0xFFFF0000u));
+      const uint32_t lbits = *reinterpret_cast<const uint32_t*>(&pl);
+      const uint32_t o0 = hoff_k + lt_swz((uint32_t)sa, hchunk) + helem, o1 = hoff_k + lt_swz((uint32_t)(sa + 1), hchunk) + helem;
+      *reinterpret_cast<uint16_t*>(h_sm + o0) = (uint16_t)(hbits & 0xFFFFu);
+      *reinterpret_cast<uint16_t*>(h_sm + o1) = (uint16_t)(hbits >> 16);
+      *reinterpret_cast<uint16_t*>(h_sm + 4 * LT_HTILE + o0) = (uint16_t)(lbits & 0xFFFFu);
+      *reinterpret_cast<uint16_t*>(h_sm + 4 * LT_HTILE + o1) = (uint16_t)(lbits >> 16);
+    };
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t qq = q0 + s0 + j;
-      const bool valid = qq < d.n_seq;
-      const int64_t so = ((int64_t)dir * d.n_seq + qq) * LT_H + u;
-      c[j] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
-      const float h = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
-      const __nv_bfloat16 hh = __float2bfloat16_rn(h);
-      const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
-      const uint32_t off = hoff_k + lt_swz((uint32_t)(s0 + j), hchunk) + helem;
-      *reinterpret_cast<__nv_bfloat16*>(h_sm + off) = hh;
-      *reinterpret_cast<__nv_bfloat16*>(h_sm + 4 * LT_HTILE + off) = hl;
+    for (int j = 0; j < SPT; j += 2) {
+      float h2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int64_t qq = q0 + s0 + j + e;
+        const bool valid = qq < d.n_seq;
+        const int64_t so = ((int64_t)dir * d.n_seq + qq) * LT_H + u;
+        c[j + e] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
+        h2[e] = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
+      }
+      store_h2(h2[0], h2[1], s0 + j);
     }
     fence_proxy_async();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_h);
+    if (lane == 0) mbar_arrive(bar_h + 8 * half);
 
     const float* gxu = d.gx + (int64_t)dir * 4 * LT_H + u;
     float* outu = d.out + (int64_t)dir * LT_H + u;
+    const int nvalid = (int)((d.n_seq - q0 - s0) < SPT ? (d.n_seq - q0 - s0) : SPT);  // real sequences of this thread (may be <= 0)
+    const int64_t stepg = d.step_stride * G, stepo = d.step_stride * OW;
     for (int64_t step = 0; step < d.L; ++step) {
       const int64_t t = dir ? d.L - 1 - step : step;
-      const int64_t toff = t * d.step_stride;
+      const int64_t toffg = t * stepg, toffo = t * stepo;
       const bool last = step + 1 == d.L;
       // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
-      if (step + 1 < d.L) {
+      if (step + 1 < d.L && lane < SPT) {
         const int64_t tn = dir ? t - 1 : t + 1;
-        const float* pn = d.gx + (pos_s[s0 + lane] + tn * d.step_stride) * G + (int64_t)dir * 4 * LT_H + q * 32;
+        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * LT_H + q * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * LT_H));
       }
-      // gx of the first 8 sequences is requested before the wait on the tensor core
-      float gxa[4][8], gxb[4][8];
-      auto load_gx = [&](float(&gx)[4][8], int j0) {
+      // gx of the first chunk is requested before the wait on the tensor core; the later chunks' loads are issued
+      // together with their TMEM reads (L2 hits after the prefetch above; the other gate warps of the SM cover them)
+      float gxa[4][CH];
+      auto load_gx = [&](float(&gx)[4][CH], int j0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float* p = gxu + (pos_s[s0 + j0 + j] + toff) * G;
+        for (int j = 0; j < CH; ++j) {
+          const float* p = gxu + posg_s[s0 + j0 + j] + toffg;
 #pragma unroll
           for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * LT_H);
         }
       };
       load_gx(gxa, 0);
-      mbar_wait(bar_mma, (uint32_t)(step & 1));
+      mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
       tc_fence_after();
-      auto chunk = [&](const float(&gx)[4][8], int j0) {
-        float a[4][8];
+      auto chunk = [&](const float(&gx)[4][CH], int j0) {
+        float a[4][CH];
         const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + LT_ACC_COL + (uint32_t)(s0 + j0);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld8(tb + (uint32_t)(g * LT_N), a[g]);
+        for (int g = 0; g < 4; ++g) tmem_ld4(tb + (uint32_t)(g * LT_N), a[g]);
         tmem_ld_wait();
+        float h[CH];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < CH; ++j) {
           const float ig = lt_sigmoid(a[0][j] + gx[0][j]);
           const float fg = lt_sigmoid(a[1][j] + gx[1][j]);
           const float gg = lt_tanh(a[2][j] + gx[2][j]);
           const float og = lt_sigmoid(a[3][j] + gx[3][j]);
           const float cn = fmaf(fg, c[j0 + j], ig * gg);
           c[j0 + j] = cn;
-          const float h = og * lt_tanh(cn);
-          const __nv_bfloat16 hh = __float2bfloat16_rn(h);
-          const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
-          const uint32_t off = hoff_k + lt_swz((uint32_t)(s0 + j0 + j), hchunk) + helem;
-          *reinterpret_cast<__nv_bfloat16*>(h_sm + off) = hh;
-          *reinterpret_cast<__nv_bfloat16*>(h_sm + 4 * LT_HTILE + off) = hl;
-          if (q0 + s0 + j0 + j < d.n_seq) {
-            outu[(pos_s[s0 + j0 + j] + toff) * OW] = h;
-            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + q0 + s0 + j0 + j) * LT_H + u] = h;
+          h[j] = og * lt_tanh(cn);
+          if (j0 + j < nvalid) {
+            outu[poso_s[s0 + j0 + j] + toffo] = h[j];
+            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + q0 + s0 + j0 + j) * LT_H + u] = h[j];
           }
         }
+#pragma unroll
+        for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], s0 + j0 + j);
       };
-      load_gx(gxb, 8);
-      chunk(gxa, 0);
-      load_gx(gxa, 16);
-      chunk(gxb, 8);
-      load_gx(gxb, 24);
-      chunk(gxa, 16);
-      chunk(gxb, 24);
+#pragma unroll
+      for (int j0 = 0; j0 < SPT; j0 += CH) {
+        if (j0 > 0) load_gx(gxa, j0);
+        chunk(gxa, j0);
+      }
       // h_t is in shared memory for the tensor core (async proxy) and this step's accumulators have been read
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_h);
+      if (lane == 0) mbar_arrive(bar_h + 8 * half);
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < SPT; ++j) {
       const int64_t qq = q0 + s0 + j;
       if (qq >= d.n_seq) continue;
       if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * LT_H + u] = c[j];
