@@ -11,6 +11,8 @@ output constraint fused.  Training (``forward(**kw)`` -> loss) is out of scope.
 """
 from __future__ import annotations
 
+import os
+from collections import OrderedDict
 from typing import Optional, Tuple
 
 import torch
@@ -50,6 +52,9 @@ class SoTaskWrapModule(nn.Module):
         self.loss_func_wav, self.loss_func_spk, self.loss_func_others = loss_func_wav, loss_func_spk, loss_func_others
         self.mask_constraint, self.output_constraint = mask_constraint, output_constraint
         self.drop_first_bin = drop_first_bin
+        # CUDA-graph cache of the waveform -> waveform path, keyed by input shapes (see _run); PS_CUDA_GRAPH=0 disables it
+        self.use_cuda_graph = os.environ.get("PS_CUDA_GRAPH", "1") != "0"
+        self._graphs = OrderedDict()
         self.task = self.check_task()
         if verbose:
             self._verbose()
@@ -150,6 +155,46 @@ class SoTaskWrapModule(nn.Module):
             return self.encoder.decode_cl(enh, None, ACT_NONE, constraint)
         return self.encoder.decode_cl(feats, mask, mask_act, constraint)
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole path
+    _GRAPH_SLOTS = 2  # input-shape combinations kept captured (each pins its intermediates in a private pool)
+
+    def _param_signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _run(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor], constrain: bool = True) -> torch.Tensor:
+        """_inference_cl through a captured CUDA graph.  A forward is 170-650 small launches; at batch 1 (cfg1) and for
+        the TSE model (cfg4) the launch gaps were longer than the kernels.  The first call with a new combination of input
+        shapes runs eagerly (it also builds the packed-weight caches), the second captures, later ones copy the inputs
+        into the graph's static buffers and replay.  Any change to a parameter or buffer (load_state_dict, .to(), an
+        optimiser step) changes the signature and drops the captured graphs."""
+        if not self.use_cuda_graph:
+            return self._inference_cl(noisy, enroll, constrain)
+        sig = self._param_signature()
+        key = (tuple(noisy.shape), None if enroll is None else tuple(enroll.shape), constrain, noisy.device.index)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["sig"] != sig:
+            self._graphs.clear()
+            ent = None
+        if ent is None:
+            self._graphs[key] = {"sig": sig, "graph": None}
+            while len(self._graphs) > self._GRAPH_SLOTS:
+                self._graphs.popitem(last=False)
+            return self._inference_cl(noisy, enroll, constrain)
+        self._graphs.move_to_end(key)
+        if ent["graph"] is None:
+            ent["in"] = noisy.clone()
+            ent["enroll"] = None if enroll is None else enroll.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent["out"] = self._inference_cl(ent["in"], ent["enroll"], constrain)
+            ent["graph"] = g
+        else:
+            ent["in"].copy_(noisy, non_blocking=True)
+            if enroll is not None:
+                ent["enroll"].copy_(enroll, non_blocking=True)
+        ent["graph"].replay()
+        return ent["out"].clone()
+
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
     def inference(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -158,7 +203,7 @@ class SoTaskWrapModule(nn.Module):
         Host tensors are accepted: they are copied to the model's GPU, and the result is copied back."""
         ops.require_device()
         on_host = not noisy.is_cuda
-        y = self._inference_cl(self._to_device(noisy), self._to_device(enroll))
+        y = self._run(self._to_device(noisy), self._to_device(enroll))
         return y.cpu() if on_host else y
 
     @torch.no_grad()
@@ -166,7 +211,7 @@ class SoTaskWrapModule(nn.Module):
         """The waveform before ``_wav_output_constrain`` (parity is also checked here: the clamp hides errors)."""
         ops.require_device()
         on_host = not noisy.is_cuda
-        y = self._inference_cl(self._to_device(noisy), self._to_device(enroll), constrain=False)
+        y = self._run(self._to_device(noisy), self._to_device(enroll), constrain=False)
         return y.cpu() if on_host else y
 
     @torch.no_grad()
