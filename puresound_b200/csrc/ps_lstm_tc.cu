@@ -29,13 +29,14 @@ namespace ps {
 
 constexpr int LT_H = 128, LT_N = 64;           // hidden units, sequences per CTA
 constexpr int LT_GWQ = 2;                      // gate warps per (half-batch, TMEM lane quarter)
-constexpr int LT_THREADS = (4 + 8 * LT_GWQ) * 32;  // warp 0 MMA, 1-3 idle, then 8*GWQ gate warps
+constexpr int LT_THREADS = (4 + 8 * LT_GWQ) * 32;  // warp 0 MMA, 1-3 idle (registers are granted per 4 warps), then the gate warps
 constexpr int LT_WTILE = 128 * 64;             // one [128 rows x 32 k] bf16 tile, 64-byte swizzle: 8 KB
 constexpr int LT_WHI_BYTES = 4 * 4 * LT_WTILE; // 4 gates x 4 k-tiles = 128 KB
 constexpr int LT_HTILE = LT_N * 64;            // [64 seqs x 32 k] bf16: 4 KB
 constexpr int LT_H_BYTES = 2 * 4 * LT_HTILE;   // hi | lo, 4 k-tiles each = 32 KB
 constexpr int LT_POS_BYTES = 2 * LT_N * 8;     // per sequence: element offset of its rows in gx and in out
-constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 64 /*barriers*/ + 1024 /*align*/;
+constexpr int LT_C_BYTES = LT_N * LT_H * 4;     // cell state [sequence][unit] fp32: 32 KB (registers go to the gx double buffer)
+constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 64 /*barriers*/ + LT_C_BYTES + 1024 /*align*/;
 constexpr uint32_t LT_ACC_COL = 256;           // TMEM: W_lo in columns [0,256), accumulators in [256,512)
 // D=f32, A=B=bf16, K-major, M=128, N=32 (one half-batch of sequences per MMA)
 constexpr int LT_NH = LT_N / 2;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   const uint32_t bars = base + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES;
   const uint32_t bar_w = bars, bar_mma = bars + 8 /*[2]*/, bar_h = bars + 24 /*[2]*/;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 48);
+  float* c_sm = reinterpret_cast<float*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
@@ -212,8 +214,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    // ---- initial state: c in registers, h0 into the B-operand tiles
-    float c[SPT];
+    // ---- initial state: c into its shared-memory slots (a thread only ever touches its own), h0 into the B tiles
+    float* cu = c_sm + s0 * LT_H + u;  // c of (sequence s0 + j, unit u) at cu[j * LT_H]
     const uint32_t hoff_k = (uint32_t)(q * LT_HTILE);                       // k-tile of this warp's 32 units = q
     const uint32_t hchunk = (uint32_t)(lane >> 3), helem = (uint32_t)(lane & 7) * 2;
     // bf16 hi/lo split of two values with packed conversions (F2FP on the ALU pipe; the scalar F2F.BF16 runs on the
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         const int64_t qq = q0 + s0 + j + e;
         const bool valid = qq < d.n_seq;
         const int64_t so = ((int64_t)dir * d.n_seq + qq) * LT_H + u;
-        c[j + e] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
+        cu[(j + e) * LT_H] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
         h2[e] = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
       }
       store_h2(h2[0], h2[1], s0 + j);
@@ -262,9 +264,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 #pragma unroll
         for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * LT_H));
       }
-      // gx of the first chunk is requested before the wait on the tensor core; the later chunks' loads are issued
-      // together with their TMEM reads (L2 hits after the prefetch above; the other gate warps of the SM cover them)
-      float gxa[4][CH];
+      // gx of the first chunk is requested before the wait on the tensor core; later chunks one chunk ahead
+      float gxa[4][CH], gxb[4][CH];
       auto load_gx = [&](float(&gx)[4][CH], int j0) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
           const float fg = lt_sigmoid(a[1][j] + gx[1][j]);
           const float gg = lt_tanh(a[2][j] + gx[2][j]);
           const float og = lt_sigmoid(a[3][j] + gx[3][j]);
-          const float cn = fmaf(fg, c[j0 + j], ig * gg);
-          c[j0 + j] = cn;
+          const float cn = fmaf(fg, cu[(j0 + j) * LT_H], ig * gg);
+          cu[(j0 + j) * LT_H] = cn;
           h[j] = og * lt_tanh(cn);
           if (j0 + j < nvalid) {
             outu[poso_s[s0 + j0 + j] + toffo] = h[j];
@@ -301,9 +302,11 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], s0 + j0 + j);
       };
 #pragma unroll
-      for (int j0 = 0; j0 < SPT; j0 += CH) {
-        if (j0 > 0) load_gx(gxa, j0);
+      for (int j0 = 0; j0 < SPT; j0 += 2 * CH) {
+        load_gx(gxb, j0 + CH);
         chunk(gxa, j0);
+        if (j0 + 2 * CH < SPT) load_gx(gxa, j0 + 2 * CH);
+        chunk(gxb, j0 + CH);
       }
       // h_t is in shared memory for the tensor core (async proxy) and this step's accumulators have been read
       fence_proxy_async();
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     for (int j = 0; j < SPT; ++j) {
       const int64_t qq = q0 + s0 + j;
       if (qq >= d.n_seq) continue;
-      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * LT_H + u] = c[j];
+      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * LT_H + u] = cu[j * LT_H];
     }
   }
 
