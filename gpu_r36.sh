@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+PS_CUDA_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lstm_tc_kernel" -s 4 -c 1 -o gpurun_out/r36_prof_lstm python bench.py --workload cfg3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r36_ncu.log 2>&1
+tail -1 gpurun_out/r36_ncu.log | cut -c1-100

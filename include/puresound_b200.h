@@ -196,6 +196,9 @@ typedef struct {
   float* out; float* hn; float* cn;
   /* tensor-core path (H = 128): image built by ps_lstm_pack_weights from w_hh_t, else NULL (exact-fp32 CUDA-core path) */
   const void* w_packed;
+  /* 0: gx rows are [D][4 gates][H] (nn.LSTM order); 1: [D][H][4 gates] (rows of W_ih permuted by the caller so the four
+   * gates of a unit are one 16-byte load) - tensor-core path only */
+  int32_t gx_interleaved;
 } ps_lstm_t;
 PS_API int ps_lstm(const ps_lstm_t* d, void* stream);
 /* bytes of the packed recurrent-weight image (0 if H is not served by the tensor-core path) */

@@ -54,7 +54,7 @@ class LstmDesc(C.Structure):
         ("inner", I64), ("outer_stride", I64), ("inner_stride", I64), ("step_stride", I64),
         ("gx", P), ("w_hh_t", P), ("h0", P), ("c0", P),
         ("out", P), ("hn", P), ("cn", P),
-        ("w_packed", P),
+        ("w_packed", P), ("gx_interleaved", I32),
     ]
 
 

@@ -4,8 +4,8 @@
 //
 //   * W_hh (512 x 128 fp32 = 256 KB) does not fit the 227 KB of shared memory, so it is kept as a bf16 hi/lo split
 //     (the 3xBF16 scheme of ps_gemm_tc.cu: hi*hi + hi*lo + lo*hi in the fp32 accumulator, ~2^-17 per product) with
-//     W_hi (128 KB) resident in SHARED MEMORY and W_lo (128 KB) resident in TENSOR MEMORY, where tcgen05.mma takes it
-//     as its A operand (TS form);
+//     W_lo (128 KB) resident in SHARED MEMORY and W_hi (128 KB) resident in TENSOR MEMORY, where tcgen05.mma takes it
+//     as its A operand (TS form; two of the three passes use W_hi, and a TMEM A operand is cheaper than a smem tile);
 //   * per step the gate pre-activations  G[512 x 64] = W_hh[512 x 128] * h_{t-1}^T[128 x 64]  are 96 tcgen05.mma
 //     (M=128 = one gate of all 128 units, N=64 sequences, K=16; 4 gates x 8 k-steps x 3 split passes) into the other
 //     256 TMEM columns; B = h_{t-1} as bf16 hi/lo, K-major 64-byte-swizzled tiles in shared memory;
@@ -106,6 +106,7 @@ __device__ __forceinline__ float lt_rcp(float x) {
 __device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.f + lt_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, lt_rcp(1.f + lt_ex2(-2.8853900817779268f * x)), -1.f); }
 
+template <bool kGxi>
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -173,11 +174,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
               const int kt = k >> 1;
               const uint64_t ko = (uint64_t)(((k & 1) * 32) >> 4);
               const uint64_t h_hi = lt_desc(hs + kt * LT_HTILE) + ko, h_lo = lt_desc(hs + (4 + kt) * LT_HTILE) + ko;
-              const uint64_t w_hi = lt_desc(base + (g * 4 + kt) * LT_WTILE) + ko;
-              const uint32_t w_lo = tmem_base + (uint32_t)(g * 64 + k * 8);  // 8 columns = 16 packed bf16
-              umma_bf16_ts(dd, w_lo, h_hi, LT_IDESC, k != 0);
-              umma_bf16(dd, w_hi, h_lo, LT_IDESC, 1);
-              umma_bf16(dd, w_hi, h_hi, LT_IDESC, 1);
+              const uint64_t w_lo = lt_desc(base + (g * 4 + kt) * LT_WTILE) + ko;
+              const uint32_t w_hi = tmem_base + (uint32_t)(g * 64 + k * 8);  // 8 columns = 16 packed bf16
+              // two of the three passes take A from tensor memory: a shared-memory A tile costs >= 32 cycles per MMA
+              // (4 KB at 128 B/cycle) however small N is
+              umma_bf16(dd, w_lo, h_hi, LT_IDESC, k != 0);
+              umma_bf16_ts(dd, w_hi, h_lo, LT_IDESC, 1);
+              umma_bf16_ts(dd, w_hi, h_hi, LT_IDESC, 1);
             }
           }
           umma_commit(bar_mma + 8 * hf);
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     const int wq = ((warp - 4) >> 2) % GWQ;
     const int u = q * 32 + lane;         // hidden unit = TMEM lane
     const int s0 = half * LT_NH + wq * SPT;
-    // ---- one-time: W_lo rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
+    // ---- one-time: W_hi rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
     if (half == 0 && wq == 0) {
       const uint32_t* wlo = reinterpret_cast<const uint32_t*>(wimg + LT_WHI_BYTES);  // [512 rows][64 words]
 #pragma unroll 1
@@ -249,7 +252,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_h + 8 * half);
 
-    const float* gxu = d.gx + (int64_t)dir * 4 * LT_H + u;
+    // gx row layout: native [dir][gate][unit] (4 loads of one float, a warp reads 128 B each) or, when the host permuted
+    // the rows of W_ih (gx_interleaved), [dir][unit][gate]: one 16-byte load per sequence, a warp reads 512 contiguous B
+    constexpr bool gxi = kGxi;
+    const float* gxu = d.gx + (int64_t)dir * 4 * LT_H + (gxi ? 4 * u : u);
     float* outu = d.out + (int64_t)dir * LT_H + u;
     const int nvalid = (int)((d.n_seq - q0 - s0) < SPT ? (d.n_seq - q0 - s0) : SPT);  // real sequences of this thread (may be <= 0)
     const int64_t stepg = d.step_stride * G, stepo = d.step_stride * OW;
@@ -260,9 +266,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
       if (step + 1 < d.L && lane < SPT) {
         const int64_t tn = dir ? t - 1 : t + 1;
-        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * LT_H + q * 32;
+        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * LT_H + (kGxi ? q * 128 : q * 32);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * LT_H));
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 32 : LT_H)));
       }
       // gx of the first chunk is requested before the wait on the tensor core; later chunks one chunk ahead
       float gxa[4][CH], gxb[4][CH];
@@ -270,8 +276,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const float* p = gxu + posg_s[s0 + j0 + j] + toffg;
+          if constexpr (gxi) {
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(p));
+            gx[0][j] = v4.x; gx[1][j] = v4.y; gx[2][j] = v4.z; gx[3][j] = v4.w;
+          } else {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * LT_H);
+            for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * LT_H);
+          }
         }
       };
       load_gx(gxa, 0);
@@ -330,8 +341,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   }
 }
 
-// w_hh_t [D, H, 4H] (W_hh transposed, the layout ps_lstm takes) -> per direction [W_hi shared-memory image 128 KB |
-// W_lo row-major bf16 [4H][H] 128 KB]
+// w_hh_t [D, H, 4H] (W_hh transposed, the layout ps_lstm takes) -> per direction [W_lo shared-memory image 128 KB |
+// W_hi row-major bf16 [4H][H] 128 KB (stored to TMEM by the kernel)]
 __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int D, uint8_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)D * 4 * LT_H * LT_H) return;
@@ -343,8 +354,8 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int D, uint8_
   uint8_t* o = out + (size_t)dir * (2 * LT_WHI_BYTES);
   const int g = r / LT_H, row = r % LT_H, kt = k / 32, kk = k % 32;
   const size_t off = (size_t)(g * 4 + kt) * LT_WTILE + lt_swz((uint32_t)row, (uint32_t)(kk >> 3)) + (size_t)(kk & 7) * 2;
-  *reinterpret_cast<__nv_bfloat16*>(o + off) = h;
-  *reinterpret_cast<__nv_bfloat16*>(o + LT_WHI_BYTES + ((size_t)r * LT_H + k) * 2) = l;
+  *reinterpret_cast<__nv_bfloat16*>(o + off) = l;                                                // shared-memory tile image: lo
+  *reinterpret_cast<__nv_bfloat16*>(o + LT_WHI_BYTES + ((size_t)r * LT_H + k) * 2) = h;          // row-major (-> TMEM): hi
 }
 
 bool lstm_tc_eligible(const ps_lstm_t& d) {
@@ -359,14 +370,16 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
   if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    e = cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(lstm_tc_kernel)"); return PS_ERR_CUDA; }
     attr_set[dev] = true;
   }
   const int64_t nblk = cdiv(d.n_seq, LT_N);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
-  lstm_tc_kernel<<<grid, LT_THREADS, LT_SMEM, s>>>(d);
+  if (d.gx_interleaved) lstm_tc_kernel<true><<<grid, LT_THREADS, LT_SMEM, s>>>(d);
+  else lstm_tc_kernel<false><<<grid, LT_THREADS, LT_SMEM, s>>>(d);
   PS_CHECK_LAUNCH("lstm_tc_kernel");
   return PS_OK;
 }

@@ -78,6 +78,12 @@ class DPRNN(nn.Module):
             w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
             # resident image for the tensor-core recurrence (None unless H == 128), tcgen05 image of W_ih for the projections
             w_hh_pk = ops.lstm_pack_weights(w_hh_t, self.hidden_size, len(sfx))
+            if w_hh_pk is not None:
+                # tensor-core recurrence: order the projection rows [dir][unit][gate] so the four gates of a unit are one
+                # 16-byte load of gx (ps_lstm_t.gx_interleaved)
+                D, H = len(sfx), self.hidden_size
+                w_ih = w_ih.view(D, 4, H, -1).permute(0, 2, 1, 3).reshape(D * 4 * H, -1).contiguous()
+                b = b.view(D, 4, H).permute(0, 2, 1).reshape(D * 4 * H).contiguous()
             w_ih_pk = ops.pack_weights(w_ih, w_ih.shape[0], w_ih.shape[1], w_ih.shape[1])
             return w_ih, b, w_hh_t, w_hh_pk, w_ih_pk
 
@@ -108,7 +114,8 @@ class DPRNN(nn.Module):
         h0 = c0 = None
         if init is not None:
             h0, c0 = init[0].contiguous(), init[1].contiguous()
-        h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk, **geo)
+        h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk,
+                            gx_interleaved=w_hh_pk is not None, **geo)
         proj_pk = self._cache.get(tag + "_proj", [proj.weight],
                                   lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
         y, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk)

@@ -283,7 +283,7 @@ def merge(seg: Tensor, T: int, overlap: bool) -> Tensor:
 
 def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inner: int, outer_stride: int,
          inner_stride: int, step_stride: int, h0: Optional[Tensor] = None, c0: Optional[Tensor] = None,
-         want_state: bool = False, w_packed: Optional[Tensor] = None):
+         want_state: bool = False, w_packed: Optional[Tensor] = None, gx_interleaved: bool = False):
     """gx [positions, D*4H] -> out [positions, D*H] (+ (hn, cn) [D, n_seq, H])."""
     lib = _lib.load()
     positions = gx.shape[0]
@@ -298,6 +298,7 @@ def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inne
     d.gx, d.w_hh_t, d.h0, d.c0 = _req(gx, "lstm gx").data_ptr(), w_hh_t.data_ptr(), _p(h0), _p(c0)
     d.out, d.hn, d.cn = out.data_ptr(), _p(hn), _p(cn)
     d.w_packed = _p(w_packed)
+    d.gx_interleaved = 1 if (gx_interleaved and w_packed is not None) else 0
     _lib.check(lib.ps_lstm(C.byref(d), _stream()), "ps_lstm")
     _launched()
     return out, ((hn, cn) if want_state else None)

@@ -229,6 +229,11 @@ def test_lstm_tensor_core_path(ops, D):
     # and it agrees with the exact-fp32 CUDA-core kernel
     out32, _ = ops.lstm(gx, w_hh_t, n_seq=N * S, L=K, H=H, D=D, inner=1, outer_stride=K, inner_stride=0, step_stride=1)
     close(out, out32, 5e-5)
+    # gx with the rows of W_ih permuted to [dir][unit][gate] (one 16-byte load per sequence) gives the same result
+    gxi = gx.view(P, D, 4, H).permute(0, 1, 3, 2).reshape(P, D * 4 * H).contiguous()
+    outi, _ = ops.lstm(gxi, w_hh_t, n_seq=N * S, L=K, H=H, D=D, inner=1, outer_stride=K, inner_stride=0, step_stride=1,
+                       w_packed=pk, gx_interleaved=True)
+    assert torch.equal(outi, out)
     h0, c0 = rnd(D, N * K, H, seed=6), rnd(D, N * K, H, seed=7)
     out, st = ops.lstm(gx, w_hh_t, n_seq=N * K, L=S, H=H, D=D, inner=K, outer_stride=S * K, inner_stride=1, step_stride=K,
                        h0=h0, c0=c0, want_state=True, w_packed=pk)
