@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv_tile_kernel(const ps_dwconv
   __shared__ Wf red[DT_THREADS / 32];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   const int64_t b = blockIdx.z;
-  const int c0 = blockIdx.y * DT_CG + tx * 4;
-  const int t0 = blockIdx.x * TC;
+  // blockIdx.x = channel group (fastest): the 16 CTAs that share a time chunk run together, so every 2 KB frame row is
+  // fetched from HBM in one go instead of as sixteen 128-byte pieces spread over the kernel's lifetime
+  const int c0 = blockIdx.x * DT_CG + tx * 4;
+  const int t0 = blockIdx.y * TC;
   const int T = (int)d.T, C = (int)d.C;
   const int P = PT ? PT : d.P;
   const int dil = d.dilation;
@@ -338,7 +340,7 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
     const int which = (d.P == 3 ? 3 : 0) + d.pro_mode;
     bool set_attr = false;
     if (dev >= 0 && dev < 64 && !attr_set[dev][which]) { set_attr = true; attr_set[dev][which] = true; }
-    dim3 tgrid((unsigned)ps::cdiv(d.T, TC), (unsigned)ps::cdiv(d.C, ps::DT_CG), (unsigned)d.batch);
+    dim3 tgrid((unsigned)ps::cdiv(d.C, ps::DT_CG), (unsigned)ps::cdiv(d.T, TC), (unsigned)d.batch);
     switch (which) {
       case 0: return ps::launch_tile<0, 0>(dd, TC, smem, tgrid, s, set_attr);
       case 1: return ps::launch_tile<0, 1>(dd, TC, smem, tgrid, s, set_attr);

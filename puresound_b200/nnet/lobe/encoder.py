@@ -148,16 +148,24 @@ class ConvEncDec(nn.Module):
         return self.n_fft // 2 + 1
 
     # ---- engine path ----
-    def encode_cl(self, wav: torch.Tensor, drop_first_bin: bool) -> torch.Tensor:
-        """wav [N, L] -> [N, T, 2F'] = cat(Re[s:], Im[s:]) on channels (base_nn.py:337-345 layout), Im = -conv(wsin)."""
+    def encode_cl(self, wav: torch.Tensor, drop_first_bin: bool, exact: bool = True) -> torch.Tensor:
+        """wav [N, L] -> [N, T, 2F'] = cat(Re[s:], Im[s:]) on channels (base_nn.py:337-345 layout), Im = -conv(wsin).
+
+        exact=True keeps the analysis GEMM in true fp32 (the spectrum that is masked and goes back through the iSTFT,
+        whose window-sum-square division amplifies rounding ~2.6e4x at the first/last hop); exact=False lets it run on
+        the tensor cores (3xBF16) - used for the enrollment spectrum, which only feeds the speaker net."""
         _check_wav(wav, self.n_fft)
         e = self.encoder
         s = 1 if drop_first_bin else 0
         w = self._cache.get(f"ana{s}", [e.wsin, e.wcos], lambda: torch.cat([e.wcos[s:, 0, :], -e.wsin[s:, 0, :]], 0).contiguous())
         N, L = wav.shape
         T = (L - self.n_fft) // self.hop_length + 1
+        pk = None
+        if not exact:
+            pk = self._cache.get(f"ana_pk{s}", [e.wsin, e.wcos], lambda: ops.pack_weights(w, w.shape[0], self.n_fft, self.n_fft))
         y, _ = ops.gemm(wav.contiguous(), w, batch=N, rows=T, M=w.shape[0], K=self.n_fft, x_batch_stride=L,
-                        x_row_stride=self.hop_length, w_row_stride=self.n_fft)
+                        x_row_stride=self.hop_length, w_row_stride=self.n_fft, w_packed=pk,
+                        backend=ops.GEMM_AUTO if pk is not None else GEMM_SIMT)
         return y
 
     def _synthesis_weight(self, s: int) -> torch.Tensor:
