@@ -118,7 +118,8 @@ __device__ __forceinline__ void epi_chunk(const float (&v)[PR_CW], float bsum, f
   }
 }
 
-template <bool kAffine, int NB>
+// PRO: PS_PRO_NONE, PS_PRO_AFFINE (norm affine + PReLU) or PS_PRO_MASK (x * act(x2): mask apply in front of the decoder)
+template <int PRO, int NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
   using Cfg = PairCfg<NB>;
@@ -281,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 #pragma unroll
       for (int mb = 0; mb < NB; ++mb) {
         const int64_t ch = ch0 + mb * 256 + cl;
-        if (ch0 + mb * 256 >= d.M) continue;  // zero-padded block (M = 128: the peer CTA's rows): nothing to store
+        if (ch0 + mb * 256 + q * 32 >= d.M) continue;  // zero-padded rows (M = 128: the peer's block; M = 32: lane quarters 1-3)
         float bsum = bias ? __ldg(bias + ch) : 0.f;
         if (bias_batch) bsum += __ldg(bias_batch + tc.b * d.M + ch);
         // real loops (not unrolled): the chunk body exists once per variant, which keeps the kernel inside the
@@ -362,6 +363,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     int s = half;  // this thread's stage: half 0 walks stages 0,2,4,.., half 1 walks 1,3,5,.. (mod the ring depth)
     uint32_t ph = 0;
 
+    struct XBuf {
+      float4 v[2][2];
+      float4 m[PRO == PS_PRO_MASK ? 2 : 1][2];  // mask operand (MASK prologue only)
+    };
     struct Cur {
       int64_t t;
       int kb;
@@ -386,7 +391,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       }
     };
     // frames past the end of the item re-read its last frame: their accumulator columns are never stored
-    auto issue = [&](float4(&x)[2][2], const Cur& c) {
+    const int64_t x2_delta = (PRO == PS_PRO_MASK) ? (d.X2 - d.X) : 0;  // the mask has the strides of X
+    const int mask_act = d.pro_act;
+    auto issue = [&](XBuf& x, const Cur& c) {
       if (dbg & 2) return;  // experiment: no activation loads
       const float* xb = c.x0 + c.kb * 64;
 #pragma unroll
@@ -394,13 +401,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
         int64_t row = c.row_base + p * 32;
         row = row < last_row ? row : last_row;
         const float4* src = reinterpret_cast<const float4*>(xb + row * d.x_row_stride);
-        x[p][0] = __ldg(src);
-        x[p][1] = __ldg(src + 1);
+        x.v[p][0] = __ldg(src);
+        x.v[p][1] = __ldg(src + 1);
+        if constexpr (PRO == PS_PRO_MASK) {
+          const float4* msrc = reinterpret_cast<const float4*>(xb + row * d.x_row_stride + x2_delta);
+          x.m[p][0] = __ldg(msrc);
+          x.m[p][1] = __ldg(msrc + 1);
+        }
       }
     };
     int64_t staged_b = -1;
     auto stage_affine = [&](int64_t b) {
-      if constexpr (kAffine) {
+      if constexpr (PRO == PS_PRO_AFFINE) {
         if (b != staged_b) {
           asm volatile("bar.sync 2, %0;" ::"n"(PR_PRODUCERS) : "memory");  // every producer is done with the old rows
           const float* pa = d.pro_a + b * d.pro_batch_stride;
@@ -414,9 +426,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
         }
       }
     };
-    auto process = [&](const float4(&x)[2][2], int kb) {
+    auto process = [&](const XBuf& x, int kb) {
       float sc[8], sh[8];
-      if constexpr (kAffine) {
+      if constexpr (PRO == PS_PRO_AFFINE) {
         const int k0 = kb * 64 + kofs;
         const float4 a0 = *reinterpret_cast<const float4*>(aff_s + k0), a1 = *reinterpret_cast<const float4*>(aff_s + k0 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(aff_s + K + k0), b1 = *reinterpret_cast<const float4*>(aff_s + K + k0 + 4);
@@ -430,12 +442,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 #pragma unroll
       for (int p = 0; p < 2 && !(dbg & 8); ++p) {
         const int r = p * 32 + r0;
-        const float v[8] = {x[p][0].x, x[p][0].y, x[p][0].z, x[p][0].w, x[p][1].x, x[p][1].y, x[p][1].z, x[p][1].w};
+        float v[8] = {x.v[p][0].x, x.v[p][0].y, x.v[p][0].z, x.v[p][0].w, x.v[p][1].x, x.v[p][1].y, x.v[p][1].z, x.v[p][1].w};
+        if constexpr (PRO == PS_PRO_MASK) {
+          const float mk[8] = {x.m[p][0].x, x.m[p][0].y, x.m[p][0].z, x.m[p][0].w, x.m[p][1].x, x.m[p][1].y, x.m[p][1].z, x.m[p][1].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] *= apply_act(mk[i], mask_act, 0.f);
+        }
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
           float u0 = v[i], u1 = v[i + 1];
-          if constexpr (kAffine) {
+          if constexpr (PRO == PS_PRO_AFFINE) {
             u0 = fmaf(u0, sc[i], sh[i]);
             u1 = fmaf(u1, sc[i + 1], sh[i + 1]);
             u0 = u0 > 0.f ? u0 : u0 * pslope;
@@ -462,18 +479,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
 
     // Register double buffer: the loads of block n+1 are in flight while block n is transformed.  (Measured: a third
     // buffer and an L2 software prefetch 4 blocks ahead were both SLOWER - the stream is not latency-bound.)
-    float4 x0[2][2], x1[2][2];
+    XBuf x0, x1;
     Cur pr, ld;
     pr.t = pair; pr.kb = 0;
     decode(pr);
     ld = pr;
-    auto ld_next = [&](float4(&x)[2][2]) {
+    auto ld_next = [&](XBuf& x) {
       if (ld.t < n_tiles) {
         issue(x, ld);
         advance(ld);
       }
     };
-    auto pr_next = [&](const float4(&x)[2][2]) -> bool {
+    auto pr_next = [&](const XBuf& x) -> bool {
       if (pr.t >= n_tiles) return false;
       stage_affine(pr.b);
       process(x, pr.kb);
@@ -528,22 +545,22 @@ int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* pack
   return PS_OK;
 }
 
-template <bool kAffine, int NB>
+template <int PRO, int NB>
 static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
   if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<kAffine, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<PRO, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_pair_kernel)"); return PS_ERR_CUDA; }
   }
   static int dbg = -1;  // PS_PAIR_DBG: bottleneck experiments only (1 no weight copies, 2 no activation loads, 4 no epilogue, 8 no transform)
   if (dbg < 0) { const char* e = getenv("PS_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
-  gemm_pair_kernel<kAffine, NB><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
+  gemm_pair_kernel<PRO, NB><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
   PS_CHECK_LAUNCH("gemm_pair_kernel");
   return PS_OK;
 }
 
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   static int sm_count[64] = {0};
-  static bool attr_set[64][2][2] = {};
+  static bool attr_set[64][4][2] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
@@ -551,18 +568,23 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
     e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
   }
-  const bool affine = d.pro_mode == PS_PRO_AFFINE;
+  const int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
   const int nb = pair_nb(d.M);
-  const bool set_attr = !attr_set[dev][affine][nb - 1];
-  attr_set[dev][affine][nb - 1] = true;
+  const bool set_attr = !attr_set[dev][pro][nb - 1];
+  attr_set[dev][pro][nb - 1] = true;
   const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
   const int64_t max_pairs = sm_count[dev] / 2;
   const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
-  if (nb == 2)
-    return affine ? launch_pair<true, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_pair<false, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-  return affine ? launch_pair<true, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_pair<false, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  if (nb == 2) {
+    if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+    if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+    return launch_pair<PS_PRO_NONE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  }
+  if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  return launch_pair<PS_PRO_NONE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
 }
 
 }  // namespace ps

@@ -519,12 +519,16 @@ bool tc_pair() {
 
 bool gemm_tc_eligible(const ps_gemm_t& d) {
   if (!d.W_packed) return false;
-  if (d.M % (tc_pair() ? 128 : TC_BN) != 0 || d.K % 64 != 0) return false;  // the pair kernel zero-pads to 256 channels
-  if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE)) return false;
+  const bool pair = tc_pair();
+  // the pair kernel zero-pads the channels to whole 256-blocks (any multiple of 32 goes), takes the mask-apply prologue
+  // and overlapping rows (framed filterbank / STFT analysis views); the single-CTA kernel does none of these
+  if (d.M % (pair ? 32 : TC_BN) != 0 || d.K % 64 != 0) return false;
+  if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE || (pair && d.pro_mode == PS_PRO_MASK))) return false;
+  if (d.pro_mode == PS_PRO_MASK && (!al16(d.X2) || !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_RELU || d.pro_act == PS_ACT_SIGMOID))) return false;
   if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU)) return false;
   if (!(d.epi_act == PS_ACT_NONE || d.epi_act == PS_ACT_RELU || d.epi_act == PS_ACT_PRELU)) return false;
   if ((d.bias && !al16(d.bias)) || (d.bias_batch && !al16(d.bias_batch))) return false;
-  if ((d.x_row_stride & 3) || (d.x_batch_stride & 3) || !al16(d.X) || d.x_row_stride < d.K) return false;
+  if ((d.x_row_stride & 3) || (d.x_batch_stride & 3) || !al16(d.X) || (!pair && d.x_row_stride < d.K)) return false;
   if ((d.y_row_stride & 3) || (d.y_batch_stride & 3) || !al16(d.Y)) return false;
   if (d.pro_mode == PS_PRO_AFFINE && ((d.pro_batch_stride & 3) || !al16(d.pro_a) || !al16(d.pro_b) || d.K > TC_MAXK)) return false;
   if (d.residual && ((d.res_row_stride & 3) || (d.res_batch_stride & 3) || !al16(d.residual))) return false;
@@ -570,7 +574,7 @@ int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
 
 extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
   if (M <= 0 || K <= 0 || K % 64 != 0) return 0;
-  if (ps::tc_pair()) return M % 128 == 0 ? (M + 255) / 256 * 256 * K * 4 : 0;  // padded to whole 256-channel blocks
+  if (ps::tc_pair()) return M % 32 == 0 ? (M + 255) / 256 * 256 * K * 4 : 0;  // padded to whole 256-channel blocks
   if (M % ps::TC_BN != 0) return 0;
   return M * K * 4;  // bf16 hi + bf16 lo
 }

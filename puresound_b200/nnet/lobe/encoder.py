@@ -62,7 +62,9 @@ class FreeEncDec(nn.Module):
         Nf, win = self.decoder.in_channels, self.win_length
         w_t = self._cache.get("dec_t", [self.decoder.weight], lambda: self.decoder.weight.view(Nf, win).t().contiguous())
         pro = Prologue(PRO_MASK, mask_act, x2=mask) if mask is not None else ops.NO_PRO
-        frames, _ = ops.linear(feats, w_t, pro=pro)
+        # tcgen05 (3xBF16) when the shape allows: the learned synthesis filterbank has no ill-conditioned step after it
+        w_pk = self._cache.get("dec_pk", [self.decoder.weight], lambda: ops.pack_weights(w_t, win, Nf, Nf))
+        frames, _ = ops.linear(feats, w_t, pro=pro, w_packed=w_pk)
         return ops.ola(frames, self.hop_length, None, constraint)
 
     # ---- reference-layout API ----

@@ -55,6 +55,32 @@ def test_tc_channel_counts_padded_to_256(ops, B, Rr, M, K):
     assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
 
 
+@pytest.mark.parametrize("act", ["none", "relu", "sigmoid"])
+def test_tc_mask_prologue_small_m(ops, act):
+    """The decoder GEMM of FreeEncDec: x * act(mask) applied on load (base_nn.py:81-95,146-159), M = win = 32 output
+    samples per frame (zero-padded to one 256-channel block, lane quarters 1-3 skipped)."""
+    B, Rr, M, K = 2, 333, 32, 512
+    x, mk, w = rnd(B, Rr, K, seed=1, scale=2), rnd(B, Rr, K, seed=2, scale=2), rnd(M, K, seed=3, scale=0.1)
+    code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "sigmoid": ops.ACT_SIGMOID}[act]
+    f = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid}[act]
+    pk = ops.pack_weights(w, M, K, K)
+    assert pk is not None
+    y, _ = ops.linear(x, w, pro=ops.Prologue(ops.PRO_MASK, code, x2=mk), w_packed=pk, backend=ops.GEMM_TCGEN05)
+    check(y, (x.double() * f(mk.double())) @ w.double().t())
+
+
+def test_tc_overlapping_rows_framed_view(ops):
+    """Framed analysis GEMM: rows are overlapping windows of a waveform (row stride = hop < K), read in place."""
+    N, L, win, hop, M = 2, 16000, 512, 128, 512
+    wav, w = rnd(N, L, seed=1), rnd(M, win, seed=2, scale=0.05)
+    T = (L - win) // hop + 1
+    pk = ops.pack_weights(w, M, win, win)
+    y, _ = ops.gemm(wav, w, batch=N, rows=T, M=M, K=win, x_batch_stride=L, x_row_stride=hop, w_row_stride=win,
+                    w_packed=pk, backend=ops.GEMM_TCGEN05)
+    frames = wav.unfold(1, win, hop)  # [N, T, win]
+    check(y, frames.double() @ w.double().t())
+
+
 def test_tc_fused_prologue_epilogue_stats(ops):
     B, Rr, M, K = 3, 413, 512, 512
     x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
@@ -105,5 +131,6 @@ def test_tc_nan_inf_rows_stay_local(ops):
 def test_tc_ineligible_shapes_are_refused(ops):
     x, w = rnd(1, 10, 60, seed=1), rnd(130, 60, seed=2)
     assert ops.pack_weights(w, 130, 60, 60) is None
+    assert ops.pack_weights(rnd(130, 64, seed=3), 130, 64, 64) is None  # channels must come in multiples of 32
     with pytest.raises(NotImplementedError):
         ops.linear(x, w, backend=ops.GEMM_TCGEN05)
