@@ -241,6 +241,125 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Short-K framed filterbank:  Y[b,r,m] = act( sum_{k<K} x[b, r*stride + k] * W[m,k] ),  K <= 64.
+// The learned encoder of FreeEncDec (lobe/encoder.py:50-56,71-83) at win = 32, hop = 16 is 0.06 FLOP per output byte:
+// it is a pure write stream (cfg2: 524 MB), which the 128 x 128 x 16 tile kernel above ran at 15 % of HBM (two k-slabs
+// per tile, then a long epilogue).  Here a lane owns two output channels with their filter taps in REGISTERS, the CTA
+// stages the contiguous piece of waveform its FR frames cover in shared memory once, and every frame is K broadcast
+// loads + 2K FMAs + two coalesced 128-byte stores per warp.  Exact fp32, same summation order over k as the tile kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FB_FR = 256;       // frames per CTA (the per-CTA cost of fetching 2 x K filter taps per lane is amortised over them)
+constexpr int FB_MAXSEG = 12288; // floats of waveform a CTA may stage (48 KB)
+
+template <int KT>
+__global__ void __launch_bounds__(256, KT == 32 ? 2 : 1) filterbank_kernel(const ps_gemm_t d, const int seg_len) {
+  extern __shared__ __align__(16) float seg[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t b = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.x * FB_FR;
+  const int nfr = (int)((d.rows - r0) < FB_FR ? (d.rows - r0) : FB_FR);
+  const int64_t m0 = (int64_t)blockIdx.y * 512 + warp * 64 + lane;  // this lane's channels: m0 and m0 + 32
+  const int K = (int)d.K, stride = (int)d.x_row_stride;
+  const float* xb = d.X + b * d.x_batch_stride + r0 * stride;
+  const int need = (nfr - 1) * stride + K;
+  for (int i = tid; i < seg_len; i += blockDim.x) seg[i] = i < need ? __ldg(xb + i) : 0.f;
+  float w0[KT], w1[KT];
+  const bool wvec = ((d.w_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
+#pragma unroll
+  for (int k = 0; k < KT; k += 4) {
+    // 16-byte loads: a lane walks its own 128-byte filter row, so every fetched line is used completely
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    if (wvec && k + 3 < K) {
+      if (m0 < d.M) t0 = __ldg(reinterpret_cast<const float4*>(d.W + m0 * d.w_row_stride + k));
+      if (m0 + 32 < d.M) t1 = __ldg(reinterpret_cast<const float4*>(d.W + (m0 + 32) * d.w_row_stride + k));
+    } else {
+      float e0[4] = {0.f, 0.f, 0.f, 0.f}, e1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (k + i < K && m0 < d.M) e0[i] = __ldg(d.W + m0 * d.w_row_stride + k + i);
+        if (k + i < K && m0 + 32 < d.M) e1[i] = __ldg(d.W + (m0 + 32) * d.w_row_stride + k + i);
+      }
+      t0 = make_float4(e0[0], e0[1], e0[2], e0[3]);
+      t1 = make_float4(e1[0], e1[1], e1[2], e1[3]);
+    }
+    w0[k] = t0.x; w0[k + 1] = t0.y; w0[k + 2] = t0.z; w0[k + 3] = t0.w;
+    w1[k] = t1.x; w1[k + 1] = t1.y; w1[k + 2] = t1.z; w1[k + 3] = t1.w;
+  }
+  float bias0 = 0.f, bias1 = 0.f;
+  if (d.bias) {
+    if (m0 < d.M) bias0 = __ldg(d.bias + m0);
+    if (m0 + 32 < d.M) bias1 = __ldg(d.bias + m0 + 32);
+  }
+  const float eslope = d.epi_slope ? __ldg(d.epi_slope) : 0.f;
+  const int act = d.epi_act;
+  __syncthreads();
+  if (warp * 64 + blockIdx.y * 512 >= d.M) return;
+  float* yp = d.Y + b * d.y_batch_stride + r0 * d.y_row_stride + m0;
+  const bool vec = (stride & 3) == 0;
+  // four frames at a time: eight independent accumulator chains per lane hide the FMA latency (one frame at a time
+  // measured 0.51 ms at cfg2, latency-bound with 8 warps per SM)
+  for (int f = 0; f < nfr; f += 4) {
+    float acc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; }
+    const float* xs = seg + f * stride;  // frames f..f+3 lie inside the staged piece (FB_FR is a multiple of 4)
+    if (vec) {
+#pragma unroll
+      for (int k = 0; k < KT; k += 4) {
+        float4 x4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x4[j] = *reinterpret_cast<const float4*>(xs + j * stride + k);  // broadcast loads
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[j][0] = fmaf(x4[j].x, w0[k], acc[j][0]); acc[j][1] = fmaf(x4[j].x, w1[k], acc[j][1]);
+          acc[j][0] = fmaf(x4[j].y, w0[k + 1], acc[j][0]); acc[j][1] = fmaf(x4[j].y, w1[k + 1], acc[j][1]);
+          acc[j][0] = fmaf(x4[j].z, w0[k + 2], acc[j][0]); acc[j][1] = fmaf(x4[j].z, w1[k + 2], acc[j][1]);
+          acc[j][0] = fmaf(x4[j].w, w0[k + 3], acc[j][0]); acc[j][1] = fmaf(x4[j].w, w1[k + 3], acc[j][1]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xv = xs[j * stride + k];
+          acc[j][0] = fmaf(xv, w0[k], acc[j][0]);
+          acc[j][1] = fmaf(xv, w1[k], acc[j][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (f + j < nfr) {
+        if (m0 < d.M) yp[0] = apply_act(acc[j][0] + bias0, act, eslope);
+        if (m0 + 32 < d.M) yp[32] = apply_act(acc[j][1] + bias1, act, eslope);
+      }
+      yp += d.y_row_stride;
+    }
+  }
+}
+
+static bool filterbank_eligible(const ps_gemm_t& d) {
+  if (d.K > 64 || d.K % 4 != 0 || d.pro_mode != PS_PRO_NONE || d.residual || d.stats_partials || d.bias_batch) return false;
+  if (d.rows < 256 || d.batch > 65535) return false;                          // skinny problems keep the latency tile
+  if ((FB_FR + 2) * d.x_row_stride + 64 > FB_MAXSEG) return false;             // the staged waveform piece must fit
+  return true;
+}
+
+static int filterbank_launch(const ps_gemm_t& d, cudaStream_t s) {
+  const int KT = d.K <= 32 ? 32 : 64;
+  int seg_len = (int)((FB_FR + 2) * d.x_row_stride + KT);  // frames are processed four at a time: a little slack past the last one
+  seg_len = (seg_len + 3) & ~3;
+  dim3 grid((unsigned)cdiv(d.rows, FB_FR), (unsigned)cdiv(d.M, 512), (unsigned)d.batch);
+  const int threads = (int)(d.M >= 512 ? 256 : ((cdiv(d.M, 64) * 32 + 31) / 32 * 32));
+  if (KT == 32) filterbank_kernel<32><<<grid, threads, seg_len * sizeof(float), s>>>(d, seg_len);
+  else filterbank_kernel<64><<<grid, threads, seg_len * sizeof(float), s>>>(d, seg_len);
+  PS_CHECK_LAUNCH("filterbank_kernel");
+  return PS_OK;
+}
+
 template <int BR, int BC>
 static int launch_shape(const ps_gemm_t& d, cudaStream_t s, int x_vec, int w_vec) {
   const int64_t nrt = cdiv(d.rows, BR), nmt = cdiv(d.M, BC);
@@ -261,6 +380,7 @@ int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s) {
                     ((reinterpret_cast<uintptr_t>(d.X) & 15) == 0) &&
                     (!d.X2 || (reinterpret_cast<uintptr_t>(d.X2) & 15) == 0);
   const int w_vec = ((d.w_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
+  if (filterbank_eligible(d)) return filterbank_launch(d, s);
   // latency shape when the throughput shape would leave most SMs idle (and no statistics are requested: the partial
   // slot layout is defined on 128 x 128 tiles)
   const int64_t big_ctas = d.batch * cdiv(d.rows, 128) * cdiv(d.M, 128);

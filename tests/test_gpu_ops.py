@@ -200,6 +200,21 @@ def test_segment_merge_bit_exact(ops, T, K):
     assert torch.equal(ops.merge(seg2, T, False), x)
 
 
+@pytest.mark.parametrize("M,K,hop,relu", [(512, 32, 16, False), (128, 32, 16, True), (96, 20, 10, False), (640, 64, 32, True)])
+def test_short_k_filterbank_kernel(ops, M, K, hop, relu):
+    """FreeEncDec analysis (lobe/encoder.py:50-56,71-83) at short windows goes through the register-resident filterbank
+    kernel: framed rows read in place, optional ReLU (output_active) and bias, ragged last CTA, channel tails."""
+    N, L = 3, 16000 + 7 * hop
+    wav, w, bias = rnd(N, L, seed=1), rnd(M, K, seed=2, scale=0.2), rnd(M, seed=3)
+    T = (L - K) // hop + 1
+    y, _ = ops.gemm(wav, w, batch=N, rows=T, M=M, K=K, x_batch_stride=L, x_row_stride=hop, w_row_stride=K, bias=bias,
+                    epi_act=ops.ACT_RELU if relu else ops.ACT_NONE, backend=ops.GEMM_SIMT)
+    ref = torch.nn.functional.conv1d(wav.unsqueeze(1).double(), w.unsqueeze(1).double(), bias.double(), stride=hop).transpose(1, 2)
+    if relu:
+        ref = torch.relu(ref)
+    close(y.double(), ref, 1e-6)
+
+
 @pytest.mark.parametrize("D", [1, 2])
 def test_lstm_tensor_core_path(ops, D):
     """H = 128: W_hh resident as bf16 hi (shared memory) + lo (tensor memory), gates on tcgen05 with the 3xBF16 split.
