@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -rfE --tb=short -p no:cacheprovider -x > gpurun_out/r42_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r42_pytest_gpu.log
+tail -12 gpurun_out/r42_pytest_gpu.log
+for W in cfg2 cfg1 cfg4; do
+timeout 600 python bench.py --workload $W --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r42_bench_$W.log 2>&1; echo "$W: $(tail -1 gpurun_out/r42_bench_$W.log | python -c 'import sys,json; j=json.loads(sys.stdin.read()); print(j["value"], j["ms_per_step"], j["e2e"]["value"], j["gpu_launches"], j["clocks"])')"
+done

@@ -99,6 +99,11 @@ typedef struct {
   float* stats_partials;     /* NULL or [batch, ps_gemm_stats_slots, 3] (count,mean,M2)   */
   /* tcgen05 path only: weights pre-packed by ps_gemm_pack_weights (else NULL)            */
   const void* W_packed;
+  /* optional fused gLN/gGN finalize (needs stats_partials): the folded affine ps_stats_finalize would produce from the
+   * partials is written to fin_scale / fin_shift [batch, M] by the CTA that completes an item's last tile (no extra
+   * launch; same fixed merge order).  fin_counter: [batch] uint32, zero before the first use, left zero afterwards. */
+  const float* fin_gamma; const float* fin_beta; float fin_eps;
+  float* fin_scale; float* fin_shift; uint32_t* fin_counter;
 } ps_gemm_t;
 
 PS_API int ps_gemm(const ps_gemm_t* d, void* stream);
@@ -138,6 +143,9 @@ typedef struct {
   const float* pro_rowstats; const float* pro_slope;
   float* stats_partials;             /* NULL or [batch, ps_dwconv_stats_slots, 3] */
   int64_t stats_slots;               /* set by the library: row pitch of stats_partials (callers leave 0) */
+  /* optional fused gLN/gGN finalize, as in ps_gemm_t (fin_scale / fin_shift are [batch, C]) */
+  const float* fin_gamma; const float* fin_beta; float fin_eps;
+  float* fin_scale; float* fin_shift; uint32_t* fin_counter;
 } ps_dwconv_t;
 PS_API int ps_dwconv(const ps_dwconv_t* d, void* stream);
 PS_API int64_t ps_dwconv_stats_slots(int64_t T, int64_t C);

@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("epi_act", I32), ("backend", I32), ("epi_slope", P),
         ("residual", P), ("res_batch_stride", I64), ("res_row_stride", I64),
         ("stats_partials", P), ("W_packed", P),
+        ("fin_gamma", P), ("fin_beta", P), ("fin_eps", F32), ("fin_scale", P), ("fin_shift", P), ("fin_counter", P),
     ]
 
 
@@ -45,6 +46,7 @@ class DwconvDesc(C.Structure):
         ("pro_a", P), ("pro_b", P), ("pro_batch_stride", I64),
         ("pro_rowstats", P), ("pro_slope", P),
         ("stats_partials", P), ("stats_slots", I64),
+        ("fin_gamma", P), ("fin_beta", P), ("fin_eps", F32), ("fin_scale", P), ("fin_shift", P), ("fin_counter", P),
     ]
 
 

@@ -16,6 +16,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s);
 bool gemm_tc_eligible(const ps_gemm_t& d);
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s);
+bool tc_pair();
 
 }  // namespace ps
 
@@ -71,11 +72,16 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
   else PS_REQUIRE(d.X2 == nullptr);
   if (d.pro_mode != PS_PRO_NONE && d.pro_act == PS_ACT_PRELU) PS_REQUIRE(d.pro_slope);
   if (d.epi_act == PS_ACT_PRELU) PS_REQUIRE(d.epi_slope);
+  if (d.fin_scale) PS_REQUIRE(d.stats_partials && d.fin_shift && d.fin_counter);
   cudaStream_t s = (cudaStream_t)stream;
-  if (d.backend == PS_GEMM_TCGEN05) {
-    if (!ps::gemm_tc_eligible(d)) return PS_ERR_UNSUPPORTED;
-    return ps::gemm_tc_launch(d, s);
-  }
-  if (d.backend == PS_GEMM_AUTO && ps::gemm_tc_eligible(d)) return ps::gemm_tc_launch(d, s);
-  return ps::gemm_simt_launch(d, s);
+  const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);
+  if (d.backend == PS_GEMM_TCGEN05 && !tc) return PS_ERR_UNSUPPORTED;
+  if (tc && ps::tc_pair()) return ps::gemm_tc_launch(d, s);  // the CTA-pair kernel fuses the statistics finalize
+  // the other kernels leave the finalize to a follow-up launch
+  ps_gemm_t dd = d;
+  dd.fin_scale = nullptr;
+  const int rc = tc ? ps::gemm_tc_launch(dd, s) : ps::gemm_simt_launch(dd, s);
+  if (rc != PS_OK || !d.fin_scale) return rc;
+  return ps_stats_finalize(d.stats_partials, d.batch, ps_gemm_stats_slots(d.rows, d.M), d.fin_gamma, d.fin_beta, d.fin_eps, d.M,
+                           d.fin_scale, d.fin_shift, nullptr, stream);
 }

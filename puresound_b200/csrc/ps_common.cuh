@@ -112,6 +112,61 @@ __device__ __forceinline__ Wf wf_block_reduce(Wf v, Wf* smem) {
   return r;
 }
 
+// ---- gLN / gGN statistics merge of ONE batch item by a group of 256 threads (tid in [0,256)) -----------------
+// Chan-merge of the (count, mean, M2) partials in a fixed order in fp64 -> folded per-channel affine
+//   scale[c] = gamma[c] * rstd,  shift[c] = beta[c] - mean * rstd * gamma[c].
+// BAR = barrier id the 256 threads share (0 = the whole 256-thread CTA).  Partials are read with ld.cg: they may have
+// been written by other CTAs of the same launch (fused finalize), so a stale L1 line must not be used.
+// Used by stats_finalize_kernel and, fused, by the CTA that completes an item's last tile in the producer kernels.
+template <int BAR>
+__device__ __forceinline__ void stats_finalize_item(const float* p, int64_t slots, const float* gamma, const float* beta, float eps,
+                                                    int64_t C, float* scale_b, float* shift_b, float* meanvar_b, int tid,
+                                                    double* sn, double* sm, double* s2) {
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int64_t i = tid; i < slots; i += 256) {
+    const double bn = __ldcg(p + i * 3), bm = __ldcg(p + i * 3 + 1), b2 = __ldcg(p + i * 3 + 2);
+    if (bn > 0.0) {
+      const double nn = n + bn, dlt = bm - mean;
+      mean += dlt * (bn / nn);
+      m2 += b2 + dlt * dlt * n * (bn / nn);
+      n = nn;
+    }
+  }
+  sn[tid] = n; sm[tid] = mean; s2[tid] = m2;
+  asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) {
+      double an = sn[tid], am = sm[tid], a2 = s2[tid];
+      const double bn = sn[tid + o], bm = sm[tid + o], b2 = s2[tid + o];
+      if (bn > 0.0) {
+        const double nn = an + bn, dlt = bm - am;
+        am += dlt * (bn / nn);
+        a2 += b2 + dlt * dlt * an * (bn / nn);
+        an = nn;
+      }
+      sn[tid] = an; sm[tid] = am; s2[tid] = a2;
+    }
+    asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");
+  }
+  const double cnt = sn[0];
+  const double mu = sm[0];
+  const double var = cnt > 0.0 ? s2[0] / cnt : 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float muf = (float)mu;
+  for (int64_t c = tid; c < C; c += 256) {
+    const float g = gamma ? gamma[c] : 1.f;
+    const float bt = beta ? beta[c] : 0.f;
+    const float sc = g * rstd;
+    scale_b[c] = sc;
+    shift_b[c] = fmaf(-muf, sc, bt);
+  }
+  if (meanvar_b && tid == 0) {
+    meanvar_b[0] = muf;
+    meanvar_b[1] = (float)var;
+  }
+  asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");  // scratch may be reused
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

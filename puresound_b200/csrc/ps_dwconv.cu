@@ -276,10 +276,28 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv_tile_kernel(const ps_dwconv
       mine.m2 = fmaxf(ssq - ssum * md, 0.f);
     }
     Wf tot = wf_block_reduce(mine, red);
+    __shared__ int fin_last;
     if (threadIdx.x == 0) {
       const int64_t slot = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
       float* o = d.stats_partials + (b * d.stats_slots + slot) * 3;
       o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
+      if (d.fin_scale) {
+        // fused gLN/gGN finalize: the CTA that writes an item's last partial merges them all (see ps_gemm_pair.cu)
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        fin_last = (atomicAdd(d.fin_counter + b, 1u) + 1u == total) ? 1 : 0;
+      }
+    }
+    if (d.fin_scale) {
+      static_assert(DT_THREADS == 256, "the fused finalize runs on a 256-thread CTA");
+      __shared__ double fin_s[3 * 256];
+      __syncthreads();
+      if (fin_last) {
+        __threadfence();
+        stats_finalize_item<0>(d.stats_partials + b * d.stats_slots * 3, d.stats_slots, d.fin_gamma, d.fin_beta, d.fin_eps, d.C,
+                               d.fin_scale + b * d.C, d.fin_shift + b * d.C, nullptr, (int)threadIdx.x, fin_s, fin_s + 256, fin_s + 512);
+        if (threadIdx.x == 0) d.fin_counter[b] = 0;
+      }
     }
   }
 }
@@ -314,6 +332,7 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
   if (d.pro_mode != PS_PRO_NONE) PS_REQUIRE(d.pro_a && d.pro_b);
   if (d.pro_mode == PS_PRO_ROWNORM) PS_REQUIRE(d.pro_rowstats);
   if (d.pro_act == PS_ACT_PRELU) PS_REQUIRE(d.pro_slope);
+  if (d.fin_scale) PS_REQUIRE(d.stats_partials && d.fin_shift && d.fin_counter);
   if (d.batch > 65535) return PS_ERR_UNSUPPORTED;
   ps::DwGeom g = ps::dw_geom(d.C);
   if (g.vec == 4) {
@@ -351,6 +370,7 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
     }
   }
   dim3 grid((unsigned)ps::cdiv(d.T, ps::DW_TT), (unsigned)ps::cdiv(d.C, g.chan_per_block), (unsigned)d.batch);
+  dd.fin_scale = nullptr;  // the streaming kernel does not fuse the finalize: a follow-up launch below does it
   if (g.vec == 4) {
     if (d.P == 3) ps::dwconv_kernel<4, 3><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
     else ps::dwconv_kernel<4, 0><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
@@ -359,5 +379,8 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
     else ps::dwconv_kernel<1, 0><<<grid, ps::DW_THREADS, 0, s>>>(dd, g.threads_c, g.rows_par);
   }
   PS_CHECK_LAUNCH("dwconv_kernel");
+  if (d.fin_scale)
+    return ps_stats_finalize(d.stats_partials, d.batch, dd.stats_slots, d.fin_gamma, d.fin_beta, d.fin_eps, d.C, d.fin_scale,
+                             d.fin_shift, nullptr, stream);
   return PS_OK;
 }

@@ -53,7 +53,8 @@ struct PairCfg {
   static constexpr int kStageBytes = 2 * PR_XPART + 2 * NB * PR_WBLK;       // NB=2: 40 KB, NB=1: 24 KB
   static constexpr int kWBytes = 2 * NB * PR_WBLK;                          // weight bytes per stage per CTA
   static constexpr int kAccCols = NB * PR_FRAMES;                           // TMEM columns of one accumulator set
-  static constexpr int kSmem = PR_STAGES * kStageBytes + PR_AFF_BYTES + 1024 /*align*/ + 512 /*barriers, scratch*/;
+  static constexpr int kFinBytes = 3 * 256 * 8;                             // fp64 scratch of the fused statistics finalize
+  static constexpr int kSmem = PR_STAGES * kStageBytes + PR_AFF_BYTES + 1024 /*align*/ + 512 /*barriers, scratch*/ + kFinBytes;
 };
 
 // byte offset of 16-byte chunk c of row r in a [rows x 32 k] bf16 tile, 64-byte swizzle (Swizzle<2,4,3>)
@@ -135,6 +136,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
   const uint32_t bar_full = bars, bar_empty = bars + 64, bar_pfull = bars + 128, bar_tfull = bars + 192, bar_tempty = bars + 208;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 224);
   Wf* wf_s = reinterpret_cast<Wf*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 240);  // [NB][epilogue warps]
+  volatile int* fin_flag_s = reinterpret_cast<volatile int*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 232);
+  double* fin_s = reinterpret_cast<double*>(sm + PR_STAGES * STAGE + PR_AFF_BYTES + 512);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
@@ -330,18 +333,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
           if (lane == 0) wf_s[mb * PR_EPI_WARPS + (warp - 2)] = w;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+        const int64_t slots_m = (d.M + 127) / 128;
+        const int64_t slots = n_rt * slots_m;
         if (et < NB && ch0 + et * 256 < d.M) {
           // fixed merge order over the epilogue warps -> deterministic
           const int mb = et;
           Wf tot = wf_s[mb * PR_EPI_WARPS];
 #pragma unroll
           for (int w = 1; w < PR_EPI_WARPS; ++w) tot = wf_merge(tot, wf_s[mb * PR_EPI_WARPS + w]);
-          const int64_t slots_m = (d.M + 127) / 128;
-          const int64_t slots = n_rt * slots_m;
           float* o = d.stats_partials + (tc.b * slots + tc.rt * slots_m + tc.nh * (2 * NB) + mb * 2 + rank) * 3;
           o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
+          if (d.fin_scale) __threadfence();  // visible device-wide before this CTA's count below
         }
         asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+        if (d.fin_scale) {
+          // Fused gLN/gGN finalize: count the slots written for this item; whoever writes the last one merges all of
+          // the item's partials (fixed slot order: the result does not depend on which CTA does it) into the folded
+          // affine the consumer kernel reads - the separate 64-CTA finalize launch after every producer is gone.
+          static_assert(PR_EPI == 256, "the fused finalize runs on the 256 epilogue threads");
+          if (et == 0) {
+            int nblk = 0;
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb) nblk += (ch0 + mb * 256 < d.M) ? 1 : 0;
+            int last = 0;
+            if (nblk > 0) {
+              __threadfence();
+              const unsigned int old = atomicAdd(d.fin_counter + tc.b, (unsigned int)nblk);
+              last = (old + (unsigned int)nblk == (unsigned int)slots) ? 1 : 0;
+            }
+            *fin_flag_s = last;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+          if (*fin_flag_s) {
+            __threadfence();
+            stats_finalize_item<1>(d.stats_partials + tc.b * slots * 3, slots, d.fin_gamma, d.fin_beta, d.fin_eps, d.M,
+                                   d.fin_scale + tc.b * d.M, d.fin_shift + tc.b * d.M, nullptr, et, fin_s, fin_s + 256, fin_s + 512);
+            if (et == 0) d.fin_counter[tc.b] = 0;  // ready for the next launch
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(PR_EPI) : "memory");
+        }
       }
     }
   } else {

@@ -11,51 +11,9 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __rest
                                                              float* __restrict__ scale, float* __restrict__ shift,
                                                              float* __restrict__ meanvar) {
   __shared__ double sn[256], sm[256], s2[256];
-  const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
-  const float* p = partials + b * slots * 3;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int64_t i = tid; i < slots; i += 256) {
-    double bn = p[i * 3], bm = p[i * 3 + 1], b2 = p[i * 3 + 2];
-    if (bn > 0.0) {
-      double nn = n + bn, dlt = bm - mean;
-      mean += dlt * (bn / nn);
-      m2 += b2 + dlt * dlt * n * (bn / nn);
-      n = nn;
-    }
-  }
-  sn[tid] = n; sm[tid] = mean; s2[tid] = m2;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      double an = sn[tid], am = sm[tid], a2 = s2[tid];
-      double bn = sn[tid + o], bm = sm[tid + o], b2 = s2[tid + o];
-      if (bn > 0.0) {
-        double nn = an + bn, dlt = bm - am;
-        am += dlt * (bn / nn);
-        a2 += b2 + dlt * dlt * an * (bn / nn);
-        an = nn;
-      }
-      sn[tid] = an; sm[tid] = am; s2[tid] = a2;
-    }
-    __syncthreads();
-  }
-  const double cnt = sn[0];
-  const double mu = sm[0];
-  const double var = cnt > 0.0 ? s2[0] / cnt : 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float muf = (float)mu;
-  for (int64_t c = tid; c < C; c += 256) {
-    const float g = gamma ? gamma[c] : 1.f;
-    const float bt = beta ? beta[c] : 0.f;
-    const float sc = g * rstd;
-    scale[b * C + c] = sc;
-    shift[b * C + c] = fmaf(-muf, sc, bt);
-  }
-  if (meanvar && tid == 0) {
-    meanvar[b * 2] = muf;
-    meanvar[b * 2 + 1] = (float)var;
-  }
+  stats_finalize_item<0>(partials + b * slots * 3, slots, gamma, beta, eps, C, scale + b * C, shift + b * C,
+                         meanvar ? meanvar + b * 2 : nullptr, (int)threadIdx.x, sn, sm, s2);
 }
 
 __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ rm,

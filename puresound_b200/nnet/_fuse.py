@@ -17,6 +17,15 @@ from .. import ops
 from ..ops import ACT_PRELU, PRO_AFFINE, PRO_ROWNORM, Prologue
 
 
+import os
+
+# Fused statistics finalize (the producer kernel's last CTA per item merges the partials): implemented and parity-tested,
+# but measured SLOWER than the separate 5 us ps_stats_finalize launches under CUDA-graph replay (run 43, same box:
+# cfg2 42.8 vs 39.9 ms, cfg4 7.5 vs 7.1 ms, cfg1 equal) - the per-tile gpu-scope fences cost the producers their L1 hits
+# and the finishing CTA stalls its own pipeline.  Off by default; PS_FUSE_FINALIZE=1 turns it on.
+FUSE_FINALIZE = os.environ.get("PS_FUSE_FINALIZE", "0") == "1"
+
+
 def norm_kind(m: nn.Module) -> str:
     n = type(m).__name__
     if n == "GlobLN":
@@ -37,6 +46,19 @@ def needs_stats(kind: str) -> bool:
     return kind in ("gLN", "gGN")
 
 
+def stats_request(norm: nn.Module) -> dict:
+    """Keyword arguments for the kernel that PRODUCES the tensor `norm` normalises: for gLN / gGN it must emit Welford
+    partials and (fused) the folded affine, so no separate finalize launch follows."""
+    kind = norm_kind(norm)
+    if not FUSE_FINALIZE:
+        return {"want_stats": needs_stats(kind)}
+    if kind == "gLN":
+        return {"want_stats": True, "fin": (norm.gamma, norm.beta, norm.eps)}
+    if kind == "gGN":
+        return {"want_stats": True, "fin": (norm.weight, norm.bias, norm.eps)}
+    return {"want_stats": False}
+
+
 def prelu_slope(m: nn.PReLU) -> torch.Tensor:
     if m.weight.numel() != 1:
         raise NotImplementedError("per-channel PReLU is not used by the reference (nn.PReLU() has one slope)")
@@ -47,6 +69,8 @@ def norm_prologue(norm: nn.Module, raw: torch.Tensor, partials: Optional[torch.T
     """Prologue that makes a consumer see ``PReLU(norm(raw))``.  raw: [B, R, C] frames-major."""
     kind = norm_kind(norm)
     C = raw.shape[-1]
+    if isinstance(partials, ops.FoldedAffine):  # the producer already finalized the statistics (stats_request)
+        return Prologue(PRO_AFFINE, ACT_PRELU, partials.scale, partials.shift, C, None, slope)
     if kind == "gLN":
         scale, shift = ops.stats_finalize(partials, norm.gamma, norm.beta, norm.eps, C)
         return Prologue(PRO_AFFINE, ACT_PRELU, scale, shift, C, None, slope)

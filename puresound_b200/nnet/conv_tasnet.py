@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._fuse import ParamCache, needs_stats, norm_kind, norm_prologue, prelu_slope
+from ._fuse import ParamCache, norm_prologue, prelu_slope, stats_request
 from .lobe.cnn import DepthwiseSeparableConv1d
 from .lobe.norm import get_norm
 
@@ -77,15 +77,15 @@ class TCN(nn.Module):
         elif E != 0:
             raise ValueError("this TCN block expects a conditioning embedding")
         n1, n2, n3 = self.in_conv[1], dsc.depthwise[1], dsc.pointwise[1]
-        u1, p1 = ops.linear(x, w_in, K=C, w_row_stride=C + E, bias_batch=bias_item, want_stats=needs_stats(norm_kind(n1)),
+        u1, p1 = ops.linear(x, w_in, K=C, w_row_stride=C + E, bias_batch=bias_item, **stats_request(n1),
                             w_packed=self._packed("in", self.in_conv[0].weight, H, C, C + E))
         pro1 = norm_prologue(n1, u1, p1, prelu_slope(self.in_conv[2]))
         dw = dsc.depthwise[0]
         u2, p2 = ops.dwconv(u1, dw.weight.view(H, self.kernel), dw.bias, self.kernel, self.dilation, self.causal, pro1,
-                            want_stats=needs_stats(norm_kind(n2)))
+                            **stats_request(n2))
         pro2 = norm_prologue(n2, u2, p2, prelu_slope(dsc.depthwise[2]))
         pw = dsc.pointwise[0]
-        u3, p3 = ops.linear(u2, pw.weight.view(H, H), pro=pro2, bias=pw.bias, want_stats=needs_stats(norm_kind(n3)),
+        u3, p3 = ops.linear(u2, pw.weight.view(H, H), pro=pro2, bias=pw.bias, **stats_request(n3),
                             w_packed=self._packed("pw", pw.weight, H, H, H))
         pro3 = norm_prologue(n3, u3, p3, prelu_slope(dsc.pointwise[2]))
         y, _ = ops.linear(u3, self.out_conv.weight.view(C, H), pro=pro3, bias=self.out_conv.bias, residual=x,

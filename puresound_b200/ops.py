@@ -79,15 +79,46 @@ class Prologue:
 NO_PRO = Prologue()
 
 
+@dataclass
+class FoldedAffine:
+    """gLN / gGN folded to the per-item per-channel affine a consumer prologue applies: scale, shift [B, C]."""
+    scale: Tensor
+    shift: Tensor
+
+
+_fin_counters = {}
+
+
+def _fin_counter(device, batch: int) -> Tensor:
+    """[>= batch] uint32 zeros, one per device: the producer kernels count finished tiles per item in it and leave it zero."""
+    c = _fin_counters.get(device)
+    if c is None or c.numel() < batch:
+        c = torch.zeros(max(batch, 4096), device=device, dtype=torch.int32)
+        _fin_counters[device] = c
+    return c
+
+
+def _set_fin(d, fin, batch: int, Cn: int, device):
+    """fin = (gamma, beta, eps): ask the producer kernel to also emit the folded norm affine (fused ps_stats_finalize)."""
+    gamma, beta, eps = fin
+    scale = torch.empty(batch, Cn, device=device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    d.fin_gamma, d.fin_beta, d.fin_eps = _p(gamma), _p(beta), float(eps)
+    d.fin_scale, d.fin_shift = scale.data_ptr(), shift.data_ptr()
+    d.fin_counter = _fin_counter(device, batch).data_ptr()
+    return FoldedAffine(scale, shift)
+
+
 def gemm(
     X: Tensor, W: Tensor, *, batch: int, rows: int, M: int, K: int,
     x_batch_stride: int, x_row_stride: int, w_row_stride: int,
     pro: Prologue = NO_PRO, bias: Optional[Tensor] = None, bias_batch: Optional[Tensor] = None,
     epi_act: int = ACT_NONE, epi_slope: Optional[Tensor] = None, residual: Optional[Tensor] = None,
     want_stats: bool = False, out: Optional[Tensor] = None, backend: int = GEMM_AUTO,
-    w_packed: Optional[Tensor] = None,
-) -> Tuple[Tensor, Optional[Tensor]]:
-    """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None)."""
+    w_packed: Optional[Tensor] = None, fin=None,
+):
+    """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None) - or, with
+    want_stats and fin=(gamma, beta, eps), (Y, FoldedAffine): the producer also finalizes the gLN/gGN statistics."""
     lib = _lib.load()
     _req(X, "gemm X")
     _dev(W, "gemm W")  # may be a row-strided view (embedding columns of in_conv)
@@ -112,6 +143,7 @@ def gemm(
         d.residual, d.res_batch_stride, d.res_row_stride = residual.data_ptr(), rows * M, M
     d.stats_partials = _p(partials)
     d.W_packed = _p(w_packed)
+    folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
     ev = None
     if gemm_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -121,7 +153,7 @@ def gemm(
         ev[1].record()
         gemm_events.append((ev[0], ev[1], (batch * rows, M, K)))
     _launched()
-    return Y, partials
+    return Y, (folded if folded is not None else partials)
 
 
 def pack_weights(W: Tensor, M: int, K: int, w_row_stride: int) -> Optional[Tensor]:
@@ -181,8 +213,8 @@ def rowstats(x: Tensor, eps: float) -> Tensor:
 
 
 def dwconv(x: Tensor, w: Tensor, bias: Optional[Tensor], P: int, dilation: int, causal: bool, pro: Prologue = NO_PRO,
-           want_stats: bool = False):
-    """x [B, T, C] -> (y [B, T, C], partials)."""
+           want_stats: bool = False, fin=None):
+    """x [B, T, C] -> (y [B, T, C], partials) - or (y, FoldedAffine) with want_stats and fin=(gamma, beta, eps)."""
     lib = _lib.load()
     B, T, Cn = _req(x, "dwconv x").shape
     y = torch.empty_like(x)
@@ -196,9 +228,10 @@ def dwconv(x: Tensor, w: Tensor, bias: Optional[Tensor], P: int, dilation: int, 
     d.pro_a, d.pro_b, d.pro_batch_stride = _p(pro.a), _p(pro.b), pro.batch_stride
     d.pro_rowstats, d.pro_slope = _p(pro.rowstats), _p(pro.slope)
     d.stats_partials = _p(partials)
+    folded = _set_fin(d, fin, B, Cn, x.device) if (want_stats and fin is not None) else None
     _lib.check(lib.ps_dwconv(C.byref(d), _stream()), "ps_dwconv")
     _launched()
-    return y, partials
+    return y, (folded if folded is not None else partials)
 
 
 def rownorm(x: Tensor, w: Optional[Tensor], b: Optional[Tensor], eps: float, res: Optional[Tensor] = None,

@@ -101,6 +101,18 @@ def test_tc_fused_prologue_epilogue_stats(ops):
     # and the two back ends agree with each other
     y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
     check(y, y2.double())
+    # fused finalize: the CTA that completes an item's last tile emits the same folded affine, bit for bit, and leaves
+    # the per-item counters at zero (run twice: the second launch depends on it)
+    gamma, beta = rnd(M, seed=8) + 1.5, rnd(M, seed=9)
+    sc_ref, sh_ref = ops.stats_finalize(part, gamma, beta, 1e-8, M)
+    for _ in range(2):
+        _, fa = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, fin=(gamma, beta, 1e-8),
+                           w_packed=pk, backend=ops.GEMM_TCGEN05)
+        assert torch.equal(fa.scale, sc_ref) and torch.equal(fa.shift, sh_ref)
+    # the exact-fp32 back end has no fused finalize: the library runs the merge as a follow-up launch, same interface
+    _, fa2 = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, fin=(gamma, beta, 1e-8),
+                        backend=ops.GEMM_SIMT)
+    assert (fa2.scale - sc_ref).abs().max() <= 1e-5 * sc_ref.abs().max()
 
 
 def test_tc_weight_columns_view_and_relu(ops):

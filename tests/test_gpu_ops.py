@@ -129,6 +129,13 @@ def test_dwconv(ops, C, T, P, d, causal, mode):
     rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
     close(scale[:, 0], rstd)
     close(shift[:, 0], -mu * rstd, 2e-5)
+    # fused finalize (tiled kernel: last CTA of an item merges; streaming kernel: follow-up launch inside the library):
+    # the same folded affine as the stand-alone merge, twice in a row (the per-item counters must come back to zero)
+    gamma, beta = rnd(C, seed=8) + 1.5, rnd(C, seed=9)
+    sc_ref, sh_ref = ops.stats_finalize(part, gamma, beta, 1e-8, C)
+    for _ in range(2):
+        y2, fa = ops.dwconv(x, w, b, P, d, causal, pro, want_stats=True, fin=(gamma, beta, 1e-8))
+        assert torch.equal(y2, y) and torch.equal(fa.scale, sc_ref) and torch.equal(fa.shift, sh_ref)
 
 
 def test_rownorm_layernorm_residual(ops):
