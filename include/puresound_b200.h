@@ -104,6 +104,10 @@ typedef struct {
    * launch; same fixed merge order).  fin_counter: [batch] uint32, zero before the first use, left zero afterwards. */
   const float* fin_gamma; const float* fin_beta; float fin_eps;
   float* fin_scale; float* fin_shift; uint32_t* fin_counter;
+  /* optional row LayerNorm in the epilogue (ln_eps > 0): Y = residual + LN_M(X W^T + bias) * ln_gamma + ln_beta, the
+   * Linear -> nn.LayerNorm -> + of the DPRNN blocks (dprnn.py:161-163,173-175).  Fused into the tcgen05 kernel when
+   * M == 128, otherwise the library runs ps_rownorm after the GEMM (Y must not alias residual in that case). */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 } ps_gemm_t;
 
 PS_API int ps_gemm(const ps_gemm_t* d, void* stream);

@@ -17,6 +17,7 @@ int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s);
 bool gemm_tc_eligible(const ps_gemm_t& d);
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s);
 bool tc_pair();
+bool gemm_pair_ln_eligible(const ps_gemm_t& d);
 
 }  // namespace ps
 
@@ -74,6 +75,20 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
   if (d.epi_act == PS_ACT_PRELU) PS_REQUIRE(d.epi_slope);
   if (d.fin_scale) PS_REQUIRE(d.stats_partials && d.fin_shift && d.fin_counter);
   cudaStream_t s = (cudaStream_t)stream;
+  if (d.ln_eps > 0.f) {
+    // Linear -> LayerNorm (-> + residual): fused epilogue on the CTA-pair kernel, else GEMM then ps_rownorm in place
+    PS_REQUIRE(!d.stats_partials && d.epi_act == PS_ACT_NONE && d.y_row_stride == d.M && d.y_batch_stride == d.rows * d.M);
+    const bool fuse = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::tc_pair() && ps::gemm_tc_eligible(d) &&
+                      ps::gemm_pair_ln_eligible(d);
+    if (fuse) return ps::gemm_tc_launch(d, s);
+    if (d.backend == PS_GEMM_TCGEN05) return PS_ERR_UNSUPPORTED;
+    PS_REQUIRE(!d.residual || (d.res_row_stride == d.M && d.res_batch_stride == d.rows * d.M && d.residual != d.Y));
+    ps_gemm_t dd = d;
+    dd.ln_eps = 0.f; dd.ln_gamma = nullptr; dd.ln_beta = nullptr; dd.residual = nullptr;
+    const int rc = ps_gemm(&dd, stream);
+    if (rc != PS_OK) return rc;
+    return ps_rownorm(d.Y, d.residual, d.Y, d.batch * d.rows, d.M, d.ln_gamma, d.ln_beta, d.ln_eps, PS_ACT_NONE, nullptr, stream);
+  }
   const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);
   if (d.backend == PS_GEMM_TCGEN05 && !tc) return PS_ERR_UNSUPPORTED;
   if (tc && ps::tc_pair()) return ps::gemm_tc_launch(d, s);  // the CTA-pair kernel fuses the statistics finalize

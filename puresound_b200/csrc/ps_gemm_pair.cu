@@ -119,8 +119,74 @@ __device__ __forceinline__ void epi_chunk(const float (&v)[PR_CW], float bsum, f
   }
 }
 
+// Epilogue chunk with a fused LayerNorm over the 128 channels of a frame (nn.LayerNorm + residual of the DPRNN blocks,
+// dprnn.py:161-163,173-175):  out = residual + (x - mean_f) * rstd_f * gamma[c] + beta[c],  x = acc + bias.
+// A frame's 128 channels are the 128 TMEM lanes of the leader CTA = the four warps (lane quarters) of one epilogue warp
+// group.  Per 16-frame chunk: a reduce-scatter butterfly leaves lane l with the 32-lane sum / sum of squares of frame
+// (l >> 1) & 15 (16 + 16 shuffles instead of 160), the four quarters meet in shared memory (two 128-thread named
+// barriers), 16 threads turn them into (mean, rstd), everyone reads them back as broadcast loads.
+__device__ __forceinline__ float ln_butterfly16(const float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a8[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 8], 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a4[i] = (b3 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? a8[i] : a8[i + 4], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) a2[i] = (b2 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? a4[i] : a4[i + 2], 4);
+  float a1 = (b1 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? a2[0] : a2[1], 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+
+template <bool kRes>
+__device__ __forceinline__ void epi_chunk_ln(float (&v)[PR_CW], float bsum, float gam, float bet, float eps, float* yp, int64_t ystride,
+                                             const float* rp, int64_t rstride, int nj, int lane, int q, int g, float2* part_s, float2* stat_s) {
+  static_assert(PR_CW == 16, "the butterfly is written for 16-frame chunks");
+  float r[PR_CW];
+  if constexpr (kRes) {
+    const float* p = rp;
+#pragma unroll
+    for (int j = 0; j < PR_CW; ++j) {
+      r[j] = j < nj ? __ldg(p) : 0.f;
+      p += rstride;
+    }
+  }
+  float sq[PR_CW];
+#pragma unroll
+  for (int j = 0; j < PR_CW; ++j) {
+    v[j] += bsum;
+    sq[j] = v[j] * v[j];
+  }
+  const float s1 = ln_butterfly16(v, lane), s2 = ln_butterfly16(sq, lane);
+  const int f = (lane >> 1) & 15;
+  if ((lane & 1) == 0) part_s[(g * 4 + q) * 16 + f] = make_float2(s1, s2);
+  asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
+  if (q == 0 && lane < 16) {
+    float S = 0.f, SS = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float2 t = part_s[(g * 4 + w) * 16 + lane];
+      S += t.x;
+      SS += t.y;
+    }
+    const float mean = S * (1.f / 128.f);
+    const float var = fmaxf(SS * (1.f / 128.f) - mean * mean, 0.f);
+    stat_s[g * 16 + lane] = make_float2(mean, rsqrtf(var + eps));
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
+#pragma unroll
+  for (int j = 0; j < PR_CW; ++j) {
+    const float2 st = stat_s[g * 16 + j];
+    float o = fmaf((v[j] - st.x) * st.y, gam, bet);
+    if constexpr (kRes) o += r[j];
+    if (j < nj) *yp = o;
+    yp += ystride;
+  }
+}
+
 // PRO: PS_PRO_NONE, PS_PRO_AFFINE (norm affine + PReLU) or PS_PRO_MASK (x * act(x2): mask apply in front of the decoder)
-template <int PRO, int NB>
+template <int PRO, int NB, bool kLN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
   using Cfg = PairCfg<NB>;
@@ -301,7 +367,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
           const bool first = cnt[mb] == 0.f;
           cnt[mb] += (float)(nj < PR_CW ? nj : PR_CW);
           if (dbg & 4) continue;
-          if (nj >= PR_CW) {
+          if constexpr (kLN) {
+            float2* part_s = reinterpret_cast<float2*>(fin_s);  // [2 groups][4 quarters][16 frames]; then [2][16] (mean, rstd)
+            float2* stat_s = part_s + 2 * 4 * 16;
+            const float gam = d.ln_gamma ? __ldg(d.ln_gamma + ch) : 1.f, bet = d.ln_beta ? __ldg(d.ln_beta + ch) : 0.f;
+            if (rp) epi_chunk_ln<true>(v, bsum, gam, bet, d.ln_eps, yp, ystride, rp, rstride, nj, lane, q, g, part_s, stat_s);
+            else epi_chunk_ln<false>(v, bsum, gam, bet, d.ln_eps, yp, ystride, rp, rstride, nj, lane, q, g, part_s, stat_s);
+          } else if (nj >= PR_CW) {
             if (rp) {
               if (epi_act == PS_ACT_NONE) epi_chunk<PS_ACT_NONE, true, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb]);
               else epi_chunk<-1, true, true>(v, bsum, eslope, yp, ystride, rp, rstride, PR_CW, first, piv[mb], ssum[mb], ssq[mb], epi_act);
@@ -575,22 +647,26 @@ int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* pack
   return PS_OK;
 }
 
-template <int PRO, int NB>
+template <int PRO, int NB, bool kLN = false>
 static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
   if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<PRO, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<PRO, NB, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_pair_kernel)"); return PS_ERR_CUDA; }
   }
   static int dbg = -1;  // PS_PAIR_DBG: bottleneck experiments only (1 no weight copies, 2 no activation loads, 4 no epilogue, 8 no transform)
   if (dbg < 0) { const char* e = getenv("PS_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
-  gemm_pair_kernel<PRO, NB><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
+  gemm_pair_kernel<PRO, NB, kLN><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
   PS_CHECK_LAUNCH("gemm_pair_kernel");
   return PS_OK;
 }
 
+bool gemm_pair_ln_eligible(const ps_gemm_t& d) {
+  return d.M == 128 && d.pro_mode == PS_PRO_NONE && d.epi_act == PS_ACT_NONE && !d.stats_partials && !d.bias_batch;
+}
+
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   static int sm_count[64] = {0};
-  static bool attr_set[64][4][2] = {};
+  static bool attr_set[64][5][2] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
@@ -600,13 +676,16 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   }
   const int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
   const int nb = pair_nb(d.M);
-  const bool set_attr = !attr_set[dev][pro][nb - 1];
-  attr_set[dev][pro][nb - 1] = true;
+  const bool ln = d.ln_eps > 0.f;  // fused LayerNorm epilogue: M == 128, no prologue (checked by gemm_pair_ln_eligible)
+  const int ai = ln ? 4 : pro;
+  const bool set_attr = !attr_set[dev][ai][nb - 1];
+  attr_set[dev][ai][nb - 1] = true;
   const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
   const int64_t max_pairs = sm_count[dev] / 2;
   const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+  if (ln) return launch_pair<PS_PRO_NONE, 1, true>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
   if (nb == 2) {
     if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
     if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);

@@ -118,9 +118,11 @@ class DPRNN(nn.Module):
                             gx_interleaved=w_hh_pk is not None, **geo)
         proj_pk = self._cache.get(tag + "_proj", [proj.weight],
                                   lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
-        y, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk)
-        new = ops.rownorm(y.view(N, S, K, Cn), norm.weight, norm.bias, norm.eps, res=out)
-        return new, state
+        # Linear -> LayerNorm -> + residual in one kernel (LayerNorm in the GEMM epilogue when Cn == 128; otherwise the
+        # library runs the row-norm kernel after the GEMM)
+        new, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk,
+                            ln=(norm.weight, norm.bias, norm.eps), residual=out.view(1, P, Cn))
+        return new.view(N, S, K, Cn), state
 
     def _blocks(self, seg: torch.Tensor, film_embed, inits, collect_hidden: bool):
         out = seg

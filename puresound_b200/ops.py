@@ -115,10 +115,11 @@ def gemm(
     pro: Prologue = NO_PRO, bias: Optional[Tensor] = None, bias_batch: Optional[Tensor] = None,
     epi_act: int = ACT_NONE, epi_slope: Optional[Tensor] = None, residual: Optional[Tensor] = None,
     want_stats: bool = False, out: Optional[Tensor] = None, backend: int = GEMM_AUTO,
-    w_packed: Optional[Tensor] = None, fin=None,
+    w_packed: Optional[Tensor] = None, fin=None, ln=None,
 ):
     """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None) - or, with
-    want_stats and fin=(gamma, beta, eps), (Y, FoldedAffine): the producer also finalizes the gLN/gGN statistics."""
+    want_stats and fin=(gamma, beta, eps), (Y, FoldedAffine): the producer also finalizes the gLN/gGN statistics.
+    ln=(weight, bias, eps): Y = residual + LayerNorm_M(X W^T + bias) (fused epilogue on the tcgen05 kernel when M == 128)."""
     lib = _lib.load()
     _req(X, "gemm X")
     _dev(W, "gemm W")  # may be a row-strided view (embedding columns of in_conv)
@@ -144,6 +145,8 @@ def gemm(
     d.stats_partials = _p(partials)
     d.W_packed = _p(w_packed)
     folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
+    if ln is not None:
+        d.ln_gamma, d.ln_beta, d.ln_eps = _p(ln[0]), _p(ln[1]), float(ln[2])
     ev = None
     if gemm_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))

@@ -81,6 +81,23 @@ def test_tc_overlapping_rows_framed_view(ops):
     check(y, frames.double() @ w.double().t())
 
 
+@pytest.mark.parametrize("with_res", [True, False])
+def test_tc_layernorm_epilogue(ops, with_res):
+    """Linear -> nn.LayerNorm -> + residual of the DPRNN blocks (dprnn.py:161-163,173-175) in the GEMM epilogue: the 128
+    channels of a frame are the 128 TMEM lanes of the leader CTA.  Ragged last tile; SIMT back end = GEMM + row-norm."""
+    B, Rr, M, K = 2, 333, 128, 256
+    x, w, bias = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1), rnd(M, seed=3)
+    g, bt, res = rnd(M, seed=4) + 1.5, rnd(M, seed=5), rnd(B, Rr, M, seed=6)
+    pk = ops.pack_weights(w, M, K, K)
+    kw = dict(bias=bias, ln=(g, bt, 1e-5), residual=res if with_res else None)
+    y, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05, **kw)
+    lin = x.double() @ w.double().t() + bias.double()
+    ref = F.layer_norm(lin, (M,), g.double(), bt.double(), 1e-5) + (res.double() if with_res else 0)
+    check(y, ref, 1e-4)  # LayerNorm divides by the row's std (~0.5 here): the GEMM's 5e-5 grows accordingly
+    y2, _ = ops.linear(x, w, backend=ops.GEMM_SIMT, **kw)
+    check(y2, ref, 1e-5)
+
+
 def test_tc_fused_prologue_epilogue_stats(ops):
     B, Rr, M, K = 3, 413, 512, 512
     x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
