@@ -105,6 +105,28 @@ __device__ __forceinline__ float lt_rcp(float x) {
 }
 __device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.f + lt_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, lt_rcp(1.f + lt_ex2(-2.8853900817779268f * x)), -1.f); }
+// clamp to [-lim, lim] that PROPAGATES NaN (fminf/fmaxf would swallow it; the reference's look-ahead probe feeds inf/NaN)
+__device__ __forceinline__ float lt_clamp(float x, float lim) {
+  float y;
+  asm("{\n\t.reg .f32 t;\n\tmax.NaN.f32 t, %1, %2;\n\tmin.NaN.f32 %0, t, %3;\n\t}" : "=f"(y) : "f"(x), "f"(-lim), "f"(lim));
+  return y;
+}
+// One LSTM cell with 7 MUFU instead of 10: with Ex = exp(-x) the three sigmoids and two tanh share reciprocals,
+//   c' = f c + i g = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ef)(1+Ei)(1+Eg)],   Eg = exp(-2 g)
+//   h  = o tanh(c') = (1 - Ec) / [(1+Eo)(1+Ec)],                                  Ec = exp(-2 c')
+// Pre-activations are clamped to +-25 (+-12.5 under tanh): exp(25)^3 = 3.7e32 stays finite in fp32, and the clamp moves
+// a gate by < 1.4e-11.  The XU pipe (16 lanes / cycle / SM) was the floor of the gate phase.
+__device__ __forceinline__ float lt_cell(float pi, float pf, float pg, float po, float& c) {
+  constexpr float L2E = 1.4426950408889634f;
+  const float Ei = lt_ex2(-L2E * lt_clamp(pi, 25.f)), Ef = lt_ex2(-L2E * lt_clamp(pf, 25.f));
+  const float Eg = lt_ex2(-2.f * L2E * lt_clamp(pg, 12.5f)), Eo = lt_ex2(-L2E * lt_clamp(po, 25.f));
+  const float A = 1.f + Ei, B = 1.f + Eg, F = 1.f + Ef;
+  const float AB = A * B;
+  const float cn = fmaf(c, AB, (2.f - B) * F) * lt_rcp(F * AB);
+  c = cn;
+  const float Cc = 1.f + lt_ex2(-2.f * L2E * lt_clamp(cn, 12.5f));
+  return (2.f - Cc) * lt_rcp((1.f + Eo) * Cc);
+}
 
 template <bool kGxi>
 __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d) {
@@ -297,13 +319,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         float h[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          const float ig = lt_sigmoid(a[0][j] + gx[0][j]);
-          const float fg = lt_sigmoid(a[1][j] + gx[1][j]);
-          const float gg = lt_tanh(a[2][j] + gx[2][j]);
-          const float og = lt_sigmoid(a[3][j] + gx[3][j]);
-          const float cn = fmaf(fg, cu[(j0 + j) * LT_H], ig * gg);
-          cu[(j0 + j) * LT_H] = cn;
-          h[j] = og * lt_tanh(cn);
+          float cv = cu[(j0 + j) * LT_H];
+          h[j] = lt_cell(a[0][j] + gx[0][j], a[1][j] + gx[1][j], a[2][j] + gx[2][j], a[3][j] + gx[3][j], cv);
+          cu[(j0 + j) * LT_H] = cv;
           if (j0 + j < nvalid) {
             outu[poso_s[s0 + j0 + j] + toffo] = h[j];
             if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + q0 + s0 + j0 + j) * LT_H + u] = h[j];
