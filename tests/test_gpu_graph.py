@@ -1,0 +1,78 @@
+"""CUDA-graph replay behind SoTaskWrapModule.inference(): same results as eager launches for changing inputs, host and
+device tensors, and invalidation when a parameter changes (load_state_dict / in-place update)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    from puresound_b200 import ops, recipes, testing
+
+    ops.require_device()
+    torch.manual_seed(0)
+    m = recipes.baseline_config("cfg1").eval()
+    testing.perturb_(m, seed=1)
+    return m.to("cuda")
+
+
+def _eager(model, x):
+    g, model.use_cuda_graph = model.use_cuda_graph, False
+    try:
+        return model.inference(x)
+    finally:
+        model.use_cuda_graph = g
+
+
+def test_graph_replay_matches_eager_for_new_inputs(model):
+    from puresound_b200 import ops, testing
+
+    model.use_cuda_graph = True
+    model._graphs.clear()
+    xs = [testing.noisy_speech(2, 16000, seed=s)[0] for s in range(5)]
+    launches = []
+    for i, x in enumerate(xs):
+        n0 = ops.launch_count
+        y = model.inference(x.cuda() if i % 2 else x)  # host and device inputs alternate
+        launches.append(ops.launch_count - n0)
+        assert y.is_cuda == bool(i % 2)
+        assert torch.equal(y.cpu(), _eager(model, x).cpu()), f"call {i}"
+    # call 0 runs eagerly, call 1 captures (its kernels are recorded, not counted twice), calls 2.. only replay
+    assert launches[0] > 100 and launches[2] == 0 and launches[4] == 0
+
+
+def test_graph_is_dropped_when_a_parameter_changes(model):
+    from puresound_b200 import testing
+
+    model.use_cuda_graph = True
+    x = testing.noisy_speech(1, 16000, seed=11)[0].cuda()
+    for _ in range(3):
+        y0 = model.inference(x)
+    p = model.masker.tcn_list[0][0].out_conv.weight
+    with torch.no_grad():
+        p.mul_(1.5)
+    try:
+        y1 = model.inference(x)
+        assert not torch.equal(y0, y1)
+        assert torch.equal(y1, _eager(model, x))
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        for _ in range(3):
+            model.inference(x)  # captured again with the new weights
+        model.load_state_dict(sd)  # copy_ into the same storage bumps the version counters
+        assert torch.equal(model.inference(x), y1)
+    finally:
+        with torch.no_grad():
+            p.div_(1.5)
+
+
+def test_input_shape_slots_are_bounded(model):
+    from puresound_b200 import testing
+
+    model.use_cuda_graph = True
+    for L in (8000, 9000, 10000, 11000):
+        x = testing.noisy_speech(1, L, seed=L)[0].cuda()
+        for _ in range(3):
+            y = model.inference(x)
+        assert torch.equal(y, _eager(model, x))
+    assert len(model._graphs) <= model._GRAPH_SLOTS
