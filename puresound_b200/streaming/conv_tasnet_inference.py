@@ -35,6 +35,8 @@ from ..ops import ACT_NONE, ACT_PRELU, ACT_RELU, ACT_SIGMOID, PRO_AFFINE, PRO_MA
 class StreamingConvTasNet(ConvTasNet):
     """Same constructor as ``ConvTasNet``; requires ``causal=True`` and per-frame norms (cLN or bN1d)."""
 
+    TC_MIN_STREAMS = 64  # concurrent streams from which the per-hop 1x1 convs run on tcgen05
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         if not self.causal:
@@ -78,7 +80,13 @@ class StreamingConvTasNet(ConvTasNet):
         if embed_bias is not None or E != 0:
             raise NotImplementedError("conditioned streaming blocks are a 'next' row (SURVEY.md 8f)")
         xin = x.view(1, S, Cc)
-        u1, _ = ops.linear(xin, blk.in_conv[0].weight.view(H, Cc), K=Cc, w_row_stride=Cc)
+        # with enough concurrent streams a hop is a [S x 512 x 512] GEMM worth the tensor cores (3xBF16, as offline);
+        # few streams keep the exact-fp32 latency tile (the CTA-pair kernel has ~10 us of fixed cost)
+        tc = S >= self.TC_MIN_STREAMS
+        pk_in = blk._packed("in", blk.in_conv[0].weight, H, Cc, Cc + E) if tc else None
+        pk_pw = blk._packed("pw", dsc.pointwise[0].weight, H, H, H) if tc else None
+        pk_out = blk._packed("out", blk.out_conv.weight, Cc, H, H) if tc else None
+        u1, _ = ops.linear(xin, blk.in_conv[0].weight.view(H, Cc), K=Cc, w_row_stride=Cc, w_packed=pk_in)
         u2 = torch.empty(S, H, device=x.device, dtype=torch.float32)
         d = _lib.StreamDwDesc()
         d.streams, d.C, d.P, d.dilation = S, H, blk.kernel, blk.dilation
@@ -97,7 +105,7 @@ class StreamingConvTasNet(ConvTasNet):
         _lib.check(_lib.load().ps_stream_dwconv_step(C.byref(d), torch.cuda.current_stream().cuda_stream), "ps_stream_dwconv_step")
         ops._launched()
         pw = dsc.pointwise[0]
-        u3, _ = ops.linear(u2.view(1, S, H), pw.weight.view(H, H), bias=pw.bias)
+        u3, _ = ops.linear(u2.view(1, S, H), pw.weight.view(H, H), bias=pw.bias, w_packed=pk_pw)
         slope3 = prelu_slope(dsc.pointwise[2])
         if kind == 0:
             u3n = ops.rownorm(u3, n3.gamma, n3.beta, n3.eps, act=ACT_PRELU, slope=slope3)
@@ -106,7 +114,7 @@ class StreamingConvTasNet(ConvTasNet):
             u3n = u3
             f = st["folded"][j]
             pro = Prologue(PRO_AFFINE, ACT_PRELU, f[2][0], f[2][1], 0, None, slope3)
-        y, _ = ops.linear(u3n, blk.out_conv.weight.view(Cc, H), pro=pro, bias=blk.out_conv.bias, residual=xin)
+        y, _ = ops.linear(u3n, blk.out_conv.weight.view(Cc, H), pro=pro, bias=blk.out_conv.bias, residual=xin, w_packed=pk_out)
         return y.view(S, Cc)
 
     def step_frame_cl(self, x: torch.Tensor, embed: Optional[torch.Tensor] = None) -> torch.Tensor:

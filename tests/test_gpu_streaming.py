@@ -69,6 +69,20 @@ def test_streaming_cfg5_full_width():
     assert err <= 1e-3
 
 
+def test_streaming_many_streams_tensor_core_path():
+    """From TC_MIN_STREAMS concurrent streams on, the per-hop 1x1 convs run on the CTA-pair tcgen05 kernel (3xBF16):
+    64 streams x 24 hops of the cfg-5 width against the offline oracle, north_star tolerance (1e-3)."""
+    m = build("cLN", 320, 160, 512, 512, 4, 1, seed=2)
+    assert StreamingConvTasNet.TC_MIN_STREAMS <= 64
+    wav = testing.noisy_speech(64, 160 * 25, seed=12)[0]
+    ref = R.inference(m.state_dict(), D.describe(m), wav)
+    y = run_stream(m.cuda(), wav, True)
+    n = y.shape[1]
+    err = (y - ref[:, :n]).abs().max().item()
+    print(f"64-stream tensor-core hop vs offline oracle: max|err|={err:.3e}")
+    assert err <= 1e-3
+
+
 def test_streaming_guards():
     with pytest.raises(AssertionError):
         StreamingConvTasNet(16, 0, tcn_dim=8, per_tcn_stack=1, repeat_tcn=1, tcn_with_embed=[0], causal=False)
