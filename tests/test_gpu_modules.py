@@ -100,3 +100,22 @@ def test_wrappers_inference(golden):
         close(yh, g["y"], 1e-4)
         if "dvec" in g:
             close(m.inference_tse_embedding(cu(g["enroll"])), g["dvec"], 5e-5)
+
+
+@pytest.mark.parametrize("name,lookahead,receptive", [
+    ("td_tse_conv_tasnet_v0_causal", "16", "24496"),   # 1530 frames x 16 + 16
+    ("veve_dprnn_v0_causal", "16", "infinite"),        # egs/tse/model.py:609-613
+])
+def test_verbose_probe_known_answers(name, lookahead, receptive, capsys):
+    """The reference's `_verbose()` probe (base_nn.py:740-777) feeds +inf into half of a 10 s signal and reads look-ahead /
+    receptive field off the first / last NaN of the output: every kernel on the path (tcgen05 GEMMs, depthwise conv,
+    norms, LSTM, overlap-add, the CUDA-graph replay) must propagate Inf/NaN exactly like ATen for the printed numbers to
+    match the recipe docstrings."""
+    from puresound_b200 import recipes
+
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).to("cuda")
+    m._verbose()
+    out = capsys.readouterr().out
+    assert f"Lookahead(samples): {lookahead}" in out, out
+    assert f"Receptive Fields(samples): {receptive}" in out, out
