@@ -64,6 +64,26 @@ def describe_masker(m: nn.Module) -> dict:
             "block_with_embed": None if m.block_with_embed is None else [bool(b) for b in m.block_with_embed],
             "embedding_free_tse": bool(m.embedding_free_tse),
         }
+    if n in ("SkiM", "StreamingSkiM"):
+        fusion = None
+        if m.embed_dim != 0:
+            kinds = {type(f).__name__ for f in m.seg_input_fusion if f is not None}
+            if kinds - {"FiLM"}:
+                raise NotImplementedError(f"SkiM embedding fusion {kinds}")
+            fusion = "FiLM"
+        return {
+            "type": "SkiM",
+            "input_size": m.seg_lstm[0].input_size,
+            "hidden_size": m.hidden_size,
+            "n_blocks": m.n_blocks,
+            "seg_size": m.seg_size,
+            "seg_overlap": bool(m.seg_overlap),
+            "causal": bool(m.causal),
+            "embed_dim": m.embed_dim,
+            "embed_norm": bool(m.embed_norm),
+            "embed_fusion": fusion,
+            "block_with_embed": None if m.block_with_embed is None else [bool(b) for b in m.block_with_embed],
+        }
     raise NotImplementedError(n)
 
 

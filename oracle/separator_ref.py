@@ -355,6 +355,84 @@ def dprnn(sd: SD, p: str, x: Tensor, embed: Optional[Tensor], a: dict, fast_lstm
 
 
 # --------------------------------------------------------------------------- #
+# F2  SkiM (skipping-memory LSTM)                       puresound/nnet/skim.py
+# --------------------------------------------------------------------------- #
+def _skim_split(x: Tensor, K: int) -> Tuple[Tensor, int]:
+    """SkiM.split, skim.py:349-383.  [N,C,T] -> ([N,S,K,C], rest): the same construction as SplitMerge.split."""
+    return split_overlap(x, K)
+
+
+def _seg_lstm(sd: SD, p: str, x: Tensor, h, c, bi: bool, fast_lstm: bool):
+    """SegLSTM.forward, skim.py:198-229: x [NS,K,C], (h,c) [D,NS,H] or None -> (x + LN(proj(LSTM(x)))), h_n, c_n."""
+    H = sd[p + "lstm.weight_hh_l0"].shape[1]
+    D = 2 if bi else 1
+    if h is None:
+        h = x.new_zeros(D, x.shape[0], H)
+    if c is None:
+        c = x.new_zeros(D, x.shape[0], H)
+    y, (hn, cn) = lstm(sd, p + "lstm.", x, bi, (h, c), fast_lstm)
+    y = F.linear(y, sd[p + "proj.weight"], sd[p + "proj.bias"])
+    y = F.layer_norm(y, (x.shape[2],), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    return x + y, hn, cn
+
+
+def _mem_lstm(sd: SD, p: str, h: Tensor, c: Tensor, causal: bool, fast_lstm: bool):
+    """MemLSTM.forward (streaming=False), skim.py:46-117: h, c [N,S,D,H] -> ([D,NS,H], [D,NS,H]) for the next SegLSTM;
+    in the causal setting segment s receives the memory of segment s-1 (zeros for the first)."""
+    N, S, D, H = h.shape
+    out = []
+    for name, v in (("h", h), ("c", c)):
+        v = v.reshape(N, S, D * H)
+        y, _ = lstm(sd, f"{p}{name}_net.", v, not causal, None, fast_lstm)
+        y = F.linear(y.reshape(N * S, -1), sd[f"{p}{name}_proj.weight"], sd[f"{p}{name}_proj.bias"]).reshape(N, S, -1)
+        v = v + F.layer_norm(y, (D * H,), sd[f"{p}{name}_norm.weight"], sd[f"{p}{name}_norm.bias"], 1e-5)
+        v = v.reshape(N * S, D, H).transpose(1, 0).contiguous()  # [D, NS, H]
+        if causal:
+            z = torch.zeros_like(v)
+            z[:, 1:, :] = v[:, :-1, :]
+            v = z
+        out.append(v)
+    return out[0], out[1]
+
+
+def skim(sd: SD, p: str, x: Tensor, embed: Optional[Tensor], a: dict, fast_lstm: bool = True) -> Tensor:
+    """SkiM.forward, skim.py:414-469.  x [N,C,T], embed [N,E] -> [N,C_out,T]."""
+    if a["embed_norm"] and embed is not None:
+        embed = F.normalize(embed, p=2, dim=1)
+    K, bi = a["seg_size"], not a["causal"]
+    N, C, T = x.shape
+    if a["seg_overlap"]:
+        seg, rest = _skim_split(x, K)
+    else:
+        xt = x.permute(0, 2, 1)
+        rest = K - T % K
+        if rest > 0:
+            xt = F.pad(xt, (0, 0, 0, rest))
+        seg = xt.reshape(N, -1, K, C)
+    S = seg.shape[1]
+    e = None
+    if embed is not None:
+        e = embed.unsqueeze(1).repeat(1, S, 1).reshape(N * S, -1)
+    out = seg.reshape(N * S, K, C).contiguous()
+    h = c = None
+    H = a["hidden_size"]
+    for i in range(a["n_blocks"]):
+        if e is not None and a["block_with_embed"][i]:
+            out = film(sd, f"{p}seg_input_fusion.{i}.", out.transpose(1, 2), e).transpose(1, 2)
+        out, h, c = _seg_lstm(sd, f"{p}seg_lstm.{i}.", out, h, c, bi, fast_lstm)
+        if i < a["n_blocks"] - 1:
+            h = h.reshape(-1, N, S, H).permute(1, 2, 0, 3)
+            c = c.reshape(-1, N, S, H).permute(1, 2, 0, 3)
+            h, c = _mem_lstm(sd, f"{p}mem_lstm.{i}.", h, c, a["causal"], fast_lstm)
+    if a["seg_overlap"]:
+        out = merge_overlap(out.reshape(N, S, K, C), rest)
+    else:
+        out = out.reshape(N, S * K, C)[:, :T, :].transpose(1, 2)
+    out = F.prelu(out, sd[p + "output_fc.0.weight"])
+    return F.conv1d(out, sd[p + "output_fc.1.weight"], sd[p + "output_fc.1.bias"])
+
+
+# --------------------------------------------------------------------------- #
 # A10  speaker path            lobe/trivial.py:21-58, lobe/pooling.py:58-126
 # --------------------------------------------------------------------------- #
 def magnitude(x: Tensor, drop_first: bool = True, log1p: bool = False) -> Tensor:
@@ -474,6 +552,8 @@ def masker_forward(sd: SD, p: str, mcfg: dict, x: Tensor, dvec: Optional[Tensor]
         return conv_tasnet(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "DPRNN":
         return dprnn(sd, p, x, dvec, mcfg, fast_lstm)
+    if mcfg["type"] == "SkiM":
+        return skim(sd, p, x, dvec, mcfg, fast_lstm)
     raise NotImplementedError(mcfg["type"])
 
 

@@ -15,6 +15,7 @@ from .nnet.dprnn import DPRNN
 from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from .nnet.lobe.pooling import AttentiveStatisticsPooling
 from .nnet.lobe.trivial import Magnitude
+from .nnet.skim import SkiM
 
 
 def _td_speaker_net():
@@ -43,6 +44,17 @@ def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Option
             masker=DPRNN(input_size=128, hidden_size=64, output_size=128, n_blocks=6, seg_size=20, seg_overlap=False, causal=True,
                          embed_dim=0, embed_norm=False, block_with_embed=(False,) * 6, embedding_free_tse=True),
             speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", embedding_free_tse=True, **kwargs)
+    if name in ("tse_skim_v0", "tse_skim_v0_causal"):
+        # egs/tse/model.py:371-463 (the causal one is the reference's demo model)
+        causal = name.endswith("_causal")
+        return SoTaskWrapModule(
+            encoder=FreeEncDec(win_length=32, hop_length=16, laten_length=128, output_active=True),
+            masker=SkiM(input_size=128, hidden_size=256, output_size=128, n_blocks=4, seg_size=150, seg_overlap=False, causal=causal,
+                        embed_dim=192, embed_norm=True, block_with_embed=[1, 1, 1, 1], embed_fusion="FiLM"),
+            speaker_net=nn.ModuleList(
+                [TCN(128, 256, 3, dilation=2 ** i, causal=False, tcn_norm="gLN", dconv_norm="gGN") for i in range(5)]
+                + [AttentiveStatisticsPooling(128, 128), nn.Conv1d(128 * 2, 192, 1, bias=False)]),
+            loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", **kwargs)
     raise NameError
 
 
@@ -72,6 +84,6 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN",
                        dconv_norm="cLN", causal=True),
             mask_constraint="ReLU", verbose=verbose)
-    if name == "veve_dprnn_v0_causal":
+    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal"):
         return init_model(name, None, None, verbose=verbose)
     raise NameError(name)

@@ -7,6 +7,7 @@ from puresound_b200.nnet.dprnn import DPRNN
 from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
 from puresound_b200.nnet.lobe.trivial import Magnitude
+from puresound_b200.nnet.skim import SkiM
 
 
 def tcn(c):
@@ -26,6 +27,10 @@ def masker(c):
     if t == "ConvTasNet":
         return ConvTasNet(**c)
     out = c.pop("output_size", c["input_size"])
+    if t == "SkiM":
+        return SkiM(c["input_size"], c["hidden_size"], out, n_blocks=c["n_blocks"], seg_size=c["seg_size"], seg_overlap=c["seg_overlap"],
+                    causal=c["causal"], embed_dim=c["embed_dim"], embed_norm=c["embed_norm"], embed_fusion=c["embed_fusion"],
+                    block_with_embed=c["block_with_embed"])
     return DPRNN(c["input_size"], c["hidden_size"], out, n_blocks=c["n_blocks"], seg_size=c["seg_size"], seg_overlap=c["seg_overlap"],
                  causal=c["causal"], embed_dim=c["embed_dim"], embed_norm=c["embed_norm"], block_with_embed=c["block_with_embed"],
                  embedding_free_tse=c["embedding_free_tse"])

@@ -41,6 +41,7 @@ from puresound.nnet.dprnn import DPRNN  # noqa: E402
 from puresound.nnet.lobe.encoder import ConvEncDec, FreeEncDec  # noqa: E402
 from puresound.nnet.lobe.pooling import AttentiveStatisticsPooling  # noqa: E402
 from puresound.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge  # noqa: E402
+from puresound.nnet.skim import MemLSTM, SegLSTM, SkiM  # noqa: E402
 
 from oracle import describe as D  # noqa: E402
 from puresound_b200 import testing as T  # noqa: E402
@@ -288,9 +289,69 @@ def full_pins():
         json.dump(pins, fh)
 
 
+def _ref_init_model(name):
+    spec = importlib.util.spec_from_file_location("ref_tse_model", os.path.join(REF, "egs/tse/model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return quiet(mod.init_model, name, None, None, verbose=False)
+
+
+@torch.no_grad()
+def skim_cases():
+    """SkiM: small variants of the masker and of its two cells, and a full-size pin of the
+    reference's demo recipe ``tse_skim_v0_causal`` (egs/tse/model.py:418-463).  Written to their own files so the
+    vectors generated earlier stay byte-identical."""
+    cases = {}
+    for tag, kw in {
+        "causal_film": dict(n_blocks=4, seg_size=10, seg_overlap=False, causal=True, embed_dim=6, embed_norm=True,
+                            embed_fusion="FiLM", block_with_embed=[1, 1, 0, 1]),
+        "bi_overlap": dict(n_blocks=3, seg_size=10, seg_overlap=True, causal=False, embed_dim=0),
+        "causal_overlap": dict(n_blocks=2, seg_size=8, seg_overlap=True, causal=True, embed_dim=0),
+        "bi_exact": dict(n_blocks=2, seg_size=10, seg_overlap=False, causal=False, embed_dim=0),  # T % K == 0: whole extra segment
+    }.items():
+        torch.manual_seed(21)
+        m = T.perturb_(SkiM(16, 12, 16, **kw).eval(), seed=22)
+        Tn = 60 if tag == "bi_exact" else 57
+        x = rnd(2, 16, Tn, seed=23)
+        e = rnd(2, 6, seed=24) if kw.get("embed_dim") else None
+        cases[tag] = {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e)}
+    # the cells on their own, with incoming states (what test/test_streaming.py:10-59 exercises upstream)
+    torch.manual_seed(25)
+    seg = T.perturb_(SegLSTM(16, 12, causal=True, dropout=0.0).eval(), seed=26)
+    x, h, c = rnd(5, 10, 16, seed=27), rnd(1, 5, 12, seed=28), rnd(1, 5, 12, seed=29)
+    y, hn, cn = seg(x, h, c)
+    cases["seg_cell"] = {"sd": sd_of(seg), "x": x, "h": h, "c": c, "y": y, "hn": hn, "cn": cn}
+    for tag, causal in (("mem_cell_causal", True), ("mem_cell_bi", False)):
+        torch.manual_seed(30)
+        mem = T.perturb_(MemLSTM(12, causal=causal, dropout=0.0).eval(), seed=31)
+        Dn = 1 if causal else 2
+        h, c = rnd(2, 7, Dn, 12, seed=32), rnd(2, 7, Dn, 12, seed=33)
+        ho, co = mem(h, c)
+        cases[tag] = {"sd": sd_of(mem), "causal": causal, "h": h, "c": c, "h_out": ho, "c_out": co}
+    save("small_skim.pt", cases)
+
+    torch.manual_seed(0)
+    m = _ref_init_model("tse_skim_v0_causal").eval()
+    T.perturb_(m, seed=1)
+    n, L, Le = 1, 64000, 96000
+    mix, _ = T.noisy_speech(n, L, seed=1234)
+    enr = T.noisy_speech(n, Le, seed=4321)[0]
+    y = m.inference(mix, enr)
+    stride = 997
+    pin = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n,
+           "length": L, "enroll_length": Le, "input_seed": 1234, "enroll_seed": 4321, "stride": stride, "out_len": y.shape[-1],
+           "out_abs_mean": float(y.abs().mean()), "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+           "samples": [[float(v) for v in row[::stride]] for row in y]}
+    print("tse_skim_v0_causal", pin["params"], pin["state_checksum"], pin["out_abs_mean"])
+    with open(os.path.join(HERE, "skim_pins.json"), "w") as fh:
+        json.dump({"tse_skim_v0_causal": pin}, fh)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "small"):
         small_cases()
     if which in ("all", "full"):
         full_pins()
+    if which in ("all", "skim"):
+        skim_cases()

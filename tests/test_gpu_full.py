@@ -63,6 +63,27 @@ def test_full_size_parity(name, backend):
     assert float((s_ours - s_ref).abs().max()) <= SISNR_TOL_DB
 
 
+def test_skim_recipe_full_size():
+    """`tse_skim_v0_causal` (4 s mixture + 6 s enrollment) against the reference's recorded output and the oracle."""
+    with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:
+        pin = json.load(fh)["tse_skim_v0_causal"]
+    torch.manual_seed(0)
+    m = recipes.init_model("tse_skim_v0_causal", verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, clean = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    enr = testing.noisy_speech(pin["batch"], pin["enroll_length"], seed=pin["enroll_seed"])[0]
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    y = m.to("cuda").inference(mix, enr)
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= WAVE_TOL
+    y_ref = R.inference(sd, cfg, mix, enr)
+    err = (y - y_ref).abs().max().item()
+    L = y.shape[-1]
+    d_sisnr = float((R.si_snr(y, clean[:, :L]) - R.si_snr(y_ref, clean[:, :L])).abs().max())
+    print(f"tse_skim_v0_causal: max|dy|={err:.3e} SI-SNR(ours,ref)={R.si_snr(y, y_ref).min():.1f} dB dSI-SNR={d_sisnr:.2e} dB")
+    assert err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
+
+
 def test_standalone_masker_reference_layout():
     """test/test_backbone.py:14-56 shape contract, with numbers: ConvTasNet(512,...,R=3,X=8,H=256) on rand(1,512,100)."""
     from puresound_b200.nnet.conv_tasnet import ConvTasNet

@@ -89,6 +89,35 @@ def test_dprnn_variants(golden):
         close(y, g["y"], 5e-5)
 
 
+def test_skim_variants(golden):
+    """SkiM and its cells on the engine against the reference's outputs."""
+    from puresound_b200.nnet.skim import MemLSTM, SegLSTM
+
+    gs = golden("small_skim.pt")
+    for tag in ("causal_film", "bi_overlap", "causal_overlap", "bi_exact"):
+        g = gs[tag]
+        c = dict(g["cfg"])
+        c["output_size"] = g["sd"]["output_fc.1.weight"].shape[0]
+        m = _build.masker(c).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        y = m(cu(g["x"]), cu(g["embed"])) if g["embed"] is not None else m(cu(g["x"]))
+        close(y, g["y"], 5e-5)
+    g = gs["seg_cell"]
+    seg = SegLSTM(16, 12, causal=True).to(DEV).eval()
+    seg.load_state_dict(g["sd"])
+    y, hn, cn = seg(cu(g["x"]), cu(g["h"]), cu(g["c"]))
+    close(y, g["y"], 2e-5)
+    close(hn, g["hn"], 2e-5)
+    close(cn, g["cn"], 2e-5)
+    for tag in ("mem_cell_causal", "mem_cell_bi"):
+        g = gs[tag]
+        mem = MemLSTM(12, causal=g["causal"]).to(DEV).eval()
+        mem.load_state_dict(g["sd"])
+        ho, co = mem(cu(g["h"]), cu(g["c"]))
+        close(ho, g["h_out"], 2e-5)
+        close(co, g["c_out"], 2e-5)
+
+
 def test_wrappers_inference(golden):
     for tag, g in golden("small_wrappers.pt").items():
         m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)
