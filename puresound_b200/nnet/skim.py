@@ -21,7 +21,10 @@ from ._fuse import ParamCache, prelu_slope
 from .lobe.trivial import FiLM, overlap_geometry
 
 
-def _lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM):
+TC_MIN_POSITIONS = 4096  # sequences x steps from which the tensor-core recurrence pays (it loads 256 KB of weights per CTA)
+
+
+def _lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM, use_tc: bool = True):
     """(W_ih stacked over directions, b_ih + b_hh, W_hh^T [D, H, 4H], resident tensor-core image or None, tcgen05 image of
     W_ih or None); the projection rows are permuted to [dir][unit][gate] when the tensor-core recurrence is used."""
     bi = rnn.bidirectional
@@ -33,7 +36,7 @@ def _lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM):
         w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
         b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
         w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
-        w_hh_pk = ops.lstm_pack_weights(w_hh_t, H, len(sfx))
+        w_hh_pk = ops.lstm_pack_weights(w_hh_t, H, len(sfx)) if use_tc else None
         if w_hh_pk is not None:
             D = len(sfx)
             w_ih = w_ih.view(D, 4, H, -1).permute(0, 2, 1, 3).reshape(D * 4 * H, -1).contiguous()
@@ -41,7 +44,7 @@ def _lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM):
         w_ih_pk = ops.pack_weights(w_ih, w_ih.shape[0], w_ih.shape[1], w_ih.shape[1])
         return w_ih, b, w_hh_t, w_hh_pk, w_ih_pk
 
-    return cache.get(tag, srcs, build)
+    return cache.get(tag + ("_tc" if use_tc else "_fp32"), srcs, build)
 
 
 def _lstm_proj_norm(cache: ParamCache, tag: str, x: torch.Tensor, rnn: nn.LSTM, proj: nn.Linear, norm: nn.LayerNorm,
@@ -50,8 +53,8 @@ def _lstm_proj_norm(cache: ParamCache, tag: str, x: torch.Tensor, rnn: nn.LSTM, 
     kernel, one GEMM with the LayerNorm + residual epilogue."""
     B, L, Cn = x.shape
     H, D = rnn.hidden_size, (2 if rnn.bidirectional else 1)
-    w_ih, b, w_hh_t, w_hh_pk, w_ih_pk = _lstm_weights(cache, tag, rnn)
     P = B * L
+    w_ih, b, w_hh_t, w_hh_pk, w_ih_pk = _lstm_weights(cache, tag, rnn, use_tc=P >= TC_MIN_POSITIONS)
     gx, _ = ops.linear(x.reshape(1, P, Cn), w_ih, bias=b, w_packed=w_ih_pk)
     h0 = c0 = None
     if init is not None:

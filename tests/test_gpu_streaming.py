@@ -83,6 +83,48 @@ def test_streaming_many_streams_tensor_core_path():
     assert err <= 1e-3
 
 
+@pytest.mark.parametrize("n_streams", [1, 3])
+def test_streaming_skim_equals_offline(n_streams):
+    """The reference's own streaming test (test/test_streaming.py:62-116): StreamingSkiM offline forward == step_chunk ==
+    step_frame (mean abs error < 1e-7 upstream, on one stream).  Here also against the oracle and for several streams.
+
+    Several streams are INDEPENDENT streams, i.e. each equals the offline model run on that item alone.  The reference's
+    batched offline forward is not that: its causal MemLSTM shifts the memories by one along the flattened [N*S] axis
+    (skim.py:103-110), so item n's first segment starts from item n-1's last memory.  The offline engine reproduces the
+    shift bit for bit (checked below against the batched oracle); the streams are checked against per-item oracle runs."""
+    from puresound_b200.streaming.skim_inference import StreamingSkiM
+
+    torch.manual_seed(4)
+    model = StreamingSkiM(5, 20, 5, seg_size=10, seg_overlap=False, causal=True, n_blocks=4, embed_dim=10, embed_norm=True,
+                          embed_fusion="FiLM", block_with_embed=[1, 1, 1, 1]).eval()
+    testing.perturb_(model, seed=5)
+    S, T = n_streams, 1000
+    x, d = torch.rand(S, 5, T), torch.rand(S, 10)
+    desc = D.describe_masker(model)
+    ref_batched = R.skim(model.state_dict(), "", x, d, desc)
+    ref = torch.cat([R.skim(model.state_dict(), "", x[s:s + 1], d[s:s + 1], desc) for s in range(S)], 0)
+    model = model.cuda()
+    assert (model(x.cuda(), d.cuda()).cpu() - ref_batched).abs().max().item() <= 2e-5
+    y1 = torch.cat([model(x[s:s + 1].cuda(), d[s:s + 1].cuda()) for s in range(S)], 0).cpu()
+    assert (y1 - ref).abs().max().item() <= 2e-5
+    if S > 1:
+        assert (ref_batched[1:, :, :10] - ref[1:, :, :10]).abs().max().item() > 1e-3  # the upstream cross-item leak is real
+    # chunk by chunk with explicit state passing (skim_inference.py:43-139)
+    xt = x.cuda().transpose(1, 2).contiguous()  # [S, T, C]
+    sh = mh = sc = mc = None
+    outs = []
+    for k in range(T // 10):
+        o, sh, mh, sc, mc = model.step_chunk(xt[:, k * 10:(k + 1) * 10, :], sh, mh, sc, mc, d.cuda())
+        outs.append(o)
+    y2 = torch.cat(outs, dim=-1).cpu()
+    assert (y2 - ref).abs().max().item() <= 2e-5 and (y2 - y1).abs().mean().item() < 1e-6
+    # frame by frame with the managed state (skim_inference.py:142-252)
+    model.init_status(S)
+    outs = [model.step_frame(xt[:, t:t + 1, :], d.cuda()) for t in range(T)]
+    y3 = torch.cat(outs, dim=-1).cpu()
+    assert (y3 - ref).abs().max().item() <= 2e-5 and (y3 - y1).abs().mean().item() < 1e-6
+
+
 def test_streaming_guards():
     with pytest.raises(AssertionError):
         StreamingConvTasNet(16, 0, tcn_dim=8, per_tcn_stack=1, repeat_tcn=1, tcn_with_embed=[0], causal=False)
