@@ -206,7 +206,7 @@ typedef struct {
   const float* gx; const float* w_hh_t;
   const float* h0; const float* c0;
   float* out; float* hn; float* cn;
-  /* tensor-core path (H = 128): image built by ps_lstm_pack_weights from w_hh_t, else NULL (exact-fp32 CUDA-core path) */
+  /* tensor-core path (H <= 128, H % 32 == 0): image built by ps_lstm_pack_weights from w_hh_t, else NULL (exact-fp32 CUDA-core path) */
   const void* w_packed;
   /* 0: gx rows are [D][4 gates][H] (nn.LSTM order); 1: [D][H][4 gates] (rows of W_ih permuted by the caller so the four
    * gates of a unit are one 16-byte load) - tensor-core path only */

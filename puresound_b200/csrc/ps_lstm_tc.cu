@@ -1,6 +1,9 @@
-// Tensor-core LSTM recurrence for H = 128 (DPRNN intra- / inter-chunk passes; reference dprnn.py:67-103 via nn.LSTM,
-// gate order i,f,g,o).  One CTA per SM owns 64 sequences of one direction for all L steps; the recurrent matrix never
-// leaves the SM:
+// Tensor-core LSTM recurrence for H <= 128, H % 32 == 0 (DPRNN intra- / inter-chunk passes; reference dprnn.py:67-103 via
+// nn.LSTM, gate order i,f,g,o).  The text below describes H = 128; smaller H run in the same layout with the missing
+// units / k-columns of W_hh zero-padded by the pack kernel: their lanes stay h = c = 0, the k loop stops at H, the gate
+// warps of all-padding lane quarters only keep the barriers in step.  One CTA per SM owns up to 64 sequences of one
+// direction for all L steps (fewer per CTA when the whole problem fits one wave of CTAs anyway: a shorter gate phase
+// is a shorter step, and the recurrence is a latency chain of L steps); the recurrent matrix never leaves the SM:
 //
 //   * W_hh (512 x 128 fp32 = 256 KB) does not fit the 227 KB of shared memory, so it is kept as a bf16 hi/lo split
 //     (the 3xBF16 scheme of ps_gemm_tc.cu: hi*hi + hi*lo + lo*hi in the fp32 accumulator, ~2^-17 per product) with
@@ -128,8 +131,10 @@ __device__ __forceinline__ float lt_cell(float pi, float pf, float pg, float po,
   return (2.f - Cc) * lt_rcp((1.f + Eo) * Cc);
 }
 
+// spq = real sequences per gate warp (1..16): sequence slot s = half*32 + wq*16 + j is real iff j < spq, and a CTA owns
+// 4*spq consecutive sequences.
 template <bool kGxi>
-__global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d) {
+__global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d, const int spq) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -144,8 +149,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
-  const int64_t q0 = (int64_t)blockIdx.x * LT_N;
-  const int64_t G = (int64_t)d.D * 4 * LT_H, OW = (int64_t)d.D * LT_H;
+  const int Hr = (int)d.H;  // real hidden size; the on-chip layout is always LT_H wide
+  const int64_t q0 = (int64_t)blockIdx.x * (4 * spq);
+  const int64_t G = (int64_t)d.D * 4 * Hr, OW = (int64_t)d.D * Hr;
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)dir * (2 * LT_WHI_BYTES);
 
   if (tid == 0) {
@@ -158,8 +164,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)tmem_ptr_s), 512);
   if (tid < LT_N) {
-    int64_t q = q0 + tid;
-    if (q >= d.n_seq) q = d.n_seq - 1;  // tail sequences shadow the last real one; their results are never stored
+    int64_t q = q0 + (int64_t)(tid >> 4) * spq + (tid & 15);
+    if ((tid & 15) >= spq || q >= d.n_seq) q = d.n_seq - 1;  // unused slots shadow the last real sequence; never stored
     const int64_t pos = (q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride;
     posg_s[tid] = pos * G;
     poso_s[tid] = pos * OW;
@@ -180,6 +186,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     mbar_wait(bar_w, 0);
     // The 64 sequences run as two independent half-batches of 32 (own barriers, own accumulator columns): while the
     // gate warps of one half compute its cell update, the tensor core is already busy with the other half's step.
+    const int nk = Hr >> 4;  // k16 steps over the real K = H
     for (int64_t step = 0; step < d.L; ++step) {
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
             const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N + hf * LT_NH);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
+              if (k >= nk) break;
               const int kt = k >> 1;
               const uint64_t ko = (uint64_t)(((k & 1) * 32) >> 4);
               const uint64_t h_hi = lt_desc(hs + kt * LT_HTILE) + ko, h_lo = lt_desc(hs + (4 + kt) * LT_HTILE) + ko;
@@ -220,6 +228,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     const int wq = ((warp - 4) >> 2) % GWQ;
     const int u = q * 32 + lane;         // hidden unit = TMEM lane
     const int s0 = half * LT_NH + wq * SPT;
+    const int64_t qb = q0 + (int64_t)(half * GWQ + wq) * spq;  // first sequence of this warp
+    const bool live = q * 32 < Hr;                             // false: every unit of this lane quarter is padding
     // ---- one-time: W_hi rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
     if (half == 0 && wq == 0) {
       const uint32_t* wlo = reinterpret_cast<const uint32_t*>(wimg + LT_WHI_BYTES);  // [512 rows][64 words]
@@ -261,9 +271,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       float h2[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t qq = q0 + s0 + j + e;
-        const bool valid = qq < d.n_seq;
-        const int64_t so = ((int64_t)dir * d.n_seq + qq) * LT_H + u;
+        const int64_t qq = qb + j + e;
+        const bool valid = live && j + e < spq && qq < d.n_seq;
+        const int64_t so = ((int64_t)dir * d.n_seq + qq) * Hr + u;
         cu[(j + e) * LT_H] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
         h2[e] = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
       }
@@ -277,20 +287,26 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     // gx row layout: native [dir][gate][unit] (4 loads of one float, a warp reads 128 B each) or, when the host permuted
     // the rows of W_ih (gx_interleaved), [dir][unit][gate]: one 16-byte load per sequence, a warp reads 512 contiguous B
     constexpr bool gxi = kGxi;
-    const float* gxu = d.gx + (int64_t)dir * 4 * LT_H + (gxi ? 4 * u : u);
-    float* outu = d.out + (int64_t)dir * LT_H + u;
-    const int nvalid = (int)((d.n_seq - q0 - s0) < SPT ? (d.n_seq - q0 - s0) : SPT);  // real sequences of this thread (may be <= 0)
+    const float* gxu = d.gx + (int64_t)dir * 4 * Hr + (gxi ? 4 * u : u);
+    float* outu = d.out + (int64_t)dir * Hr + u;
+    const int nvalid = (int)((d.n_seq - qb) < spq ? (d.n_seq - qb) : spq);  // real sequences of this thread (may be <= 0)
     const int64_t stepg = d.step_stride * G, stepo = d.step_stride * OW;
     for (int64_t step = 0; step < d.L; ++step) {
       const int64_t t = dir ? d.L - 1 - step : step;
       const int64_t toffg = t * stepg, toffo = t * stepo;
       const bool last = step + 1 == d.L;
+      if (!live) {  // padding lanes: h stays 0 in the B tiles; only keep the two barriers in step
+        mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_h + 8 * half);
+        continue;
+      }
       // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
-      if (step + 1 < d.L && lane < SPT) {
+      if (step + 1 < d.L && lane < spq) {
         const int64_t tn = dir ? t - 1 : t + 1;
-        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * LT_H + (kGxi ? q * 128 : q * 32);
+        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * Hr + (kGxi ? q * 128 : q * 32);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 32 : LT_H)));
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 32 : Hr)));
       }
       // gx of the first chunk is requested before the wait on the tensor core; later chunks one chunk ahead
       float gxa[4][CH], gxb[4][CH];
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
             gx[0][j] = v4.x; gx[1][j] = v4.y; gx[2][j] = v4.z; gx[3][j] = v4.w;
           } else {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * LT_H);
+            for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * Hr);
           }
         }
       };
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
           cu[(j0 + j) * LT_H] = cv;
           if (j0 + j < nvalid) {
             outu[poso_s[s0 + j0 + j] + toffo] = h[j];
-            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + q0 + s0 + j0 + j) * LT_H + u] = h[j];
+            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + qb + j0 + j) * Hr + u] = h[j];
           }
         }
 #pragma unroll
@@ -332,10 +348,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       };
 #pragma unroll
       for (int j0 = 0; j0 < SPT; j0 += 2 * CH) {
-        load_gx(gxb, j0 + CH);
+        if (j0 >= spq) break;
+        const bool two = j0 + CH < spq;
+        if (two) load_gx(gxb, j0 + CH);
         chunk(gxa, j0);
-        if (j0 + 2 * CH < SPT) load_gx(gxa, j0 + 2 * CH);
-        chunk(gxb, j0 + CH);
+        if (j0 + 2 * CH < spq) load_gx(gxa, j0 + 2 * CH);
+        if (two) chunk(gxb, j0 + CH);
       }
       // h_t is in shared memory for the tensor core (async proxy) and this step's accumulators have been read
       fence_proxy_async();
@@ -345,9 +363,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     }
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
-      const int64_t qq = q0 + s0 + j;
-      if (qq >= d.n_seq) continue;
-      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * LT_H + u] = cu[j * LT_H];
+      const int64_t qq = qb + j;
+      if (!live || j >= spq || qq >= d.n_seq) continue;
+      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * Hr + u] = cu[j * LT_H];
     }
   }
 
@@ -360,13 +378,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 }
 
 // w_hh_t [D, H, 4H] (W_hh transposed, the layout ps_lstm takes) -> per direction [W_lo shared-memory image 128 KB |
-// W_hi row-major bf16 [4H][H] 128 KB (stored to TMEM by the kernel)]
-__global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int D, uint8_t* __restrict__ out) {
+// W_hi row-major bf16 [4*128][128] 128 KB (stored to TMEM by the kernel)]; units / k-columns beyond H are zero
+__global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int H, int D, uint8_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)D * 4 * LT_H * LT_H) return;
   const int dir = (int)(i / (4 * LT_H * LT_H));
-  const int r = (int)((i / LT_H) % (4 * LT_H)), k = (int)(i % LT_H);  // W_hh[r][k] = w_hh_t[dir][k][r]
-  const float w = w_hh_t[((int64_t)dir * LT_H + k) * 4 * LT_H + r];
+  const int r = (int)((i / LT_H) % (4 * LT_H)), k = (int)(i % LT_H);  // padded W_hh[gate*128 + unit][k]
+  const bool real = (r % LT_H) < H && k < H;
+  const float w = real ? w_hh_t[((int64_t)dir * H + k) * 4 * H + (r / LT_H) * H + (r % LT_H)] : 0.f;  // W_hh[g*H+unit][k]
   const __nv_bfloat16 h = __float2bfloat16_rn(w);
   const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
   uint8_t* o = out + (size_t)dir * (2 * LT_WHI_BYTES);
@@ -379,7 +398,8 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int D, uint8_
 bool lstm_tc_eligible(const ps_lstm_t& d) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("PS_LSTM"); off = (e && e[0] == 's') ? 1 : 0; }  // PS_LSTM=simt forces the fp32 kernel
-  return !off && d.w_packed != nullptr && d.H == LT_H && (reinterpret_cast<uintptr_t>(d.w_packed) & 15) == 0;
+  return !off && d.w_packed != nullptr && d.H <= LT_H && d.H % 32 == 0 && (reinterpret_cast<uintptr_t>(d.w_packed) & 15) == 0 &&
+         (!d.gx_interleaved || (reinterpret_cast<uintptr_t>(d.gx) & 15) == 0);
 }
 
 int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
@@ -393,11 +413,24 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(lstm_tc_kernel)"); return PS_ERR_CUDA; }
     attr_set[dev] = true;
   }
-  const int64_t nblk = cdiv(d.n_seq, LT_N);
+  // Sequences per CTA: 64 when the problem needs more than one wave of CTAs anyway, else the smallest count whose grid
+  // still fits one wave (each CTA's step shortens with its sequence count).
+  static int n_sm[64] = {};
+  if (!n_sm[dev]) {
+    e = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
+  }
+  int spq = LT_N / 4;
+  static int spq_env = -1;
+  if (spq_env < 0) { const char* ev = getenv("PS_LSTM_SPQ"); spq_env = ev ? atoi(ev) : 0; }
+  if (spq_env >= 1 && spq_env <= 16) spq = spq_env;
+  else
+    while (spq > 4 && cdiv(d.n_seq, 2 * spq) * d.D <= n_sm[dev]) spq >>= 1;
+  const int64_t nblk = cdiv(d.n_seq, 4 * spq);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
-  if (d.gx_interleaved) lstm_tc_kernel<true><<<grid, LT_THREADS, LT_SMEM, s>>>(d);
-  else lstm_tc_kernel<false><<<grid, LT_THREADS, LT_SMEM, s>>>(d);
+  if (d.gx_interleaved) lstm_tc_kernel<true><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq);
+  else lstm_tc_kernel<false><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq);
   PS_CHECK_LAUNCH("lstm_tc_kernel");
   return PS_OK;
 }
@@ -405,15 +438,15 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
 }  // namespace ps
 
 extern "C" int64_t ps_lstm_packed_bytes(int64_t H, int32_t D) {
-  if (H != ps::LT_H || (D != 1 && D != 2)) return 0;
+  if (H < 32 || H > ps::LT_H || H % 32 != 0 || (D != 1 && D != 2)) return 0;
   return (int64_t)D * 2 * ps::LT_WHI_BYTES;
 }
 
 extern "C" int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void* packed, void* stream) {
   PS_REQUIRE(w_hh_t && packed);
   if (ps_lstm_packed_bytes(H, D) == 0) return PS_ERR_UNSUPPORTED;
-  const int64_t n = (int64_t)D * 4 * H * H;
-  ps::lstm_pack_kernel<<<(unsigned)ps::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh_t, D, reinterpret_cast<uint8_t*>(packed));
+  const int64_t n = (int64_t)D * 4 * ps::LT_H * ps::LT_H;
+  ps::lstm_pack_kernel<<<(unsigned)ps::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh_t, (int)H, D, reinterpret_cast<uint8_t*>(packed));
   PS_CHECK_LAUNCH("lstm_pack_kernel");
   return PS_OK;
 }

@@ -76,7 +76,7 @@ class DPRNN(nn.Module):
             w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
             b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
             w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
-            # resident image for the tensor-core recurrence (None unless H == 128), tcgen05 image of W_ih for the projections
+            # resident image for the tensor-core recurrence (None unless H <= 128 and H % 32 == 0), tcgen05 image of W_ih for the projections
             w_hh_pk = ops.lstm_pack_weights(w_hh_t, self.hidden_size, len(sfx))
             if w_hh_pk is not None:
                 # tensor-core recurrence: order the projection rows [dir][unit][gate] so the four gates of a unit are one

@@ -342,7 +342,7 @@ def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inne
 
 def lstm_pack_weights(w_hh_t: Tensor, H: int, D: int) -> Optional[Tensor]:
     """Recurrent weights [D, H, 4H] -> the tensor-core LSTM's resident image (bf16 hi for shared memory, bf16 lo for
-    tensor memory); None when H is not served by that kernel (it handles H = 128)."""
+    tensor memory); None when H is not served by that kernel (it handles H <= 128, H % 32 == 0, zero-padded to 128 units)."""
     lib = _lib.load()
     nbytes = lib.ps_lstm_packed_bytes(H, D)
     if nbytes == 0:

@@ -222,12 +222,18 @@ def test_short_k_filterbank_kernel(ops, M, K, hop, relu):
     close(y.double(), ref, 1e-6)
 
 
-@pytest.mark.parametrize("D", [1, 2])
-def test_lstm_tensor_core_path(ops, D):
-    """H = 128: W_hh resident as bf16 hi (shared memory) + lo (tensor memory), gates on tcgen05 with the 3xBF16 split.
-    Same oracle (step-by-step LSTM cell, dprnn.py:67-103 via nn.LSTM) as the exact-fp32 kernel; ragged last CTA
-    (n_seq % 64 != 0), both addressing modes, initial and final state."""
-    H, N, S, K, C = 128, 2, 37, 50, 16
+@pytest.mark.parametrize("H,D,N,S,K", [
+    (128, 1, 2, 37, 50), (128, 2, 2, 37, 50),   # 74 / 100 sequences: 16 per CTA
+    (64, 1, 2, 37, 50), (64, 2, 1, 21, 30),     # veve_dprnn_v0_causal's hidden size: units 64..127 are zero padding
+    (96, 2, 1, 19, 12), (32, 1, 3, 11, 9),
+    (128, 2, 4, 601, 6),                         # 2404 sequences x 2 directions: more than a wave -> 64 per CTA
+    (64, 1, 4, 751, 5),                          # 3004 sequences: 32 per CTA
+])
+def test_lstm_tensor_core_path(ops, H, D, N, S, K):
+    """H <= 128: W_hh resident as bf16 hi (tensor memory) + lo (shared memory), gates on tcgen05 with the 3xBF16 split.
+    Same oracle (step-by-step LSTM cell, dprnn.py:67-103 via nn.LSTM) as the exact-fp32 kernel; ragged last CTA, every
+    sequences-per-CTA choice of the launcher, both addressing modes, initial and final state."""
+    C = 16
     sd = {}
     for s in ["", "_reverse"][:D]:
         sd[f"weight_ih_l0{s}"], sd[f"weight_hh_l0{s}"] = rnd(4 * H, C, seed=1, scale=0.3).cpu(), rnd(4 * H, H, seed=2, scale=0.15).cpu()
@@ -237,7 +243,7 @@ def test_lstm_tensor_core_path(ops, D):
     b = torch.cat([sd[f"bias_ih_l0{s}"] + sd[f"bias_hh_l0{s}"] for s in sfx]).to(DEV)
     w_hh_t = torch.stack([sd[f"weight_hh_l0{s}"].t().contiguous() for s in sfx]).to(DEV)
     pk = ops.lstm_pack_weights(w_hh_t, H, D)
-    assert pk is not None and pk.numel() == D * 4 * H * H * 4
+    assert pk is not None and pk.numel() == D * 4 * 128 * 128 * 4  # the on-chip layout is always 128 units wide
     x = rnd(N, S, K, C, seed=5)
     P = N * S * K
     gx, _ = ops.linear(x.view(1, P, C), w_ih, bias=b)
