@@ -347,6 +347,37 @@ def skim_cases():
         json.dump({"tse_skim_v0_causal": pin}, fh)
 
 
+@torch.no_grad()
+def real_input_pins():
+    """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
+    (test/test_case/1272-128104-0000_2035-147961-0014.wav, a two-speaker mixture, 16 kHz int16) cropped to 4 s as the
+    mixture and tiled to 6 s as the enrollment, and full-scale white noise (output clamp active), through the reference's
+    full-size models.  The int16 samples travel inside the fixture so that the GPU box needs neither the reference nor
+    its test assets."""
+    from scipy.io import wavfile
+
+    sr, pcm = wavfile.read(os.path.join(REF, "test/test_case/1272-128104-0000_2035-147961-0014.wav"))
+    assert sr == 16000 and pcm.dtype.name == "int16" and pcm.ndim == 1
+    pcm = torch.from_numpy(pcm.copy())
+    mix_i16 = pcm[:64000].clone()
+    enr_i16 = torch.cat([pcm[20000:], pcm])[:96000].clone()
+    mix, enr = (mix_i16.float() / 32768.0)[None], (enr_i16.float() / 32768.0)[None]
+    stride = 97
+    cfgs = full_cfgs()
+    pins = {}
+    for tag, name, x, e in (("speech_cfg1", "cfg1", mix, None), ("speech_cfg3", "cfg3", mix, None), ("speech_cfg4", "cfg4", mix, enr),
+                            ("speech_veve", "veve_dprnn_v0_causal", mix, enr), ("white_a1_cfg1", "cfg1", T.white(1, 64000, amp=1.0, seed=77), None)):
+        torch.manual_seed(0)
+        m = cfgs[name][0]().eval()
+        T.perturb_(m, seed=1)
+        y = m.inference(x, e)
+        pins[tag] = {"config": name, "state_checksum": T.state_checksum(m.state_dict()), "stride": stride, "out_len": y.shape[-1],
+                     "out_abs_mean": float(y.abs().mean()), "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+                     "samples": [float(v) for v in y[0, ::stride]]}
+        print(tag, pins[tag]["out_abs_mean"], pins[tag]["out_clamped_frac"])
+    save("real_input_pins.pt", {"mix_i16": mix_i16, "enroll_i16": enr_i16, "white_seed": 77, "pins": pins})
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "small"):
@@ -355,3 +386,5 @@ if __name__ == "__main__":
         full_pins()
     if which in ("all", "skim"):
         skim_cases()
+    if which in ("all", "real"):
+        real_input_pins()

@@ -63,6 +63,26 @@ def test_full_size_parity(name, backend):
     assert float((s_ours - s_ref).abs().max()) <= SISNR_TOL_DB
 
 
+@pytest.mark.parametrize("tag", ["speech_cfg1", "speech_cfg3", "speech_cfg4", "speech_veve", "white_a1_cfg1"])
+def test_real_speech_and_full_scale_noise(tag):
+    """SURVEY.md 8d inputs (iii) — the reference's own two-speaker speech fixture (int16 samples carried in the golden file)
+    — and (i) at a = 1.0 with the output clamp active on most samples, against outputs recorded from the reference."""
+    from test_oracle_full_pins import _real_inputs
+
+    g = torch.load(os.path.join(GOLDEN, "real_input_pins.pt"))
+    pin = g["pins"][tag]
+    torch.manual_seed(0)
+    m = recipes.baseline_config(pin["config"]).eval()
+    testing.perturb_(m, seed=1)
+    mix, enr = _real_inputs(g, tag)
+    y = m.to("cuda").inference(mix, enr)
+    assert y.shape[-1] == pin["out_len"]
+    err = (y[0, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item()
+    print(f"{tag}: max|dy| vs the reference's samples = {err:.3e}, clamped {float((y.abs() >= 1).float().mean()):.4f}")
+    assert err <= WAVE_TOL
+    assert float((y.abs() >= 1).float().mean()) == pytest.approx(pin["out_clamped_frac"], abs=2e-3)
+
+
 def test_skim_recipe_full_size():
     """`tse_skim_v0_causal` (4 s mixture + 6 s enrollment) against the reference's recorded output and the oracle."""
     with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:

@@ -45,3 +45,28 @@ def test_oracle_matches_reference_skim_recipe():
     y = R.inference(m.state_dict(), D.describe(m), mix, enr)
     assert y.shape[-1] == pin["out_len"]
     assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+
+
+def _real_inputs(g, tag):
+    mix = (g["mix_i16"].float() / 32768.0)[None]
+    enr = (g["enroll_i16"].float() / 32768.0)[None]
+    if tag.startswith("white"):
+        return testing.white(1, 64000, amp=1.0, seed=g["white_seed"]), None
+    return mix, (enr if g["pins"][tag]["config"] in ("cfg4", "veve_dprnn_v0_causal") else None)
+
+
+@pytest.mark.parametrize("tag", ["speech_cfg1", "speech_cfg3", "speech_cfg4", "speech_veve", "white_a1_cfg1"])
+def test_oracle_matches_reference_on_real_speech_and_full_scale_noise(tag):
+    """SURVEY.md 8d inputs (iii) — the reference's own two-speaker speech fixture, 4 s (+ 6 s enrollment) — and (i) at
+    a = 1.0, where 58 % of the output samples sit on the [-1, 1] clamp; outputs recorded from the reference."""
+    g = torch.load(os.path.join(GOLDEN, "real_input_pins.pt"))
+    pin = g["pins"][tag]
+    torch.manual_seed(0)
+    m = recipes.baseline_config(pin["config"]).eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, enr = _real_inputs(g, tag)
+    y = R.inference(m.state_dict(), D.describe(m), mix, enr)
+    assert y.shape[-1] == pin["out_len"]
+    assert (y[0, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+    assert float((y.abs() >= 1).float().mean()) == pytest.approx(pin["out_clamped_frac"], abs=1e-4)
