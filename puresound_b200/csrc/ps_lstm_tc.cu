@@ -37,7 +37,7 @@ constexpr int LT_WTILE = 128 * 64;             // one [128 rows x 32 k] bf16 til
 constexpr int LT_WHI_BYTES = 4 * 4 * LT_WTILE; // 4 gates x 4 k-tiles = 128 KB
 constexpr int LT_HTILE = LT_N * 64;            // [64 seqs x 32 k] bf16: 4 KB
 constexpr int LT_H_BYTES = 2 * 4 * LT_HTILE;   // hi | lo, 4 k-tiles each = 32 KB
-constexpr int LT_POS_BYTES = 2 * LT_N * 8;     // per sequence: element offset of its rows in gx and in out
+constexpr int LT_POS_BYTES = 2 * LT_N * 8;     // per sequence slot: its first row (position) as int32 (the rest is spare)
 constexpr int LT_C_BYTES = LT_N * LT_H * 4;     // cell state [sequence][unit] fp32: 32 KB (registers go to the gx double buffer)
 constexpr int LT_SMEM = LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 64 /*barriers*/ + LT_C_BYTES + 1024 /*align*/;
 constexpr uint32_t LT_ACC_COL = 256;           // TMEM: W_lo in columns [0,256), accumulators in [256,512)
@@ -108,26 +108,27 @@ __device__ __forceinline__ float lt_rcp(float x) {
 }
 __device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.f + lt_ex2(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float lt_tanh(float x) { return fmaf(2.f, lt_rcp(1.f + lt_ex2(-2.8853900817779268f * x)), -1.f); }
-// clamp to [-lim, lim] that PROPAGATES NaN (fminf/fmaxf would swallow it; the reference's look-ahead probe feeds inf/NaN)
-__device__ __forceinline__ float lt_clamp(float x, float lim) {
+// min that PROPAGATES NaN (fminf would swallow it; the reference's look-ahead probe feeds inf/NaN)
+__device__ __forceinline__ float lt_min_nan(float x, float lim) {
   float y;
-  asm("{\n\t.reg .f32 t;\n\tmax.NaN.f32 t, %1, %2;\n\tmin.NaN.f32 %0, t, %3;\n\t}" : "=f"(y) : "f"(x), "f"(-lim), "f"(lim));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(y) : "f"(x), "f"(lim));
   return y;
 }
 // One LSTM cell with 7 MUFU instead of 10: with Ex = exp(-x) the three sigmoids and two tanh share reciprocals,
 //   c' = f c + i g = [c (1+Ei)(1+Eg) + (1-Eg)(1+Ef)] / [(1+Ef)(1+Ei)(1+Eg)],   Eg = exp(-2 g)
 //   h  = o tanh(c') = (1 - Ec) / [(1+Eo)(1+Ec)],                                  Ec = exp(-2 c')
-// Pre-activations are clamped to +-25 (+-12.5 under tanh): exp(25)^3 = 3.7e32 stays finite in fp32, and the clamp moves
-// a gate by < 1.4e-11.  The XU pipe (16 lanes / cycle / SM) was the floor of the gate phase.
+// The exponents are capped at 2^36 = exp(25) (a pre-activation below -25, or -12.5 under tanh): exp(25)^3 = 3.7e32 stays
+// finite in fp32, and the cap moves a gate by < 1.4e-11; towards -inf ex2 underflows to 0 on its own.  One FMNMX per
+// exponential.  The XU pipe (16 lanes / cycle / SM) is the floor of the gate phase.
 __device__ __forceinline__ float lt_cell(float pi, float pf, float pg, float po, float& c) {
-  constexpr float L2E = 1.4426950408889634f;
-  const float Ei = lt_ex2(-L2E * lt_clamp(pi, 25.f)), Ef = lt_ex2(-L2E * lt_clamp(pf, 25.f));
-  const float Eg = lt_ex2(-2.f * L2E * lt_clamp(pg, 12.5f)), Eo = lt_ex2(-L2E * lt_clamp(po, 25.f));
+  constexpr float L2E = 1.4426950408889634f, CAP = 36.0673760222f;
+  const float Ei = lt_ex2(lt_min_nan(-L2E * pi, CAP)), Ef = lt_ex2(lt_min_nan(-L2E * pf, CAP));
+  const float Eg = lt_ex2(lt_min_nan(-2.f * L2E * pg, CAP)), Eo = lt_ex2(lt_min_nan(-L2E * po, CAP));
   const float A = 1.f + Ei, B = 1.f + Eg, F = 1.f + Ef;
   const float AB = A * B;
   const float cn = fmaf(c, AB, (2.f - B) * F) * lt_rcp(F * AB);
   c = cn;
-  const float Cc = 1.f + lt_ex2(-2.f * L2E * lt_clamp(cn, 12.5f));
+  const float Cc = 1.f + lt_ex2(lt_min_nan(-2.f * L2E * cn, CAP));
   return (2.f - Cc) * lt_rcp((1.f + Eo) * Cc);
 }
 
@@ -140,8 +141,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   uint8_t* h_sm = sm + LT_WHI_BYTES;                       // [hi: 4 tiles][lo: 4 tiles]
-  int64_t* posg_s = reinterpret_cast<int64_t*>(sm + LT_WHI_BYTES + LT_H_BYTES);  // base position * gx row width
-  int64_t* poso_s = posg_s + LT_N;                                                 // base position * out row width
+  int32_t* row_s = reinterpret_cast<int32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES);  // first row (position) of every sequence slot
   const uint32_t bars = base + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES;
   const uint32_t bar_w = bars, bar_mma = bars + 8 /*[2]*/, bar_h = bars + 24 /*[2]*/;
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + LT_WHI_BYTES + LT_H_BYTES + LT_POS_BYTES + 48);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   const int dir = blockIdx.y;
   const int Hr = (int)d.H;  // real hidden size; the on-chip layout is always LT_H wide
   const int64_t q0 = (int64_t)blockIdx.x * (4 * spq);
-  const int64_t G = (int64_t)d.D * 4 * Hr, OW = (int64_t)d.D * Hr;
+  const int G = d.D * 4 * Hr, OW = d.D * Hr;  // row widths of gx and out
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)dir * (2 * LT_WHI_BYTES);
 
   if (tid == 0) {
@@ -166,9 +166,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   if (tid < LT_N) {
     int64_t q = q0 + (int64_t)(tid >> 4) * spq + (tid & 15);
     if ((tid & 15) >= spq || q >= d.n_seq) q = d.n_seq - 1;  // unused slots shadow the last real sequence; never stored
-    const int64_t pos = (q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride;
-    posg_s[tid] = pos * G;
-    poso_s[tid] = pos * OW;
+    row_s[tid] = (int32_t)((q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride);  // < 2^31: checked by the launcher
   }
   tc_fence_before();
   __syncthreads();
@@ -251,20 +249,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     }
     // ---- initial state: c into its shared-memory slots (a thread only ever touches its own), h0 into the B tiles
     float* cu = c_sm + s0 * LT_H + u;  // c of (sequence s0 + j, unit u) at cu[j * LT_H]
-    const uint32_t hoff_k = (uint32_t)(q * LT_HTILE);                       // k-tile of this warp's 32 units = q
-    const uint32_t hchunk = (uint32_t)(lane >> 3), helem = (uint32_t)(lane & 7) * 2;
+    // This thread's 16-bit slot in the swizzled h tiles: k-tile q (its warp's 32 units), 16-byte chunk lane / 8; the row of
+    // sequence s0 + j is 64 B further per j and swaps chunks by (j / 2) % 4 (s0 is a multiple of 16), so four base
+    // pointers cover every j with compile-time offsets.
+    uint8_t* hb[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) hb[x] = h_sm + q * LT_HTILE + s0 * 64 + ((((lane >> 3) ^ x) & 3) << 4) + (lane & 7) * 2;
     // bf16 hi/lo split of two values with packed conversions (F2FP on the ALU pipe; the scalar F2F.BF16 runs on the
     // XU pipe, which the ex2/rcp of the gates already saturate) and 16-bit stores into the swizzled h tiles
-    auto store_h2 = [&](float ha, float hb, int sa) {
-      const __nv_bfloat162 ph = __floats2bfloat162_rn(ha, hb);
+    auto store_h2 = [&](float ha, float hb_, int j) {  // sequences s0 + j and s0 + j + 1, j even and compile-time
+      const __nv_bfloat162 ph = __floats2bfloat162_rn(ha, hb_);
       const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&ph);
-      const __nv_bfloat162 pl = __floats2bfloat162_rn(ha - __uint_as_float(hbits << 16), hb - __uint_as_float(hbits & 0xFFFF0000u));
+      const __nv_bfloat162 pl = __floats2bfloat162_rn(ha - __uint_as_float(hbits << 16), hb_ - __uint_as_float(hbits & 0xFFFF0000u));
       const uint32_t lbits = *reinterpret_cast<const uint32_t*>(&pl);
-      const uint32_t o0 = hoff_k + lt_swz((uint32_t)sa, hchunk) + helem, o1 = hoff_k + lt_swz((uint32_t)(sa + 1), hchunk) + helem;
-      *reinterpret_cast<uint16_t*>(h_sm + o0) = (uint16_t)(hbits & 0xFFFFu);
-      *reinterpret_cast<uint16_t*>(h_sm + o1) = (uint16_t)(hbits >> 16);
-      *reinterpret_cast<uint16_t*>(h_sm + 4 * LT_HTILE + o0) = (uint16_t)(lbits & 0xFFFFu);
-      *reinterpret_cast<uint16_t*>(h_sm + 4 * LT_HTILE + o1) = (uint16_t)(lbits >> 16);
+      uint8_t* o = hb[(j >> 1) & 3] + j * 64;
+      *reinterpret_cast<uint16_t*>(o) = (uint16_t)(hbits & 0xFFFFu);
+      *reinterpret_cast<uint16_t*>(o + 64) = (uint16_t)(hbits >> 16);
+      *reinterpret_cast<uint16_t*>(o + 4 * LT_HTILE) = (uint16_t)(lbits & 0xFFFFu);
+      *reinterpret_cast<uint16_t*>(o + 4 * LT_HTILE + 64) = (uint16_t)(lbits >> 16);
     };
 #pragma unroll
     for (int j = 0; j < SPT; j += 2) {
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         cu[(j + e) * LT_H] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
         h2[e] = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
       }
-      store_h2(h2[0], h2[1], s0 + j);
+      store_h2(h2[0], h2[1], j);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -285,15 +287,24 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     if (lane == 0) mbar_arrive(bar_h + 8 * half);
 
     // gx row layout: native [dir][gate][unit] (4 loads of one float, a warp reads 128 B each) or, when the host permuted
-    // the rows of W_ih (gx_interleaved), [dir][unit][gate]: one 16-byte load per sequence, a warp reads 512 contiguous B
+    // the rows of W_ih (gx_interleaved), [dir][unit][gate]: one 16-byte load per sequence, a warp reads 512 contiguous B.
+    // Addresses: byte pointer of this thread's column at step t, plus row * (row width in bytes): one IMAD.WIDE per row.
     constexpr bool gxi = kGxi;
-    const float* gxu = d.gx + (int64_t)dir * 4 * Hr + (gxi ? 4 * u : u);
-    float* outu = d.out + (int64_t)dir * Hr + u;
-    const int nvalid = (int)((d.n_seq - qb) < spq ? (d.n_seq - qb) : spq);  // real sequences of this thread (may be <= 0)
-    const int64_t stepg = d.step_stride * G, stepo = d.step_stride * OW;
+    // (the empty asm statements make these values opaque: under register pressure the compiler otherwise re-derives them
+    // from the descriptor inside every chunk, ~25 integer instructions per cell)
+    uint32_t Gb = (uint32_t)G * 4u, OWb = (uint32_t)OW * 4u;
+    asm volatile("" : "+r"(Gb), "+r"(OWb));
+    const char* gxu = reinterpret_cast<const char*>(d.gx + (int64_t)dir * 4 * Hr + (gxi ? 4 * u : u));
+    char* outu = reinterpret_cast<char*>(d.out + (int64_t)dir * Hr + u);
+    int nvalid = (int)((d.n_seq - qb) < spq ? (d.n_seq - qb) : spq);  // real sequences of this thread (may be <= 0)
+    asm volatile("" : "+r"(nvalid));
+    const int64_t stepg = d.step_stride * (int64_t)Gb, stepo = d.step_stride * (int64_t)OWb;
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(row_s) + s0;  // unsigned: row * width is one IMAD.WIDE.U32
     for (int64_t step = 0; step < d.L; ++step) {
       const int64_t t = dir ? d.L - 1 - step : step;
-      const int64_t toffg = t * stepg, toffo = t * stepo;
+      const char* gxt = gxu + t * stepg;
+      char* outt = outu + t * stepo;
+      asm volatile("" : "+l"(gxt), "+l"(outt));
       const bool last = step + 1 == d.L;
       if (!live) {  // padding lanes: h stays 0 in the B tiles; only keep the two barriers in step
         mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
@@ -302,18 +313,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         continue;
       }
       // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
-      if (step + 1 < d.L && lane < spq) {
-        const int64_t tn = dir ? t - 1 : t + 1;
-        const float* pn = d.gx + posg_s[s0 + lane] + tn * stepg + (int64_t)dir * 4 * Hr + (kGxi ? q * 128 : q * 32);
+      if (!last && lane < spq) {
+        const char* pn = gxt + (dir ? -stepg : stepg) + (uint64_t)rows[lane] * Gb - (gxi ? 4 * u : u) * 4 + (kGxi ? q * 512 : q * 128);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 32 : Hr)));
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 128 : Hr * 4)));
       }
       // gx of the first chunk is requested before the wait on the tensor core; later chunks one chunk ahead
       float gxa[4][CH], gxb[4][CH];
       auto load_gx = [&](float(&gx)[4][CH], int j0) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + j0);
+        const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          const float* p = gxu + posg_s[s0 + j0 + j] + toffg;
+          const float* p = reinterpret_cast<const float*>(gxt + (uint64_t)r[j] * Gb);
           if constexpr (gxi) {
             const float4 v4 = __ldg(reinterpret_cast<const float4*>(p));
             gx[0][j] = v4.x; gx[1][j] = v4.y; gx[2][j] = v4.z; gx[3][j] = v4.w;
@@ -332,19 +344,18 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld4(tb + (uint32_t)(g * LT_N), a[g]);
         tmem_ld_wait();
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + j0);
+        const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
         float h[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           float cv = cu[(j0 + j) * LT_H];
           h[j] = lt_cell(a[0][j] + gx[0][j], a[1][j] + gx[1][j], a[2][j] + gx[2][j], a[3][j] + gx[3][j], cv);
           cu[(j0 + j) * LT_H] = cv;
-          if (j0 + j < nvalid) {
-            outu[poso_s[s0 + j0 + j] + toffo] = h[j];
-            if (last && d.hn) d.hn[((int64_t)dir * d.n_seq + qb + j0 + j) * Hr + u] = h[j];
-          }
+          if (j0 + j < nvalid) *reinterpret_cast<float*>(outt + (uint64_t)r[j] * OWb) = h[j];
         }
 #pragma unroll
-        for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], s0 + j0 + j);
+        for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], j0 + j);
       };
 #pragma unroll
       for (int j0 = 0; j0 < SPT; j0 += 2 * CH) {
@@ -361,11 +372,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_h + 8 * half);
     }
-#pragma unroll
+    // final states: c from its slot, h_n = this thread's own last output row (read back; same thread, same address)
+    const char* outl = outu + (dir ? 0 : d.L - 1) * stepo;
+#pragma unroll 1
     for (int j = 0; j < SPT; ++j) {
-      const int64_t qq = qb + j;
-      if (!live || j >= spq || qq >= d.n_seq) continue;
-      if (d.cn) d.cn[((int64_t)dir * d.n_seq + qq) * Hr + u] = cu[j * LT_H];
+      if (!live || j >= nvalid) break;
+      const int64_t so = ((int64_t)dir * d.n_seq + qb + j) * Hr + u;
+      if (d.cn) d.cn[so] = cu[j * LT_H];
+      if (d.hn) d.hn[so] = *reinterpret_cast<const float*>(outl + (uint64_t)rows[j] * OWb);
     }
   }
 
@@ -398,6 +412,9 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int H, int D,
 bool lstm_tc_eligible(const ps_lstm_t& d) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("PS_LSTM"); off = (e && e[0] == 's') ? 1 : 0; }  // PS_LSTM=simt forces the fp32 kernel
+  // the kernel keeps 32-bit row indices: the last position touched must stay below 2^31
+  const int64_t last_pos = ((d.n_seq - 1) / d.inner) * d.outer_stride + (d.inner - 1) * d.inner_stride + (d.L - 1) * d.step_stride;
+  if (last_pos >= 2147483647LL || d.outer_stride < 0 || d.inner_stride < 0 || d.step_stride < 0) return false;
   return !off && d.w_packed != nullptr && d.H <= LT_H && d.H % 32 == 0 && (reinterpret_cast<uintptr_t>(d.w_packed) & 15) == 0 &&
          (!d.gx_interleaved || (reinterpret_cast<uintptr_t>(d.gx) & 15) == 0);
 }
