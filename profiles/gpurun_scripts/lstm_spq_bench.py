@@ -6,7 +6,7 @@ sys.path.insert(0, ".")
 from puresound_b200 import ops
 ops.require_device()
 H = int(sys.argv[1]); spq = int(os.environ["PS_LSTM_SPQ"]); D = 1; L = 100
-n_seq = 148 * 4 * spq
+n_seq = 148 * 8 * spq
 g = torch.Generator().manual_seed(0)
 w_hh_t = (0.15 * (2 * torch.rand(D, H, 4 * H, generator=g) - 1)).cuda()
 pk = ops.lstm_pack_weights(w_hh_t, H, D)
@@ -18,4 +18,4 @@ torch.cuda.synchronize(); ev[0].record()
 for _ in range(10): ops.lstm(gx, w_hh_t, **kw)
 ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / 10
-print(f"H={H} spq={spq} seqs/CTA={4*spq}: {ms*1e3:.1f} us per launch, {ms*1e3/L:.2f} us per step, {ms*1e6/L/(4*spq):.0f} ns per step and sequence")
+print(f"H={H} spq={spq} seqs/CTA={8*spq}: {ms*1e3:.1f} us per launch, {ms*1e3/L:.2f} us per step, {ms*1e6/L/(8*spq):.0f} ns per step and sequence")

@@ -19,10 +19,11 @@
 //   * gx = W_ih x + b (ps_gemm) is read in its native [position, D*4H] layout: for one gate and sequence a warp reads
 //     128 contiguous bytes; next step's lines are prefetched into L2 while this step computes.
 //
-// Warps: 0 = MMA issuer (+ TMEM allocation), 4..19 = gate warps (per half-batch two per TMEM lane quarter, 16
-// sequences each).
+// Warps: 0 = MMA issuer (+ TMEM allocation), 4..19 = gate warps (four per TMEM lane quarter; each owns 8 sequences in
+// EACH half-batch).
 // Barriers, one pair per half-batch of 32 sequences: mma_done (tcgen05.commit -> gate warps), h_ready (gate warps ->
-// MMA issuer); the halves run in antiphase, so the tensor core works on one while the other's gates are computed.
+// MMA issuer); all gate warps work through half A, then half B: the tensor core computes one half's gates while the
+// cells of the other are updated.
 // The strided position function of ps_lstm_t is honoured, so one [N,S,K,*] tensor serves both passes without a permute.
 #include <stdlib.h>
 
@@ -120,10 +121,12 @@ __device__ __forceinline__ float lt_min_nan(float x, float lim) {
 // The exponents are capped at 2^36 = exp(25) (a pre-activation below -25, or -12.5 under tanh): exp(25)^3 = 3.7e32 stays
 // finite in fp32, and the cap moves a gate by < 1.4e-11; towards -inf ex2 underflows to 0 on its own.  One FMNMX per
 // exponential.  The XU pipe (16 lanes / cycle / SM) is the floor of the gate phase.
-__device__ __forceinline__ float lt_cell(float pi, float pf, float pg, float po, float& c) {
+// The arguments are the exponents themselves: xi = -log2(e) * pre-activation (xg = -2 log2(e) * ...): the pack kernel
+// folds these factors into W_hh, and gx joins with one FFMA (LT_SCALE).
+__device__ __forceinline__ float lt_cell(float xi, float xf, float xg, float xo, float& c) {
   constexpr float L2E = 1.4426950408889634f, CAP = 36.0673760222f;
-  const float Ei = lt_ex2(lt_min_nan(-L2E * pi, CAP)), Ef = lt_ex2(lt_min_nan(-L2E * pf, CAP));
-  const float Eg = lt_ex2(lt_min_nan(-2.f * L2E * pg, CAP)), Eo = lt_ex2(lt_min_nan(-L2E * po, CAP));
+  const float Ei = lt_ex2(lt_min_nan(xi, CAP)), Ef = lt_ex2(lt_min_nan(xf, CAP));
+  const float Eg = lt_ex2(lt_min_nan(xg, CAP)), Eo = lt_ex2(lt_min_nan(xo, CAP));
   const float A = 1.f + Ei, B = 1.f + Eg, F = 1.f + Ef;
   const float AB = A * B;
   const float cn = fmaf(c, AB, (2.f - B) * F) * lt_rcp(F * AB);
@@ -132,10 +135,13 @@ __device__ __forceinline__ float lt_cell(float pi, float pf, float pg, float po,
   return (2.f - Cc) * lt_rcp((1.f + Eo) * Cc);
 }
 
-// spq = real sequences per gate warp (1..16): sequence slot s = half*32 + wq*16 + j is real iff j < spq, and a CTA owns
-// 4*spq consecutive sequences.
-template <bool kGxi>
-__global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d, const int spq) {
+// spq = real sequences per (gate warp, half-batch) (1..8): sequence slot s = half*32 + wq*8 + j is real iff j < spq, and a
+// CTA owns 8*spq consecutive sequences.  kCh2: spq > 4, i.e. two chunks of four sequences per warp and half.
+// exponent scale of gate g (i, f, g, o): sigmoid(p) = 1 / (1 + 2^(-log2(e) p)), tanh(p) = 2 / (1 + 2^(-2 log2(e) p)) - 1
+__host__ __device__ constexpr float lt_scale(int g) { return g == 2 ? -2.8853900817779268f : -1.4426950408889634f; }
+
+template <bool kGxi, bool kCh2>
+__global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t d, const int spq, const int dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
   const int Hr = (int)d.H;  // real hidden size; the on-chip layout is always LT_H wide
-  const int64_t q0 = (int64_t)blockIdx.x * (4 * spq);
+  const int64_t q0 = (int64_t)blockIdx.x * (8 * spq);
   const int G = d.D * 4 * Hr, OW = d.D * Hr;  // row widths of gx and out
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(d.w_packed) + (size_t)dir * (2 * LT_WHI_BYTES);
 
@@ -158,14 +164,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     mbar_init(bar_w, 1);
     for (int hf = 0; hf < 2; ++hf) {
       mbar_init(bar_mma + 8 * hf, 1);
-      mbar_init(bar_h + 8 * hf, 4 * LT_GWQ);  // the gate warps of a half-batch
+      mbar_init(bar_h + 8 * hf, 8 * LT_GWQ);  // every gate warp serves both half-batches
     }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)tmem_ptr_s), 512);
   if (tid < LT_N) {
-    int64_t q = q0 + (int64_t)(tid >> 4) * spq + (tid & 15);
-    if ((tid & 15) >= spq || q >= d.n_seq) q = d.n_seq - 1;  // unused slots shadow the last real sequence; never stored
+    int64_t q = q0 + (int64_t)(tid >> 3) * spq + (tid & 7);
+    if ((tid & 7) >= spq || q >= d.n_seq) q = d.n_seq - 1;  // unused slots shadow the last real sequence; never stored
     row_s[tid] = (int32_t)((q / d.inner) * d.outer_stride + (q % d.inner) * d.inner_stride);  // < 2^31: checked by the launcher
   }
   tc_fence_before();
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
           const uint32_t hs = base + LT_WHI_BYTES + (uint32_t)(hf * LT_NH * 64);  // rows [32*hf, 32*hf+32) of every h tile
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            if (dbg & 1) break;  // experiment: gate phase alone (PS_LSTM_DBG=1, results are garbage)
             const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N + hf * LT_NH);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
@@ -218,18 +225,17 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     }
   } else if (warp >= 4) {
     // ===================== gate warps =====================
-    // warp = 4 + half*4*GWQ + wq*4 + q: q = TMEM lane quarter (hardware rule: warp id % 4), half = half-batch,
-    // wq = which SPT-sequence slice of the half this warp owns
-    constexpr int GWQ = LT_GWQ, SPT = LT_NH / GWQ, CH = 4;
+    // warp = 4 + wq*4 + q: q = TMEM lane quarter (hardware rule: warp id % 4), wq = which SPH-sequence slice it owns in
+    // EACH half-batch.  Every gate warp serves both halves in turn: while it updates the cells of half A the tensor core
+    // computes half B's gates and vice versa, so with G = gate time of all 64 sequences and M = MMA time of one half the
+    // step costs max(G, G/2 + M, 2M) instead of the G/2' + M of warps bound to one half (which idle during their M).
+    constexpr int NW = LT_GWQ * 2, SPH = LT_NH / NW, CH = 4;  // 4 warps per lane quarter, 8 slots per (warp, half)
     const int q = warp & 3;
-    const int half = (warp - 4) / (4 * GWQ);
-    const int wq = ((warp - 4) >> 2) % GWQ;
+    const int wq = (warp - 4) >> 2;
     const int u = q * 32 + lane;         // hidden unit = TMEM lane
-    const int s0 = half * LT_NH + wq * SPT;
-    const int64_t qb = q0 + (int64_t)(half * GWQ + wq) * spq;  // first sequence of this warp
-    const bool live = q * 32 < Hr;                             // false: every unit of this lane quarter is padding
+    const bool live = q * 32 < Hr;       // false: every unit of this lane quarter is padding
     // ---- one-time: W_hi rows of this lane into TMEM columns [g*64, g*64+64) (each 32-bit column = 2 consecutive k)
-    if (half == 0 && wq == 0) {
+    if (wq == 0) {
       const uint32_t* wlo = reinterpret_cast<const uint32_t*>(wimg + LT_WHI_BYTES);  // [512 rows][64 words]
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -247,81 +253,94 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
+    // Sequence slot of (half, j): half*32 + wq*8 + j, holding sequence q0 + (half*4 + wq)*spq + j when j < spq.
     // ---- initial state: c into its shared-memory slots (a thread only ever touches its own), h0 into the B tiles
-    float* cu = c_sm + s0 * LT_H + u;  // c of (sequence s0 + j, unit u) at cu[j * LT_H]
+    float* cu = c_sm + (wq * SPH) * LT_H + u;  // c of (half, j) at cu[(half*32 + j) * LT_H]
     // This thread's 16-bit slot in the swizzled h tiles: k-tile q (its warp's 32 units), 16-byte chunk lane / 8; the row of
-    // sequence s0 + j is 64 B further per j and swaps chunks by (j / 2) % 4 (s0 is a multiple of 16), so four base
-    // pointers cover every j with compile-time offsets.
+    // slot (half, j) is 64 B further per sequence and swaps chunks by (j / 2) % 4 (the slot base is a multiple of 8), so
+    // four base pointers cover every (half, j) with compile-time offsets.
     uint8_t* hb[4];
 #pragma unroll
-    for (int x = 0; x < 4; ++x) hb[x] = h_sm + q * LT_HTILE + s0 * 64 + ((((lane >> 3) ^ x) & 3) << 4) + (lane & 7) * 2;
+    for (int x = 0; x < 4; ++x) hb[x] = h_sm + q * LT_HTILE + (wq * SPH) * 64 + ((((lane >> 3) ^ x) & 3) << 4) + (lane & 7) * 2;
     // bf16 hi/lo split of two values with packed conversions (F2FP on the ALU pipe; the scalar F2F.BF16 runs on the
     // XU pipe, which the ex2/rcp of the gates already saturate) and 16-bit stores into the swizzled h tiles
-    auto store_h2 = [&](float ha, float hb_, int j) {  // sequences s0 + j and s0 + j + 1, j even and compile-time
+    auto store_h2 = [&](float ha, float hb_, int half, int j) {  // slots (half, j) and (half, j + 1); j even, compile-time
       const __nv_bfloat162 ph = __floats2bfloat162_rn(ha, hb_);
       const uint32_t hbits = *reinterpret_cast<const uint32_t*>(&ph);
       const __nv_bfloat162 pl = __floats2bfloat162_rn(ha - __uint_as_float(hbits << 16), hb_ - __uint_as_float(hbits & 0xFFFF0000u));
       const uint32_t lbits = *reinterpret_cast<const uint32_t*>(&pl);
-      uint8_t* o = hb[(j >> 1) & 3] + j * 64;
+      uint8_t* o = hb[(j >> 1) & 3] + (half * LT_NH + j) * 64;
       *reinterpret_cast<uint16_t*>(o) = (uint16_t)(hbits & 0xFFFFu);
       *reinterpret_cast<uint16_t*>(o + 64) = (uint16_t)(hbits >> 16);
       *reinterpret_cast<uint16_t*>(o + 4 * LT_HTILE) = (uint16_t)(lbits & 0xFFFFu);
       *reinterpret_cast<uint16_t*>(o + 4 * LT_HTILE + 64) = (uint16_t)(lbits >> 16);
     };
+    int nv[2];  // real sequences of this warp in each half (may be <= 0)
 #pragma unroll
-    for (int j = 0; j < SPT; j += 2) {
-      float h2[2];
+    for (int half = 0; half < 2; ++half) {
+      const int64_t qb = q0 + (int64_t)(half * NW + wq) * spq;
+      nv[half] = (int)((d.n_seq - qb) < spq ? (d.n_seq - qb) : spq);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int64_t qq = qb + j + e;
-        const bool valid = live && j + e < spq && qq < d.n_seq;
-        const int64_t so = ((int64_t)dir * d.n_seq + qq) * Hr + u;
-        cu[(j + e) * LT_H] = (valid && d.c0) ? __ldg(d.c0 + so) : 0.f;
-        h2[e] = (valid && d.h0) ? __ldg(d.h0 + so) : 0.f;
+      for (int j = 0; j < SPH; j += 2) {
+        float h2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          // unused slots (j >= spq, or beyond the last sequence) are exact shadows of sequence n_seq - 1
+          const int64_t qq = (j + e < nv[half]) ? qb + j + e : d.n_seq - 1;
+          const int64_t so = ((int64_t)dir * d.n_seq + qq) * Hr + u;
+          cu[(half * LT_NH + j + e) * LT_H] = (live && d.c0) ? __ldg(d.c0 + so) : 0.f;
+          h2[e] = (live && d.h0) ? __ldg(d.h0 + so) : 0.f;
+        }
+        store_h2(h2[0], h2[1], half, j);
       }
-      store_h2(h2[0], h2[1], j);
     }
+    auto release_half = [&](int half) {  // h_t of this half is in shared memory (async proxy), its accumulators are read
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_h + 8 * half);
+    };
     fence_proxy_async();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_h + 8 * half);
+    if (lane == 0) { mbar_arrive(bar_h); mbar_arrive(bar_h + 8); }
 
     // gx row layout: native [dir][gate][unit] (4 loads of one float, a warp reads 128 B each) or, when the host permuted
     // the rows of W_ih (gx_interleaved), [dir][unit][gate]: one 16-byte load per sequence, a warp reads 512 contiguous B.
     // Addresses: byte pointer of this thread's column at step t, plus row * (row width in bytes): one IMAD.WIDE per row.
-    constexpr bool gxi = kGxi;
     // (the empty asm statements make these values opaque: under register pressure the compiler otherwise re-derives them
     // from the descriptor inside every chunk, ~25 integer instructions per cell)
+    constexpr bool gxi = kGxi;
     uint32_t Gb = (uint32_t)G * 4u, OWb = (uint32_t)OW * 4u;
-    asm volatile("" : "+r"(Gb), "+r"(OWb));
+    asm volatile("" : "+r"(Gb), "+r"(OWb), "+r"(nv[0]), "+r"(nv[1]));
     const char* gxu = reinterpret_cast<const char*>(d.gx + (int64_t)dir * 4 * Hr + (gxi ? 4 * u : u));
     char* outu = reinterpret_cast<char*>(d.out + (int64_t)dir * Hr + u);
-    int nvalid = (int)((d.n_seq - qb) < spq ? (d.n_seq - qb) : spq);  // real sequences of this thread (may be <= 0)
-    asm volatile("" : "+r"(nvalid));
     const int64_t stepg = d.step_stride * (int64_t)Gb, stepo = d.step_stride * (int64_t)OWb;
-    const uint32_t* rows = reinterpret_cast<const uint32_t*>(row_s) + s0;  // unsigned: row * width is one IMAD.WIDE.U32
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(row_s) + wq * SPH;  // unsigned: row * width is one IMAD.WIDE.U32
     for (int64_t step = 0; step < d.L; ++step) {
       const int64_t t = dir ? d.L - 1 - step : step;
       const char* gxt = gxu + t * stepg;
       char* outt = outu + t * stepo;
       asm volatile("" : "+l"(gxt), "+l"(outt));
-      const bool last = step + 1 == d.L;
-      if (!live) {  // padding lanes: h stays 0 in the B tiles; only keep the two barriers in step
-        mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_h + 8 * half);
+      if (!live) {  // padding lanes: h stays 0 in the B tiles; only keep the barriers in step
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_h + 8 * half);
+        }
         continue;
       }
-      // next step's gx lines -> L2 (lane j covers sequence s0+j; 4 gates x 128 B per warp quarter)
-      if (!last && lane < spq) {
-        const char* pn = gxt + (dir ? -stepg : stepg) + (uint64_t)rows[lane] * Gb - (gxi ? 4 * u : u) * 4 + (kGxi ? q * 512 : q * 128);
+      // next step's gx lines -> L2 (lanes 0-7 / 8-15 cover the slots of half A / B; 4 gates x 128 B per warp quarter)
+      if (step + 1 < d.L && lane < 16 && (lane & 7) < spq) {
+        const char* pn = gxt + (dir ? -stepg : stepg) + (uint64_t)rows[(lane >> 3) * LT_NH + (lane & 7)] * Gb - (gxi ? 4 * u : u) * 4 +
+                         (kGxi ? q * 512 : q * 128);
 #pragma unroll
         for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 128 : Hr * 4)));
       }
-      // gx of the first chunk is requested before the wait on the tensor core; later chunks one chunk ahead
       float gxa[4][CH], gxb[4][CH];
-      auto load_gx = [&](float(&gx)[4][CH], int j0) {
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + j0);
+      auto load_gx = [&](float(&gx)[4][CH], int half, int j0) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + half * LT_NH + j0);
         const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
@@ -335,51 +354,65 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
           }
         }
       };
-      load_gx(gxa, 0);
-      mbar_wait(bar_mma + 8 * half, (uint32_t)(step & 1));
-      tc_fence_after();
-      auto chunk = [&](const float(&gx)[4][CH], int j0) {
+      auto chunk = [&](const float(&gx)[4][CH], int half, int j0) {
         float a[4][CH];
-        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + LT_ACC_COL + (uint32_t)(s0 + j0);
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + LT_ACC_COL + (uint32_t)(half * LT_NH + wq * SPH + j0);
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld4(tb + (uint32_t)(g * LT_N), a[g]);
         tmem_ld_wait();
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + j0);
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + half * LT_NH + j0);
         const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
         float h[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
-          float cv = cu[(j0 + j) * LT_H];
-          h[j] = lt_cell(a[0][j] + gx[0][j], a[1][j] + gx[1][j], a[2][j] + gx[2][j], a[3][j] + gx[3][j], cv);
-          cu[(j0 + j) * LT_H] = cv;
-          if (j0 + j < nvalid) *reinterpret_cast<float*>(outt + (uint64_t)r[j] * OWb) = h[j];
+          float cv = cu[(half * LT_NH + j0 + j) * LT_H];
+          h[j] = lt_cell(fmaf(gx[0][j], lt_scale(0), a[0][j]), fmaf(gx[1][j], lt_scale(1), a[1][j]),
+                         fmaf(gx[2][j], lt_scale(2), a[2][j]), fmaf(gx[3][j], lt_scale(3), a[3][j]), cv);
+          cu[(half * LT_NH + j0 + j) * LT_H] = cv;
+          // unconditional: an unused slot shadows the last real sequence from its initial state on, so it stores the
+          // same value to the same address
+          *reinterpret_cast<float*>(outt + (uint64_t)r[j] * OWb) = h[j];
         }
 #pragma unroll
-        for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], j0 + j);
+        for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], half, j0 + j);
       };
-#pragma unroll
-      for (int j0 = 0; j0 < SPT; j0 += 2 * CH) {
-        if (j0 >= spq) break;
-        const bool two = j0 + CH < spq;
-        if (two) load_gx(gxb, j0 + CH);
-        chunk(gxa, j0);
-        if (j0 + 2 * CH < spq) load_gx(gxa, j0 + 2 * CH);
-        if (two) chunk(gxb, j0 + CH);
+      // gx of a chunk is requested one chunk ahead (the first one before the wait on the tensor core)
+      const uint32_t par = (uint32_t)(step & 1);
+      load_gx(gxa, 0, 0);
+      mbar_wait(bar_mma, par);
+      tc_fence_after();
+      if constexpr (kCh2) {
+        load_gx(gxb, 0, CH);
+        chunk(gxa, 0, 0);
+        load_gx(gxa, 1, 0);
+        chunk(gxb, 0, CH);
+        release_half(0);
+        mbar_wait(bar_mma + 8, par);
+        tc_fence_after();
+        load_gx(gxb, 1, CH);
+        chunk(gxa, 1, 0);
+        chunk(gxb, 1, CH);
+      } else {
+        load_gx(gxb, 1, 0);
+        chunk(gxa, 0, 0);
+        release_half(0);
+        mbar_wait(bar_mma + 8, par);
+        tc_fence_after();
+        chunk(gxb, 1, 0);
       }
-      // h_t is in shared memory for the tensor core (async proxy) and this step's accumulators have been read
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_h + 8 * half);
+      release_half(1);
     }
     // final states: c from its slot, h_n = this thread's own last output row (read back; same thread, same address)
     const char* outl = outu + (dir ? 0 : d.L - 1) * stepo;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
 #pragma unroll 1
-    for (int j = 0; j < SPT; ++j) {
-      if (!live || j >= nvalid) break;
-      const int64_t so = ((int64_t)dir * d.n_seq + qb + j) * Hr + u;
-      if (d.cn) d.cn[so] = cu[j * LT_H];
-      if (d.hn) d.hn[so] = *reinterpret_cast<const float*>(outl + (uint64_t)rows[j] * OWb);
+      for (int j = 0; j < SPH; ++j) {
+        if (!live || j >= nv[half]) break;
+        const int64_t so = ((int64_t)dir * d.n_seq + q0 + (int64_t)(half * NW + wq) * spq + j) * Hr + u;
+        if (d.cn) d.cn[so] = cu[(half * LT_NH + j) * LT_H];
+        if (d.hn) d.hn[so] = *reinterpret_cast<const float*>(outl + (uint64_t)rows[half * LT_NH + j] * OWb);
+      }
     }
   }
 
@@ -399,7 +432,8 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int H, int D,
   const int dir = (int)(i / (4 * LT_H * LT_H));
   const int r = (int)((i / LT_H) % (4 * LT_H)), k = (int)(i % LT_H);  // padded W_hh[gate*128 + unit][k]
   const bool real = (r % LT_H) < H && k < H;
-  const float w = real ? w_hh_t[((int64_t)dir * H + k) * 4 * H + (r / LT_H) * H + (r % LT_H)] : 0.f;  // W_hh[g*H+unit][k]
+  // W_hh[g*H+unit][k], times the gate's exponent scale (lt_cell takes exponents)
+  const float w = real ? lt_scale(r / LT_H) * w_hh_t[((int64_t)dir * H + k) * 4 * H + (r / LT_H) * H + (r % LT_H)] : 0.f;
   const __nv_bfloat16 h = __float2bfloat16_rn(w);
   const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
   uint8_t* o = out + (size_t)dir * (2 * LT_WHI_BYTES);
@@ -425,29 +459,48 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
   if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(lstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    e = cudaFuncSetAttribute(lstm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(lstm_tc_kernel)"); return PS_ERR_CUDA; }
     attr_set[dev] = true;
   }
-  // Sequences per CTA: 64 when the problem needs more than one wave of CTAs anyway, else the smallest count whose grid
-  // still fits one wave (each CTA's step shortens with its sequence count).
+  // Sequences per CTA = 8 * spq.  A step costs about the same up to 32 sequences (the 192 MMAs of a step are the floor) and
+  // grows with the number of 4-sequence chunks per warp beyond (measured on B200, H = 128: 3.7 / 4.7 / 5.1 us for
+  // <= 32 / 48 / 64 sequences, profiles/r01_s3_lstm_notes.md); the launch takes ceil(CTAs / SMs) waves of L such steps.
+  // Pick the cheapest, larger CTAs on a tie.
   static int n_sm[64] = {};
   if (!n_sm[dev]) {
     e = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
   }
-  int spq = LT_N / 4;
   static int spq_env = -1;
   if (spq_env < 0) { const char* ev = getenv("PS_LSTM_SPQ"); spq_env = ev ? atoi(ev) : 0; }
-  if (spq_env >= 1 && spq_env <= 16) spq = spq_env;
-  else
-    while (spq > 4 && cdiv(d.n_seq, 2 * spq) * d.D <= n_sm[dev]) spq >>= 1;
-  const int64_t nblk = cdiv(d.n_seq, 4 * spq);
+  int spq = 8;
+  if (spq_env >= 1 && spq_env <= 8) {
+    spq = spq_env;
+  } else {
+    static const int step_cost[9] = {0, 37, 37, 37, 37, 47, 47, 51, 51};
+    int64_t best = 0;
+    for (int c = 8; c >= 1; --c) {
+      const int64_t waves = cdiv(cdiv(d.n_seq, 8 * c) * d.D, n_sm[dev]);
+      const int64_t cost = waves * step_cost[c];
+      if (c == 8 || cost < best) { best = cost; spq = c; }
+    }
+  }
+  static int dbg = -1;
+  if (dbg < 0) { const char* ev = getenv("PS_LSTM_DBG"); dbg = ev ? atoi(ev) : 0; }
+  const int64_t nblk = cdiv(d.n_seq, 8 * spq);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
-  if (d.gx_interleaved) lstm_tc_kernel<true><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq);
-  else lstm_tc_kernel<false><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq);
+  if (d.gx_interleaved) {
+    if (spq > 4) lstm_tc_kernel<true, true><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq, dbg);
+    else lstm_tc_kernel<true, false><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq, dbg);
+  } else {
+    if (spq > 4) lstm_tc_kernel<false, true><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq, dbg);
+    else lstm_tc_kernel<false, false><<<grid, LT_THREADS, LT_SMEM, s>>>(d, spq, dbg);
+  }
   PS_CHECK_LAUNCH("lstm_tc_kernel");
   return PS_OK;
 }

@@ -223,10 +223,11 @@ def test_short_k_filterbank_kernel(ops, M, K, hop, relu):
 
 
 @pytest.mark.parametrize("H,D,N,S,K", [
-    (128, 1, 2, 37, 50), (128, 2, 2, 37, 50),   # 74 / 100 sequences: 16 per CTA
+    (128, 1, 2, 37, 50), (128, 2, 2, 37, 50),   # 74 sequences: one wave whatever the CTA size -> 32 per CTA
     (64, 1, 2, 37, 50), (64, 2, 1, 21, 30),     # veve_dprnn_v0_causal's hidden size: units 64..127 are zero padding
     (96, 2, 1, 19, 12), (32, 1, 3, 11, 9),
-    (128, 2, 4, 601, 6),                         # 2404 sequences x 2 directions: more than a wave -> 64 per CTA
+    (128, 2, 4, 601, 6),                         # 2404 sequences x 2 directions: 48 per CTA (second chunk half empty)
+    (128, 1, 4, 2250, 3),                        # 9000 sequences: one wave only with 64 per CTA
     (64, 1, 4, 751, 5),                          # 3004 sequences: 32 per CTA
 ])
 def test_lstm_tensor_core_path(ops, H, D, N, S, K):
