@@ -221,6 +221,21 @@ PS_API int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void*
 /* FiLM combine (lobe/trivial.py:163-165): y = sb[:, :C] * xn + sb[:, C:]; sb [rows, 2C] */
 PS_API int ps_film_combine(const float* sb, const float* xn, float* y, int64_t rows, int64_t C, void* stream);
 
+/* Gated product of GatedTCN (conv_tasnet.py:141-205):  y = a' * sigmoid(b'),  a' = act_a(pro_a(a)), b' = act_b(pro_b(b)),
+ * with pro_* as in ps_gemm_t (NONE / AFFINE / ROWNORM; rowstats are [batch, rows, 2]) so the two branch norms + PReLUs
+ * are applied on load.  b == NULL: y = a' (strided copy-transform, used to write the FiLM-modulated right-branch input
+ * into the zero-padded conv buffer, conv_tasnet.py:197-200).  All strides in floats (float4 path when C, the strides
+ * and the pointers are 16-byte friendly, scalar otherwise). */
+typedef struct {
+  int64_t batch, rows, C;
+  const float* a; int64_t a_batch_stride, a_row_stride;
+  const float* b; int64_t b_batch_stride, b_row_stride;
+  float* y; int64_t y_batch_stride, y_row_stride;
+  int32_t a_mode, a_act; const float* a_pa; const float* a_pb; int64_t a_pro_batch_stride; const float* a_rowstats; const float* a_slope;
+  int32_t b_mode, b_act; const float* b_pa; const float* b_pb; int64_t b_pro_batch_stride; const float* b_rowstats; const float* b_slope;
+} ps_gated_t;
+PS_API int ps_gated(const ps_gated_t* d, void* stream);
+
 /* [batch, R, C] -> [batch, C, R] (boundary conversion to/from the reference's [N,C,T]) */
 PS_API int ps_transpose(const float* x, float* y, int64_t batch, int64_t R, int64_t C, void* stream);
 

@@ -31,6 +31,21 @@ def describe_tcn(m: nn.Module) -> dict:
     }
 
 
+def describe_gated_tcn(m: nn.Module) -> dict:
+    c = m.left_conv[0]
+    return {
+        "type": "GatedTCN",
+        "in_channels": m.out_conv.out_channels,
+        "hid_channels": m.out_conv.in_channels,
+        "emb_dim": (m.cond_scale.in_channels if m.use_film else m.right_conv[0].in_channels - m.out_conv.in_channels),
+        "kernel": c.kernel_size[0],
+        "dilation": c.dilation[0],
+        "causal": bool(m.causal),
+        "tcn_norm": _norm_kind(m.left_conv[1]),
+        "use_film": bool(m.use_film),
+    }
+
+
 def describe_encoder(m: nn.Module) -> dict:
     n = type(m).__name__
     if n == "FreeEncDec":
@@ -96,6 +111,8 @@ def describe_speaker_net(m) -> list:
             out.append({"type": "Magnitude", "drop_first": bool(l.drop_first), "log1p": bool(l.log1p)})
         elif n == "TCN":
             out.append(describe_tcn(l))
+        elif n == "GatedTCN":
+            out.append(describe_gated_tcn(l))
         elif n == "AttentiveStatisticsPooling":
             out.append({"type": n, "channels": l.conv.out_channels, "attention_channels": l.conv.in_channels})
         elif n == "Conv1d":

@@ -164,26 +164,49 @@ def tcn_block(
     return x + res
 
 
+def gated_tcn_block(
+    sd: SD, p: str, x: Tensor, embed: Optional[Tensor], kernel: int, dilation: int, causal: bool, tcn_norm: str
+) -> Tensor:
+    """GatedTCN.forward, conv_tasnet.py:174-215.  Padding rule :122-124: both sides by ``padd`` (the
+    causal variant pads (k-1)*d on both sides and trims the tail after out_conv, :209-210); the embedding is concatenated
+    before the zero padding of the right conv (:191-194) or applied as FiLM (:196-200, present iff the block holds
+    ``cond_scale``)."""
+    pad = (kernel - 1) * dilation if causal else (kernel - 1) * dilation // 2
+    res = x
+    x = F.conv1d(x, sd[p + "in_conv.weight"])
+    if embed is not None:
+        if p + "cond_scale.weight" not in sd:
+            x_r = torch.cat([x, embed.unsqueeze(-1).repeat(1, 1, x.size(2))], dim=1)
+        else:
+            c = embed.unsqueeze(-1)
+            x_r = F.conv1d(c, sd[p + "cond_scale.weight"]) * x + F.conv1d(c, sd[p + "cond_bias.weight"])
+    else:
+        x_r = x
+    left = F.conv1d(x, sd[p + "left_conv.0.weight"], dilation=dilation, padding=pad)
+    left = F.prelu(norm_apply(tcn_norm, sd, p + "left_conv.1.", left), sd[p + "left_conv.2.weight"])
+    right = F.conv1d(x_r, sd[p + "right_conv.0.weight"], dilation=dilation, padding=pad)
+    right = torch.sigmoid(F.prelu(norm_apply(tcn_norm, sd, p + "right_conv.1.", right), sd[p + "right_conv.2.weight"]))
+    x = F.conv1d(left * right, sd[p + "out_conv.weight"])
+    if causal:
+        x = x[..., :-pad]
+    return x + res
+
+
 def conv_tasnet(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tensor:
-    """ConvTasNet.forward (tcn_layer='normal'), conv_tasnet.py:338-359; dilation
-    schedule ``tcn_dilated_basic ** i`` from :290."""
-    if a["tcn_layer"].lower() != "normal":
-        raise NotImplementedError("GatedTCN is a 'next' row (SURVEY 8f)")
+    """ConvTasNet.forward, conv_tasnet.py:338-359; dilation schedule ``tcn_dilated_basic ** i`` from :290; block class
+    by ``tcn_layer`` (:270-275; GatedTCN takes no dconv_norm)."""
+    layer = a["tcn_layer"].lower()
+    if layer not in ("normal", "gated"):
+        raise NameError
     if a["embed_norm"] and dvec is not None:
         dvec = F.normalize(dvec, p=2, dim=1)
     for r in range(a["repeat_tcn"]):
         for i in range(a["per_tcn_stack"]):
-            x = tcn_block(
-                sd,
-                f"{p}tcn_list.{r}.{i}.",
-                x,
-                dvec if a["tcn_with_embed"][i] else None,
-                a["tcn_kernel"],
-                a["tcn_dilated_basic"] ** i,
-                a["causal"],
-                a["tcn_norm"],
-                a["dconv_norm"],
-            )
+            q, e, d = f"{p}tcn_list.{r}.{i}.", dvec if a["tcn_with_embed"][i] else None, a["tcn_dilated_basic"] ** i
+            if layer == "gated":
+                x = gated_tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"])
+            else:
+                x = tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"], a["dconv_norm"])
     return x
 
 
@@ -470,6 +493,8 @@ def speaker_net(sd: SD, p: str, layers: Sequence[dict], x: Tensor) -> Tensor:
             x = magnitude(x, l["drop_first"], l["log1p"])
         elif t == "TCN":
             x = tcn_block(sd, q, x, None, l["kernel"], l["dilation"], l["causal"], l["tcn_norm"], l["dconv_norm"])
+        elif t == "GatedTCN":  # the speaker nets of the tse_unet_tcn recipes (egs/tse/model.py:226-236)
+            x = gated_tcn_block(sd, q, x, None, l["kernel"], l["dilation"], l["causal"], l["tcn_norm"])
         elif t == "AttentiveStatisticsPooling":
             x = asp(sd, q, x)
         elif t == "Conv1d":

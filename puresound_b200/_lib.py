@@ -71,7 +71,18 @@ class StreamDwDesc(C.Structure):
     ]
 
 
-STRUCTS = {0: GemmDesc, 1: DwconvDesc, 2: LstmDesc, 3: StreamDwDesc}
+class GatedDesc(C.Structure):
+    _fields_ = [
+        ("batch", I64), ("rows", I64), ("C", I64),
+        ("a", P), ("a_batch_stride", I64), ("a_row_stride", I64),
+        ("b", P), ("b_batch_stride", I64), ("b_row_stride", I64),
+        ("y", P), ("y_batch_stride", I64), ("y_row_stride", I64),
+        ("a_mode", I32), ("a_act", I32), ("a_pa", P), ("a_pb", P), ("a_pro_batch_stride", I64), ("a_rowstats", P), ("a_slope", P),
+        ("b_mode", I32), ("b_act", I32), ("b_pa", P), ("b_pb", P), ("b_pro_batch_stride", I64), ("b_rowstats", P), ("b_slope", P),
+    ]
+
+
+STRUCTS = {0: GemmDesc, 1: DwconvDesc, 2: LstmDesc, 3: StreamDwDesc, 4: GatedDesc}
 
 # name -> (restype, argtypes); must list every symbol include/puresound_b200.h declares
 SIGNATURES = {
@@ -101,6 +112,7 @@ SIGNATURES = {
     "ps_lstm_packed_bytes": (I64, [I64, I32]),
     "ps_lstm_pack_weights": (C.c_int, [P, I64, I32, P, P]),
     "ps_film_combine": (C.c_int, [P, P, P, I64, I64, P]),
+    "ps_gated": (C.c_int, [C.POINTER(GatedDesc), P]),
     "ps_transpose": (C.c_int, [P, P, I64, I64, I64, P]),
     "ps_stream_dwconv_step": (C.c_int, [C.POINTER(StreamDwDesc), P]),
     "ps_stream_push": (C.c_int, [P, P, P, I64, I64, I64, P]),

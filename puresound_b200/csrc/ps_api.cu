@@ -52,6 +52,7 @@ extern "C" int64_t ps_struct_size(int which) {
     case 1: return (int64_t)sizeof(ps_dwconv_t);
     case 2: return (int64_t)sizeof(ps_lstm_t);
     case 3: return (int64_t)sizeof(ps_stream_dw_t);
+    case 4: return (int64_t)sizeof(ps_gated_t);
     default: return -1;
   }
 }

@@ -116,10 +116,13 @@ def gemm(
     epi_act: int = ACT_NONE, epi_slope: Optional[Tensor] = None, residual: Optional[Tensor] = None,
     want_stats: bool = False, out: Optional[Tensor] = None, backend: int = GEMM_AUTO,
     w_packed: Optional[Tensor] = None, fin=None, ln=None,
+    y_strides: Optional[tuple] = None, res_strides: Optional[tuple] = None,
 ):
     """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None) - or, with
     want_stats and fin=(gamma, beta, eps), (Y, FoldedAffine): the producer also finalizes the gLN/gGN statistics.
-    ln=(weight, bias, eps): Y = residual + LayerNorm_M(X W^T + bias) (fused epilogue on the tcgen05 kernel when M == 128)."""
+    ln=(weight, bias, eps): Y = residual + LayerNorm_M(X W^T + bias) (fused epilogue on the tcgen05 kernel when M == 128).
+    y_strides / res_strides = (batch stride, row stride) in floats when `out` / `residual` are views into larger buffers
+    (`out` is then the tensor whose data_ptr is the first output element)."""
     lib = _lib.load()
     _req(X, "gemm X")
     _dev(W, "gemm W")  # may be a row-strided view (embedding columns of in_conv)
@@ -132,7 +135,7 @@ def gemm(
     d.batch, d.rows, d.M, d.K = batch, rows, M, K
     d.X, d.x_batch_stride, d.x_row_stride = X.data_ptr(), x_batch_stride, x_row_stride
     d.W, d.w_row_stride = W.data_ptr(), w_row_stride
-    d.Y, d.y_batch_stride, d.y_row_stride = Y.data_ptr(), rows * M, M
+    d.Y, (d.y_batch_stride, d.y_row_stride) = Y.data_ptr(), (y_strides if y_strides is not None else (rows * M, M))
     d.pro_mode, d.pro_act = pro.mode, pro.act
     d.pro_a, d.pro_b, d.pro_batch_stride = _p(pro.a), _p(pro.b), pro.batch_stride
     d.pro_rowstats, d.pro_slope, d.X2 = _p(pro.rowstats), _p(pro.slope), _p(pro.x2)
@@ -141,7 +144,8 @@ def gemm(
     d.backend = force_gemm_backend if force_gemm_backend is not None else backend
     d.epi_slope = _p(epi_slope)
     if residual is not None:
-        d.residual, d.res_batch_stride, d.res_row_stride = residual.data_ptr(), rows * M, M
+        d.residual = residual.data_ptr()
+        d.res_batch_stride, d.res_row_stride = res_strides if res_strides is not None else (rows * M, M)
     d.stats_partials = _p(partials)
     d.W_packed = _p(w_packed)
     folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
@@ -351,6 +355,39 @@ def lstm_pack_weights(w_hh_t: Tensor, H: int, D: int) -> Optional[Tensor]:
     _lib.check(lib.ps_lstm_pack_weights(_req(w_hh_t, "lstm w_hh_t").data_ptr(), H, D, out.data_ptr(), _stream()), "ps_lstm_pack_weights")
     _launched()
     return out
+
+
+def _set_side(d, side: str, x: Tensor, strides, pro: Prologue):
+    setattr(d, side, x.data_ptr())
+    setattr(d, side + "_batch_stride", strides[0])
+    setattr(d, side + "_row_stride", strides[1])
+    setattr(d, side + "_mode", pro.mode)
+    setattr(d, side + "_act", pro.act)
+    setattr(d, side + "_pa", _p(pro.a))
+    setattr(d, side + "_pb", _p(pro.b))
+    setattr(d, side + "_pro_batch_stride", pro.batch_stride)
+    setattr(d, side + "_rowstats", _p(pro.rowstats))
+    setattr(d, side + "_slope", _p(pro.slope))
+
+
+def gated(a: Tensor, pro_a: Prologue, b: Optional[Tensor] = None, pro_b: Prologue = NO_PRO, *, batch: int, rows: int, C_: int,
+          a_strides: Optional[tuple] = None, b_strides: Optional[tuple] = None, out: Optional[Tensor] = None,
+          y_strides: Optional[tuple] = None) -> Tensor:
+    """y = a' * sigmoid(b') with a' = act(pro_a(a)), b' = act(pro_b(b)) (the GatedTCN product, conv_tasnet.py:205); with
+    b=None y = a' (strided transform copy).  Strides are (batch, row) in floats; default contiguous [batch, rows, C]."""
+    lib = _lib.load()
+    y = out if out is not None else torch.empty(batch, rows, C_, device=a.device, dtype=torch.float32)
+    d = _lib.GatedDesc()
+    d.batch, d.rows, d.C = batch, rows, C_
+    dflt = (rows * C_, C_)
+    _set_side(d, "a", _dev(a, "gated a"), a_strides or dflt, pro_a)
+    if b is not None:
+        _set_side(d, "b", _dev(b, "gated b"), b_strides or dflt, pro_b)
+    d.y = y.data_ptr()
+    d.y_batch_stride, d.y_row_stride = y_strides or dflt
+    _lib.check(lib.ps_gated(C.byref(d), _stream()), "ps_gated")
+    _launched()
+    return y
 
 
 def film_combine(sb: Tensor, xn: Tensor) -> Tensor:

@@ -10,7 +10,7 @@ from typing import Optional
 import torch.nn as nn
 
 from .nnet.base_nn import SoTaskWrapModule
-from .nnet.conv_tasnet import TCN, ConvTasNet
+from .nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
 from .nnet.dprnn import DPRNN
 from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from .nnet.lobe.pooling import AttentiveStatisticsPooling
@@ -76,6 +76,17 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvEncDec(512, "hann", 512, hop_length=128, trainable=True, output_format="Complex"),
             ConvTasNet(512, 192, True, tcn_dim=256, repeat_tcn=3, per_tcn_stack=8, tcn_with_embed=[1, 0, 0, 0, 0, 0, 0, 0]),
             speaker_net=nn.ModuleList([Magnitude(drop_first=False)] + [TCN(256, 256, 3, dilation=2 ** i) for i in range(5)]
+                                      + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(512, 192, 1, bias=False)]),
+            mask_constraint="linear", drop_first_bin=True, verbose=verbose)
+    if name == "cfg4_gated":
+        # cfg4 with the GatedTCN blocks of the reference's STFT-domain TSE recipes (tse_unet_tcn_v0, egs/tse/model.py:184-243:
+        # gated masker blocks tcn_dim 256 with the embedding concatenated in block 0 of each repeat, and their speaker net
+        # of five GatedTCN(256, 128) blocks) - the recipes' U-Net shell itself is a later row
+        return SoTaskWrapModule(
+            ConvEncDec(512, "hann", 512, hop_length=128, trainable=True, output_format="Complex"),
+            ConvTasNet(512, 192, True, tcn_layer="gated", tcn_dim=256, repeat_tcn=3, per_tcn_stack=5, tcn_with_embed=[1, 0, 0, 0, 0]),
+            speaker_net=nn.ModuleList([Magnitude(drop_first=False)]
+                                      + [GatedTCN(256, 128, 3, dilation=2 ** i, causal=False, tcn_norm="gLN") for i in range(5)]
                                       + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(512, 192, 1, bias=False)]),
             mask_constraint="linear", drop_first_bin=True, verbose=verbose)
     if name in ("cfg5", "cfg5_offline"):

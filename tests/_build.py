@@ -2,7 +2,7 @@
 import torch.nn as nn
 
 from puresound_b200.nnet.base_nn import SoTaskWrapModule
-from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet
+from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
 from puresound_b200.nnet.dprnn import DPRNN
 from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
@@ -13,6 +13,11 @@ from puresound_b200.nnet.skim import SkiM
 def tcn(c):
     return TCN(c["in_channels"], c["hid_channels"], c["kernel"], c["dilation"], emb_dim=c["emb_dim"], causal=c["causal"],
                tcn_norm=c["tcn_norm"], dconv_norm=c["dconv_norm"])
+
+
+def gated_tcn(c):
+    return GatedTCN(c["in_channels"], c["hid_channels"], c["kernel"], c["dilation"], emb_dim=c["emb_dim"], causal=c["causal"],
+                    tcn_norm=c["tcn_norm"], use_film=c["use_film"])
 
 
 def encoder(c):
@@ -44,6 +49,8 @@ def speaker_net(layers):
             mods.append(Magnitude(l["drop_first"], l["log1p"]))
         elif t == "TCN":
             mods.append(tcn(l))
+        elif t == "GatedTCN":
+            mods.append(gated_tcn(l))
         elif t == "AttentiveStatisticsPooling":
             mods.append(AttentiveStatisticsPooling(l["channels"], l["attention_channels"]))
         elif t == "Conv1d":

@@ -36,7 +36,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 
 from puresound.nnet.base_nn import SoTaskWrapModule  # noqa: E402
-from puresound.nnet.conv_tasnet import TCN, ConvTasNet  # noqa: E402
+from puresound.nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN  # noqa: E402
 from puresound.nnet.dprnn import DPRNN  # noqa: E402
 from puresound.nnet.lobe.encoder import ConvEncDec, FreeEncDec  # noqa: E402
 from puresound.nnet.lobe.pooling import AttentiveStatisticsPooling  # noqa: E402
@@ -348,6 +348,70 @@ def skim_cases():
 
 
 @torch.no_grad()
+def gated_cases():
+    """GatedTCN (conv_tasnet.py:93-215): every conditioning mode and norm, an odd channel count, a
+    gated Conv-TasNet stack, and a wrapper whose speaker net is built from GatedTCN blocks as in the tse_unet_tcn recipes
+    (egs/tse/model.py:226-236).  Own file, so the vectors generated earlier stay byte-identical."""
+    cases = {}
+    for tag, (cin, hid, kw) in {
+        "gln": (16, 24, dict(dilation=2, causal=False, tcn_norm="gLN", emb_dim=0)),
+        "gln_concat": (16, 24, dict(dilation=4, causal=False, tcn_norm="gLN", emb_dim=8)),
+        "gln_film": (16, 24, dict(dilation=2, causal=False, tcn_norm="gLN", emb_dim=8, use_film=True)),
+        "cln_causal_concat": (16, 24, dict(dilation=2, causal=True, tcn_norm="cLN", emb_dim=8)),
+        "bn_causal": (16, 24, dict(dilation=1, causal=True, tcn_norm="bN1d", emb_dim=0)),
+        "bn_causal_film": (16, 24, dict(dilation=3, causal=True, tcn_norm="bN1d", emb_dim=6, use_film=True)),
+        "odd_sizes": (10, 14, dict(dilation=2, causal=False, tcn_norm="gLN", emb_dim=5)),
+        "wide_tc": (64, 64, dict(dilation=2, causal=False, tcn_norm="gLN", emb_dim=32)),  # shapes the tcgen05 GEMM takes
+    }.items():
+        torch.manual_seed(31)
+        m = T.perturb_(GatedTCN(cin, hid, 3, **kw).eval(), seed=32)
+        x = rnd(2, cin, 300 if tag == "wide_tc" else 50, seed=33)
+        e = rnd(2, kw["emb_dim"], seed=34) if kw["emb_dim"] else None
+        cases[tag] = {"cfg": D.describe_gated_tcn(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e) if e is not None else m(x)}
+    torch.manual_seed(35)
+    net = T.perturb_(ConvTasNet(16, 8, True, tcn_layer="gated", tcn_dim=24, per_tcn_stack=3, repeat_tcn=2, tcn_with_embed=[1, 0, 0]).eval(), seed=36)
+    x, dv = rnd(2, 16, 70, seed=37), rnd(2, 8, seed=38)
+    cases["conv_tasnet_gated"] = {"cfg": D.describe_masker(net), "sd": sd_of(net), "x": x, "dvec": dv, "y": net(x, dv)}
+    torch.manual_seed(39)
+    wrap = quiet(
+        SoTaskWrapModule,
+        encoder=ConvEncDec(fft_length=64, win_type="hann", win_length=64, hop_length=16, trainable=True, output_format="Complex"),
+        masker=ConvTasNet(64, 12, True, tcn_layer="gated", tcn_dim=24, per_tcn_stack=2, repeat_tcn=2, tcn_with_embed=[1, 0]),
+        speaker_net=nn.ModuleList([Magnitude(drop_first=False)] + [GatedTCN(32, 16, 3, dilation=2 ** i, causal=False, tcn_norm="gLN") for i in range(2)]
+                                  + [AttentiveStatisticsPooling(32, 8), nn.Conv1d(64, 12, 1, bias=False)]),
+        mask_constraint="linear", drop_first_bin=True, verbose=False,
+    ).eval()
+    T.perturb_(wrap, seed=40)
+    noisy, enroll = 0.1 * rnd(2, 64 + 16 * 40, seed=41), 0.1 * rnd(2, 64 + 16 * 55, seed=42)
+    cases["wrapper_gated"] = {"cfg": D.describe(wrap), "sd": sd_of(wrap), "noisy": noisy, "enroll": enroll,
+                              "y": wrap.inference(noisy, enroll), "dvec": wrap.inference_tse_embedding(enroll)}
+    save("small_gated.pt", cases)
+    # full size: cfg4 with gated blocks (recipes.baseline_config("cfg4_gated")), pinned like full_size_pins.json
+    torch.manual_seed(0)
+    m = quiet(
+        SoTaskWrapModule,
+        encoder=ConvEncDec(512, "hann", 512, hop_length=128, trainable=True, output_format="Complex"),
+        masker=ConvTasNet(512, 192, True, tcn_layer="gated", tcn_dim=256, repeat_tcn=3, per_tcn_stack=5, tcn_with_embed=[1, 0, 0, 0, 0]),
+        speaker_net=nn.ModuleList([Magnitude(drop_first=False)]
+                                  + [GatedTCN(256, 128, 3, dilation=2 ** i, causal=False, tcn_norm="gLN") for i in range(5)]
+                                  + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(512, 192, 1, bias=False)]),
+        mask_constraint="linear", drop_first_bin=True, verbose=False,
+    ).eval()
+    T.perturb_(m, seed=1)
+    n, L, Le, stride = 2, 64000, 96000, 997
+    mix, _ = T.noisy_speech(n, L, seed=1234)
+    enr = T.noisy_speech(n, Le, seed=4321)[0]
+    y = m.inference(mix, enr)
+    pin = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n, "length": L,
+           "enroll_length": Le, "input_seed": 1234, "enroll_seed": 4321, "stride": stride, "out_len": y.shape[-1],
+           "out_abs_mean": float(y.abs().mean()), "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+           "samples": [[float(v) for v in row[::stride]] for row in y]}
+    print("cfg4_gated", pin["params"], pin["out_abs_mean"], pin["out_clamped_frac"])
+    with open(os.path.join(HERE, "gated_pins.json"), "w") as fh:
+        json.dump({"cfg4_gated": pin}, fh)
+
+
+@torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
     (test/test_case/1272-128104-0000_2035-147961-0014.wav, a two-speaker mixture, 16 kHz int16) cropped to 4 s as the
@@ -388,3 +452,5 @@ if __name__ == "__main__":
         skim_cases()
     if which in ("all", "real"):
         real_input_pins()
+    if which in ("all", "gated"):
+        gated_cases()

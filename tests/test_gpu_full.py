@@ -31,10 +31,11 @@ def backend(request):
     ops.force_gemm_backend = None
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal", "cfg4_gated"])
 def test_full_size_parity(name, backend):
-    with open(os.path.join(GOLDEN, "full_size_pins.json")) as fh:
-        pin = json.load(fh)[name]
+    from test_oracle_full_pins import load_pin
+
+    pin = load_pin(name)
     torch.manual_seed(0)
     m = recipes.baseline_config(name).eval()
     testing.perturb_(m, seed=1)

@@ -53,6 +53,36 @@ def test_tcn_variants(golden):
         close(y, g["y"])
 
 
+@pytest.mark.parametrize("backend", ["auto", "simt"])
+def test_gated_tcn(golden, backend):
+    """GatedTCN on the engine against the reference's outputs: concat / FiLM / no conditioning,
+    gLN / cLN / bN1d, causal trim, channel counts that are not multiples of 4 (scalar `ps_gated` path), shapes the tcgen05
+    GEMM takes (`wide_tc`, auto back end), a gated Conv-TasNet stack and a wrapper whose speaker net is GatedTCN blocks."""
+    from puresound_b200 import ops
+
+    ops.force_gemm_backend = ops.GEMM_SIMT if backend == "simt" else None
+    try:
+        gs = golden("small_gated.pt")
+        for tag, g in gs.items():
+            if tag in ("conv_tasnet_gated", "wrapper_gated"):
+                continue
+            m = _build.gated_tcn(g["cfg"]).to(DEV).eval()
+            m.load_state_dict(g["sd"])
+            y = m(cu(g["x"]), cu(g["embed"])) if g["embed"] is not None else m(cu(g["x"]))
+            close(y, g["y"], 5e-5 if tag == "wide_tc" else TOL)
+        g = gs["conv_tasnet_gated"]
+        m = _build.masker(g["cfg"]).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        close(m(cu(g["x"]), cu(g["dvec"])), g["y"])
+        g = gs["wrapper_gated"]
+        m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)
+        close(m.inference(cu(g["noisy"]), cu(g["enroll"])), g["y"], 1e-4)
+        close(m.inference_tse_embedding(cu(g["enroll"])), g["dvec"], 5e-5)
+        close(m.inference(g["noisy"], g["enroll"]), g["y"], 1e-4)  # third call: CUDA-graph replay, host buffers
+    finally:
+        ops.force_gemm_backend = None
+
+
 def test_conv_tasnet(golden):
     g = golden("small_conv_tasnet.pt")
     m = _build.masker(g["cfg"]).to(DEV).eval()

@@ -14,10 +14,15 @@ from oracle import separator_ref as R
 from puresound_b200 import recipes, testing
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal"])
+def load_pin(name):
+    """full_size_pins.json (the BASELINE configs) or gated_pins.json (cfg4 with GatedTCN blocks)."""
+    with open(os.path.join(GOLDEN, "gated_pins.json" if name == "cfg4_gated" else "full_size_pins.json")) as fh:
+        return json.load(fh)[name]
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal", "cfg4_gated"])
 def test_oracle_matches_reference_at_full_size(name):
-    with open(os.path.join(GOLDEN, "full_size_pins.json")) as fh:
-        pin = json.load(fh)[name]
+    pin = load_pin(name)
     torch.manual_seed(0)
     m = recipes.baseline_config(name).eval()
     testing.perturb_(m, seed=1)
