@@ -231,6 +231,10 @@ typedef struct {
   const float* a; int64_t a_batch_stride, a_row_stride;
   const float* b; int64_t b_batch_stride, b_row_stride;
   float* y; int64_t y_batch_stride, y_row_stride;
+  /* optional middle level (0 or 1: none): element (n, m, r, c) at batch*n + mid*m + row*r + c; the per-item AFFINE
+   * parameters are indexed by n, ROWNORM statistics by ((n*mid + m)*rows + r).  Used by the U-Net shell to copy
+   * [N, T, F, C] tensors into the time-shifted, frequency-padded tap buffers of its 2-D convs (unet.py:100-175). */
+  int64_t mid, a_mid_stride, b_mid_stride, y_mid_stride;
   int32_t a_mode, a_act; const float* a_pa; const float* a_pb; int64_t a_pro_batch_stride; const float* a_rowstats; const float* a_slope;
   int32_t b_mode, b_act; const float* b_pa; const float* b_pb; int64_t b_pro_batch_stride; const float* b_rowstats; const float* b_slope;
 } ps_gated_t;

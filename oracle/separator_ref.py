@@ -572,7 +572,70 @@ def wav_constrain(wav: Tensor, mode: str) -> Tensor:
     raise NameError("Non support type.")
 
 
+# --------------------------------------------------------------------------- #
+# U-Net shell with a TCN bottleneck                 puresound/nnet/unet.py
+# --------------------------------------------------------------------------- #
+def _norm2d(kind: str, sd: SD, p: str, x: Tensor) -> Tensor:
+    """The 2-D norms of the U-Net recipes on [N, C, F, T]: gLN (GlobLN over all non-batch dims, lobe/norm.py:20-34) and
+    bN2d (nn.BatchNorm2d in eval mode, lobe/norm.py:95)."""
+    if kind == "gLN":
+        return norm_apply("gLN", sd, p, x)
+    if kind == "bN2d":
+        return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, 1e-5)
+    raise NotImplementedError(kind)
+
+
+def unet_tcn(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tensor:
+    """UnetTcn.forward, unet.py:454-517 (layers built at :100-175 and :371-451): ZeroPad2d + Conv2d + norm + PReLU down
+    path, TCN / GatedTCN stack on the flattened [N, ch*F', T] bottleneck, cat-skip + ConvTranspose2d (+ norm + PReLU) up path
+    with the time trim of :529-537."""
+    if a["embed_norm"] and dvec is not None:
+        dvec = F.normalize(dvec, p=2, dim=1)
+    n_cnn = len(a["kernel_t"])
+    if a["input_type"].lower() == "ri":
+        re, im = torch.chunk(x, 2, dim=-2)
+        x = torch.stack([re, im], dim=1)
+    else:
+        x = x.unsqueeze(1)
+    skip = [x]
+    for i in range(n_cnn):
+        kf, kt = a["kernel_f"][i], a["kernel_t"][i]
+        q = f"{p}cnn_down.{i}."
+        x = F.pad(x, (kt - a["delay"][i] - 1, a["delay"][i], kf // 2, kf // 2))
+        x = F.conv2d(x, sd[q + "1.weight"], sd[q + "1.bias"], stride=(a["stride_f"][i], a["stride_t"][i]))
+        x = F.prelu(_norm2d(a["norm_type"], sd, q + "2.", x), sd[q + "3.weight"])
+        skip.append(x)
+    N, ch, Fb, T = x.shape
+    x = x.reshape(N, ch * Fb, T)
+    gated = a["tcn_layer"].lower() == "gated"
+    for r in range(a["repeat_tcn"]):
+        for i in range(a["per_tcn_stack"]):
+            q, e, d = f"{p}tcn_list.{r}.{i}.", dvec if a["tcn_with_embed"][i] else None, a["tcn_dilated_basic"] ** i
+            if gated:
+                x = gated_tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"])
+            else:
+                x = tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"], a["dconv_norm"])
+    x = x.reshape(N, ch, Fb, T)
+    tk = a["transpose_t_size"]
+    for i in range(n_cnn):
+        idx = n_cnn - 1 - i
+        k, s = a["kernel_f"][idx], a["stride_f"][idx]
+        q = f"{p}cnn_up.{i}."
+        x = torch.cat([x, skip[-i - 1]], dim=1)
+        x = F.conv_transpose2d(x, sd[q + "0.weight"], sd[q + "0.bias"], stride=(s, a["stride_t"][idx]), padding=(k // 2, 0),
+                               output_padding=(s - k + 2 * (k // 2), 0))
+        if idx != 0:
+            x = F.prelu(_norm2d(a["norm_type"], sd, q + "1.", x), sd[q + "2.weight"])
+        if tk != 1:
+            x = x[..., (tk - 1):] if a["transpose_delay"] else x[..., : -(tk - 1)]
+    if a["input_type"].lower() == "ri":
+        return torch.cat([x[:, 0], x[:, 1]], dim=1)
+    return x.squeeze(1)
+
+
 def masker_forward(sd: SD, p: str, mcfg: dict, x: Tensor, dvec: Optional[Tensor], fast_lstm: bool = True) -> Tensor:
+    if mcfg["type"] == "UnetTcn":
+        return unet_tcn(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "ConvTasNet":
         return conv_tasnet(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "DPRNN":

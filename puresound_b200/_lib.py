@@ -77,6 +77,7 @@ class GatedDesc(C.Structure):
         ("a", P), ("a_batch_stride", I64), ("a_row_stride", I64),
         ("b", P), ("b_batch_stride", I64), ("b_row_stride", I64),
         ("y", P), ("y_batch_stride", I64), ("y_row_stride", I64),
+        ("mid", I64), ("a_mid_stride", I64), ("b_mid_stride", I64), ("y_mid_stride", I64),
         ("a_mode", I32), ("a_act", I32), ("a_pa", P), ("a_pb", P), ("a_pro_batch_stride", I64), ("a_rowstats", P), ("a_slope", P),
         ("b_mode", I32), ("b_act", I32), ("b_pa", P), ("b_pb", P), ("b_pro_batch_stride", I64), ("b_rowstats", P), ("b_slope", P),
     ]

@@ -12,7 +12,7 @@
 namespace ps {
 
 struct GatedSide {
-  const float* x; int64_t bs, rs;
+  const float* x; int64_t bs, ms, rs;  // batch / mid / row strides
   int mode, act; const float* pa; const float* pb; int64_t pbs; const float* rowstats; const float* slope_p;
 };
 
@@ -23,14 +23,15 @@ __device__ __forceinline__ float4 gated_ld(const float* p) {
 }
 
 template <int V>
-__device__ __forceinline__ float4 gated_load(const GatedSide& s, float slope, int64_t b, int64_t r, int64_t rows, int c) {
-  float4 v = gated_ld<V>(s.x + b * s.bs + r * s.rs + c);
+__device__ __forceinline__ float4 gated_load(const GatedSide& s, float slope, int64_t b, int64_t m, int64_t mid, int64_t r, int64_t rows,
+                                             int c) {
+  float4 v = gated_ld<V>(s.x + b * s.bs + m * s.ms + r * s.rs + c);
   if (s.mode != PS_PRO_NONE) {
     const int64_t po = (s.mode == PS_PRO_AFFINE ? b * s.pbs : 0) + c;
     const float4 a = gated_ld<V>(s.pa + po);
     const float4 sh = gated_ld<V>(s.pb + po);
     if (s.mode == PS_PRO_ROWNORM) {
-      const float2 st = __ldg(reinterpret_cast<const float2*>(s.rowstats + (b * rows + r) * 2));
+      const float2 st = __ldg(reinterpret_cast<const float2*>(s.rowstats + ((b * mid + m) * rows + r) * 2));
       v.x = (v.x - st.x) * st.y; v.y = (v.y - st.x) * st.y; v.z = (v.z - st.x) * st.y; v.w = (v.w - st.x) * st.y;
     }
     v.x = fmaf(v.x, a.x, sh.x); v.y = fmaf(v.y, a.y, sh.y); v.z = fmaf(v.z, a.z, sh.z); v.w = fmaf(v.w, a.w, sh.w);
@@ -45,20 +46,20 @@ __device__ __forceinline__ float gated_sigmoid(float v) { return 1.f / (1.f + ex
 // V = 4: float4 per thread (C % 4 == 0, 16-byte aligned operands and strides); V = 1: scalar fallback for odd shapes
 template <int V>
 __global__ void __launch_bounds__(256) gated_kernel(const GatedSide A, const GatedSide B, float* __restrict__ y, int64_t ybs,
-                                                    int64_t yrs, int64_t batch, int64_t rows, int C4) {
+                                                    int64_t yms, int64_t yrs, int64_t batch, int64_t mid, int64_t rows, int C4) {
   const float sa = A.slope_p ? __ldg(A.slope_p) : 0.f;
   const float sb = (B.x && B.slope_p) ? __ldg(B.slope_p) : 0.f;
-  const int64_t total = batch * rows * C4;
+  const int64_t total = batch * mid * rows * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * V;
-    const int64_t br = i / C4, r = br % rows, b = br / rows;
-    float4 v = gated_load<V>(A, sa, b, r, rows, c);
+    const int64_t br = i / C4, r = br % rows, bm = br / rows, m = bm % mid, b = bm / mid;
+    float4 v = gated_load<V>(A, sa, b, m, mid, r, rows, c);
     if (B.x) {
-      const float4 g = gated_load<V>(B, sb, b, r, rows, c);
+      const float4 g = gated_load<V>(B, sb, b, m, mid, r, rows, c);
       v.x *= gated_sigmoid(g.x); v.y *= gated_sigmoid(g.y); v.z *= gated_sigmoid(g.z); v.w *= gated_sigmoid(g.w);
     }
-    if constexpr (V == 4) *reinterpret_cast<float4*>(y + b * ybs + r * yrs + c) = v;
-    else y[b * ybs + r * yrs + c] = v.x;
+    if constexpr (V == 4) *reinterpret_cast<float4*>(y + b * ybs + m * yms + r * yrs + c) = v;
+    else y[b * ybs + m * yms + r * yrs + c] = v.x;
   }
 }
 
@@ -72,7 +73,7 @@ static bool gated_side_ok(const GatedSide& s, int64_t C) {
 }
 static bool gated_side_vec(const GatedSide& s) {
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al(s.x) || (s.bs & 3) || (s.rs & 3)) return false;
+  if (!al(s.x) || (s.bs & 3) || (s.ms & 3) || (s.rs & 3)) return false;
   if (s.mode != PS_PRO_NONE && (!al(s.pa) || !al(s.pb) || (s.pbs & 3))) return false;
   return true;
 }
@@ -83,20 +84,21 @@ extern "C" int ps_gated(const ps_gated_t* dp, void* stream) {
   PS_REQUIRE(dp != nullptr);
   const ps_gated_t& d = *dp;
   PS_REQUIRE(d.batch > 0 && d.rows > 0 && d.C > 0 && d.y && d.y_row_stride >= d.C);
-  const ps::GatedSide A{d.a, d.a_batch_stride, d.a_row_stride, d.a_mode, d.a_act, d.a_pa, d.a_pb, d.a_pro_batch_stride, d.a_rowstats, d.a_slope};
-  const ps::GatedSide B{d.b, d.b_batch_stride, d.b_row_stride, d.b_mode, d.b_act, d.b_pa, d.b_pb, d.b_pro_batch_stride, d.b_rowstats, d.b_slope};
+  const int64_t mid = d.mid > 0 ? d.mid : 1;
+  const ps::GatedSide A{d.a, d.a_batch_stride, d.a_mid_stride, d.a_row_stride, d.a_mode, d.a_act, d.a_pa, d.a_pb, d.a_pro_batch_stride, d.a_rowstats, d.a_slope};
+  const ps::GatedSide B{d.b, d.b_batch_stride, d.b_mid_stride, d.b_row_stride, d.b_mode, d.b_act, d.b_pa, d.b_pb, d.b_pro_batch_stride, d.b_rowstats, d.b_slope};
   PS_REQUIRE(ps::gated_side_ok(A, d.C));
   if (d.b) PS_REQUIRE(ps::gated_side_ok(B, d.C));
   const bool vec = d.C % 4 == 0 && (reinterpret_cast<uintptr_t>(d.y) & 15) == 0 && (d.y_batch_stride & 3) == 0 &&
-                   (d.y_row_stride & 3) == 0 && ps::gated_side_vec(A) && (!d.b || ps::gated_side_vec(B));
+                   (d.y_mid_stride & 3) == 0 && (d.y_row_stride & 3) == 0 && ps::gated_side_vec(A) && (!d.b || ps::gated_side_vec(B));
   const int64_t cols = vec ? d.C / 4 : d.C;
-  const int64_t total = d.batch * d.rows * cols;
+  const int64_t total = d.batch * mid * d.rows * cols;
   int64_t blocks = ps::cdiv(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs of 256 threads per SM
   if (vec)
-    ps::gated_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d.y, d.y_batch_stride, d.y_row_stride, d.batch, d.rows, (int)cols);
+    ps::gated_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d.y, d.y_batch_stride, d.y_mid_stride, d.y_row_stride, d.batch, mid, d.rows, (int)cols);
   else
-    ps::gated_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d.y, d.y_batch_stride, d.y_row_stride, d.batch, d.rows, (int)cols);
+    ps::gated_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d.y, d.y_batch_stride, d.y_mid_stride, d.y_row_stride, d.batch, mid, d.rows, (int)cols);
   PS_CHECK_LAUNCH("gated_kernel");
   return PS_OK;
 }

@@ -360,7 +360,9 @@ def lstm_pack_weights(w_hh_t: Tensor, H: int, D: int) -> Optional[Tensor]:
 def _set_side(d, side: str, x: Tensor, strides, pro: Prologue):
     setattr(d, side, x.data_ptr())
     setattr(d, side + "_batch_stride", strides[0])
-    setattr(d, side + "_row_stride", strides[1])
+    setattr(d, side + "_row_stride", strides[-1])
+    if len(strides) == 3:
+        setattr(d, side + "_mid_stride", strides[1])
     setattr(d, side + "_mode", pro.mode)
     setattr(d, side + "_act", pro.act)
     setattr(d, side + "_pa", _p(pro.a))
@@ -372,19 +374,23 @@ def _set_side(d, side: str, x: Tensor, strides, pro: Prologue):
 
 def gated(a: Tensor, pro_a: Prologue, b: Optional[Tensor] = None, pro_b: Prologue = NO_PRO, *, batch: int, rows: int, C_: int,
           a_strides: Optional[tuple] = None, b_strides: Optional[tuple] = None, out: Optional[Tensor] = None,
-          y_strides: Optional[tuple] = None) -> Tensor:
+          y_strides: Optional[tuple] = None, mid: int = 1) -> Tensor:
     """y = a' * sigmoid(b') with a' = act(pro_a(a)), b' = act(pro_b(b)) (the GatedTCN product, conv_tasnet.py:205); with
-    b=None y = a' (strided transform copy).  Strides are (batch, row) in floats; default contiguous [batch, rows, C]."""
+    b=None y = a' (strided transform copy).  Strides are (batch, row) - or (batch, mid, row) with a middle level of `mid`
+    entries - in floats; default contiguous [batch, mid, rows, C]."""
     lib = _lib.load()
-    y = out if out is not None else torch.empty(batch, rows, C_, device=a.device, dtype=torch.float32)
+    y = out if out is not None else torch.empty(batch, mid * rows, C_, device=a.device, dtype=torch.float32)
     d = _lib.GatedDesc()
-    d.batch, d.rows, d.C = batch, rows, C_
-    dflt = (rows * C_, C_)
+    d.batch, d.rows, d.C, d.mid = batch, rows, C_, mid
+    dflt = (mid * rows * C_, rows * C_, C_)
     _set_side(d, "a", _dev(a, "gated a"), a_strides or dflt, pro_a)
     if b is not None:
         _set_side(d, "b", _dev(b, "gated b"), b_strides or dflt, pro_b)
     d.y = y.data_ptr()
-    d.y_batch_stride, d.y_row_stride = y_strides or dflt
+    ys = y_strides or dflt
+    d.y_batch_stride, d.y_row_stride = ys[0], ys[-1]
+    if len(ys) == 3:
+        d.y_mid_stride = ys[1]
     _lib.check(lib.ps_gated(C.byref(d), _stream()), "ps_gated")
     _launched()
     return y

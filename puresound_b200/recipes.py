@@ -16,6 +16,7 @@ from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from .nnet.lobe.pooling import AttentiveStatisticsPooling
 from .nnet.lobe.trivial import Magnitude
 from .nnet.skim import SkiM
+from .nnet.unet import UnetTcn
 
 
 def _td_speaker_net():
@@ -44,6 +45,23 @@ def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Option
             masker=DPRNN(input_size=128, hidden_size=64, output_size=128, n_blocks=6, seg_size=20, seg_overlap=False, causal=True,
                          embed_dim=0, embed_norm=False, block_with_embed=(False,) * 6, embedding_free_tse=True),
             speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", embedding_free_tse=True, **kwargs)
+    if name in ("tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"):
+        # egs/tse/model.py:184-369: STFT 512/128, 6-layer U-Net shell (kernel 5x2, frequency stride 2) around 3 x 5 GatedTCN
+        # blocks (embedding concatenated - v1: FiLM - in the first block of each repeat), GatedTCN speaker net
+        causal = name.endswith("_causal")
+        return SoTaskWrapModule(
+            encoder=ConvEncDec(fft_length=512, win_type="hann", win_length=512, hop_length=128, trainable=True, output_format="Complex"),
+            masker=UnetTcn(
+                embed_dim=192, embed_norm=True, input_type="RI", input_dim=512, activation_type="PReLU",
+                norm_type="bN2d" if causal else "gLN", channels=(1, 32, 64, 128, 128, 128, 128), transpose_t_size=2, transpose_delay=True,
+                skip_conv=False, kernel_t=(2,) * 6, kernel_f=(5,) * 6, stride_t=(1,) * 6, stride_f=(2,) * 6, dilation_t=(1,) * 6,
+                dilation_f=(1,) * 6, delay=(0,) * 6, tcn_layer="gated", tcn_kernel=3, tcn_dim=256, tcn_dilated_basic=2, per_tcn_stack=5,
+                repeat_tcn=3, tcn_with_embed=[1, 0, 0, 0, 0], tcn_norm="bN1d" if causal else "gLN", dconv_norm="bN1d" if causal else "gGN",
+                causal=causal, **({"tcn_use_film": True} if name.endswith("_v1") else {})),
+            speaker_net=nn.ModuleList(
+                [Magnitude(drop_first=False)] + [GatedTCN(256, 128, 3, dilation=2 ** i, causal=False, tcn_norm="gLN") for i in range(5)]
+                + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(256 * 2, 192, 1, bias=False)]),
+            loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="linear", drop_first_bin=True, **kwargs)
     if name in ("tse_skim_v0", "tse_skim_v0_causal"):
         # egs/tse/model.py:371-463 (the causal one is the reference's demo model)
         causal = name.endswith("_causal")
@@ -95,6 +113,6 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN",
                        dconv_norm="cLN", causal=True),
             mask_constraint="ReLU", verbose=verbose)
-    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal"):
+    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"):
         return init_model(name, None, None, verbose=verbose)
     raise NameError(name)

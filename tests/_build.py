@@ -8,6 +8,7 @@ from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
 from puresound_b200.nnet.lobe.trivial import Magnitude
 from puresound_b200.nnet.skim import SkiM
+from puresound_b200.nnet.unet import UnetTcn
 
 
 def tcn(c):
@@ -31,6 +32,8 @@ def masker(c):
     t = c.pop("type")
     if t == "ConvTasNet":
         return ConvTasNet(**c)
+    if t == "UnetTcn":
+        return UnetTcn(**c)
     out = c.pop("output_size", c["input_size"])
     if t == "SkiM":
         return SkiM(c["input_size"], c["hidden_size"], out, n_blocks=c["n_blocks"], seg_size=c["seg_size"], seg_overlap=c["seg_overlap"],

@@ -42,6 +42,7 @@ from puresound.nnet.lobe.encoder import ConvEncDec, FreeEncDec  # noqa: E402
 from puresound.nnet.lobe.pooling import AttentiveStatisticsPooling  # noqa: E402
 from puresound.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge  # noqa: E402
 from puresound.nnet.skim import MemLSTM, SegLSTM, SkiM  # noqa: E402
+from puresound.nnet.unet import UnetTcn  # noqa: E402
 
 from oracle import describe as D  # noqa: E402
 from puresound_b200 import testing as T  # noqa: E402
@@ -412,6 +413,50 @@ def gated_cases():
 
 
 @torch.no_grad()
+def unet_cases():
+    """UnetTcn (second half; unet.py:298-556): small variants of the shell, and full-size pins of the
+    reference's STFT-domain TSE recipes tse_unet_tcn_v0 / _v0_causal / _v1 (egs/tse/model.py:184-369)."""
+    base = dict(input_type="RI", input_dim=32, channels=(1, 4, 8, 8), transpose_t_size=2, kernel_t=(2, 2, 2), kernel_f=(5, 5, 5),
+                stride_t=(1, 1, 1), stride_f=(2, 2, 2), dilation_t=(1, 1, 1), dilation_f=(1, 1, 1), delay=(0, 0, 0), tcn_dim=12,
+                per_tcn_stack=2, repeat_tcn=2, dropout=0.0)
+    cases = {}
+    for tag, kw in {
+        "gln_gated_concat": dict(embed_dim=6, embed_norm=True, norm_type="gLN", transpose_delay=True, tcn_layer="gated", tcn_with_embed=[1, 0],
+                                 tcn_norm="gLN", causal=False),
+        "bn_causal_gated_film": dict(embed_dim=6, embed_norm=True, norm_type="bN2d", transpose_delay=True, tcn_layer="gated",
+                                     tcn_with_embed=[1, 0], tcn_norm="bN1d", dconv_norm="bN1d", causal=True, tcn_use_film=True),
+        "gln_normal_nodelay": dict(embed_dim=0, norm_type="gLN", transpose_delay=False, tcn_layer="normal", tcn_with_embed=[0, 0],
+                                   tcn_norm="gLN", dconv_norm="gGN", causal=False),
+        "real_lookahead_k3": dict(embed_dim=0, norm_type="bN2d", input_type="Real", input_dim=24, channels=(1, 4, 4, 8), kernel_t=(3, 1, 2),
+                                  kernel_f=(3, 5, 1), stride_f=(1, 4, 1), delay=(1, 0, 0), transpose_t_size=1, tcn_layer="normal",
+                                  tcn_with_embed=[0, 0], tcn_norm="cLN", dconv_norm="cLN", causal=True),
+    }.items():
+        torch.manual_seed(51)
+        m = T.perturb_(quiet(UnetTcn, **{**base, **kw}).eval(), seed=52)
+        cin = kw.get("input_dim", 32)
+        x = rnd(2, cin, 37, seed=53)
+        e = rnd(2, 6, seed=54) if kw["embed_dim"] else None
+        cases[tag] = {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "embed": e, "y": m(x, e) if e is not None else m(x)}
+    save("small_unet.pt", cases)
+    pins = {}
+    for name in ("tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"):
+        torch.manual_seed(0)
+        m = _ref_init_model(name).eval()
+        T.perturb_(m, seed=1)
+        n, L, Le, stride = 2, 64000, 96000, 997
+        mix, _ = T.noisy_speech(n, L, seed=1234)
+        enr = T.noisy_speech(n, Le, seed=4321)[0]
+        y = m.inference(mix, enr)
+        pins[name] = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n,
+                      "length": L, "enroll_length": Le, "input_seed": 1234, "enroll_seed": 4321, "stride": stride, "out_len": y.shape[-1],
+                      "out_abs_mean": float(y.abs().mean()), "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+                      "samples": [[float(v) for v in row[::stride]] for row in y]}
+        print(name, pins[name]["params"], pins[name]["out_abs_mean"], pins[name]["out_clamped_frac"])
+    with open(os.path.join(HERE, "unet_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
+@torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
     (test/test_case/1272-128104-0000_2035-147961-0014.wav, a two-speaker mixture, 16 kHz int16) cropped to 4 s as the
@@ -454,3 +499,5 @@ if __name__ == "__main__":
         real_input_pins()
     if which in ("all", "gated"):
         gated_cases()
+    if which in ("all", "unet"):
+        unet_cases()

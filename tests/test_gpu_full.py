@@ -84,6 +84,29 @@ def test_real_speech_and_full_scale_noise(tag):
     assert float((y.abs() >= 1).float().mean()) == pytest.approx(pin["out_clamped_frac"], abs=2e-3)
 
 
+@pytest.mark.parametrize("name", ["tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"])
+def test_unet_recipes_full_size(name):
+    """The reference's STFT-domain TSE recipes (egs/tse/model.py:184-369), 2 x (4 s + 6 s), against the reference's recorded
+    output and the oracle on the host (north_star tolerances)."""
+    with open(os.path.join(GOLDEN, "unet_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, clean = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    enr = testing.noisy_speech(pin["batch"], pin["enroll_length"], seed=pin["enroll_seed"])[0]
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    y = m.to("cuda").inference(mix, enr)
+    err_pin = (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item()
+    y_ref = R.inference(sd, cfg, mix, enr)
+    err = (y - y_ref).abs().max().item()
+    L = y.shape[-1]
+    d_sisnr = float((R.si_snr(y, clean[:, :L]) - R.si_snr(y_ref, clean[:, :L])).abs().max())
+    print(f"{name}: max|dy|={err:.3e} (vs reference samples {err_pin:.3e}) dSI-SNR={d_sisnr:.2e} dB")
+    assert err_pin <= WAVE_TOL and err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
+
+
 def test_skim_recipe_full_size():
     """`tse_skim_v0_causal` (4 s mixture + 6 s enrollment) against the reference's recorded output and the oracle."""
     with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:

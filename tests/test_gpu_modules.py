@@ -83,6 +83,23 @@ def test_gated_tcn(golden, backend):
         ops.force_gemm_backend = None
 
 
+@pytest.mark.parametrize("backend", ["auto", "simt"])
+def test_unet_tcn(golden, backend):
+    """UnetTcn shell on the engine against the reference's outputs: 2-D convs as framed GEMMs over tap
+    buffers, transposed convs per output phase, gLN / bN2d, time trims, gated / normal bottlenecks."""
+    from puresound_b200 import ops
+
+    ops.force_gemm_backend = ops.GEMM_SIMT if backend == "simt" else None
+    try:
+        for tag, g in golden("small_unet.pt").items():
+            m = _build.masker(g["cfg"]).to(DEV).eval()
+            m.load_state_dict(g["sd"])
+            y = m(cu(g["x"]), cu(g["embed"])) if g["embed"] is not None else m(cu(g["x"]))
+            close(y, g["y"], 5e-5)
+    finally:
+        ops.force_gemm_backend = None
+
+
 def test_conv_tasnet(golden):
     g = golden("small_conv_tasnet.pt")
     m = _build.masker(g["cfg"]).to(DEV).eval()

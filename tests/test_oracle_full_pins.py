@@ -36,6 +36,23 @@ def test_oracle_matches_reference_at_full_size(name):
     assert abs(float(y.abs().mean()) - pin["out_abs_mean"]) <= 1e-6
 
 
+@pytest.mark.parametrize("name", ["tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"])
+def test_oracle_matches_reference_unet_recipes(name):
+    """The reference's STFT-domain TSE recipes (egs/tse/model.py:184-369) at full size, 2 x (4 s + 6 s)."""
+    with open(os.path.join(GOLDEN, "unet_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert m.overall_parameters == pin["params"]
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, _ = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    enr = testing.noisy_speech(pin["batch"], pin["enroll_length"], seed=pin["enroll_seed"])[0]
+    y = R.inference(m.state_dict(), D.describe(m), mix, enr)
+    assert y.shape[-1] == pin["out_len"]
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+
+
 def test_oracle_matches_reference_skim_recipe():
     """`tse_skim_v0_causal` (egs/tse/model.py:418-463, the reference's demo model) at full size."""
     with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:
