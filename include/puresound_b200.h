@@ -125,6 +125,12 @@ PS_API int ps_gemm_pack_weights(const float* W, int64_t w_row_stride, int64_t M,
  * -------------------------------------------------------------------------- */
 PS_API int ps_stats_finalize(const float* partials, int64_t batch, int64_t slots, const float* gamma, const float* beta,
                       float eps, int64_t C, float* scale, float* shift, float* meanvar, void* stream);
+/* Welford partials (count, mean, M2) of a strided region, `slots` per item: element (n, m, r, c) at
+ * x + n*batch_stride + m*mid_stride + r*row_stride + c.  partials [batch, slots, 3] feed ps_stats_finalize.  gLN of the
+ * U-Net layers (lobe/norm.py:20-34 on [N,C,F,T], unet.py:121,147), whose conv outputs are strided views. */
+PS_API int ps_stats_region(const float* x, int64_t batch, int64_t mid, int64_t rows, int64_t C, int64_t batch_stride,
+                           int64_t mid_stride, int64_t row_stride, int64_t slots, float* partials, void* stream);
+
 /* bN1d in eval mode (lobe/norm.py:94): scale = w/sqrt(rv+eps), shift = b - rm*scale; [C] each */
 PS_API int ps_bn_fold(const float* weight, const float* bias, const float* running_mean, const float* running_var,
                float eps, int64_t C, float* scale, float* shift, void* stream);

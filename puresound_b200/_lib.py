@@ -97,6 +97,7 @@ SIGNATURES = {
     "ps_gemm_packed_bytes": (I64, [I64, I64]),
     "ps_gemm_pack_weights": (C.c_int, [P, I64, I64, I64, P, P]),
     "ps_stats_finalize": (C.c_int, [P, I64, I64, P, P, F32, I64, P, P, P, P]),
+    "ps_stats_region": (C.c_int, [P, I64, I64, I64, I64, I64, I64, I64, I64, P, P]),
     "ps_bn_fold": (C.c_int, [P, P, P, P, F32, I64, P, P, P]),
     "ps_rowstats": (C.c_int, [P, I64, I64, I64, F32, P, P]),
     "ps_dwconv": (C.c_int, [C.POINTER(DwconvDesc), P]),

@@ -73,7 +73,44 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
   }
 }
 
+// Welford partials of a strided region: item n, element (m, r, c) at x + n*bs + m*ms + r*rs + c, m < mid, r < rows, c < C.
+// blockIdx.y = item, blockIdx.x = slot: the slot's CTA takes a contiguous share of the item's mid*rows rows.  Used for
+// the gLN statistics of U-Net layers, whose GEMM outputs carry rows that are not part of the tensor (unet.py: the
+// 2-D convs run as flat framed GEMMs over frequency-padded frames).
+__global__ void __launch_bounds__(256) stats_region_kernel(const float* __restrict__ x, int64_t bs, int64_t ms, int64_t rs,
+                                                           int64_t mid, int64_t rows, int C, float* __restrict__ partials) {
+  __shared__ Wf red[8];
+  const int64_t n = blockIdx.y, slots = gridDim.x;
+  const int64_t total = mid * rows;
+  const int64_t per = (total + slots - 1) / slots;
+  const int64_t r0 = blockIdx.x * per, r1 = (r0 + per < total) ? r0 + per : total;
+  const float* xb = x + n * bs;
+  WfAcc acc;
+  acc.init();
+  const int64_t cnt = (r1 > r0 ? r1 - r0 : 0) * C;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int64_t row = r0 + i / C;
+    const int c = (int)(i % C);
+    acc.add(__ldg(xb + (row / rows) * ms + (row % rows) * rs + c));
+  }
+  const Wf w = wf_block_reduce(acc.finish(), red);
+  if (threadIdx.x == 0) {
+    float* o = partials + (n * slots + blockIdx.x) * 3;
+    o[0] = w.n; o[1] = w.mean; o[2] = w.m2;
+  }
+}
+
 }  // namespace ps
+
+extern "C" int ps_stats_region(const float* x, int64_t batch, int64_t mid, int64_t rows, int64_t C, int64_t batch_stride,
+                               int64_t mid_stride, int64_t row_stride, int64_t slots, float* partials, void* stream) {
+  PS_REQUIRE(x && partials && batch > 0 && mid > 0 && rows > 0 && C > 0 && slots > 0 && row_stride >= C);
+  if (batch > 65535 || slots > 2147483647LL || C > 2147483647LL) return PS_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)slots, (unsigned)batch);
+  ps::stats_region_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, batch_stride, mid_stride, row_stride, mid, rows, (int)C, partials);
+  PS_CHECK_LAUNCH("stats_region_kernel");
+  return PS_OK;
+}
 
 extern "C" int ps_stats_finalize(const float* partials, int64_t batch, int64_t slots, const float* gamma,
                                  const float* beta, float eps, int64_t C, float* scale, float* shift, float* meanvar,

@@ -130,20 +130,25 @@ class Unet(nn.Module):
         if self.training and self.dropout > 0:
             raise NotImplementedError("dropout > 0 in train mode is a training feature (out of scope)")
 
-    def _activate(self, raw: torch.Tensor, parts: List[torch.Tensor], norm: nn.Module, act: nn.PReLU, N: int) -> torch.Tensor:
-        """raw [N*T, F, C] (+ the Welford partials of the launches that produced it) -> PReLU(norm(raw)), same shape."""
-        C_ = raw.shape[-1]
-        if isinstance(norm, GlobLN):
-            merged = torch.cat([p.reshape(N, -1, 3) for p in parts], 1).contiguous()
-            scale, shift = ops.stats_finalize(merged, norm.gamma, norm.beta, norm.eps, C_)
+    def _activate(self, rawv, norm: Optional[nn.Module], act: Optional[nn.PReLU], N: int) -> torch.Tensor:
+        """rawv = (tensor, frames per item, rows allocated per frame, valid rows per frame, C): the raw output of a layer's
+        GEMMs, whose allocation carries rows that are not part of the tensor -> PReLU(norm(raw)) (or a plain copy when the
+        layer has no norm) as a contiguous [N*frames, valid rows, C] tensor.  gLN statistics are taken over the valid region
+        only (`ps_stats_region`), then folded to a per-item per-channel affine applied by the copy."""
+        raw, Tn, R, Fv, C_ = rawv
+        strides = (Tn * R * C_, R * C_, C_)
+        if norm is None:
+            pro = ops.NO_PRO
+        elif isinstance(norm, GlobLN):
+            part = ops.stats_region(raw, batch=N, mid=Tn, rows=Fv, C_=C_, strides=strides)
+            scale, shift = ops.stats_finalize(part, norm.gamma, norm.beta, norm.eps, C_)
             pro = Prologue(PRO_AFFINE, ACT_PRELU, scale, shift, C_, None, prelu_slope(act))
         else:  # BatchNorm2d, eval
             if norm.training:
                 raise NotImplementedError("train-mode BatchNorm couples batch items; the engine runs .eval() models only")
             scale, shift = ops.bn_fold(norm.weight, norm.bias, norm.running_mean, norm.running_var, norm.eps)
             pro = Prologue(PRO_AFFINE, ACT_PRELU, scale, shift, 0, None, prelu_slope(act))
-        rows = raw.numel() // (N * C_)
-        return ops.gated(raw, pro, batch=N, rows=rows, C_=C_).view(raw.shape)
+        return ops.gated(raw, pro, batch=N, mid=Tn, rows=Fv, C_=C_, a_strides=strides).view(N * Tn, Fv, C_)
 
     @staticmethod
     def _stack(dst: torch.Tensor, T_dst: int, src, N: int, slot_width: int, col: int, shifts: List[int], f_lo: int):
@@ -163,32 +168,33 @@ class Unet(nn.Module):
                       out=y, y_strides=(T_dst * Fp * W, Fp * W, W))
 
     def _down(self, i: int, x: torch.Tensor, N: int, T: int):
-        """Activated layer input x [N*T, F, C] -> (raw conv output [N*T, F', C'], its statistics partials)."""
-        return self._down_impl(i, x, N, T)
-
-    def _down_impl(self, i: int, x: torch.Tensor, N: int, T: int):
+        """Activated layer input x [N*T, F, C] -> raw conv output as (tensor, T, R, F', C'): one flat framed GEMM per item over
+        all T*R window positions (R = padded frequency rows / stride >= F'; the trailing R - F' positions of a frame straddle
+        two frames and are never read back), so tiles stay dense however few frequency rows a deep layer has."""
         conv = self.cnn_down[i][1]
         kf, kt = self.kernel[i]
         s = self.stride[i][0]
         F_, C_ = x.shape[1], x.shape[2]
         pf = kf // 2
         left = kt - self.delay[i] - 1
-        buf = torch.zeros(N * T, F_ + 2 * pf, kt * C_, device=x.device, dtype=torch.float32)
-        self._stack(buf, T, (x, T, 0, T), N, C_, 0, [j - left for j in range(kt)], pf)
+        Fp = -(-(F_ + 2 * pf) // s) * s   # frequency rows per frame, a multiple of the stride so window positions are equidistant
+        W = kt * C_
+        buf = torch.zeros(N * T + 1, Fp, W, device=x.device, dtype=torch.float32)  # +1 frame: the last window positions read past the end
+        self._stack(buf[:N * T], T, (x, T, 0, T), N, C_, 0, [j - left for j in range(kt)], pf)
         F_out = (F_ + 2 * pf - kf) // s + 1
-        M, K = conv.out_channels, kf * kt * C_
+        R = Fp // s
+        M, K = conv.out_channels, kf * W
         w = self._cache.get(f"down{i}", [conv.weight], lambda: conv.weight.permute(0, 2, 3, 1).reshape(M, K).contiguous())
         pk = self._cache.get(f"down{i}_pk", [conv.weight], lambda: ops.pack_weights(w, M, K, K))
-        want = isinstance(self.cnn_down[i][2], GlobLN)
-        y, part = ops.gemm(buf.view(-1), w, batch=N * T, rows=F_out, M=M, K=K, x_batch_stride=(F_ + 2 * pf) * kt * C_,
-                           x_row_stride=s * kt * C_, w_row_stride=K, bias=conv.bias, want_stats=want, w_packed=pk)
-        return y, [part]
+        y, _ = ops.gemm(buf.view(-1), w, batch=N, rows=T * R, M=M, K=K, x_batch_stride=T * Fp * W, x_row_stride=s * W, w_row_stride=K,
+                        bias=conv.bias, w_packed=pk)
+        return (y, T, R, F_out, M)
 
     def _up(self, i: int, xs, skip: torch.Tensor, N: int, T: int):
-        """cat([x, skip]) -> raw transposed-conv output over ALL T + tk - 1 output frames, as (tensor [N*(T+tk-1), s*F, C_out],
-        partials, T_alloc, t_off): the reference normalises the untrimmed tensor (gLN statistics include the frames the trim
+        """cat([x, skip]) -> raw transposed-conv output over ALL T + tk - 1 output frames, as ((tensor, To, rows allocated,
+        valid rows, C_out), t_off): the reference normalises the untrimmed tensor (gLN statistics include the frames the trim
         then drops, unet.py:527-537), so the extra frames are computed and only skipped when the next layer reads.
-        xs = (tensor, T_alloc, t_off, T) view of the layer input; skip [N*T, F, C]."""
+        xs = (tensor, T_alloc, t_off, T) view of the layer input; skip [N*T, F, C].  One flat GEMM per item and output phase."""
         x = xs[0]
         conv = self.cnn_up[i][0]
         idx = self.n_cnn - 1 - i
@@ -204,22 +210,18 @@ class Unet(nn.Module):
             kappa = (phi + p) % s
             Mp = len(range(kappa, k, s))
             phases.append((phi, kappa, Mp, (phi + p - kappa) // s))
-        phases = [ph for ph in phases if ph[2] > 0]
+        if any(Mp == 0 for _, _, Mp, _ in phases):
+            raise NotImplementedError("transposed conv with stride > kernel")
         pad_lo = max(max(Mp - 1 - q for _, _, Mp, q in phases), 0)
         pad_hi = max(max(q for _, _, _, q in phases), 0)
         W = tk * Cin
+        Rb = F_ + pad_lo + pad_hi
         To = T + tk - 1  # output frame t_o = t_i + kt: slot kt holds input frame t_o - kt
-        buf = torch.zeros(N * To, F_ + pad_lo + pad_hi, W, device=x.device, dtype=torch.float32)
+        buf = torch.zeros(N * To + 1, Rb, W, device=x.device, dtype=torch.float32)  # +1 frame of slack for the last windows
         shifts = [-j for j in range(tk)]
-        self._stack(buf, To, xs, N, Cin, 0, shifts, pad_lo)
-        self._stack(buf, To, (skip, T, 0, T), N, Cin, C_, shifts, pad_lo)
-        F_out = s * F_
-        y = torch.zeros(N * To, F_out, Cout, device=x.device, dtype=torch.float32) if len(phases) < s else \
-            torch.empty(N * To, F_out, Cout, device=x.device, dtype=torch.float32)
-        if len(phases) < s:
-            y += conv.bias  # phases no tap reaches keep the bare bias
-        parts = []
-        want = len(self.cnn_up[i]) > 1 and isinstance(self.cnn_up[i][1], GlobLN)
+        self._stack(buf[:N * To], To, xs, N, Cin, 0, shifts, pad_lo)
+        self._stack(buf[:N * To], To, (skip, T, 0, T), N, Cin, C_, shifts, pad_lo)
+        y = torch.empty(N * To, s * Rb, Cout, device=x.device, dtype=torch.float32)
         for phi, kappa, Mp, q in phases:
             K = Mp * W
 
@@ -230,11 +232,9 @@ class Unet(nn.Module):
             w = self._cache.get(f"up{i}_{phi}", [conv.weight], build)
             pk = self._cache.get(f"up{i}_{phi}_pk", [conv.weight], lambda w=w, K=K: ops.pack_weights(w, Cout, K, K))
             x0 = (pad_lo + q - (Mp - 1)) * W
-            _, part = ops.gemm(buf.view(-1)[x0:], w, batch=N * To, rows=F_, M=Cout, K=K, x_batch_stride=(F_ + pad_lo + pad_hi) * W,
-                               x_row_stride=W, w_row_stride=K, bias=conv.bias, want_stats=want, w_packed=pk,
-                               out=y.view(-1)[phi * Cout:], y_strides=(F_out * Cout, s * Cout))
-            parts.append(part)
-        return y, parts, To, ((tk - 1) if self.transpose_delay else 0)
+            ops.gemm(buf.view(-1)[x0:], w, batch=N, rows=To * Rb, M=Cout, K=K, x_batch_stride=To * Rb * W, x_row_stride=W, w_row_stride=K,
+                     bias=conv.bias, w_packed=pk, out=y.view(-1)[phi * Cout:], y_strides=(To * s * Rb * Cout, s * Cout))
+        return (y, To, s * Rb, s * F_, Cout), ((tk - 1) if self.transpose_delay else 0)
 
     # ------------------------------------------------------------------ forward
     def _to_cl4(self, x: torch.Tensor) -> torch.Tensor:
@@ -261,15 +261,14 @@ class Unet(nn.Module):
         cur = self._to_cl4(x.contiguous())
         skips = []
         for i in range(self.n_cnn):
-            raw, parts = self._down(i, cur, N, T)
-            cur = self._activate(raw, parts, self.cnn_down[i][2], self.cnn_down[i][3], N)
+            cur = self._activate(self._down(i, cur, N, T), self.cnn_down[i][2], self.cnn_down[i][3], N)
             skips.append(cur)
         cur = (self._bottleneck(cur, N, T, dvec), T, 0, T)
         for i in range(self.n_cnn):
-            raw, parts, T_alloc, t_off = self._up(i, cur, skips[-i - 1], N, T)
-            if len(self.cnn_up[i]) > 1:
-                raw = self._activate(raw, parts, self.cnn_up[i][1], self.cnn_up[i][2], N)
-            cur = (raw, T_alloc, t_off, T)
+            rawv, t_off = self._up(i, cur, skips[-i - 1], N, T)
+            last = len(self.cnn_up[i]) == 1  # the output layer is linear (unet.py:154-170)
+            act = self._activate(rawv, None if last else self.cnn_up[i][1], None if last else self.cnn_up[i][2], N)
+            cur = (act, rawv[1], t_off, T)
         return self._from_cl4(cur, N, T)
 
     @torch.no_grad()

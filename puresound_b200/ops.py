@@ -197,6 +197,16 @@ def stats_finalize(partials: Tensor, gamma: Optional[Tensor], beta: Optional[Ten
     return scale, shift
 
 
+def stats_region(x: Tensor, *, batch: int, mid: int, rows: int, C_: int, strides: tuple, slots: int = 64) -> Tensor:
+    """Welford partials [batch, slots, 3] of the strided region x[n, m, r, :C] (strides = (batch, mid, row) in floats)."""
+    lib = _lib.load()
+    part = torch.empty(batch, slots, 3, device=x.device, dtype=torch.float32)
+    _lib.check(lib.ps_stats_region(_dev(x, "stats_region").data_ptr(), batch, mid, rows, C_, strides[0], strides[1], strides[2], slots,
+                                   part.data_ptr(), _stream()), "ps_stats_region")
+    _launched()
+    return part
+
+
 def bn_fold(weight, bias, running_mean, running_var, eps: float):
     lib = _lib.load()
     Cn = running_mean.numel()
