@@ -360,6 +360,71 @@ static int filterbank_launch(const ps_gemm_t& d, cudaStream_t s) {
   return PS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Thin outputs (M <= 8): Y[b,r,m] = act(bias[m] + sum_k x[b, r*stride + k] * W[m,k]).  The output layer of the U-Net shell
+// (ConvTranspose2d to 2 channels, unet.py:154-170: M = 2, K = 256 / 384) and similar projections: a 128 x 128 tile would
+// spend 98 % of its FMAs on padding.  One warp per row: lanes stride K with 16-byte loads (rows overlap, so consecutive
+// rows of a CTA hit L1), the filter taps sit in shared memory, M butterfly reductions, lane m stores output m.
+// ---------------------------------------------------------------------------------------------------
+constexpr int THIN_MAXM = 8;
+constexpr int THIN_MAXWK = 8192;  // floats of weights in shared memory (32 KB)
+
+template <int TM>
+__global__ void __launch_bounds__(256) thin_gemm_kernel(const ps_gemm_t d) {
+  extern __shared__ __align__(16) float wsm[];  // [TM][K]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = (int)d.K, M = (int)d.M;
+  for (int i = tid; i < TM * K; i += blockDim.x) wsm[i] = (i / K < M) ? __ldg(d.W + (int64_t)(i / K) * d.w_row_stride + i % K) : 0.f;
+  __syncthreads();
+  const float eslope = d.epi_slope ? __ldg(d.epi_slope) : 0.f;
+  const float bias = (d.bias && lane < M) ? __ldg(d.bias + lane) : 0.f;
+  const int64_t total = d.batch * d.rows;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;  // a CTA walks a contiguous run of rows (L1 reuse of the overlap)
+  const int64_t g0 = (int64_t)blockIdx.x * per, g1 = (g0 + per < total) ? g0 + per : total;
+  for (int64_t g = g0 + warp; g < g1; g += 8) {
+    const int64_t b = g / d.rows, r = g % d.rows;
+    const float* xr = d.X + b * d.x_batch_stride + r * d.x_row_stride;
+    float acc[TM];
+#pragma unroll
+    for (int m = 0; m < TM; ++m) acc[m] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(xr + k));
+#pragma unroll
+      for (int m = 0; m < TM; ++m) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wsm + m * K + k);
+        acc[m] = fmaf(x4.x, w4.x, acc[m]); acc[m] = fmaf(x4.y, w4.y, acc[m]);
+        acc[m] = fmaf(x4.z, w4.z, acc[m]); acc[m] = fmaf(x4.w, w4.w, acc[m]);
+      }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int m = 0; m < TM; ++m) {
+      const float v = warp_sum(acc[m]);
+      if (lane == m) mine = v;
+    }
+    if (lane < M) d.Y[b * d.y_batch_stride + r * d.y_row_stride + lane] = apply_act(mine + bias, d.epi_act, eslope);
+  }
+}
+
+static bool thin_eligible(const ps_gemm_t& d, int x_vec) {
+  if (d.M > THIN_MAXM || !x_vec || d.K % 4 != 0 || d.K * THIN_MAXM > THIN_MAXWK * 1) return false;
+  if (d.pro_mode != PS_PRO_NONE || d.residual || d.stats_partials || d.bias_batch || d.ln_eps > 0.f) return false;
+  return d.batch * d.rows >= 4096;  // small problems keep the latency tile
+}
+
+static int thin_launch(const ps_gemm_t& d, cudaStream_t s) {
+  const int64_t total = d.batch * d.rows;
+  int64_t blocks = cdiv(total, 64);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int TM = d.M <= 2 ? 2 : (d.M <= 4 ? 4 : 8);
+  const size_t smem = (size_t)TM * d.K * sizeof(float);
+  if (TM == 2) thin_gemm_kernel<2><<<(unsigned)blocks, 256, smem, s>>>(d);
+  else if (TM == 4) thin_gemm_kernel<4><<<(unsigned)blocks, 256, smem, s>>>(d);
+  else thin_gemm_kernel<8><<<(unsigned)blocks, 256, smem, s>>>(d);
+  PS_CHECK_LAUNCH("thin_gemm_kernel");
+  return PS_OK;
+}
+
 template <int BR, int BC>
 static int launch_shape(const ps_gemm_t& d, cudaStream_t s, int x_vec, int w_vec) {
   const int64_t nrt = cdiv(d.rows, BR), nmt = cdiv(d.M, BC);
@@ -381,6 +446,7 @@ int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s) {
                     (!d.X2 || (reinterpret_cast<uintptr_t>(d.X2) & 15) == 0);
   const int w_vec = ((d.w_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
   if (filterbank_eligible(d)) return filterbank_launch(d, s);
+  if (thin_eligible(d, x_vec)) return thin_launch(d, s);
   // latency shape when the throughput shape would leave most SMs idle (and no statistics are requested: the partial
   // slot layout is defined on 128 x 128 tiles)
   const int64_t big_ctas = d.batch * cdiv(d.rows, 128) * cdiv(d.M, 128);

@@ -87,11 +87,23 @@ __global__ void __launch_bounds__(256) stats_region_kernel(const float* __restri
   const float* xb = x + n * bs;
   WfAcc acc;
   acc.init();
-  const int64_t cnt = (r1 > r0 ? r1 - r0 : 0) * C;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int64_t row = r0 + i / C;
-    const int c = (int)(i % C);
-    acc.add(__ldg(xb + (row / rows) * ms + (row % rows) * rs + c));
+  const bool vec = (C & 3) == 0 && ((bs | ms | rs) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec) {
+    const int C4 = C >> 2;
+    const int64_t cnt = (r1 > r0 ? r1 - r0 : 0) * C4;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int64_t row = r0 + i / C4;
+      const int c = (int)(i % C4) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (row / rows) * ms + (row % rows) * rs + c));
+      acc.add(v.x); acc.add(v.y); acc.add(v.z); acc.add(v.w);
+    }
+  } else {
+    const int64_t cnt = (r1 > r0 ? r1 - r0 : 0) * C;
+    for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int64_t row = r0 + i / C;
+      const int c = (int)(i % C);
+      acc.add(__ldg(xb + (row / rows) * ms + (row % rows) * rs + c));
+    }
   }
   const Wf w = wf_block_reduce(acc.finish(), red);
   if (threadIdx.x == 0) {

@@ -222,6 +222,23 @@ def test_short_k_filterbank_kernel(ops, M, K, hop, relu):
     close(y.double(), ref, 1e-6)
 
 
+@pytest.mark.parametrize("M,K,hop,relu", [(2, 384, 128, False), (2, 256, 128, True), (5, 100, 100, False), (8, 1024, 64, False)])
+def test_thin_output_gemm_kernel(ops, M, K, hop, relu):
+    """M <= 8 output channels (the U-Net shell's output layer: ConvTranspose2d to 2 channels as framed GEMM rows,
+    unet.py:154-170) go through the warp-per-row kernel: overlapping rows read in place, bias, activation, strided output."""
+    N, L = 3, K + hop * 2999
+    x, w, bias = rnd(N, L, seed=1), rnd(M, K, seed=2, scale=0.2), rnd(M, seed=3)
+    T = (L - K) // hop + 1
+    out = torch.full((N, T, 2 * M + 3), 7.0, device=DEV)
+    ops.gemm(x, w, batch=N, rows=T, M=M, K=K, x_batch_stride=L, x_row_stride=hop, w_row_stride=K, bias=bias,
+             epi_act=ops.ACT_RELU if relu else ops.ACT_NONE, backend=ops.GEMM_SIMT, out=out.view(-1)[M:], y_strides=(T * (2 * M + 3), 2 * M + 3))
+    ref = torch.nn.functional.conv1d(x.unsqueeze(1).double(), w.unsqueeze(1).double(), bias.double(), stride=hop).transpose(1, 2)
+    if relu:
+        ref = torch.relu(ref)
+    close(out[:, :, M:2 * M].double(), ref, 2e-6)
+    assert (out[:, :, :M] == 7.0).all() and (out[:, :, 2 * M:] == 7.0).all()  # only its own columns are written
+
+
 @pytest.mark.parametrize("H,D,N,S,K", [
     (128, 1, 2, 37, 50), (128, 2, 2, 37, 50),   # 74 sequences: one wave whatever the CTA size -> 32 per CTA
     (64, 1, 2, 37, 50), (64, 2, 1, 21, 30),     # veve_dprnn_v0_causal's hidden size: units 64..127 are zero padding
