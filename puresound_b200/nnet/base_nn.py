@@ -26,6 +26,13 @@ _MASK_ACT = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
 _OUT_CONSTRAINT = {"linear": 1, "sigmoid": 2}
 
 
+# The mixture's STFT analysis GEMM runs on the tensor cores (3xBF16, ~2^-17 per product) like the masker's GEMMs, whose
+# errors reach the iSTFT through the mask anyway: measured at full size (run 81) cfg4 max|dy| 3.0e-5 / pre-clamp 6.6e-5 against
+# 2.3e-5 / 5.7e-5 with the exact-fp32 analysis (tolerance 1e-3).  The synthesis GEMM + overlap-add + window-sum-square
+# division stay exact fp32.  PS_STFT_EXACT=1 puts the analysis back on the fp32 CUDA-core kernel.
+_STFT_EXACT = os.environ.get("PS_STFT_EXACT", "0") == "1"
+
+
 class SoTaskWrapModule(nn.Module):
     def __init__(
         self,
@@ -138,7 +145,7 @@ class SoTaskWrapModule(nn.Module):
                 raise NotImplementedError("this mask/feature combination is broken upstream (base_nn.py:127, :75)")
             raise NameError
 
-        feats = self._encode_cl(self.encoder, noisy)
+        feats = self._encode_cl(self.encoder, noisy, exact=_STFT_EXACT)
         dvec = None
         if enroll is not None:
             enc = self.encoder if self.encoder_spk is None else self.encoder_spk

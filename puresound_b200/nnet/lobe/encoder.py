@@ -153,9 +153,9 @@ class ConvEncDec(nn.Module):
     def encode_cl(self, wav: torch.Tensor, drop_first_bin: bool, exact: bool = True) -> torch.Tensor:
         """wav [N, L] -> [N, T, 2F'] = cat(Re[s:], Im[s:]) on channels (base_nn.py:337-345 layout), Im = -conv(wsin).
 
-        exact=True keeps the analysis GEMM in true fp32 (the spectrum that is masked and goes back through the iSTFT,
-        whose window-sum-square division amplifies rounding ~2.6e4x at the first/last hop); exact=False lets it run on
-        the tensor cores (3xBF16) - used for the enrollment spectrum, which only feeds the speaker net."""
+        exact=True keeps the analysis GEMM in true fp32; exact=False (what the task wrapper uses, see base_nn._STFT_EXACT)
+        lets it run on the tensor cores (3xBF16).  The synthesis side (decode_cl) is always exact fp32: its
+        window-sum-square division amplifies rounding ~2.6e4x at the first/last hop."""
         _check_wav(wav, self.n_fft)
         e = self.encoder
         s = 1 if drop_first_bin else 0
