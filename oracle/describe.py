@@ -65,11 +65,11 @@ def describe_masker(m: nn.Module) -> dict:
     n = type(m).__name__
     if n in ("ConvTasNet", "StreamingConvTasNet"):
         return {"type": "ConvTasNet", **m.get_args}
-    if n == "UnetTcn":
+    if n in ("UnetTcn", "DPCRN"):
         a = {k: (list(v) if isinstance(v, tuple) else v) for k, v in m.get_args.items()}
         if a["input_type"].lower() == "ri":  # get_args reports the channel list AFTER the constructor doubled entry 0 (unet.py:91-93)
             a["channels"] = [a["channels"][0] // 2] + list(a["channels"][1:])
-        return {"type": "UnetTcn", **a}
+        return {"type": n, **a}
     if n == "DPRNN":
         return {
             "type": "DPRNN",

@@ -585,12 +585,10 @@ def _norm2d(kind: str, sd: SD, p: str, x: Tensor) -> Tensor:
     raise NotImplementedError(kind)
 
 
-def unet_tcn(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tensor:
-    """UnetTcn.forward, unet.py:454-517 (layers built at :100-175 and :371-451): ZeroPad2d + Conv2d + norm + PReLU down
-    path, TCN / GatedTCN stack on the flattened [N, ch*F', T] bottleneck, cat-skip + ConvTranspose2d (+ norm + PReLU) up path
-    with the time trim of :529-537."""
-    if a["embed_norm"] and dvec is not None:
-        dvec = F.normalize(dvec, p=2, dim=1)
+def _unet_shell(sd: SD, p: str, x: Tensor, a: dict, bottleneck) -> Tensor:
+    """The U-Net shell shared by Unet / UnetTcn / DPCRN (unet.py:219-273,454-517; dpcrn.py:136-190; layers built at
+    unet.py:100-175): ZeroPad2d + Conv2d + norm + PReLU down path, ``bottleneck`` on [N, ch, F', T], cat-skip +
+    ConvTranspose2d (+ norm + PReLU) up path with the time trim of unet.py:529-537."""
     n_cnn = len(a["kernel_t"])
     if a["input_type"].lower() == "ri":
         re, im = torch.chunk(x, 2, dim=-2)
@@ -605,17 +603,7 @@ def unet_tcn(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tens
         x = F.conv2d(x, sd[q + "1.weight"], sd[q + "1.bias"], stride=(a["stride_f"][i], a["stride_t"][i]))
         x = F.prelu(_norm2d(a["norm_type"], sd, q + "2.", x), sd[q + "3.weight"])
         skip.append(x)
-    N, ch, Fb, T = x.shape
-    x = x.reshape(N, ch * Fb, T)
-    gated = a["tcn_layer"].lower() == "gated"
-    for r in range(a["repeat_tcn"]):
-        for i in range(a["per_tcn_stack"]):
-            q, e, d = f"{p}tcn_list.{r}.{i}.", dvec if a["tcn_with_embed"][i] else None, a["tcn_dilated_basic"] ** i
-            if gated:
-                x = gated_tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"])
-            else:
-                x = tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"], a["dconv_norm"])
-    x = x.reshape(N, ch, Fb, T)
+    x = bottleneck(x)
     tk = a["transpose_t_size"]
     for i in range(n_cnn):
         idx = n_cnn - 1 - i
@@ -633,9 +621,55 @@ def unet_tcn(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tens
     return x.squeeze(1)
 
 
+def unet_tcn(sd: SD, p: str, x: Tensor, dvec: Optional[Tensor], a: dict) -> Tensor:
+    """UnetTcn.forward, unet.py:454-517: the shell around a TCN / GatedTCN stack on the flattened [N, ch*F', T] tensor
+    (stack built at unet.py:371-451)."""
+    if a["embed_norm"] and dvec is not None:
+        dvec = F.normalize(dvec, p=2, dim=1)
+
+    def bottleneck(x):
+        N, ch, Fb, T = x.shape
+        x = x.reshape(N, ch * Fb, T)
+        gated = a["tcn_layer"].lower() == "gated"
+        for r in range(a["repeat_tcn"]):
+            for i in range(a["per_tcn_stack"]):
+                q, e, d = f"{p}tcn_list.{r}.{i}.", dvec if a["tcn_with_embed"][i] else None, a["tcn_dilated_basic"] ** i
+                if gated:
+                    x = gated_tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"])
+                else:
+                    x = tcn_block(sd, q, x, e, a["tcn_kernel"], d, a["causal"], a["tcn_norm"], a["dconv_norm"])
+        return x.reshape(N, ch, Fb, T)
+
+    return _unet_shell(sd, p, x, a, bottleneck)
+
+
+def _dprnn_block2d(sd: SD, p: str, x: Tensor, fast_lstm: bool) -> Tensor:
+    """DPRNNblock2D.forward, dpcrn.py:34-81 (SingleRNN = LSTM + Linear, lobe/rnn.py:36-52): bidirectional LSTM over the
+    frequency rows of every frame, uni-directional LSTM over the frames of every frequency row, each followed by
+    Linear -> LayerNorm(channels) -> + skip.  x [N, CH, C, T]."""
+    N, CH, C, T = x.shape
+    v = x.permute(0, 3, 2, 1).reshape(N * T, C, CH)
+    y, _ = lstm(sd, p + "intra_rnn.rnn.", v, True, None, fast=fast_lstm)
+    y = F.linear(y, sd[p + "intra_rnn.proj.weight"], sd[p + "intra_rnn.proj.bias"])
+    y = F.layer_norm(y, (CH,), sd[p + "intra_norm.weight"], sd[p + "intra_norm.bias"], 1e-5)
+    x = x + y.reshape(N, T, C, CH).permute(0, 3, 2, 1)
+    v = x.permute(0, 2, 3, 1).reshape(N * C, T, CH)
+    y, _ = lstm(sd, p + "inter_rnn.rnn.", v, False, None, fast=fast_lstm)
+    y = F.linear(y, sd[p + "inter_rnn.proj.weight"], sd[p + "inter_rnn.proj.bias"])
+    y = F.layer_norm(y, (CH,), sd[p + "inter_norm.weight"], sd[p + "inter_norm.bias"], 1e-5)
+    return x + y.reshape(N, C, T, CH).permute(0, 3, 1, 2)
+
+
+def dpcrn(sd: SD, p: str, x: Tensor, a: dict, fast_lstm: bool = True) -> Tensor:
+    """DPCRN.forward, dpcrn.py:136-190: the U-Net shell around two DPRNNblock2D."""
+    return _unet_shell(sd, p, x, a, lambda v: _dprnn_block2d(sd, p + "dprnn_block2.", _dprnn_block2d(sd, p + "dprnn_block1.", v, fast_lstm), fast_lstm))
+
+
 def masker_forward(sd: SD, p: str, mcfg: dict, x: Tensor, dvec: Optional[Tensor], fast_lstm: bool = True) -> Tensor:
     if mcfg["type"] == "UnetTcn":
         return unet_tcn(sd, p, x, dvec, mcfg)
+    if mcfg["type"] == "DPCRN":
+        return dpcrn(sd, p, x, mcfg, fast_lstm)
     if mcfg["type"] == "ConvTasNet":
         return conv_tasnet(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "DPRNN":

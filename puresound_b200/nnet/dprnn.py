@@ -24,6 +24,60 @@ from ._fuse import ParamCache, prelu_slope
 from .lobe.trivial import FiLM, overlap_geometry
 
 
+def lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM):
+    """(W_ih stacked over directions [D*4H, C], b_ih + b_hh [D*4H], W_hh transposed [D, H, 4H], resident tensor-core image of
+    W_hh or None, tcgen05 image of W_ih or None); with the tensor-core recurrence the projection rows are [dir][unit][gate]."""
+    sfx = ["", "_reverse"] if rnn.bidirectional else [""]
+    H = rnn.hidden_size
+    srcs = [getattr(rnn, f"{n}_l0{s}") for s in sfx for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+    def build():
+        w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
+        b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
+        w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
+        # resident image for the tensor-core recurrence (None unless H <= 128 and H % 32 == 0), tcgen05 image of W_ih for the projections
+        w_hh_pk = ops.lstm_pack_weights(w_hh_t, H, len(sfx))
+        if w_hh_pk is not None:
+            # tensor-core recurrence: order the projection rows [dir][unit][gate] so the four gates of a unit are one
+            # 16-byte load of gx (ps_lstm_t.gx_interleaved)
+            D = len(sfx)
+            w_ih = w_ih.view(D, 4, H, -1).permute(0, 2, 1, 3).reshape(D * 4 * H, -1).contiguous()
+            b = b.view(D, 4, H).permute(0, 2, 1).reshape(D * 4 * H).contiguous()
+        w_ih_pk = ops.pack_weights(w_ih, w_ih.shape[0], w_ih.shape[1], w_ih.shape[1])
+        return w_ih, b, w_hh_t, w_hh_pk, w_ih_pk
+
+    return cache.get(tag, srcs, build)
+
+
+def dual_path_pass(cache: ParamCache, out: torch.Tensor, rnn: nn.LSTM, proj: nn.Linear, norm: nn.LayerNorm, tag: str, inter: bool,
+                   init=None, want_state: bool = False):
+    """One intra- or inter-chunk pass on out [N, S, K, C]: out + LN(Linear(LSTM(out))) (dprnn.py:157-178; the same pattern
+    is DPRNNblock2D of DPCRN, dpcrn.py:48-80, with S = frames and K = frequency rows).  Intra: N*S sequences over K; inter: N*K
+    sequences over S, addressed in place (no permute)."""
+    N, S, K, Cn = out.shape
+    H, D = rnn.hidden_size, (2 if rnn.bidirectional else 1)
+    w_ih, b, w_hh_t, w_hh_pk, w_ih_pk = lstm_weights(cache, tag, rnn)
+    P = N * S * K
+    flat = out.view(1, P, Cn)
+    gx, _ = ops.linear(flat, w_ih, bias=b, w_packed=w_ih_pk)  # [1, P, D*4H]
+    if inter:
+        geo = dict(n_seq=N * K, L=S, inner=K, outer_stride=S * K, inner_stride=1, step_stride=K)
+    else:
+        geo = dict(n_seq=N * S, L=K, inner=1, outer_stride=K, inner_stride=0, step_stride=1)
+    h0 = c0 = None
+    if init is not None:
+        h0, c0 = init[0].contiguous(), init[1].contiguous()
+    h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk,
+                        gx_interleaved=w_hh_pk is not None, **geo)
+    proj_pk = cache.get(tag + "_proj", [proj.weight],
+                        lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
+    # Linear -> LayerNorm -> + residual in one kernel (LayerNorm in the GEMM epilogue when Cn == 128; otherwise the
+    # library runs the row-norm kernel after the GEMM)
+    new, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk,
+                        ln=(norm.weight, norm.bias, norm.eps), residual=out.view(1, P, Cn))
+    return new.view(N, S, K, Cn), state
+
+
 class DPRNN(nn.Module):
     """reference: dprnn.py:10-244."""
 
@@ -68,26 +122,7 @@ class DPRNN(nn.Module):
 
     # ------------------------------------------------------------------ helpers
     def _lstm_weights(self, tag: str, rnn: nn.LSTM):
-        """(W_ih stacked over directions [D*4H, C], b_ih + b_hh [D*4H], W_hh transposed [D, H, 4H])."""
-        sfx = ["", "_reverse"] if self.bi_direct else [""]
-        srcs = [getattr(rnn, f"{n}_l0{s}") for s in sfx for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-
-        def build():
-            w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
-            b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
-            w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
-            # resident image for the tensor-core recurrence (None unless H <= 128 and H % 32 == 0), tcgen05 image of W_ih for the projections
-            w_hh_pk = ops.lstm_pack_weights(w_hh_t, self.hidden_size, len(sfx))
-            if w_hh_pk is not None:
-                # tensor-core recurrence: order the projection rows [dir][unit][gate] so the four gates of a unit are one
-                # 16-byte load of gx (ps_lstm_t.gx_interleaved)
-                D, H = len(sfx), self.hidden_size
-                w_ih = w_ih.view(D, 4, H, -1).permute(0, 2, 1, 3).reshape(D * 4 * H, -1).contiguous()
-                b = b.view(D, 4, H).permute(0, 2, 1).reshape(D * 4 * H).contiguous()
-            w_ih_pk = ops.pack_weights(w_ih, w_ih.shape[0], w_ih.shape[1], w_ih.shape[1])
-            return w_ih, b, w_hh_t, w_hh_pk, w_ih_pk
-
-        return self._cache.get(tag, srcs, build)
+        return lstm_weights(self._cache, tag, rnn)
 
     def _geometry(self, T: int):
         K = self.seg_size
@@ -100,29 +135,7 @@ class DPRNN(nn.Module):
 
     def _pass(self, out: torch.Tensor, rnn: nn.LSTM, proj: nn.Linear, norm: nn.LayerNorm, tag: str, inter: bool,
               init=None, want_state: bool = False):
-        """One intra- or inter-chunk pass on out [N, S, K, C]: out + LN(Linear(LSTM(out)))."""
-        N, S, K, Cn = out.shape
-        H, D = self.hidden_size, (2 if self.bi_direct else 1)
-        w_ih, b, w_hh_t, w_hh_pk, w_ih_pk = self._lstm_weights(tag, rnn)
-        P = N * S * K
-        flat = out.view(1, P, Cn)
-        gx, _ = ops.linear(flat, w_ih, bias=b, w_packed=w_ih_pk)  # [1, P, D*4H]
-        if inter:
-            geo = dict(n_seq=N * K, L=S, inner=K, outer_stride=S * K, inner_stride=1, step_stride=K)
-        else:
-            geo = dict(n_seq=N * S, L=K, inner=1, outer_stride=K, inner_stride=0, step_stride=1)
-        h0 = c0 = None
-        if init is not None:
-            h0, c0 = init[0].contiguous(), init[1].contiguous()
-        h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk,
-                            gx_interleaved=w_hh_pk is not None, **geo)
-        proj_pk = self._cache.get(tag + "_proj", [proj.weight],
-                                  lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
-        # Linear -> LayerNorm -> + residual in one kernel (LayerNorm in the GEMM epilogue when Cn == 128; otherwise the
-        # library runs the row-norm kernel after the GEMM)
-        new, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk,
-                            ln=(norm.weight, norm.bias, norm.eps), residual=out.view(1, P, Cn))
-        return new.view(N, S, K, Cn), state
+        return dual_path_pass(self._cache, out, rnn, proj, norm, tag, inter, init, want_state)
 
     def _blocks(self, seg: torch.Tensor, film_embed, inits, collect_hidden: bool):
         out = seg

@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from .nnet.base_nn import SoTaskWrapModule
 from .nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
+from .nnet.dpcrn import DPCRN
 from .nnet.dprnn import DPRNN
 from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
 from .nnet.lobe.pooling import AttentiveStatisticsPooling
@@ -62,6 +63,17 @@ def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Option
                 [Magnitude(drop_first=False)] + [GatedTCN(256, 128, 3, dilation=2 ** i, causal=False, tcn_norm="gLN") for i in range(5)]
                 + [AttentiveStatisticsPooling(256, 128), nn.Conv1d(256 * 2, 192, 1, bias=False)]),
             loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="linear", drop_first_bin=True, **kwargs)
+    if name in ("ns_dpcrn_v0", "ns_dpcrn_v0_causal"):
+        # egs/ns/model.py:38-126 (noise suppression: complex mask on the STFT, no speaker branch); the non-causal variant
+        # only differs in which frame the up-path trim drops (transpose_delay)
+        return SoTaskWrapModule(
+            encoder=ConvEncDec(fft_length=512, win_type="hann", win_length=512, hop_length=128, trainable=True, output_format="Complex"),
+            masker=DPCRN(input_type="RI", input_dim=512, activation_type="PReLU", norm_type="bN2d", dropout=0.1,
+                         channels=(1, 32, 32, 32, 64, 128), transpose_t_size=2, transpose_delay=not name.endswith("_causal"), skip_conv=False,
+                         kernel_t=(2,) * 5, kernel_f=(5, 3, 3, 3, 3), stride_t=(1,) * 5, stride_f=(2, 2, 1, 1, 1), dilation_t=(1,) * 5,
+                         dilation_f=(1,) * 5, delay=(0,) * 5, rnn_hidden=128),
+            speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=None, drop_first_bin=True, mask_constraint="linear",
+            f_type="Complex", mask_type="Complex", **kwargs)
     if name in ("tse_skim_v0", "tse_skim_v0_causal"):
         # egs/tse/model.py:371-463 (the causal one is the reference's demo model)
         causal = name.endswith("_causal")
@@ -113,6 +125,7 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN",
                        dconv_norm="cLN", causal=True),
             mask_constraint="ReLU", verbose=verbose)
-    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1"):
+    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1",
+                "ns_dpcrn_v0", "ns_dpcrn_v0_causal"):
         return init_model(name, None, None, verbose=verbose)
     raise NameError(name)

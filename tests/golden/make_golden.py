@@ -43,6 +43,7 @@ from puresound.nnet.lobe.pooling import AttentiveStatisticsPooling  # noqa: E402
 from puresound.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge  # noqa: E402
 from puresound.nnet.skim import MemLSTM, SegLSTM, SkiM  # noqa: E402
 from puresound.nnet.unet import UnetTcn  # noqa: E402
+from puresound.nnet.dpcrn import DPCRN, DPRNNblock2D  # noqa: E402
 
 from oracle import describe as D  # noqa: E402
 from puresound_b200 import testing as T  # noqa: E402
@@ -456,6 +457,50 @@ def unet_cases():
         json.dump(pins, fh)
 
 
+def _ref_ns_model(name):
+    spec = importlib.util.spec_from_file_location("ref_ns_model", os.path.join(REF, "egs/ns/model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return quiet(mod.init_model, name, None, verbose=False)
+
+
+@torch.no_grad()
+def dpcrn_cases():
+    """DPCRN (dpcrn.py:11-213): the dual-path block on its own, small variants of the masker, and
+    full-size pins of the egs/ns recipes ns_dpcrn_v0 / ns_dpcrn_v0_causal (egs/ns/model.py:38-126)."""
+    cases = {}
+    torch.manual_seed(61)
+    blk = T.perturb_(DPRNNblock2D(16, 12, dropout=0.0).eval(), seed=62)
+    x = rnd(2, 16, 9, 11, seed=63)
+    cases["block2d"] = {"sd": sd_of(blk), "x": x, "y": blk(x)}
+    base = dict(input_type="RI", input_dim=32, channels=(1, 4, 8, 16), transpose_t_size=2, kernel_t=(2, 2, 2), kernel_f=(5, 3, 3),
+                stride_t=(1, 1, 1), stride_f=(2, 2, 1), dilation_t=(1, 1, 1), dilation_f=(1, 1, 1), delay=(0, 0, 0), dropout=0.0)
+    for tag, kw in {
+        "bn_delay_h32": dict(norm_type="bN2d", transpose_delay=True, rnn_hidden=32),     # tensor-core recurrence (H % 32 == 0)
+        "bn_causal_h12": dict(norm_type="bN2d", transpose_delay=False, rnn_hidden=12),   # exact-fp32 recurrence
+        "gln_h32": dict(norm_type="gLN", transpose_delay=False, rnn_hidden=32),
+    }.items():
+        torch.manual_seed(64)
+        m = T.perturb_(quiet(DPCRN, **{**base, **kw}).eval(), seed=65)
+        x = rnd(2, 32, 29, seed=66)
+        cases[tag] = {"cfg": D.describe_masker(m), "sd": sd_of(m), "x": x, "y": m(x)}
+    save("small_dpcrn.pt", cases)
+    pins = {}
+    for name in ("ns_dpcrn_v0", "ns_dpcrn_v0_causal"):
+        torch.manual_seed(0)
+        m = _ref_ns_model(name).eval()
+        T.perturb_(m, seed=1)
+        n, L, stride = 2, 64000, 997
+        mix, _ = T.noisy_speech(n, L, seed=1234)
+        y = m.inference(mix)
+        pins[name] = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n,
+                      "length": L, "input_seed": 1234, "stride": stride, "out_len": y.shape[-1], "out_abs_mean": float(y.abs().mean()),
+                      "out_clamped_frac": float((y.abs() >= 1).float().mean()), "samples": [[float(v) for v in row[::stride]] for row in y]}
+        print(name, pins[name]["params"], pins[name]["out_abs_mean"], pins[name]["out_clamped_frac"])
+    with open(os.path.join(HERE, "dpcrn_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
 @torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
@@ -501,3 +546,5 @@ if __name__ == "__main__":
         gated_cases()
     if which in ("all", "unet"):
         unet_cases()
+    if which in ("all", "dpcrn"):
+        dpcrn_cases()

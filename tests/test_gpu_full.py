@@ -107,6 +107,27 @@ def test_unet_recipes_full_size(name):
     assert err_pin <= WAVE_TOL and err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
 
 
+@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal"])
+def test_dpcrn_recipes_full_size(name):
+    """The egs/ns recipes (egs/ns/model.py:38-126), 2 x 4 s, against the reference's recorded output and the oracle."""
+    with open(os.path.join(GOLDEN, "dpcrn_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, clean = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    y = m.to("cuda").inference(mix)
+    err_pin = (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item()
+    y_ref = R.inference(sd, cfg, mix, None)
+    err = (y - y_ref).abs().max().item()
+    L = y.shape[-1]
+    d_sisnr = float((R.si_snr(y, clean[:, :L]) - R.si_snr(y_ref, clean[:, :L])).abs().max())
+    print(f"{name}: max|dy|={err:.3e} (vs reference samples {err_pin:.3e}) dSI-SNR={d_sisnr:.2e} dB")
+    assert err_pin <= WAVE_TOL and err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
+
+
 def test_skim_recipe_full_size():
     """`tse_skim_v0_causal` (4 s mixture + 6 s enrollment) against the reference's recorded output and the oracle."""
     with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:

@@ -100,6 +100,23 @@ def test_unet_tcn(golden, backend):
         ops.force_gemm_backend = None
 
 
+def test_dpcrn(golden):
+    """DPCRN on the engine against the reference's outputs: the 2-D dual-path block (bidirectional
+    LSTM over frequency, uni-directional over time, in place on [N, T, F, C]) and the masker inside bN2d / gLN shells."""
+    from puresound_b200.nnet.dpcrn import DPRNNblock2D
+
+    gs = golden("small_dpcrn.pt")
+    blk = DPRNNblock2D(16, 12).to(DEV).eval()
+    blk.load_state_dict(gs["block2d"]["sd"])
+    close(blk(cu(gs["block2d"]["x"])), gs["block2d"]["y"], 5e-5)
+    for tag, g in gs.items():
+        if tag == "block2d":
+            continue
+        m = _build.masker(g["cfg"]).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        close(m(cu(g["x"])), g["y"], 1e-4)
+
+
 def test_conv_tasnet(golden):
     g = golden("small_conv_tasnet.pt")
     m = _build.masker(g["cfg"]).to(DEV).eval()

@@ -53,6 +53,22 @@ def test_oracle_matches_reference_unet_recipes(name):
     assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal"])
+def test_oracle_matches_reference_dpcrn_recipes(name):
+    """The egs/ns noise-suppression recipes (egs/ns/model.py:38-126: complex mask on the STFT) at full size, 2 x 4 s."""
+    with open(os.path.join(GOLDEN, "dpcrn_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert m.overall_parameters == pin["params"] == 1380043  # the count the reference documents (egs/ns/model.py:40-42)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, _ = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    y = R.inference(m.state_dict(), D.describe(m), mix, None)
+    assert y.shape[-1] == pin["out_len"]
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+
+
 def test_oracle_matches_reference_skim_recipe():
     """`tse_skim_v0_causal` (egs/tse/model.py:418-463, the reference's demo model) at full size."""
     with open(os.path.join(GOLDEN, "skim_pins.json")) as fh:
