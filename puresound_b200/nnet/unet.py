@@ -177,17 +177,35 @@ class Unet(nn.Module):
         F_, C_ = x.shape[1], x.shape[2]
         pf = kf // 2
         left = kt - self.delay[i] - 1
-        Fp = -(-(F_ + 2 * pf) // s) * s   # frequency rows per frame, a multiple of the stride so window positions are equidistant
+        # P adjacent output positions share one GEMM row (output channels (p, co), window kf + (P-1)*s rows, a position's
+        # weights zero outside its own kf rows): M = P * C_out fills the 256-channel MMA of the tensor-core kernel instead
+        # of zero-padding C_out = 32..128 to it, at the price of (kf + (P-1)*s) / (P*kf) of the K work.
+        M1 = conv.out_channels
+        F_out = (F_ + 2 * pf - kf) // s + 1
+        P = 1
+        while P * 2 * M1 <= 256 and P * 2 <= F_out:
+            P *= 2
+        step = P * s
+        Fp = -(-(F_ + 2 * pf) // step) * step   # frequency rows per frame, a multiple of the row step so windows are equidistant
         W = kt * C_
         buf = torch.zeros(N * T + 1, Fp, W, device=x.device, dtype=torch.float32)  # +1 frame: the last window positions read past the end
         self._stack(buf[:N * T], T, (x, T, 0, T), N, C_, 0, [j - left for j in range(kt)], pf)
-        F_out = (F_ + 2 * pf - kf) // s + 1
-        R = Fp // s
-        M, K = conv.out_channels, kf * W
-        w = self._cache.get(f"down{i}", [conv.weight], lambda: conv.weight.permute(0, 2, 3, 1).reshape(M, K).contiguous())
-        pk = self._cache.get(f"down{i}_pk", [conv.weight], lambda: ops.pack_weights(w, M, K, K))
-        y, _ = ops.gemm(buf.view(-1), w, batch=N, rows=T * R, M=M, K=K, x_batch_stride=T * Fp * W, x_row_stride=s * W, w_row_stride=K,
-                        bias=conv.bias, w_packed=pk)
+        rows_w = kf + (P - 1) * s
+        R = Fp // step
+        M, K = P * M1, rows_w * W
+
+        def build():
+            w = torch.zeros(P, M1, rows_w, kt, C_, device=conv.weight.device, dtype=torch.float32)
+            for pp in range(P):
+                w[pp, :, pp * s:pp * s + kf] = conv.weight.permute(0, 2, 3, 1)  # [C_out, C_in, kf, kt] -> [C_out, kf, kt, C_in]
+            w = w.reshape(M, K).contiguous()
+            bias = conv.bias.repeat(P).contiguous() if conv.bias is not None else None
+            return w, bias, ops.pack_weights(w, M, K, K)
+
+        w, bias, pk = self._cache.get(f"down{i}", [conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
+        y, _ = ops.gemm(buf.view(-1), w, batch=N, rows=T * R, M=M, K=K, x_batch_stride=T * Fp * W, x_row_stride=step * W, w_row_stride=K,
+                        bias=bias, w_packed=pk)
+        R, M = R * P, M1  # the same memory as [frames, R*P positions, C_out]
         return (y, T, R, F_out, M)
 
     def _up(self, i: int, xs, skip: torch.Tensor, N: int, T: int):
@@ -221,19 +239,29 @@ class Unet(nn.Module):
         shifts = [-j for j in range(tk)]
         self._stack(buf[:N * To], To, xs, N, Cin, 0, shifts, pad_lo)
         self._stack(buf[:N * To], To, (skip, T, 0, T), N, Cin, C_, shifts, pad_lo)
-        y = torch.empty(N * To, s * Rb, Cout, device=x.device, dtype=torch.float32)
-        for phi, kappa, Mp, q in phases:
-            K = Mp * W
+        # All s phases in ONE GEMM: output channels (phi, co) over the union of the phases' windows (rows j + lo .. j + hi of
+        # the tap buffer; a phase's weights are zero on rows it does not reach).  M = s * C_out fills the 256-channel MMA
+        # better than s launches of C_out, and the row (j, phi, co) IS the interleaved output layout f_out = s*j + phi.
+        lo = min(q - (Mp - 1) for _, _, Mp, q in phases)
+        hi = max(q for _, _, _, q in phases)
+        rows_w = hi - lo + 1
+        K, M = rows_w * W, s * Cout
 
-            def build(kappa=kappa, Mp=Mp):
-                taps = [conv.weight[:, :, kappa + s * (Mp - 1 - o), :] for o in range(Mp)]  # each [Cin, Cout, tk]
-                return torch.stack(taps, 0).permute(2, 0, 3, 1).reshape(Cout, Mp * tk * Cin).contiguous()  # [co, (o, kt, ci)]
+        def build():
+            w = torch.zeros(s, Cout, rows_w, tk, Cin, device=conv.weight.device, dtype=torch.float32)
+            for phi, kappa, Mp, q in phases:
+                for o in range(rows_w):
+                    m = q - (lo + o)
+                    if 0 <= m < Mp:
+                        w[phi, :, o] = conv.weight[:, :, kappa + s * m, :].permute(1, 2, 0)  # [Cin, Cout, tk] -> [Cout, tk, Cin]
+            bias = conv.bias.repeat(s).contiguous() if conv.bias is not None else None
+            w = w.reshape(M, K).contiguous()
+            return w, bias, ops.pack_weights(w, M, K, K)
 
-            w = self._cache.get(f"up{i}_{phi}", [conv.weight], build)
-            pk = self._cache.get(f"up{i}_{phi}_pk", [conv.weight], lambda w=w, K=K: ops.pack_weights(w, Cout, K, K))
-            x0 = (pad_lo + q - (Mp - 1)) * W
-            ops.gemm(buf.view(-1)[x0:], w, batch=N, rows=To * Rb, M=Cout, K=K, x_batch_stride=To * Rb * W, x_row_stride=W, w_row_stride=K,
-                     bias=conv.bias, w_packed=pk, out=y.view(-1)[phi * Cout:], y_strides=(To * s * Rb * Cout, s * Cout))
+        w, bias, pk = self._cache.get(f"up{i}", [conv.weight] + ([conv.bias] if conv.bias is not None else []), build)
+        y, _ = ops.gemm(buf.view(-1)[(pad_lo + lo) * W:], w, batch=N, rows=To * Rb, M=M, K=K, x_batch_stride=To * Rb * W, x_row_stride=W,
+                        w_row_stride=K, bias=bias, w_packed=pk)
+        y = y.view(N * To, s * Rb, Cout)
         return (y, To, s * Rb, s * F_, Cout), ((tk - 1) if self.transpose_delay else 0)
 
     # ------------------------------------------------------------------ forward
