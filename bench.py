@@ -42,6 +42,7 @@ WORKLOADS = {
     "tse_unet_tcn_v0": ("tse_unet_tcn_v0", 64, 64000, 96000, "TSE recipe tse_unet_tcn_v0: STFT 512/128 + 6-layer U-Net shell + 15 GatedTCN blocks + GatedTCN speaker net, 64 x (4 s mix + 6 s enroll) per GPU"),
     # widening row: the egs/ns noise-suppression recipe (egs/ns/model.py:84-126)
     "ns_dpcrn_v0": ("ns_dpcrn_v0", 64, 64000, None, "NS recipe ns_dpcrn_v0: STFT 512/128 + 5-layer U-Net shell + 2 DPRNN-2D blocks (H=128), complex mask, 64 x 4 s per GPU"),
+    "ns_dparn_v0": ("ns_dparn_v0", 64, 64000, None, "NS recipe ns_dparn_v0: STFT 512/128 + 5-layer U-Net shell + 2 DPARN-2D blocks (8-head attention over frequency, LSTM over time), complex mask, 64 x 4 s per GPU"),
     # streaming: a step is one 10 ms hop of every stream (batch = concurrent streams, samples = hop)
     "cfg5": ("cfg5", 256, 160, None, "causal cLN Conv-TasNet (N=512,H=512,X=8,R=3), 10 ms hop, 256 concurrent streams per GPU, frame-by-frame"),
 }
@@ -255,7 +256,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name, batch, L, Le, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "cfg5": 1}[args.workload]
+    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "ns_dparn_v0": 4, "cfg5": 1}[args.workload]
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

@@ -246,6 +246,12 @@ typedef struct {
 } ps_gated_t;
 PS_API int ps_gated(const ps_gated_t* d, void* stream);
 
+/* Multi-head self-attention core (nn.MultiheadAttention inside lobe/attention.py:37-113, used by DPARNblock2D,
+ * dparn.py:12-108): qkv [batch, L, 3E] = fused in-projection (q | k | v), out [batch, L, E];
+ * out[b,t,head] = sum_j softmax_j(q_t . k_j / sqrt(E/heads)) v_j, j <= t only when causal.  Head dim in {4,8,16,32,64}. */
+PS_API int ps_attention(const float* qkv, float* out, int64_t batch, int64_t L, int64_t E, int32_t heads, int32_t causal,
+                        void* stream);
+
 /* [batch, R, C] -> [batch, C, R] (boundary conversion to/from the reference's [N,C,T]) */
 PS_API int ps_transpose(const float* x, float* y, int64_t batch, int64_t R, int64_t C, void* stream);
 

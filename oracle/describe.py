@@ -65,8 +65,10 @@ def describe_masker(m: nn.Module) -> dict:
     n = type(m).__name__
     if n in ("ConvTasNet", "StreamingConvTasNet"):
         return {"type": "ConvTasNet", **m.get_args}
-    if n in ("UnetTcn", "DPCRN"):
+    if n in ("UnetTcn", "DPCRN", "DPARN"):
         a = {k: (list(v) if isinstance(v, tuple) else v) for k, v in m.get_args.items()}
+        if n == "DPARN":  # the reference's get_args omits nhead (dparn.py:226-246): read it off the attention module
+            a["nhead"] = m.dprnn_block1.intra_atten1.self_atten.atten.num_heads
         if a["input_type"].lower() == "ri":  # get_args reports the channel list AFTER the constructor doubled entry 0 (unet.py:91-93)
             a["channels"] = [a["channels"][0] // 2] + list(a["channels"][1:])
         return {"type": n, **a}

@@ -660,6 +660,51 @@ def _dprnn_block2d(sd: SD, p: str, x: Tensor, fast_lstm: bool) -> Tensor:
     return x + y.reshape(N, C, T, CH).permute(0, 3, 1, 2)
 
 
+def _mha_layer(sd: SD, p: str, x: Tensor, nhead: int, causal: bool = False) -> Tensor:
+    """MhaSelfAttenLayer.forward (improved=False), lobe/attention.py:187-232, on x [B, L, E]: positional encoding added to
+    the attention input only (:209-213, PositionalEncoding :27-34), nn.MultiheadAttention without biases (:49-55), post-norm
+    residual blocks.  The layer has a positional encoding iff it holds the ``pos.pe`` buffer."""
+    E = x.shape[-1]
+    src = x
+    if p + "pos.pe" in sd:
+        x = x + sd[p + "pos.pe"][: x.size(1), 0].unsqueeze(0)
+    mask = None
+    if causal:
+        L = x.size(1)
+        mask = torch.full((L, L), float("-inf")).triu(1)
+    x, _ = F.multi_head_attention_forward(
+        x.transpose(0, 1), x.transpose(0, 1), x.transpose(0, 1), E, nhead, sd[p + "self_atten.atten.in_proj_weight"], None, None, None,
+        False, 0.0, sd[p + "self_atten.atten.out_proj.weight"], None, training=False, need_weights=False, attn_mask=mask)
+    x = x.transpose(0, 1)
+    x = F.layer_norm(src + x, (E,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    src = x
+    x = F.linear(torch.relu(F.linear(x, sd[p + "feedforward.0.weight"], sd[p + "feedforward.0.bias"])),
+                 sd[p + "feedforward.3.weight"], sd[p + "feedforward.3.bias"])
+    return F.layer_norm(src + x, (E,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+
+
+def _dparn_block2d(sd: SD, p: str, x: Tensor, nhead: int, fast_lstm: bool) -> Tensor:
+    """DPARNblock2D.forward, dparn.py:54-108: two transformer encoder layers over the frequency rows of every frame
+    (non-causal), Linear -> LayerNorm -> + skip; then the uni-directional inter-chunk LSTM pass of DPRNNblock2D."""
+    N, CH, C, T = x.shape
+    v = x.permute(0, 3, 2, 1).reshape(N * T, C, CH)
+    v = _mha_layer(sd, p + "intra_atten2.", _mha_layer(sd, p + "intra_atten1.", v, nhead), nhead)
+    v = F.layer_norm(F.linear(v, sd[p + "intra_fc.weight"], sd[p + "intra_fc.bias"]), (CH,), sd[p + "intra_norm.weight"],
+                     sd[p + "intra_norm.bias"], 1e-5)
+    x = x + v.reshape(N, T, C, CH).permute(0, 3, 2, 1)
+    v = x.permute(0, 2, 3, 1).reshape(N * C, T, CH)
+    y, _ = lstm(sd, p + "inter_rnn.rnn.", v, False, None, fast=fast_lstm)
+    y = F.linear(y, sd[p + "inter_rnn.proj.weight"], sd[p + "inter_rnn.proj.bias"])
+    y = F.layer_norm(y, (CH,), sd[p + "inter_norm.weight"], sd[p + "inter_norm.bias"], 1e-5)
+    return x + y.reshape(N, C, T, CH).permute(0, 3, 1, 2)
+
+
+def dparn(sd: SD, p: str, x: Tensor, a: dict, fast_lstm: bool = True) -> Tensor:
+    """DPARN.forward, dparn.py:169-223: the U-Net shell around two DPARNblock2D."""
+    h = a["nhead"]
+    return _unet_shell(sd, p, x, a, lambda v: _dparn_block2d(sd, p + "dprnn_block2.", _dparn_block2d(sd, p + "dprnn_block1.", v, h, fast_lstm), h, fast_lstm))
+
+
 def dpcrn(sd: SD, p: str, x: Tensor, a: dict, fast_lstm: bool = True) -> Tensor:
     """DPCRN.forward, dpcrn.py:136-190: the U-Net shell around two DPRNNblock2D."""
     return _unet_shell(sd, p, x, a, lambda v: _dprnn_block2d(sd, p + "dprnn_block2.", _dprnn_block2d(sd, p + "dprnn_block1.", v, fast_lstm), fast_lstm))
@@ -670,6 +715,8 @@ def masker_forward(sd: SD, p: str, mcfg: dict, x: Tensor, dvec: Optional[Tensor]
         return unet_tcn(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "DPCRN":
         return dpcrn(sd, p, x, mcfg, fast_lstm)
+    if mcfg["type"] == "DPARN":
+        return dparn(sd, p, x, mcfg, fast_lstm)
     if mcfg["type"] == "ConvTasNet":
         return conv_tasnet(sd, p, x, dvec, mcfg)
     if mcfg["type"] == "DPRNN":

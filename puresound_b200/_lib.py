@@ -115,6 +115,7 @@ SIGNATURES = {
     "ps_lstm_pack_weights": (C.c_int, [P, I64, I32, P, P]),
     "ps_film_combine": (C.c_int, [P, P, P, I64, I64, P]),
     "ps_gated": (C.c_int, [C.POINTER(GatedDesc), P]),
+    "ps_attention": (C.c_int, [P, P, I64, I64, I64, I32, I32, P]),
     "ps_transpose": (C.c_int, [P, P, I64, I64, I64, P]),
     "ps_stream_dwconv_step": (C.c_int, [C.POINTER(StreamDwDesc), P]),
     "ps_stream_push": (C.c_int, [P, P, P, I64, I64, I64, P]),

@@ -406,6 +406,17 @@ def gated(a: Tensor, pro_a: Prologue, b: Optional[Tensor] = None, pro_b: Prologu
     return y
 
 
+def attention(qkv: Tensor, heads: int, causal: bool = False) -> Tensor:
+    """qkv [B, L, 3E] (fused in-projection q | k | v) -> softmax(q k^T / sqrt(E/heads)) v, [B, L, E]."""
+    lib = _lib.load()
+    B, L, E3 = _req(qkv, "attention qkv").shape
+    E = E3 // 3
+    out = torch.empty(B, L, E, device=qkv.device, dtype=torch.float32)
+    _lib.check(lib.ps_attention(qkv.data_ptr(), out.data_ptr(), B, L, E, heads, 1 if causal else 0, _stream()), "ps_attention")
+    _launched()
+    return out
+
+
 def film_combine(sb: Tensor, xn: Tensor) -> Tensor:
     lib = _lib.load()
     Cn = xn.shape[-1]

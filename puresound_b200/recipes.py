@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from .nnet.base_nn import SoTaskWrapModule
 from .nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
+from .nnet.dparn import DPARN
 from .nnet.dpcrn import DPCRN
 from .nnet.dprnn import DPRNN
 from .nnet.lobe.encoder import ConvEncDec, FreeEncDec
@@ -74,6 +75,16 @@ def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Option
                          dilation_f=(1,) * 5, delay=(0,) * 5, rnn_hidden=128),
             speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=None, drop_first_bin=True, mask_constraint="linear",
             f_type="Complex", mask_type="Complex", **kwargs)
+    if name in ("ns_dparn_v0", "ns_dparn_v0_causal"):
+        # egs/ns/model.py:128-216: DPCRN with the intra-chunk LSTM replaced by two 8-head transformer encoder layers
+        return SoTaskWrapModule(
+            encoder=ConvEncDec(fft_length=512, win_type="hann", win_length=512, hop_length=128, trainable=True, output_format="Complex"),
+            masker=DPARN(input_type="RI", input_dim=512, activation_type="PReLU", norm_type="bN2d", dropout=0.1,
+                         channels=(1, 32, 32, 32, 64, 128), transpose_t_size=2, transpose_delay=not name.endswith("_causal"), skip_conv=False,
+                         kernel_t=(2,) * 5, kernel_f=(5, 3, 3, 3, 3), stride_t=(1,) * 5, stride_f=(2, 2, 1, 1, 1), dilation_t=(1,) * 5,
+                         dilation_f=(1,) * 5, delay=(0,) * 5, rnn_hidden=128, nhead=8),
+            speaker_net=None, loss_func_wav=sig_loss, loss_func_spk=None, drop_first_bin=True, mask_constraint="linear",
+            f_type="Complex", mask_type="Complex", **kwargs)
     if name in ("tse_skim_v0", "tse_skim_v0_causal"):
         # egs/tse/model.py:371-463 (the causal one is the reference's demo model)
         causal = name.endswith("_causal")
@@ -126,6 +137,6 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
                        dconv_norm="cLN", causal=True),
             mask_constraint="ReLU", verbose=verbose)
     if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1",
-                "ns_dpcrn_v0", "ns_dpcrn_v0_causal"):
+                "ns_dpcrn_v0", "ns_dpcrn_v0_causal", "ns_dparn_v0", "ns_dparn_v0_causal"):
         return init_model(name, None, None, verbose=verbose)
     raise NameError(name)

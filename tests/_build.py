@@ -3,6 +3,7 @@ import torch.nn as nn
 
 from puresound_b200.nnet.base_nn import SoTaskWrapModule
 from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
+from puresound_b200.nnet.dparn import DPARN
 from puresound_b200.nnet.dpcrn import DPCRN
 from puresound_b200.nnet.dprnn import DPRNN
 from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
@@ -37,6 +38,8 @@ def masker(c):
         return UnetTcn(**c)
     if t == "DPCRN":
         return DPCRN(**c)
+    if t == "DPARN":
+        return DPARN(**c)
     out = c.pop("output_size", c["input_size"])
     if t == "SkiM":
         return SkiM(c["input_size"], c["hidden_size"], out, n_blocks=c["n_blocks"], seg_size=c["seg_size"], seg_overlap=c["seg_overlap"],

@@ -44,6 +44,8 @@ from puresound.nnet.lobe.trivial import FiLM, Magnitude, SplitMerge  # noqa: E40
 from puresound.nnet.skim import MemLSTM, SegLSTM, SkiM  # noqa: E402
 from puresound.nnet.unet import UnetTcn  # noqa: E402
 from puresound.nnet.dpcrn import DPCRN, DPRNNblock2D  # noqa: E402
+from puresound.nnet.dparn import DPARN  # noqa: E402
+from puresound.nnet.lobe.attention import MhaSelfAttenLayer  # noqa: E402
 
 from oracle import describe as D  # noqa: E402
 from puresound_b200 import testing as T  # noqa: E402
@@ -501,6 +503,49 @@ def dpcrn_cases():
         json.dump(pins, fh)
 
 
+def _no_pe(sd):
+    """The sin/cos table (5000 x d) is rebuilt by the constructor: keep it out of the fixture."""
+    return {k: v for k, v in sd.items() if not k.endswith("pos.pe")}
+
+
+@torch.no_grad()
+def dparn_cases():
+    """DPARN (second half; dparn.py:12-246, lobe/attention.py:8-232): the transformer encoder layer
+    (with / without positional encoding, causal mask), small variants of the masker, full-size pins of ns_dparn_v0[_causal]."""
+    cases = {}
+    for tag, (pe, causal) in {"layer_pe": (True, False), "layer_nope_causal": (False, True)}.items():
+        torch.manual_seed(71)
+        m = T.perturb_(MhaSelfAttenLayer(16, 24, nhead=2, dropout=0.0, improved=False, position_encoding=pe).eval(), seed=72)
+        x = rnd(3, 16, 21, seed=73)
+        cases[tag] = {"sd": _no_pe(sd_of(m)), "x": x, "pe": pe, "causal": causal, "y": m(x, causal=causal)}
+    base = dict(input_type="RI", input_dim=32, channels=(1, 4, 8, 16), transpose_t_size=2, kernel_t=(2, 2, 2), kernel_f=(5, 3, 3),
+                stride_t=(1, 1, 1), stride_f=(2, 2, 1), dilation_t=(1, 1, 1), dilation_f=(1, 1, 1), delay=(0, 0, 0), dropout=0.0)
+    for tag, kw in {
+        "bn_delay_h32_heads4": dict(norm_type="bN2d", transpose_delay=True, rnn_hidden=32, nhead=4),
+        "gln_h12_heads1": dict(norm_type="gLN", transpose_delay=False, rnn_hidden=12, nhead=1),
+    }.items():
+        torch.manual_seed(74)
+        m = T.perturb_(quiet(DPARN, **{**base, **kw}).eval(), seed=75)
+        x = rnd(2, 32, 29, seed=76)
+        cfg = D.describe_masker(m)
+        cases[tag] = {"cfg": cfg, "sd": _no_pe(sd_of(m)), "x": x, "y": m(x)}
+    save("small_dparn.pt", cases)
+    pins = {}
+    for name in ("ns_dparn_v0", "ns_dparn_v0_causal"):
+        torch.manual_seed(0)
+        m = _ref_ns_model(name).eval()
+        T.perturb_(m, seed=1)
+        n, L, stride = 2, 64000, 997
+        mix, _ = T.noisy_speech(n, L, seed=1234)
+        y = m.inference(mix)
+        pins[name] = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n,
+                      "length": L, "input_seed": 1234, "stride": stride, "out_len": y.shape[-1], "out_abs_mean": float(y.abs().mean()),
+                      "out_clamped_frac": float((y.abs() >= 1).float().mean()), "samples": [[float(v) for v in row[::stride]] for row in y]}
+        print(name, pins[name]["params"], pins[name]["out_abs_mean"], pins[name]["out_clamped_frac"])
+    with open(os.path.join(HERE, "dparn_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
 @torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
@@ -548,3 +593,5 @@ if __name__ == "__main__":
         unet_cases()
     if which in ("all", "dpcrn"):
         dpcrn_cases()
+    if which in ("all", "dparn"):
+        dparn_cases()

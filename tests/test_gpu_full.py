@@ -107,10 +107,10 @@ def test_unet_recipes_full_size(name):
     assert err_pin <= WAVE_TOL and err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
 
 
-@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal"])
+@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal", "ns_dparn_v0", "ns_dparn_v0_causal"])
 def test_dpcrn_recipes_full_size(name):
-    """The egs/ns recipes (egs/ns/model.py:38-126), 2 x 4 s, against the reference's recorded output and the oracle."""
-    with open(os.path.join(GOLDEN, "dpcrn_pins.json")) as fh:
+    """The egs/ns recipes (egs/ns/model.py:38-216), 2 x 4 s, against the reference's recorded output and the oracle."""
+    with open(os.path.join(GOLDEN, "dparn_pins.json" if "dparn" in name else "dpcrn_pins.json")) as fh:
         pin = json.load(fh)[name]
     torch.manual_seed(0)
     m = recipes.init_model(name, verbose=False).eval()

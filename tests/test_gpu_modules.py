@@ -117,6 +117,39 @@ def test_dpcrn(golden):
         close(m(cu(g["x"])), g["y"], 1e-4)
 
 
+def test_dparn(golden):
+    """DPARN on the engine against the reference's outputs: the transformer encoder layer (attention
+    kernel, positional encoding as a GEMM residual table, causal mask) and the masker inside bN2d / gLN shells."""
+    from puresound_b200.nnet.dparn import MhaSelfAttenLayer
+
+    gs = golden("small_dparn.pt")
+    for tag in ("layer_pe", "layer_nope_causal"):
+        g = gs[tag]
+        m = MhaSelfAttenLayer(16, 24, nhead=2, position_encoding=g["pe"]).to(DEV).eval()
+        assert not m.load_state_dict(g["sd"], strict=False).unexpected_keys
+        close(m(cu(g["x"]), causal=g["causal"]), g["y"], 5e-5)
+    for tag, g in gs.items():
+        if tag.startswith("layer"):
+            continue
+        m = _build.masker(g["cfg"]).to(DEV).eval()
+        missing = m.load_state_dict(g["sd"], strict=False)
+        assert not missing.unexpected_keys and all(k.endswith("pos.pe") for k in missing.missing_keys)
+        close(m(cu(g["x"])), g["y"], 1e-4)
+
+
+def test_attention_kernel():
+    """ps_attention against torch's scaled_dot_product_attention: head dims 4..64, ragged lengths, causal."""
+    from puresound_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    for B, L, E, H, causal in [(5, 64, 128, 8, False), (3, 37, 64, 2, True), (2, 130, 48, 12, False), (4, 9, 64, 1, True)]:
+        qkv = (2 * torch.rand(B, L, 3 * E, generator=g) - 1).to(DEV)
+        out = ops.attention(qkv, H, causal)
+        q, k, v = [t.view(B, L, H, E // H).transpose(1, 2).double() for t in qkv.split(E, dim=-1)]
+        ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, L, E)
+        assert (out.double() - ref).abs().max().item() <= 2e-6
+
+
 def test_conv_tasnet(golden):
     g = golden("small_conv_tasnet.pt")
     m = _build.masker(g["cfg"]).to(DEV).eval()

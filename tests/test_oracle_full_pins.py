@@ -53,15 +53,15 @@ def test_oracle_matches_reference_unet_recipes(name):
     assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
 
 
-@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal"])
+@pytest.mark.parametrize("name", ["ns_dpcrn_v0", "ns_dpcrn_v0_causal", "ns_dparn_v0", "ns_dparn_v0_causal"])
 def test_oracle_matches_reference_dpcrn_recipes(name):
-    """The egs/ns noise-suppression recipes (egs/ns/model.py:38-126: complex mask on the STFT) at full size, 2 x 4 s."""
-    with open(os.path.join(GOLDEN, "dpcrn_pins.json")) as fh:
+    """The egs/ns noise-suppression recipes (egs/ns/model.py:38-216: complex mask on the STFT) at full size, 2 x 4 s."""
+    with open(os.path.join(GOLDEN, "dparn_pins.json" if "dparn" in name else "dpcrn_pins.json")) as fh:
         pin = json.load(fh)[name]
     torch.manual_seed(0)
     m = recipes.init_model(name, verbose=False).eval()
     testing.perturb_(m, seed=1)
-    assert m.overall_parameters == pin["params"] == 1380043  # the count the reference documents (egs/ns/model.py:40-42)
+    assert m.overall_parameters == pin["params"] == (1215179 if "dparn" in name else 1380043)  # the counts the reference documents
     assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
     mix, _ = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
     y = R.inference(m.state_dict(), D.describe(m), mix, None)
