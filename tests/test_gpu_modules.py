@@ -142,7 +142,9 @@ def test_attention_kernel():
     from puresound_b200 import ops
 
     g = torch.Generator().manual_seed(3)
-    for B, L, E, H, causal in [(5, 64, 128, 8, False), (3, 37, 64, 2, True), (2, 130, 48, 12, False), (4, 9, 64, 1, True)]:
+    # the last two cases exceed the whole-sequence kernel's shared-memory tile and take the per-(sequence, head) kernel
+    for B, L, E, H, causal in [(5, 64, 128, 8, False), (3, 37, 64, 2, True), (2, 130, 48, 12, False), (4, 9, 64, 1, True),
+                               (1, 200, 384, 12, False), (2, 150, 384, 6, True)]:
         qkv = (2 * torch.rand(B, L, 3 * E, generator=g) - 1).to(DEV)
         out = ops.attention(qkv, H, causal)
         q, k, v = [t.view(B, L, H, E // H).transpose(1, 2).double() for t in qkv.split(E, dim=-1)]
