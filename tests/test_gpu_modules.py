@@ -233,6 +233,12 @@ def test_wrappers_inference(golden):
 @pytest.mark.parametrize("name,lookahead,receptive", [
     ("td_tse_conv_tasnet_v0_causal", "16", "24496"),   # 1530 frames x 16 + 16
     ("veve_dprnn_v0_causal", "16", "infinite"),        # egs/tse/model.py:609-613
+    # the widening rows: numbers printed by the reference's own _verbose() on these recipes
+    ("tse_skim_v0_causal", "16", "infinite"),          # egs/tse/model.py:418-423
+    ("tse_unet_tcn_v0_causal", "1152", "24960"),       # egs/tse/model.py:245-250
+    ("ns_dpcrn_v0_causal", "384", "infinite"),         # egs/ns/model.py:38-43
+    ("ns_dpcrn_v0", "1024", "infinite"),               # egs/ns/model.py:84-89 (semi-causal: transpose_delay)
+    ("ns_dparn_v0_causal", "384", "infinite"),         # egs/ns/model.py:128-133
 ])
 def test_verbose_probe_known_answers(name, lookahead, receptive, capsys):
     """The reference's `_verbose()` probe (base_nn.py:740-777) feeds +inf into half of a 10 s signal and reads look-ahead /
