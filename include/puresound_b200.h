@@ -252,6 +252,12 @@ PS_API int ps_gated(const ps_gated_t* d, void* stream);
 PS_API int ps_attention(const float* qkv, float* out, int64_t batch, int64_t L, int64_t E, int32_t heads, int32_t causal,
                         void* stream);
 
+/* SDR / SI-SNR scoring (loss/sdr.py:104-185, 263-299): out[r] = 10 log10(|t|^2 / (|e|^2 + tau |t|^2 + eps) + eps) in dB with
+ * t = alpha s2 (alpha = <s1,s2>/(<s2,s2>+eps) when scaled, else 1), e = s1 - t (s1 - s2 when scale_dependent), both signals
+ * mean-removed first when zero_mean; tau = 10^(-sdr_max/10) or 0.  s1, s2: rows of L samples `stride` floats apart. */
+PS_API int ps_sdr(const float* s1, const float* s2, int64_t rows, int64_t L, int64_t stride1, int64_t stride2, int32_t scaled,
+                  int32_t scale_dependent, int32_t zero_mean, float tau, float eps, float* out, void* stream);
+
 /* [batch, R, C] -> [batch, C, R] (boundary conversion to/from the reference's [N,C,T]) */
 PS_API int ps_transpose(const float* x, float* y, int64_t batch, int64_t R, int64_t C, void* stream);
 

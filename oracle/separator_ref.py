@@ -762,6 +762,21 @@ def inference(
 # --------------------------------------------------------------------------- #
 # acceptance metric                     puresound/nnet/loss/sdr.py:263-299
 # --------------------------------------------------------------------------- #
+def sdr_score(s1: Tensor, s2: Tensor, scaled: bool = True, scale_dependent: bool = False, zero_mean: bool = True,
+              sdr_max: Optional[float] = None, eps: float = 1e-8) -> Tensor:
+    """SDRLoss.forward without the final sign flip / reduction, loss/sdr.py:139-166 (per item, in dB): [N, L] -> [N, 1]."""
+    if zero_mean:
+        s1 = s1 - s1.mean(dim=-1, keepdim=True)
+        s2 = s2 - s2.mean(dim=-1, keepdim=True)
+    l2 = lambda a, b: torch.sum(a * b, -1, keepdim=True)
+    s_target = l2(s1, s2) / (l2(s2, s2) + eps) * s2 if scaled else s2
+    e_noise = s1 - s2 if scale_dependent else s1 - s_target
+    target_norm, noise_norm = l2(s_target, s_target), l2(e_noise, e_noise)
+    if sdr_max is not None:
+        noise_norm = noise_norm + 10 ** (-sdr_max / 10) * target_norm
+    return 10 * torch.log10(target_norm / (noise_norm + eps) + eps)
+
+
 def si_snr(est: Tensor, ref: Tensor, eps: float = 1e-8) -> Tensor:
     """si_snr(reduction=False): zero-mean, project, 10*log10 power ratio."""
     est = est - est.mean(-1, keepdim=True)

@@ -116,6 +116,7 @@ SIGNATURES = {
     "ps_film_combine": (C.c_int, [P, P, P, I64, I64, P]),
     "ps_gated": (C.c_int, [C.POINTER(GatedDesc), P]),
     "ps_attention": (C.c_int, [P, P, I64, I64, I64, I32, I32, P]),
+    "ps_sdr": (C.c_int, [P, P, I64, I64, I64, I64, I32, I32, I32, F32, F32, P, P]),
     "ps_transpose": (C.c_int, [P, P, I64, I64, I64, P]),
     "ps_stream_dwconv_step": (C.c_int, [C.POINTER(StreamDwDesc), P]),
     "ps_stream_push": (C.c_int, [P, P, P, I64, I64, I64, P]),

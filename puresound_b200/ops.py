@@ -417,6 +417,23 @@ def attention(qkv: Tensor, heads: int, causal: bool = False) -> Tensor:
     return out
 
 
+def sdr(s1: Tensor, s2: Tensor, *, scaled: bool = True, scale_dependent: bool = False, zero_mean: bool = True,
+        sdr_max: Optional[float] = None, eps: float = 1e-8) -> Tensor:
+    """s1 (estimate), s2 (reference) [rows, L] -> SDR-family score in dB per row [rows] (loss/sdr.py:104-185)."""
+    lib = _lib.load()
+    _req(s1, "sdr s1")
+    _req(s2, "sdr s2")
+    if s1.shape != s2.shape or s1.dim() != 2:
+        raise ValueError(f"sdr: expected two [rows, L] tensors, got {tuple(s1.shape)} and {tuple(s2.shape)}")
+    rows, L = s1.shape
+    out = torch.empty(rows, device=s1.device, dtype=torch.float32)
+    tau = 0.0 if sdr_max is None else 10.0 ** (-sdr_max / 10.0)
+    _lib.check(lib.ps_sdr(s1.data_ptr(), s2.data_ptr(), rows, L, L, L, int(scaled), int(scale_dependent), int(zero_mean), tau, eps,
+                          out.data_ptr(), _stream()), "ps_sdr")
+    _launched()
+    return out
+
+
 def film_combine(sb: Tensor, xn: Tensor) -> Tensor:
     lib = _lib.load()
     Cn = xn.shape[-1]

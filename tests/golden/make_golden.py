@@ -547,6 +547,24 @@ def dparn_cases():
 
 
 @torch.no_grad()
+def sdr_cases():
+    """SDR-family scores (loss/sdr.py): every alias of SDRLoss.init_mode that is not source-aggregated,
+    per item (reduction=False), and the si_snr function, on estimates at about -5 .. 45 dB and with DC offsets."""
+    from puresound.nnet.loss.sdr import SDRLoss, si_snr
+
+    g = torch.Generator().manual_seed(81)
+    ref = torch.randn(6, 16000, generator=g) * 0.1 + torch.tensor([0.0, 0.02, -0.05, 0.0, 0.1, 0.0]).unsqueeze(1)
+    noise = torch.randn(6, 16000, generator=g) * 0.1
+    gains = torch.tensor([1.8, 0.5, 0.1, 0.02, 0.005, 0.3]).unsqueeze(1)
+    est = torch.tensor([1.0, 0.7, 1.3, 1.0, 0.9, 1.0]).unsqueeze(1) * ref + gains * noise + 0.01
+    out = {"est": est, "ref": ref, "si_snr": si_snr(est, ref, reduction=False), "si_snr_mean": si_snr(est, ref)}
+    for mode in ("sisnr", "sdsdr", "sdr", "tsdr"):
+        out[mode] = quiet(SDRLoss.init_mode, mode, reduction=False)(est, ref)
+        out[mode + "_mean"] = quiet(SDRLoss.init_mode, mode, reduction=True)(est, ref)
+    save("small_sdr.pt", out)
+
+
+@torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
     (test/test_case/1272-128104-0000_2035-147961-0014.wav, a two-speaker mixture, 16 kHz int16) cropped to 4 s as the
@@ -595,3 +613,5 @@ if __name__ == "__main__":
         dpcrn_cases()
     if which in ("all", "dparn"):
         dparn_cases()
+    if which in ("all", "sdr"):
+        sdr_cases()

@@ -152,6 +152,29 @@ def test_attention_kernel():
         assert (out.double() - ref).abs().max().item() <= 2e-6
 
 
+def test_sdr_scores_on_device(golden):
+    """`ps_sdr` (one pass, fp64 moments) behind the reference's SDRLoss / si_snr API against the reference's outputs: every
+    non-aggregated alias, per item and reduced, DC offsets, -5 .. 45 dB; tolerance 1e-3 dB."""
+    from puresound_b200.nnet.loss.sdr import SDRLoss, align_waveform, si_snr
+
+    g = golden("small_sdr.pt")
+    est, ref = cu(g["est"]), cu(g["ref"])
+    for mode in ("sisnr", "sdsdr", "sdr", "tsdr"):
+        got = SDRLoss.init_mode(mode, reduction=False)(est, ref).cpu()
+        assert got.shape == g[mode].shape and (got - g[mode]).abs().max().item() <= 1e-3, mode
+        assert abs(float(SDRLoss.init_mode(mode)(est, ref)) - float(g[mode + "_mean"])) <= 1e-3
+    assert (si_snr(est, ref, reduction=False).cpu().view(-1) - g["si_snr"].view(-1)).abs().max().item() <= 1e-3
+    assert abs(float(si_snr(est, ref)) - float(g["si_snr_mean"])) <= 1e-3
+    with pytest.raises(NameError):
+        SDRLoss.init_mode("nope")
+    with pytest.raises(NotImplementedError):
+        SDRLoss.init_mode("sasdr")
+    a, b = align_waveform(est, ref[:, :15000])           # shorter reference: left-padded (base_nn.py:404-408)
+    assert b.shape == a.shape and bool((b[:, :1000] == 0).all()) and torch.equal(b[:, 1000:], ref[:, :15000])
+    a, b = align_waveform(est[:, :12000], ref)
+    assert torch.equal(b, ref[:, :12000])
+
+
 def test_conv_tasnet(golden):
     g = golden("small_conv_tasnet.pt")
     m = _build.masker(g["cfg"]).to(DEV).eval()
