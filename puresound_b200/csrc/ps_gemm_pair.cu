@@ -458,9 +458,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     const int u = pt & 127;
     const uint32_t chunk = (uint32_t)(u & 3);
     const int r0 = u >> 2;  // 0..31
-    const int kofs = half * 32 + (int)chunk * 8;
-    const int KB64 = (int)(d.K / 64);
+    // K == 32 (the learned encoder's window, lobe/encoder.py:50-56): a tile is ONE stage, so the two halves take alternate
+    // tiles of this pair instead of alternate stages of one tile - the stage walk (s, s+2, ..) is the same.
+    const bool k32 = d.K == 32;
+    const int kofs = (k32 ? 0 : half * 32) + (int)chunk * 8;
+    const int KB64 = k32 ? 1 : (int)(d.K / 64);
     const int K = (int)d.K;
+    const int64_t t_step = k32 ? 2 * n_pairs : n_pairs;
     const float pslope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;  // AFFINE w/o act = slope 1
     int s = half;  // this thread's stage: half 0 walks stages 0,2,4,.., half 1 walks 1,3,5,.. (mod the ring depth)
     uint32_t ph = 0;
@@ -488,7 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     auto advance = [&](Cur& c) {
       if (++c.kb == KB64) {
         c.kb = 0;
-        c.t += n_pairs;
+        c.t += t_step;
         decode(c);
       }
     };
@@ -583,7 +587,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     // buffer and an L2 software prefetch 4 blocks ahead were both SLOWER - the stream is not latency-bound.)
     XBuf x0, x1;
     Cur pr, ld;
-    pr.t = pair; pr.kb = 0;
+    pr.t = pair + (k32 ? half * n_pairs : 0); pr.kb = 0;
     decode(pr);
     ld = pr;
     auto ld_next = [&](XBuf& x) {

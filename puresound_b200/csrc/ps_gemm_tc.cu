@@ -522,7 +522,9 @@ bool gemm_tc_eligible(const ps_gemm_t& d) {
   const bool pair = tc_pair();
   // the pair kernel zero-pads the channels to whole 256-blocks (any multiple of 32 goes), takes the mask-apply prologue
   // and overlapping rows (framed filterbank / STFT analysis views); the single-CTA kernel does none of these
-  if (d.M % (pair ? 32 : TC_BN) != 0 || d.K % 64 != 0) return false;
+  // K == 32 (one shared-memory stage per tile): pair kernel without a prologue only
+  const bool k32 = pair && d.K == 32 && d.pro_mode == PS_PRO_NONE;
+  if (d.M % (pair ? 32 : TC_BN) != 0 || (d.K % 64 != 0 && !k32)) return false;
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE || (pair && d.pro_mode == PS_PRO_MASK))) return false;
   if (d.pro_mode == PS_PRO_MASK && (!al16(d.X2) || !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_RELU || d.pro_act == PS_ACT_SIGMOID))) return false;
   if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU)) return false;
@@ -573,7 +575,7 @@ int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
 }  // namespace ps
 
 extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
-  if (M <= 0 || K <= 0 || K % 64 != 0) return 0;
+  if (M <= 0 || K <= 0 || (K % 64 != 0 && !(K == 32 && ps::tc_pair()))) return 0;
   if (ps::tc_pair()) return M % 32 == 0 ? (M + 255) / 256 * 256 * K * 4 : 0;  // padded to whole 256-channel blocks
   if (M % ps::TC_BN != 0) return 0;
   return M * K * 4;  // bf16 hi + bf16 lo

@@ -12,6 +12,7 @@ constraint fused.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -21,6 +22,9 @@ import torch.nn as nn
 from ... import ops
 from ...ops import ACT_NONE, ACT_RELU, GEMM_SIMT, PRO_MASK, Prologue
 from .._fuse import ParamCache
+
+
+_ENC_EXACT = os.environ.get("PS_ENC_EXACT", "0") == "1"
 
 
 def _check_wav(x: torch.Tensor, win: int) -> None:
@@ -51,8 +55,12 @@ class FreeEncDec(nn.Module):
         N, L = wav.shape
         Nf, win, hop = self.encoder.out_channels, self.win_length, self.hop_length
         T = (L - win) // hop + 1
-        y, _ = ops.gemm(wav.contiguous(), self.encoder.weight.view(Nf, win), batch=N, rows=T, M=Nf, K=win,
-                        x_batch_stride=L, x_row_stride=hop, w_row_stride=win,
+        w = self.encoder.weight.view(Nf, win)
+        # tcgen05 (3xBF16, ~2^-17 per product) when the shape allows (win 32 or a multiple of 64, Nf % 32 == 0): the analysis is
+        # then a pure write stream; PS_ENC_EXACT=1 keeps the exact-fp32 register filterbank kernel
+        pk = None if _ENC_EXACT else self._cache.get("enc_pk", [self.encoder.weight], lambda: ops.pack_weights(w, Nf, win, win))
+        y, _ = ops.gemm(wav.contiguous(), w, batch=N, rows=T, M=Nf, K=win,
+                        x_batch_stride=L, x_row_stride=hop, w_row_stride=win, w_packed=pk,
                         epi_act=ACT_RELU if self.output_active else ACT_NONE)
         return y
 

@@ -81,6 +81,28 @@ def test_tc_overlapping_rows_framed_view(ops):
     check(y, frames.double() @ w.double().t())
 
 
+@pytest.mark.parametrize("N,L,M,relu", [(1, 16 * 127 + 32, 512, False), (3, 16000, 512, True), (2, 64000, 128, True), (5, 4000, 256, False),
+                                        (64, 64000, 512, False)])
+def test_tc_short_window_k32(ops, N, L, M, relu):
+    """The learned encoder of FreeEncDec (lobe/encoder.py:50-56,71-83) at win = 32, hop = 16: K = 32 is ONE shared-memory
+    stage per tile, the two producer halves take alternate tiles.  One tile, odd / even tile counts per CTA pair, M = 128
+    (DPRNN front-end) and the full cfg2 shape (more tiles than CTA pairs)."""
+    win, hop = 32, 16
+    wav, w = rnd(N, L, seed=1), rnd(M, win, seed=2, scale=0.2)
+    T = (L - win) // hop + 1
+    pk = ops.pack_weights(w, M, win, win)
+    assert pk is not None
+    y, _ = ops.gemm(wav, w, batch=N, rows=T, M=M, K=win, x_batch_stride=L, x_row_stride=hop, w_row_stride=win,
+                    w_packed=pk, backend=ops.GEMM_TCGEN05, epi_act=ops.ACT_RELU if relu else ops.ACT_NONE)
+    y2, _ = ops.gemm(wav, w, batch=N, rows=T, M=M, K=win, x_batch_stride=L, x_row_stride=hop, w_row_stride=win,
+                     backend=ops.GEMM_SIMT, epi_act=ops.ACT_RELU if relu else ops.ACT_NONE)
+    for n0 in range(0, N, 8):  # fp64 reference in slices (the cfg2 shape is 1 GB in fp64)
+        ref = wav[n0:n0 + 8].unfold(1, win, hop).double() @ w.double().t()
+        ref = torch.relu(ref) if relu else ref
+        check(y[n0:n0 + 8], ref)
+        check(y2[n0:n0 + 8], ref, 1e-5)
+
+
 @pytest.mark.parametrize("with_res", [True, False])
 def test_tc_layernorm_epilogue(ops, with_res):
     """Linear -> nn.LayerNorm -> + residual of the DPRNN blocks (dprnn.py:161-163,173-175) in the GEMM epilogue: the 128
