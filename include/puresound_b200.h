@@ -184,6 +184,11 @@ PS_API int ps_mask_apply(const float* feats, const float* mask, float* y, int64_
  * optional DC drop and log1p.  x [n_rows, 2F]; y [n_rows, F - drop_first]. */
 PS_API int ps_magnitude(const float* x, float* y, int64_t n_rows, int64_t F, int32_t drop_first, int32_t log1p, void* stream);
 
+/* SpecAugment of the mel speaker front-end (lobe/trivial.py:307-335 -> torchaudio mask_along_axis): in place,
+ * x[b,t,c] = value where bounds[0] <= c < bounds[1] or bounds[2] <= t < bounds[3]; one band per axis for the whole
+ * batch.  bounds = 4 int32 in DEVICE memory (the host draws them per call; a captured graph replays with new bands). */
+PS_API int ps_band_fill(float* x, int64_t batch, int64_t T, int64_t C, const int32_t* bounds, float value, void* stream);
+
 /* AttentiveStatisticsPooling tail (lobe/pooling.py:108-126): softmax over frames of
  * logits[b,t,c], weighted mean and sqrt(clamp(sum w (x-mean)^2, 1e-12)).  out [batch, 2C]. */
 PS_API int ps_asp_pool(const float* x, const float* logits, int64_t batch, int64_t T, int64_t C, float* out, void* stream);

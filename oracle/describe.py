@@ -58,6 +58,8 @@ def describe_encoder(m: nn.Module) -> dict:
         }
     if n == "ConvEncDec":
         return {"type": "ConvEncDec", "fft_length": m.n_fft, "win_length": m.win_length, "hop_length": m.hop_length}
+    if n == "FbankEnc":
+        return {"type": "FbankEnc", "fft_length": m.n_fft, "hop_length": m.hop_length, "n_banks": m.n_banks, "trainable": bool(m.trainable)}
     raise NotImplementedError(n)
 
 
@@ -122,6 +124,10 @@ def describe_speaker_net(m) -> list:
             out.append(describe_gated_tcn(l))
         elif n == "AttentiveStatisticsPooling":
             out.append({"type": n, "channels": l.conv.out_channels, "attention_channels": l.conv.in_channels})
+        elif n == "SpecAugment":
+            out.append({"type": n, "freq_mask": l.freq_mask, "time_mask": l.time_mask, "mask_value": l.mask_value})
+        elif n == "SingleRNN":
+            out.append({"type": n, "bidirectional": l.num_direction == 2})
         elif n == "Conv1d":
             assert l.kernel_size == (1,)
             out.append({"type": "Conv1d", "bias": l.bias is not None})

@@ -73,6 +73,18 @@ def stft_encode(wav: Tensor, wsin: Tensor, wcos: Tensor, hop: int) -> Tensor:
     return torch.stack((re, -im), dim=-1)
 
 
+def mel_encode(wav: Tensor, wsin: Tensor, wcos: Tensor, filterbank: Tensor, hop: int, trainable: bool) -> Tensor:
+    """FbankEnc.forward -> ConvMelSpectrogram.forward with output_format='Magnitude', lobe/encoder.py:249-259,509-535:
+    POWER spectrum (no square root; + 1e-8 when trainable) times the mel filterbank [bins, n_banks].  [N, L] -> [N, n_banks, T]."""
+    x = wav.unsqueeze(1)
+    im = F.conv1d(x, wsin, stride=hop)
+    re = F.conv1d(x, wcos, stride=hop)
+    spec = re.pow(2) + im.pow(2)
+    if trainable:
+        spec = spec + 1e-8
+    return torch.matmul(spec.permute(0, 2, 1), filterbank).permute(0, 2, 1)
+
+
 def stft_decode(
     X: Tensor, kernel_cos_inv: Tensor, kernel_sin_inv: Tensor, window_mask: Tensor, hop: int, n_fft: int
 ) -> Tensor:
@@ -483,6 +495,29 @@ def asp(sd: SD, p: str, x: Tensor) -> Tensor:
     return torch.cat((mean, std), dim=1).unsqueeze(2)
 
 
+def spec_augment(x: Tensor, freq_mask: int, time_mask: int, value: float) -> Tensor:
+    """SpecAugment.forward, lobe/trivial.py:324-335 - applied in eval mode too (there is no `self.training` test upstream).
+    Restates torchaudio.functional.mask_along_axis (torchaudio 2.11, the function trivial.py:7 imports): per axis with a
+    mask length >= 1, `value = rand(1) * mask_param`, `min_value = rand(1) * (axis_len - value)` from the GLOBAL CPU generator,
+    band [long(min_value), long(min_value) + long(value)) filled for every item alike.  x [N, C, T]."""
+    for axis, param in ((1, freq_mask), (2, time_mask)):
+        if param < 1:
+            continue
+        v = torch.rand(1) * param
+        v0 = torch.rand(1) * (x.shape[axis] - v)
+        start, end = int(v0.long()), int(v0.long()) + int(v.long())
+        idx = torch.arange(x.shape[axis])
+        band = (idx >= start) & (idx < end)
+        x = x.masked_fill(band.view(1, -1, 1) if axis == 1 else band.view(1, 1, -1), value)
+    return x
+
+
+def single_rnn(sd: SD, p: str, x: Tensor, bidirectional: bool, fast_lstm: bool = True) -> Tensor:
+    """SingleRNN.forward (LSTM), lobe/rnn.py:36-52: x [N, C, T] -> LSTM over T -> dropout (eval) -> Linear -> [N, C, T]."""
+    h, _ = lstm(sd, p + "rnn.", x.permute(0, 2, 1), bidirectional, fast=fast_lstm)
+    return F.linear(h, sd[p + "proj.weight"], sd[p + "proj.bias"]).permute(0, 2, 1)
+
+
 def speaker_net(sd: SD, p: str, layers: Sequence[dict], x: Tensor) -> Tensor:
     """The ModuleList speaker nets of the TSE recipes (egs/tse/model.py:118-135),
     applied layer by layer as base_nn.py:699-705 does.  Returns [N, E]."""
@@ -497,6 +532,10 @@ def speaker_net(sd: SD, p: str, layers: Sequence[dict], x: Tensor) -> Tensor:
             x = gated_tcn_block(sd, q, x, None, l["kernel"], l["dilation"], l["causal"], l["tcn_norm"])
         elif t == "AttentiveStatisticsPooling":
             x = asp(sd, q, x)
+        elif t == "SpecAugment":  # speaker net of tse_skim_v2_causal (egs/tse/model.py:536)
+            x = spec_augment(x, l["freq_mask"], l["time_mask"], l["mask_value"])
+        elif t == "SingleRNN":  # speaker net of tse_skim_v1_causal (egs/tse/model.py:489-499)
+            x = single_rnn(sd, q, x, l["bidirectional"])
         elif t == "Conv1d":
             x = F.conv1d(x, sd[q + "weight"], sd.get(q + "bias"))
         else:
@@ -545,6 +584,8 @@ def _encode(sd: SD, p: str, e: dict, wav: Tensor, drop_first_bin: bool) -> Tenso
         if drop_first_bin:
             re, im = re[:, 1:, :], im[:, 1:, :]
         return torch.cat([re, im], dim=1)
+    if e["type"] == "FbankEnc":
+        return mel_encode(wav, sd[p + "encoder.wsin"], sd[p + "encoder.wcos"], sd[p + "encoder.filterbank"], e["hop_length"], e["trainable"])
     raise NotImplementedError(e["type"])
 
 

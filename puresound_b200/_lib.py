@@ -106,6 +106,7 @@ SIGNATURES = {
     "ps_ola": (C.c_int, [P, I64, I64, I64, I64, P, I32, P, P]),
     "ps_mask_apply": (C.c_int, [P, P, P, I64, I64, I32, I32, P]),
     "ps_magnitude": (C.c_int, [P, P, I64, I64, I32, I32, P]),
+    "ps_band_fill": (C.c_int, [P, I64, I64, I64, P, F32, P]),
     "ps_asp_pool": (C.c_int, [P, P, I64, I64, I64, P, P]),
     "ps_l2normalize": (C.c_int, [P, P, I64, I64, P]),
     "ps_segment": (C.c_int, [P, P, I64, I64, I64, I64, I64, I32, P]),

@@ -63,6 +63,18 @@ __global__ void __launch_bounds__(256) magnitude_kernel(const float* __restrict_
   y[i] = mag;
 }
 
+// SpecAugment (lobe/trivial.py:307-335; torchaudio mask_along_axis): one [start, end) band on the channel axis and one on
+// the frame axis, the same for every item; the bounds are READ FROM DEVICE MEMORY so a captured CUDA graph replays with
+// the bands the host drew for this call.
+__global__ void __launch_bounds__(256) band_fill_kernel(float* __restrict__ x, int64_t n, int64_t T, int64_t C,
+                                                        const int32_t* __restrict__ bounds, float value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = i % C, t = (i / C) % T;
+  const int32_t c0 = __ldg(bounds), c1 = __ldg(bounds + 1), t0 = __ldg(bounds + 2), t1 = __ldg(bounds + 3);
+  if ((c >= c0 && c < c1) || (t >= t0 && t < t1)) x[i] = value;
+}
+
 // grid (ceil(C/32), batch); block (32 channels, 8 frame lanes).  Three sweeps over the
 // [T, 32] column strip (L2 resident): max, exp-sum + weighted mean, weighted variance —
 // the same two-stage definition the reference uses (pooling.py:120-126).
@@ -228,6 +240,14 @@ extern "C" int ps_magnitude(const float* x, float* y, int64_t n_rows, int64_t F,
   ps::magnitude_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n_rows, F, drop_first ? 1 : 0,
                                                                                 log1p_);
   PS_CHECK_LAUNCH("magnitude_kernel");
+  return PS_OK;
+}
+
+extern "C" int ps_band_fill(float* x, int64_t batch, int64_t T, int64_t C, const int32_t* bounds, float value, void* stream) {
+  PS_REQUIRE(x && bounds && batch > 0 && T > 0 && C > 0);
+  const int64_t n = batch * T * C;
+  ps::band_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, T, C, bounds, value);
+  PS_CHECK_LAUNCH("band_fill_kernel");
   return PS_OK;
 }
 

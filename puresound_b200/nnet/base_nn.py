@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops import ACT_NONE, ACT_RELU, ACT_SIGMOID
-from .lobe.encoder import ConvEncDec, FreeEncDec
+from .lobe.encoder import ConvEncDec, FbankEnc, FreeEncDec
 
 _MASK_ACT = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
 _OUT_CONSTRAINT = {"linear": 1, "sigmoid": 2}
@@ -62,6 +62,7 @@ class SoTaskWrapModule(nn.Module):
         # CUDA-graph cache of the waveform -> waveform path, keyed by input shapes (see _run); PS_CUDA_GRAPH=0 disables it
         self.use_cuda_graph = os.environ.get("PS_CUDA_GRAPH", "1") != "0"
         self._graphs = OrderedDict()
+        self._host_hooks = None
         self.task = self.check_task()
         if verbose:
             self._verbose()
@@ -100,6 +101,8 @@ class SoTaskWrapModule(nn.Module):
             return enc.encode_cl(wav, self.drop_first_bin, exact)
         if isinstance(enc, FreeEncDec):
             return enc.encode_cl(wav)
+        if isinstance(enc, FbankEnc):  # mel speaker front-end (base_nn.py:373-375: used as it comes)
+            return enc.encode_cl(wav, exact)
         raise NotImplementedError(f"encoder {type(enc).__name__} is outside the separator hot path")
 
     def _speaker_net_cl(self, feats: torch.Tensor) -> torch.Tensor:
@@ -166,6 +169,14 @@ class SoTaskWrapModule(nn.Module):
     # ------------------------------------------------------------------ CUDA-graph replay of the whole path
     _GRAPH_SLOTS = 2  # input-shape combinations kept captured (each pins its intermediates in a private pool)
 
+    def _host_prepare(self, device) -> None:
+        """Per-call host-side state of modules that have any (SpecAugment draws its random bands from the host RNG): written
+        into device buffers BEFORE the forward, so eager runs and graph replays see this call's values."""
+        if self._host_hooks is None:
+            self._host_hooks = [m for m in self.modules() if m is not self and hasattr(m, "host_prepare")]
+        for m in self._host_hooks:
+            m.host_prepare(device)
+
     def _param_signature(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
@@ -175,6 +186,7 @@ class SoTaskWrapModule(nn.Module):
         shapes runs eagerly (it also builds the packed-weight caches), the second captures, later ones copy the inputs
         into the graph's static buffers and replay.  Any change to a parameter or buffer (load_state_dict, .to(), an
         optimiser step) changes the signature and drops the captured graphs."""
+        self._host_prepare(noisy.device)
         if not self.use_cuda_graph:
             return self._inference_cl(noisy, enroll, constrain)
         sig = self._param_signature()
@@ -237,7 +249,9 @@ class SoTaskWrapModule(nn.Module):
         ops.require_device()
         on_host = not enroll.is_cuda
         enc = self.encoder if self.encoder_spk is None else self.encoder_spk
-        dvec = self._speaker_net_cl(self._encode_cl(enc, self._to_device(enroll), exact=False)).unsqueeze(-1)
+        enroll = self._to_device(enroll)
+        self._host_prepare(enroll.device)
+        dvec = self._speaker_net_cl(self._encode_cl(enc, enroll, exact=False)).unsqueeze(-1)
         return dvec.cpu() if on_host else dvec
 
     def _verbose(self):

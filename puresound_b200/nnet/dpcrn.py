@@ -14,23 +14,8 @@ import torch.nn as nn
 
 from ._fuse import ParamCache
 from .dprnn import dual_path_pass
+from .lobe.rnn import SingleRNN  # noqa: F401  (parameter holder of the blocks below; re-exported)
 from .unet import Unet
-
-
-class SingleRNN(nn.Module):
-    """Parameter holder with the reference's keys (lobe/rnn.py:9-52): ``rnn`` (1 layer), ``proj``."""
-
-    def __init__(self, rnn_type: str, input_size: int, hidden_size: int, bidirectional: bool = False, dropout: float = 0.0):
-        super().__init__()
-        rnn_type = rnn_type.upper()
-        assert rnn_type in ["RNN", "LSTM", "GRU"], f"Only support 'RNN', 'LSTM' and 'GRU', current type: {rnn_type}"
-        if rnn_type != "LSTM":
-            raise NotImplementedError("the engine's recurrent kernel is an LSTM (the reference's recipes use LSTM)")
-        self.rnn_type, self.input_size, self.hidden_size = rnn_type, input_size, hidden_size
-        self.num_direction = int(bidirectional) + 1
-        self.rnn = nn.LSTM(input_size, hidden_size, 1, batch_first=True, bidirectional=bidirectional)
-        self.drop = nn.Dropout(p=dropout)
-        self.proj = nn.Linear(hidden_size * self.num_direction, input_size)
 
 
 class DPRNNblock2D(nn.Module):

@@ -120,6 +120,126 @@ class ConvSTFT(nn.Module):
         self.register_buffer("window_mask", window.unsqueeze(0).unsqueeze(-1))
 
 
+def _mel_scale(hz: np.ndarray) -> np.ndarray:
+    """Slaney mel scale (lobe/stft.py:127-158): linear below 1 kHz (200/3 Hz per mel), logarithmic above (27 mels per factor 6.4)."""
+    hz = np.asarray(hz, dtype=np.float64)
+    lin = hz / (200.0 / 3)
+    brk = 1000.0 / (200.0 / 3)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        log = brk + np.log(hz / 1000.0) / (np.log(6.4) / 27.0)
+    return np.where(hz >= 1000.0, log, lin)
+
+
+def _mel_scale_inv(mel: np.ndarray) -> np.ndarray:
+    """Inverse of _mel_scale (lobe/stft.py:161-190)."""
+    mel = np.asarray(mel, dtype=np.float64)
+    brk = 1000.0 / (200.0 / 3)
+    return np.where(mel >= brk, 1000.0 * np.exp((np.log(6.4) / 27.0) * (mel - brk)), (200.0 / 3) * mel)
+
+
+def mel_filterbank(sr: int, n_fft: int, n_banks: int = 128, fmin: float = 0.0, fmax: Optional[float] = None) -> torch.Tensor:
+    """Triangular, area-normalised (Slaney) mel filters [n_banks, n_fft//2 + 1], fp32 — the values of the reference's
+    ``mel_filterbank`` (lobe/stft.py:237-293): band edges uniform on the mel scale between fmin and fmax (default
+    Nyquist), each triangle = max(0, min(rising ramp, falling ramp)) over the FFT bin centres, scaled by 2 / band width."""
+    fmax = float(sr / 2) if fmax is None else fmax
+    bins = np.linspace(0, float(sr) / 2, int(1 + n_fft // 2), endpoint=True)
+    edges = _mel_scale_inv(np.linspace(_mel_scale(fmin), _mel_scale(fmax), n_banks + 2))
+    width = np.diff(edges)
+    ramps = np.subtract.outer(edges, bins)                      # [n_banks + 2, bins]: edge - bin centre
+    rising = -ramps[:-2] / width[:-1, None]
+    falling = ramps[2:] / width[1:, None]
+    tri = np.maximum(0, np.minimum(rising, falling)).astype(np.float32)
+    tri *= (2.0 / (edges[2:n_banks + 2] - edges[:n_banks]))[:, None]
+    if not np.all((edges[:-2] == 0) | (tri.max(axis=1) > 0)):
+        raise ValueError("Empty filters detected in mel frequency basis.")
+    return torch.from_numpy(tri)
+
+
+class ConvMelSpectrogram(ConvSTFT):
+    """Holder of the mel front-end's tensors under the reference's keys (lobe/encoder.py:459-507): the conv-STFT kernels
+    plus ``filterbank`` [bins, n_banks] and its pseudo-inverse ``inv_filterbank`` (Parameters iff trainable)."""
+
+    def __init__(self, window: torch.Tensor, n_fft: int, hop_length: int, trainable: bool, n_banks: int):
+        super().__init__(window, n_fft, hop_length, False, trainable)
+        fb = mel_filterbank(sr=16000, n_fft=n_fft, n_banks=n_banks).permute(1, 0)  # the reference fixes sr = 16 kHz here (:494-496)
+        inv = torch.pinverse(fb)
+        if trainable:
+            self.filterbank = nn.Parameter(fb)
+            self.inv_filterbank = nn.Parameter(inv)
+        else:
+            self.register_buffer("filterbank", fb)
+            self.register_buffer("inv_filterbank", inv)
+
+
+class FbankEnc(nn.Module):
+    """Mel-spectrogram speaker front-end (reference lobe/encoder.py:186-272; used as ``encoder_spk`` by
+    ``tse_skim_v2_causal``, egs/tse/model.py:519-521): power spectrum of the conv-STFT times the mel filterbank.
+
+    Engine path: the framed analysis GEMM (cos | -sin, as ConvEncDec) gives X [N, T, 2F]; the mel projection is ONE more
+    GEMM over K = 2F with the square taken on load (the mask prologue with the operand as its own mask) against the
+    filterbank stacked twice - mel[m] = sum_f fb[f, m] (re_f^2 + im_f^2) - so the power spectrum is never written."""
+
+    def __init__(
+        self,
+        fft_length: int = 512,
+        win_type: str = "hann",
+        win_length: int = 512,
+        freq_bins: int = None,
+        hop_length: int = 128,
+        freq_scale: str = "no",
+        fmin: int = 0,
+        fmax: int = 8000,
+        sr: int = 16000,
+        trainable: bool = True,
+        output_format: str = "Magnitude",
+        n_banks=80,
+    ):
+        super().__init__()
+        if freq_scale != "no" or freq_bins is not None:
+            raise NotImplementedError("only the linear full-band STFT (freq_scale='no') is on the separator path")
+        if output_format.lower() != "magnitude":
+            raise NotImplementedError("only output_format='Magnitude' feeds a speaker net (MagPhase / inverse are synthesis-side)")
+        self.n_fft, self.win_length, self.freq_bins, self.hop_length = fft_length, win_length, freq_bins, hop_length
+        self.freq_scale, self.iSTFT, self.fmin, self.fmax, self.sr = freq_scale, False, fmin, fmax, sr
+        self.trainable, self.output_format, self.n_banks = trainable, output_format, n_banks
+        if win_type.lower() != "hann":
+            raise NotImplementedError("window type not support")
+        self.window = torch.hann_window(win_length)
+        self.encoder = ConvMelSpectrogram(self.window, fft_length, hop_length, trainable, n_banks)
+        self._cache = ParamCache()
+
+    def encode_cl(self, wav: torch.Tensor, exact: bool = True) -> torch.Tensor:
+        """wav [N, L] -> mel power spectrum [N, T, n_banks]."""
+        _check_wav(wav, self.n_fft)
+        e = self.encoder
+        F2 = 2 * e.wcos.shape[0]
+        Mp = (F2 + 31) // 32 * 32  # 514 -> 544 zero rows: a channel count the tcgen05 kernel takes (their mel weights are zero too)
+        w = self._cache.get("ana", [e.wsin, e.wcos], lambda: torch.cat(
+            [e.wcos[:, 0, :], -e.wsin[:, 0, :], e.wcos.new_zeros(Mp - F2, self.n_fft)], 0).contiguous())
+        N, L = wav.shape
+        T = (L - self.n_fft) // self.hop_length + 1
+        pk = None
+        if not exact:
+            pk = self._cache.get("ana_pk", [e.wsin, e.wcos], lambda: ops.pack_weights(w, w.shape[0], self.n_fft, self.n_fft))
+        X, _ = ops.gemm(wav.contiguous(), w, batch=N, rows=T, M=w.shape[0], K=self.n_fft, x_batch_stride=L,
+                        x_row_stride=self.hop_length, w_row_stride=self.n_fft, w_packed=pk,
+                        backend=ops.GEMM_AUTO if pk is not None else GEMM_SIMT)
+        fb2 = self._cache.get("fb2", [e.filterbank], lambda: torch.cat(
+            [e.filterbank, e.filterbank, e.filterbank.new_zeros(Mp - F2, e.filterbank.shape[1])], 0).t().contiguous())  # [n_banks, Mp]
+        # trainable: the reference adds 1e-8 to every power bin before the projection (:530) = a per-band constant
+        bias = self._cache.get("fb_bias", [e.filterbank], lambda: (1e-8 * e.filterbank.sum(0)).contiguous()) if self.trainable else None
+        mel, _ = ops.linear(X, fb2, pro=Prologue(PRO_MASK, ACT_NONE, x2=X), bias=bias, backend=GEMM_SIMT)
+        return mel
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, L] -> [N, n_banks, T]"""
+        return ops.transpose(self.encode_cl(x))
+
+    def inverse(self, magphase: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError("Inverse only support magphase input")
+
+
 class ConvEncDec(nn.Module):
     """Conv-STFT encoder / conv-iSTFT decoder (reference lobe/encoder.py:97-183)."""
 

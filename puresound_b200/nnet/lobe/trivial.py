@@ -32,6 +32,72 @@ class Magnitude(nn.Module):
         return ops.transpose(self.forward_cl(ops.transpose(x)))
 
 
+class SpecAugment(nn.Module):
+    """Random frequency / time band masking (reference lobe/trivial.py:307-335).
+
+    Upstream quirk kept: the reference applies the mask in ``forward`` regardless of train / eval mode, so the speaker
+    branch of ``tse_skim_v2_causal`` masks a random band of mel channels at inference too.  ``torchaudio``'s
+    ``mask_along_axis`` draws ``torch.rand(1)`` twice per axis from the global CPU generator and masks ONE band for the
+    whole batch; ``host_prepare`` draws the same numbers in the same order (same seed => same band as the reference) into a
+    device buffer that the fill kernel reads, so the task wrapper can call it outside a captured CUDA graph."""
+
+    def __init__(self, freq_mask_length: int, time_mask_length: int, fill_value: float) -> None:
+        super().__init__()
+        self.freq_mask = freq_mask_length
+        self.time_mask = time_mask_length
+        self.mask_value = fill_value
+        self._bounds = None   # int32[4] on the device: channel band, frame band
+        self._shape = None    # (channels, frames) of the last tensor seen: the band positions depend on the axis lengths
+        self._fresh = False
+
+    @staticmethod
+    def _draw(mask_param: int, axis_len: int):
+        # torchaudio.functional.mask_along_axis: value = rand * mask_param; min_value = rand * (len - value)
+        if mask_param < 1:
+            return 0, 0
+        value = torch.rand(1) * mask_param
+        min_value = torch.rand(1) * (axis_len - value)
+        start = int(min_value.long())
+        return start, start + int(value.long())
+
+    def host_prepare(self, device=None) -> None:
+        """Draw this call's bands (host RNG) into the device buffer.  Needs the axis lengths, i.e. one earlier eager call."""
+        if self._shape is None:
+            return
+        Cn, Tn = self._shape
+        f0, f1 = self._draw(self.freq_mask, Cn)
+        t0, t1 = self._draw(self.time_mask, Tn)
+        vals = torch.tensor([f0, f1, t0, t1], dtype=torch.int32)
+        if self._bounds is None or (device is not None and self._bounds.device != torch.device(device)):
+            self._bounds = vals.to(device if device is not None else "cuda")
+        else:
+            self._bounds.copy_(vals)
+        self._fresh = True
+
+    def _mask(self, x: torch.Tensor, rows: int, cols: int, channel_axis_is_rows: bool) -> torch.Tensor:
+        Cn, Tn = (rows, cols) if channel_axis_is_rows else (cols, rows)
+        if self.freq_mask < 1 and self.time_mask < 1:
+            return x
+        capturing = torch.cuda.is_current_stream_capturing()
+        if (self._shape != (Cn, Tn) or not self._fresh) and not capturing:
+            self._shape = (Cn, Tn)
+            self.host_prepare(x.device)
+        self._fresh = False
+        b = self._bounds
+        if channel_axis_is_rows:  # [N, C, T] layout: the kernel's row axis is the channel axis -> swap the two bands
+            b = torch.stack([b[2], b[3], b[0], b[1]])
+        return ops.band_fill(x, rows, cols, b, self.mask_value)
+
+    def forward_cl(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, T, C] frames-major, masked in place (the input is the mel encoder's fresh output)."""
+        return self._mask(x, x.shape[1], x.shape[2], False)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, C, T] (reference layout) -> masked copy."""
+        return self._mask(x.contiguous().clone(), x.shape[1], x.shape[2], True)
+
+
 class FiLM(nn.Module):
     """Feature-wise linear modulation (reference lobe/trivial.py:129-167):
     y = (W_s [x~; e]) * x~ + (W_b [x~; e]),  x~ = LayerNorm_C(x).

@@ -294,6 +294,17 @@ def magnitude(x: Tensor, drop_first: bool, log1p: bool) -> Tensor:
     return y
 
 
+def band_fill(x: Tensor, T: int, Cn: int, bounds: Tensor, value: float) -> Tensor:
+    """In place: x[..., t, c] = value for c in [bounds[0], bounds[1]) or t in [bounds[2], bounds[3]); bounds = int32[4] on the device."""
+    lib = _lib.load()
+    if not (bounds.is_cuda and bounds.dtype == torch.int32 and bounds.numel() == 4):
+        raise TypeError("band_fill: bounds must be 4 int32 on the device")
+    _lib.check(lib.ps_band_fill(_req(x, "band_fill x").data_ptr(), x.numel() // (T * Cn), T, Cn, bounds.data_ptr(), float(value),
+                                _stream()), "ps_band_fill")
+    _launched()
+    return x
+
+
 def asp_pool(x: Tensor, logits: Tensor) -> Tensor:
     lib = _lib.load()
     B, T, Cn = _req(x, "asp x").shape

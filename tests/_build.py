@@ -6,9 +6,10 @@ from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet, GatedTCN
 from puresound_b200.nnet.dparn import DPARN
 from puresound_b200.nnet.dpcrn import DPCRN
 from puresound_b200.nnet.dprnn import DPRNN
-from puresound_b200.nnet.lobe.encoder import ConvEncDec, FreeEncDec
+from puresound_b200.nnet.lobe.encoder import ConvEncDec, FbankEnc, FreeEncDec
 from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
-from puresound_b200.nnet.lobe.trivial import Magnitude
+from puresound_b200.nnet.lobe.rnn import SingleRNN
+from puresound_b200.nnet.lobe.trivial import Magnitude, SpecAugment
 from puresound_b200.nnet.skim import SkiM
 from puresound_b200.nnet.unet import UnetTcn
 
@@ -26,6 +27,9 @@ def gated_tcn(c):
 def encoder(c):
     if c["type"] == "FreeEncDec":
         return FreeEncDec(c["win_length"], c["laten_length"], c["hop_length"], c["output_active"])
+    if c["type"] == "FbankEnc":
+        return FbankEnc(c["fft_length"], "hann", c["fft_length"], hop_length=c["hop_length"], trainable=c["trainable"],
+                        output_format="Magnitude", n_banks=c["n_banks"])
     return ConvEncDec(c["fft_length"], "hann", c["win_length"], hop_length=c["hop_length"], trainable=True, output_format="Complex")
 
 
@@ -62,6 +66,10 @@ def speaker_net(layers):
             mods.append(gated_tcn(l))
         elif t == "AttentiveStatisticsPooling":
             mods.append(AttentiveStatisticsPooling(l["channels"], l["attention_channels"]))
+        elif t == "SpecAugment":
+            mods.append(SpecAugment(l["freq_mask"], l["time_mask"], l["mask_value"]))
+        elif t == "SingleRNN":
+            mods.append("SingleRNN" if not l["bidirectional"] else "SingleRNN_bi")  # sized from the state dict by the caller
         elif t == "Conv1d":
             mods.append(None)  # sized from the state dict by the caller
     return mods
@@ -75,6 +83,9 @@ def wrapper(cfg, sd):
             if m is None:
                 w = sd[f"speaker_net.{j}.weight"]
                 mods[j] = nn.Conv1d(w.shape[1], w.shape[0], 1, bias=f"speaker_net.{j}.bias" in sd)
+            elif isinstance(m, str):
+                w = sd[f"speaker_net.{j}.rnn.weight_hh_l0"]  # [4H, H]
+                mods[j] = SingleRNN("LSTM", sd[f"speaker_net.{j}.rnn.weight_ih_l0"].shape[1], w.shape[1], bidirectional=m.endswith("_bi"))
         spk = nn.ModuleList(mods)
     m = SoTaskWrapModule(
         encoder(cfg["encoder"]), masker(cfg["masker"]), embedding_free_tse=cfg["embedding_free_tse"],

@@ -565,6 +565,77 @@ def sdr_cases():
 
 
 @torch.no_grad()
+def mel_cases():
+    """Mel speaker front-end (second half): FbankEnc (lobe/encoder.py:186-272,459-535), SpecAugment
+    (lobe/trivial.py:307-335; random, applied in eval mode too - the global seed set right before each call is stored),
+    SingleRNN (lobe/rnn.py:9-52), small wrappers with both speaker nets, and full-size pins of the two recipes that use them
+    (tse_skim_v1_causal / tse_skim_v2_causal, egs/tse/model.py:465-549)."""
+    from puresound.nnet.lobe.encoder import FbankEnc
+    from puresound.nnet.lobe.rnn import SingleRNN
+    from puresound.nnet.lobe.trivial import SpecAugment
+
+    cases = {}
+    for tag, kw in {"fixed_512": dict(fft_length=512, win_length=512, hop_length=128, trainable=False, n_banks=80),
+                    "trainable_128": dict(fft_length=128, win_length=128, hop_length=32, trainable=True, n_banks=20)}.items():
+        enc = FbankEnc(output_format="Magnitude", **kw).eval()
+        wav = T.noisy_speech(2, 4000, seed=91)[0]
+        # the recipe-size tensors (2 x 257 x 512 Fourier kernels) are deterministic: the tests rebuild them from the
+        # drop-in constructor (bit-identical, tests/test_host_logic.py) instead of carrying 2 MB here
+        cases[tag] = {"cfg": D.describe_encoder(enc), "kw": kw, "sd": sd_of(enc) if tag != "fixed_512" else None, "wav": wav, "mel": enc(wav)}
+    for tag, (fm, tm, val, shape) in {"freq": (10, 0, 0.0, (3, 40, 50)), "both": (6, 9, -1.5, (2, 24, 31)), "none": (0, 0, 0.0, (2, 8, 9))}.items():
+        x = rnd(*shape, seed=92)
+        torch.manual_seed(93)
+        cases["specaug_" + tag] = {"freq_mask": fm, "time_mask": tm, "mask_value": val, "x": x, "seed": 93, "y": SpecAugment(fm, tm, val)(x)}
+    for tag, bi in (("rnn_bi", True), ("rnn_uni", False)):
+        torch.manual_seed(94)
+        m = SingleRNN("LSTM", 16, 12, bidirectional=bi, dropout=0.05).eval()
+        x = rnd(3, 16, 37, seed=95)
+        cases[tag] = {"sd": sd_of(m), "bidirectional": bi, "x": x, "y": m(x)}
+    for tag in ("wrapper_mel", "wrapper_rnn"):
+        torch.manual_seed(96)
+        enc = FreeEncDec(win_length=32, hop_length=16, laten_length=24, output_active=True)
+        spk_enc = FbankEnc(fft_length=128, win_length=128, hop_length=32, trainable=False, output_format="Magnitude", n_banks=20) if tag == "wrapper_mel" else None
+        masker = SkiM(24, 12, 24, n_blocks=2, seg_size=10, seg_overlap=False, causal=True, embed_dim=6, embed_norm=True,
+                      block_with_embed=[1, 1], embed_fusion="FiLM")
+        if tag == "wrapper_mel":
+            spk = [SpecAugment(freq_mask_length=8, time_mask_length=0, fill_value=0.0)] + [TCN(20, 16, 3, dilation=2 ** i) for i in range(2)] \
+                + [AttentiveStatisticsPooling(20, 8), nn.Conv1d(40, 6, 1, bias=False)]
+        else:
+            spk = [SingleRNN("LSTM", 24, 10, bidirectional=True, dropout=0.05), AttentiveStatisticsPooling(24, 8), nn.Conv1d(48, 6, 1, bias=False)]
+        m = quiet(SoTaskWrapModule, encoder=enc, encoder_spk=spk_enc, masker=masker, speaker_net=nn.ModuleList(spk), mask_constraint="ReLU",
+                  verbose=False).eval()
+        T.perturb_(m, seed=97)
+        mix, enr = T.noisy_speech(2, 3200, seed=98)[0], T.noisy_speech(2, 4800, seed=99)[0]
+        torch.manual_seed(100)
+        y = m.inference(mix, enr)
+        torch.manual_seed(100)
+        emb = m.inference_tse_embedding(enr)
+        cases[tag] = {"cfg": D.describe(m), "sd": sd_of(m), "noisy": mix, "enroll": enr, "seed": 100, "y": y, "emb": emb}
+    save("small_mel.pt", cases)
+
+    pins = {}
+    for name in ("tse_skim_v1_causal", "tse_skim_v2_causal"):
+        torch.manual_seed(0)
+        m = _ref_init_model(name).eval()
+        T.perturb_(m, seed=1)
+        n, L, Le = 1, 64000, 96000
+        mix, _ = T.noisy_speech(n, L, seed=1234)
+        enr = T.noisy_speech(n, Le, seed=4321)[0]
+        torch.manual_seed(7)
+        y = m.inference(mix, enr)
+        torch.manual_seed(7)
+        emb = m.inference_tse_embedding(enr)
+        stride = 997
+        pins[name] = {"params": sum(p.numel() for p in m.parameters()), "state_checksum": T.state_checksum(m.state_dict()), "batch": n,
+                      "length": L, "enroll_length": Le, "input_seed": 1234, "enroll_seed": 4321, "rng_seed": 7, "stride": stride,
+                      "out_len": y.shape[-1], "out_abs_mean": float(y.abs().mean()), "out_clamped_frac": float((y.abs() >= 1).float().mean()),
+                      "samples": [[float(v) for v in row[::stride]] for row in y], "embedding": [float(v) for v in emb.flatten()]}
+        print(name, pins[name]["params"], pins[name]["state_checksum"], pins[name]["out_abs_mean"])
+    with open(os.path.join(HERE, "mel_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
+@torch.no_grad()
 def real_input_pins():
     """SURVEY.md 8d inputs (iii) and (i at a = 1.0): the reference's own speech fixture
     (test/test_case/1272-128104-0000_2035-147961-0014.wav, a two-speaker mixture, 16 kHz int16) cropped to 4 s as the
@@ -615,3 +686,5 @@ if __name__ == "__main__":
         dparn_cases()
     if which in ("all", "sdr"):
         sdr_cases()
+    if which in ("all", "mel"):
+        mel_cases()

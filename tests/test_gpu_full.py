@@ -149,6 +149,36 @@ def test_skim_recipe_full_size():
     assert err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
 
 
+@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal"])
+def test_skim_recipes_with_rnn_and_mel_speaker_nets(name):
+    """`tse_skim_v1_causal` (SingleRNN speaker net) / `tse_skim_v2_causal` (FbankEnc + SpecAugment + TCN speaker net), 4 s mixture +
+    6 s enrollment, against the reference's recorded output / embedding and the oracle (same global seed before each call:
+    the reference masks a random mel band at inference too)."""
+    with open(os.path.join(GOLDEN, "mel_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-9)
+    mix, clean = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    enr = testing.noisy_speech(pin["batch"], pin["enroll_length"], seed=pin["enroll_seed"])[0]
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    m = m.to("cuda")
+    torch.manual_seed(pin["rng_seed"])
+    y = m.inference(mix, enr)
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= WAVE_TOL
+    torch.manual_seed(pin["rng_seed"])
+    emb = m.inference_tse_embedding(enr)
+    e_err = (emb.flatten().cpu() - torch.tensor(pin["embedding"])).abs().max().item()
+    torch.manual_seed(pin["rng_seed"])
+    y_ref = R.inference(sd, cfg, mix, enr)
+    err = (y - y_ref).abs().max().item()
+    L = y.shape[-1]
+    d_sisnr = float((R.si_snr(y, clean[:, :L]) - R.si_snr(y_ref, clean[:, :L])).abs().max())
+    print(f"{name}: max|dy|={err:.3e} max|d emb|={e_err:.3e} SI-SNR(ours,ref)={R.si_snr(y, y_ref).min():.1f} dB dSI-SNR={d_sisnr:.2e} dB")
+    assert err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB and e_err <= 1e-3
+
+
 def test_standalone_masker_reference_layout():
     """test/test_backbone.py:14-56 shape contract, with numbers: ConvTasNet(512,...,R=3,X=8,H=256) on rand(1,512,100)."""
     from puresound_b200.nnet.conv_tasnet import ConvTasNet

@@ -240,6 +240,55 @@ def test_skim_variants(golden):
         close(co, g["c_out"], 2e-5)
 
 
+def test_mel_front_end(golden):
+    """Mel speaker front-end (second half) on the engine against the reference's outputs: FbankEnc (both
+    GEMM back ends for the analysis), SpecAugment under the recorded seed in both layouts, SingleRNN, and the wrappers."""
+    from puresound_b200.nnet.lobe.encoder import FbankEnc
+    from puresound_b200.nnet.lobe.rnn import SingleRNN
+    from puresound_b200.nnet.lobe.trivial import SpecAugment
+
+    gs = golden("small_mel.pt")
+    for tag in ("fixed_512", "trainable_128"):
+        g = gs[tag]
+        enc = FbankEnc(output_format="Magnitude", **g["kw"]).to(DEV).eval()
+        if g["sd"] is not None:
+            enc.load_state_dict(g["sd"])
+        close(enc(cu(g["wav"])), g["mel"], 2e-5)  # exact-fp32 analysis
+        mel_tc = enc.encode_cl(cu(g["wav"]), exact=False).transpose(1, 2)  # tcgen05 analysis where the shape allows
+        close(mel_tc, g["mel"], 1e-4)
+    for tag in ("specaug_freq", "specaug_both", "specaug_none"):
+        g = gs[tag]
+        aug = SpecAugment(g["freq_mask"], g["time_mask"], g["mask_value"])
+        torch.manual_seed(g["seed"])
+        y = aug(cu(g["x"]))
+        assert torch.equal(y.cpu(), g["y"])
+        torch.manual_seed(g["seed"])
+        ycl = aug.forward_cl(cu(g["x"]).transpose(1, 2).contiguous()).transpose(1, 2)
+        assert torch.equal(ycl.cpu(), g["y"])
+    for tag in ("rnn_bi", "rnn_uni"):
+        g = gs[tag]
+        m = SingleRNN("LSTM", 16, 12, bidirectional=g["bidirectional"]).to(DEV).eval()
+        m.load_state_dict(g["sd"])
+        close(m(cu(g["x"])), g["y"], 2e-5)
+    for tag in ("wrapper_mel", "wrapper_rnn"):
+        g = gs[tag]
+        m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)
+        for rep in range(3):  # eager, graph capture, graph replay: every call draws its band like the reference would
+            torch.manual_seed(g["seed"])
+            close(m.inference(cu(g["noisy"]), cu(g["enroll"])), g["y"], 1e-4)
+        torch.manual_seed(g["seed"])
+        close(m.inference_tse_embedding(cu(g["enroll"])), g["emb"], 5e-5)
+    # a different seed moves the band: the replayed graph must follow the host's draw, not the captured one
+    g = gs["wrapper_mel"]
+    m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)
+    from oracle import separator_ref as R
+    for seed in (1, 2, 3, 4):
+        torch.manual_seed(seed)
+        y = m.inference(cu(g["noisy"]), cu(g["enroll"]))
+        torch.manual_seed(seed)
+        close(y, R.inference(g["sd"], g["cfg"], g["noisy"], g["enroll"]), 1e-4)
+
+
 def test_wrappers_inference(golden):
     for tag, g in golden("small_wrappers.pt").items():
         m = _build.wrapper(g["cfg"], g["sd"]).to(DEV)

@@ -88,3 +88,47 @@ def test_overlap_geometry_matches_oracle(T, K):
 def test_get_args_roundtrip():
     a = ConvTasNet(32, 8, True, tcn_dim=16, per_tcn_stack=2, repeat_tcn=1, tcn_with_embed=[1, 0]).get_args
     assert ConvTasNet(**a).get_args == a
+
+
+def test_mel_front_end_schema_and_filters():
+    """FbankEnc / ConvMelSpectrogram (lobe/encoder.py:186-272,459-507): state-dict keys, buffers vs parameters, the Slaney mel
+    filters' defining properties; against the live reference when it is present (authoring container)."""
+    import sys
+
+    from puresound_b200.nnet.lobe.encoder import FbankEnc, mel_filterbank
+
+    fixed, train = FbankEnc(trainable=False, n_banks=80), FbankEnc(trainable=True, n_banks=40)
+    assert list(fixed.state_dict()) == ["encoder.wsin", "encoder.wcos", "encoder.window_mask", "encoder.filterbank", "encoder.inv_filterbank"]
+    assert len(list(fixed.parameters())) == 0 and len(list(train.parameters())) == 4
+    assert fixed.state_dict()["encoder.filterbank"].shape == (257, 80) and fixed.state_dict()["encoder.inv_filterbank"].shape == (80, 257)
+    fb = mel_filterbank(16000, 512, 80)
+    assert fb.shape == (80, 257) and fb.dtype == torch.float32 and (fb >= 0).all() and (fb.max(1).values > 0).all()
+    peaks = fb.argmax(1)
+    assert (peaks[1:] >= peaks[:-1]).all() and fb[:, 0].abs().max() == 0  # centres rise with the band; DC belongs to no band
+    with pytest.raises(NotImplementedError):
+        FbankEnc(output_format="MagPhase")
+    if os.path.isdir("/root/reference/puresound"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from puresound.nnet.lobe.encoder import FbankEnc as RefFbank
+        finally:
+            sys.path.remove("/root/reference")
+        for ours, kw in ((fixed, dict(trainable=False, n_banks=80)), (train, dict(trainable=True, n_banks=40))):
+            ref = RefFbank(**kw).state_dict()
+            assert list(ref) == list(ours.state_dict()) and all(torch.equal(ref[k], ours.state_dict()[k]) for k in ref)
+
+
+def test_spec_augment_draws_like_torchaudio():
+    """SpecAugment's host-side band draw consumes the global generator exactly like torchaudio.functional.mask_along_axis
+    (two torch.rand(1) per masked axis), so the same seed gives the reference's band."""
+    from puresound_b200.nnet.lobe.trivial import SpecAugment
+
+    torch.manual_seed(11)
+    v = torch.rand(1) * 10
+    v0 = torch.rand(1) * (80 - v)
+    nxt = torch.rand(1)
+    torch.manual_seed(11)
+    s, e = SpecAugment._draw(10, 80)
+    assert (s, e) == (int(v0.long()), int(v0.long()) + int(v.long())) and torch.equal(torch.rand(1), nxt)
+    torch.manual_seed(11)
+    assert SpecAugment._draw(0, 80) == (0, 0) and torch.equal(torch.rand(1), v / 10)  # no mask, no draw

@@ -85,6 +85,28 @@ def test_oracle_matches_reference_skim_recipe():
     assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
 
 
+@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal"])
+def test_oracle_matches_reference_mel_and_rnn_speaker_recipes(name):
+    """`tse_skim_v1_causal` (bidirectional-LSTM speaker net) and `tse_skim_v2_causal` (mel front-end + SpecAugment, which the
+    reference applies at inference too: the global seed recorded with the pin is set right before the call) at full size."""
+    with open(os.path.join(GOLDEN, "mel_pins.json")) as fh:
+        pin = json.load(fh)[name]
+    torch.manual_seed(0)
+    m = recipes.init_model(name, verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    assert m.overall_parameters == pin["params"]
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-9)
+    mix, _ = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    enr = testing.noisy_speech(pin["batch"], pin["enroll_length"], seed=pin["enroll_seed"])[0]
+    torch.manual_seed(pin["rng_seed"])
+    y = R.inference(m.state_dict(), D.describe(m), mix, enr)
+    assert y.shape[-1] == pin["out_len"]
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+    torch.manual_seed(pin["rng_seed"])
+    emb = R.tse_embedding(m.state_dict(), D.describe(m), enr)
+    assert (emb.flatten() - torch.tensor(pin["embedding"])).abs().max().item() <= 2e-5
+
+
 def _real_inputs(g, tag):
     mix = (g["mix_i16"].float() / 32768.0)[None]
     enr = (g["enroll_i16"].float() / 32768.0)[None]
