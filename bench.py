@@ -42,6 +42,9 @@ WORKLOADS = {
     "tse_unet_tcn_v0": ("tse_unet_tcn_v0", 64, 64000, 96000, "TSE recipe tse_unet_tcn_v0: STFT 512/128 + 6-layer U-Net shell + 15 GatedTCN blocks + GatedTCN speaker net, 64 x (4 s mix + 6 s enroll) per GPU"),
     # widening row: the egs/ns noise-suppression recipe (egs/ns/model.py:84-126)
     "ns_dpcrn_v0": ("ns_dpcrn_v0", 64, 64000, None, "NS recipe ns_dpcrn_v0: STFT 512/128 + 5-layer U-Net shell + 2 DPRNN-2D blocks (H=128), complex mask, 64 x 4 s per GPU"),
+    # widening rows: the reference's demo recipe and its mel-front-end variant (egs/tse/model.py:418-463,509-558)
+    "tse_skim_v0_causal": ("tse_skim_v0_causal", 32, 160000, 96000, "TSE recipe tse_skim_v0_causal: learned encoder 32/16 + causal SkiM (H=256, 4 blocks, seg 150, FiLM) + TCN speaker net, 32 x (10 s mix + 6 s enroll) per GPU"),
+    "tse_skim_v2_causal": ("tse_skim_v2_causal", 32, 160000, 96000, "TSE recipe tse_skim_v2_causal: learned encoder 32/16 + causal SkiM (H=256) + mel front-end (FbankEnc 80 bands, SpecAugment) + TCN speaker net, 32 x (10 s mix + 6 s enroll) per GPU"),
     "ns_dparn_v0": ("ns_dparn_v0", 64, 64000, None, "NS recipe ns_dparn_v0: STFT 512/128 + 5-layer U-Net shell + 2 DPARN-2D blocks (8-head attention over frequency, LSTM over time), complex mask, 64 x 4 s per GPU"),
     # streaming: a step is one 10 ms hop of every stream (batch = concurrent streams, samples = hop)
     "cfg5": ("cfg5", 256, 160, None, "causal cLN Conv-TasNet (N=512,H=512,X=8,R=3), 10 ms hop, 256 concurrent streams per GPU, frame-by-frame"),
@@ -256,7 +259,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name, batch, L, Le, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "ns_dparn_v0": 4, "cfg5": 1}[args.workload]
+    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "ns_dparn_v0": 4, "cfg5": 1,
+                                                "tse_skim_v0_causal": 2, "tse_skim_v2_causal": 2}[args.workload]
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

@@ -97,6 +97,16 @@ def init_model(name: str, sig_loss: Optional[nn.Module] = None, cls_loss: Option
                 [TCN(128, 256, 3, dilation=2 ** i, causal=False, tcn_norm="gLN", dconv_norm="gGN") for i in range(5)]
                 + [AttentiveStatisticsPooling(128, 128), nn.Conv1d(128 * 2, 192, 1, bias=False)]),
             loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", **kwargs)
+    if name == "tse_skim_v0_causal_vad":
+        # egs/tse/model.py:560-606: the small causal SkiM (hidden 64, 2 blocks) with the sigmoid output constraint
+        return SoTaskWrapModule(
+            encoder=FreeEncDec(win_length=32, hop_length=16, laten_length=128, output_active=True),
+            masker=SkiM(input_size=128, hidden_size=64, output_size=128, n_blocks=2, seg_size=150, seg_overlap=False, causal=True,
+                        embed_dim=192, embed_norm=True, block_with_embed=[1, 1], embed_fusion="FiLM"),
+            speaker_net=nn.ModuleList(
+                [TCN(128, 256, 3, dilation=2 ** i, causal=False, tcn_norm="gLN", dconv_norm="gGN") for i in range(5)]
+                + [AttentiveStatisticsPooling(128, 128), nn.Conv1d(128 * 2, 192, 1, bias=False)]),
+            loss_func_wav=sig_loss, loss_func_spk=cls_loss, mask_constraint="ReLU", output_constraint="Sigmoid", **kwargs)
     if name in ("tse_skim_v1_causal", "tse_skim_v2_causal"):
         # egs/tse/model.py:465-549: the causal SkiM masker with (v1) a bidirectional-LSTM speaker net on the learned encoder's
         # features, or (v2) a mel front-end (FbankEnc, 80 bands, fixed filters) + SpecAugment + five TCN blocks
@@ -156,7 +166,7 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvTasNet(512, 0, False, tcn_dim=512, per_tcn_stack=8, repeat_tcn=3, tcn_with_embed=[0] * 8, tcn_norm="cLN",
                        dconv_norm="cLN", causal=True),
             mask_constraint="ReLU", verbose=verbose)
-    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_skim_v1_causal", "tse_skim_v2_causal", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1",
+    if name in ("veve_dprnn_v0_causal", "tse_skim_v0", "tse_skim_v0_causal", "tse_skim_v1_causal", "tse_skim_v2_causal", "tse_skim_v0_causal_vad", "tse_unet_tcn_v0", "tse_unet_tcn_v0_causal", "tse_unet_tcn_v1",
                 "ns_dpcrn_v0", "ns_dpcrn_v0_causal", "ns_dparn_v0", "ns_dparn_v0_causal"):
         return init_model(name, None, None, verbose=verbose)
     raise NameError(name)

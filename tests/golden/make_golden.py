@@ -614,7 +614,7 @@ def mel_cases():
     save("small_mel.pt", cases)
 
     pins = {}
-    for name in ("tse_skim_v1_causal", "tse_skim_v2_causal"):
+    for name in ("tse_skim_v1_causal", "tse_skim_v2_causal", "tse_skim_v0_causal_vad"):
         torch.manual_seed(0)
         m = _ref_init_model(name).eval()
         T.perturb_(m, seed=1)

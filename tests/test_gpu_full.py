@@ -149,7 +149,7 @@ def test_skim_recipe_full_size():
     assert err <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
 
 
-@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal"])
+@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal", "tse_skim_v0_causal_vad"])
 def test_skim_recipes_with_rnn_and_mel_speaker_nets(name):
     """`tse_skim_v1_causal` (SingleRNN speaker net) / `tse_skim_v2_causal` (FbankEnc + SpecAugment + TCN speaker net), 4 s mixture +
     6 s enrollment, against the reference's recorded output / embedding and the oracle (same global seed before each call:

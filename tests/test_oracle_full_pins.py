@@ -85,7 +85,7 @@ def test_oracle_matches_reference_skim_recipe():
     assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
 
 
-@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal"])
+@pytest.mark.parametrize("name", ["tse_skim_v1_causal", "tse_skim_v2_causal", "tse_skim_v0_causal_vad"])
 def test_oracle_matches_reference_mel_and_rnn_speaker_recipes(name):
     """`tse_skim_v1_causal` (bidirectional-LSTM speaker net) and `tse_skim_v2_causal` (mel front-end + SpecAugment, which the
     reference applies at inference too: the global seed recorded with the pin is set right before the call) at full size."""
