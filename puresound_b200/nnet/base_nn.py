@@ -236,6 +236,62 @@ class SoTaskWrapModule(nn.Module):
         return self._to_host(y) if on_host else y
 
     @torch.no_grad()
+    def inference_stream(self, batches, depth: int = 2):
+        """Serving loop over HOST batches: yields the enhanced waveform (pinned host tensor) of every item of `batches` - a
+        `noisy` tensor or a `(noisy, enroll)` pair, as `inference` takes them - in order.  Three streams: the host-to-device
+        copy of batch i+1 and the device-to-host copy of result i-1 overlap the forward of batch i, so a long run costs
+        max(copy, compute) per batch instead of their sum; `depth` results may be in flight before the first is yielded.
+        Every batch is computed exactly as `inference` computes it (same kernels, same CUDA-graph replay)."""
+        from collections import deque
+
+        ops.require_device()
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("puresound_b200 modules run on a CUDA device only: call model.to('cuda') (no CPU fallback)")
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def upload(item):
+            noisy, enroll = item if isinstance(item, (tuple, list)) else (item, None)
+            with torch.cuda.stream(h2d):
+                xs = [None if t is None else t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous() for t in (noisy, enroll)]
+                ev = torch.cuda.Event()
+                ev.record(h2d)
+            return xs[0], xs[1], ev
+
+        it = iter(batches)
+        pending = deque()
+        nxt = next(it, None)
+        up = upload(nxt) if nxt is not None else None
+        while up is not None:
+            xn, xe, ev = up
+            nxt = next(it, None)
+            up = upload(nxt) if nxt is not None else None  # the next batch's copy runs under this batch's forward
+            cur.wait_event(ev)
+            for t in (xn, xe):
+                if t is not None:
+                    t.record_stream(cur)
+            y = self._run(xn, xe)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+                out.copy_(y, non_blocking=True)
+                y.record_stream(d2h)
+                fin = torch.cuda.Event()
+                fin.record(d2h)
+            pending.append((out, fin))
+            if len(pending) > depth:
+                o, f = pending.popleft()
+                f.synchronize()
+                yield o
+        while pending:
+            o, f = pending.popleft()
+            f.synchronize()
+            yield o
+
+    @torch.no_grad()
     def inference_pre_constraint(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
         """The waveform before ``_wav_output_constrain`` (parity is also checked here: the clamp hides errors)."""
         ops.require_device()

@@ -23,7 +23,7 @@ import torch.nn as nn
 from .. import ops
 from ._fuse import ParamCache
 from .dpcrn import SingleRNN
-from .dprnn import dual_path_pass
+from .dprnn import dual_path_pass, proj_ln_residual
 from .unet import Unet
 
 
@@ -131,10 +131,8 @@ class DPARNblock2D(nn.Module):
         N, T, F_, C_ = x.shape
         v = self.intra_atten2.forward_cl(self.intra_atten1.forward_cl(x.view(N * T, F_, C_)))
         fc = self.intra_fc
-        pk = self._cache.get("fc", [fc.weight], lambda: ops.pack_weights(fc.weight, C_, C_, C_))
         P = N * T * F_
-        x, _ = ops.linear(v.view(1, P, C_), fc.weight, bias=fc.bias, w_packed=pk,
-                          ln=(self.intra_norm.weight, self.intra_norm.bias, self.intra_norm.eps), residual=x.reshape(1, P, C_))
+        x = proj_ln_residual(self._cache, "fc", v.view(1, P, C_), fc, self.intra_norm, x.reshape(1, P, C_))
         x, _ = dual_path_pass(self._cache, x.view(N, T, F_, C_), self.inter_rnn.rnn, self.inter_rnn.proj, self.inter_norm, "inter", True)
         return x
 

@@ -69,13 +69,18 @@ def dual_path_pass(cache: ParamCache, out: torch.Tensor, rnn: nn.LSTM, proj: nn.
         h0, c0 = init[0].contiguous(), init[1].contiguous()
     h, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, H=H, D=D, h0=h0, c0=c0, want_state=want_state, w_packed=w_hh_pk,
                         gx_interleaved=w_hh_pk is not None, **geo)
-    proj_pk = cache.get(tag + "_proj", [proj.weight],
-                        lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
     # Linear -> LayerNorm -> + residual in one kernel (LayerNorm in the GEMM epilogue when Cn == 128; otherwise the
     # library runs the row-norm kernel after the GEMM)
-    new, _ = ops.linear(h.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk,
-                        ln=(norm.weight, norm.bias, norm.eps), residual=out.view(1, P, Cn))
+    new = proj_ln_residual(cache, tag + "_proj", h.view(1, P, D * H), proj, norm, out.view(1, P, Cn))
     return new.view(N, S, K, Cn), state
+
+
+def proj_ln_residual(cache: ParamCache, tag: str, h: torch.Tensor, proj: nn.Linear, norm: nn.LayerNorm, residual: torch.Tensor) -> torch.Tensor:
+    """residual + LayerNorm(Linear(h)) on [1, P, *] tensors with the packed / paired operands cached per module."""
+    pk = cache.get(tag, [proj.weight], lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
+    paired = cache.get(tag + "_pair", [proj.weight, proj.bias, norm.weight, norm.bias],
+                       lambda: ops.paired_ln_weights(proj.weight, proj.bias, norm.weight, norm.bias))
+    return ops.linear_ln_residual(h, proj.weight, proj.bias, norm.weight, norm.bias, norm.eps, residual, w_packed=pk, paired=paired)
 
 
 class DPRNN(nn.Module):

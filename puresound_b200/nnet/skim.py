@@ -18,6 +18,7 @@ import torch.nn as nn
 from .. import ops
 from ..ops import ACT_PRELU, PRO_AFFINE, Prologue
 from ._fuse import ParamCache, prelu_slope
+from .dprnn import proj_ln_residual
 from .lobe.trivial import FiLM, overlap_geometry
 
 
@@ -61,10 +62,7 @@ def _lstm_proj_norm(cache: ParamCache, tag: str, x: torch.Tensor, rnn: nn.LSTM, 
         h0, c0 = init[0].contiguous(), init[1].contiguous()
     hseq, state = ops.lstm(gx.view(P, D * 4 * H), w_hh_t, n_seq=B, L=L, H=H, D=D, inner=1, outer_stride=L, inner_stride=0,
                            step_stride=1, h0=h0, c0=c0, want_state=True, w_packed=w_hh_pk, gx_interleaved=w_hh_pk is not None)
-    proj_pk = cache.get(tag + "_proj", [proj.weight],
-                        lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
-    y, _ = ops.linear(hseq.view(1, P, D * H), proj.weight, bias=proj.bias, w_packed=proj_pk,
-                      ln=(norm.weight, norm.bias, norm.eps), residual=x.reshape(1, P, Cn))
+    y = proj_ln_residual(cache, tag + "_proj", hseq.view(1, P, D * H), proj, norm, x.reshape(1, P, Cn))
     return y.view(B, L, Cn), state
 
 

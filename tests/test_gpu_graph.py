@@ -76,3 +76,25 @@ def test_input_shape_slots_are_bounded(model):
             y = model.inference(x)
         assert torch.equal(y, _eager(model, x))
     assert len(model._graphs) <= model._GRAPH_SLOTS
+
+
+def test_inference_stream_equals_inference(model):
+    """The serving loop (H2D / forward / D2H on three streams) returns, in order, exactly what inference() returns for each
+    host batch - pinned and pageable inputs, a generator as the source, more batches than the pipeline depth."""
+    from puresound_b200 import recipes, testing
+
+    model.use_cuda_graph = True
+    xs = [testing.noisy_speech(2, 16000, seed=20 + s)[0] for s in range(7)]
+    xs = [x.pin_memory() if i % 2 else x for i, x in enumerate(xs)]
+    ys = list(model.inference_stream(x for x in xs))
+    assert len(ys) == len(xs)
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        assert not y.is_cuda and y.is_pinned()
+        assert torch.equal(y, model.inference(x)), f"batch {i}"
+    assert list(model.inference_stream([])) == []
+    # (noisy, enroll) pairs through a TSE model
+    torch.manual_seed(0)
+    tse = recipes.init_model("td_tse_conv_tasnet_v0", verbose=False).eval().to("cuda")
+    pairs = [(testing.noisy_speech(1, 16000, seed=40 + s)[0], testing.noisy_speech(1, 24000, seed=50 + s)[0]) for s in range(4)]
+    for (x, e), y in zip(pairs, tse.inference_stream(pairs, depth=1)):
+        assert torch.equal(y, tse.inference(x, e))
