@@ -311,6 +311,9 @@ def test_wrappers_inference(golden):
     ("ns_dpcrn_v0_causal", "384", "infinite"),         # egs/ns/model.py:38-43
     ("ns_dpcrn_v0", "1024", "infinite"),               # egs/ns/model.py:84-89 (semi-causal: transpose_delay)
     ("ns_dparn_v0_causal", "384", "infinite"),         # egs/ns/model.py:128-133
+    ("tse_skim_v1_causal", "16", "infinite"),          # egs/tse/model.py:465-470
+    ("tse_skim_v2_causal", "16", "infinite"),          # egs/tse/model.py:509-514 (mel speaker front-end, SpecAugment)
+    ("tse_skim_v0_causal_vad", "16", "infinite"),      # egs/tse/model.py:560-565
 ])
 def test_verbose_probe_known_answers(name, lookahead, receptive, capsys):
     """The reference's `_verbose()` probe (base_nn.py:740-777) feeds +inf into half of a 10 s signal and reads look-ahead /
