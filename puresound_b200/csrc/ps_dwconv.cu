@@ -151,14 +151,21 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_kernel(const ps_dwconv_t d,
 constexpr int DT_THREADS = 256;
 constexpr int DT_CG = 32;  // channels per CTA: one 128-byte row segment
 
-static inline int dt_chunk(int P, int dilation) { return ((P - 1) * dilation <= 128) ? 256 : 512; }
+static inline int dt_chunk(int P, int dilation) {
+  static int forced = -1;  // PS_DW_TC: frames per CTA for A/B runs (the statistics slot count assumes >= 256)
+  if (forced < 0) { const char* e = getenv("PS_DW_TC"); forced = e ? atoi(e) : 0; }
+  if (forced >= 256) return forced;
+  return ((P - 1) * dilation <= 128) ? 256 : 512;
+}
 
 // PT: compile-time taps (3) or 0 = runtime (<= 8).  PRO: 0 none, 1 folded affine + PReLU, 2 row-norm (cLN) + PReLU;
 // "no activation" runs as PReLU with slope 1.  Everything per-element is compile-time selected: with runtime
 // mode/activation dispatch inside the unrolled loops this kernel executed 65 instructions per element and was
 // issue-bound at 27 % of HBM peak (ncu, round 1 run 5).
-template <int PT, int PRO>
-__global__ void __launch_bounds__(DT_THREADS) dwconv_tile_kernel(const ps_dwconv_t d, const int TC) {
+// MINB: CTAs per SM the register allocation must allow (4 caps the kernel at 64 registers: four 54 KB CTAs = 32 warps per SM
+// instead of three at 80 registers)
+template <int PT, int PRO, int MINB = 1>
+__global__ void __launch_bounds__(DT_THREADS, MINB) dwconv_tile_kernel(const ps_dwconv_t d, const int TC) {
   extern __shared__ __align__(16) float tile[];  // [(TC + halo) rows][32 channels]
   __shared__ Wf red[DT_THREADS / 32];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -302,13 +309,13 @@ __global__ void __launch_bounds__(DT_THREADS) dwconv_tile_kernel(const ps_dwconv
   }
 }
 
-template <int PT, int PRO>
+template <int PT, int PRO, int MINB = 1>
 static int launch_tile(const ps_dwconv_t& dd, int TC, size_t smem, dim3 grid, cudaStream_t s, bool set_attr) {
   if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<PT, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<PT, PRO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(dwconv_tile_kernel)"); return PS_ERR_CUDA; }
   }
-  dwconv_tile_kernel<PT, PRO><<<grid, DT_THREADS, smem, s>>>(dd, TC);
+  dwconv_tile_kernel<PT, PRO, MINB><<<grid, DT_THREADS, smem, s>>>(dd, TC);
   PS_CHECK_LAUNCH("dwconv_tile_kernel");
   return PS_OK;
 }
@@ -351,12 +358,15 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
   const int halo = (d.P - 1) * d.dilation;
   const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
   if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {
-    static bool attr_set[64][6] = {};
+    static bool attr_set[64][7] = {};
+    static int lb4 = -1;  // PS_DW_LB4=1: the 64-register build of the gLN-prologue variant (A/B switch)
+    if (lb4 < 0) { const char* e = getenv("PS_DW_LB4"); lb4 = (e && e[0] == '1') ? 1 : 0; }
     int dev = 0;
     cudaGetDevice(&dev);
     const int TC = ps::dt_chunk(d.P, d.dilation);
     const size_t smem = (size_t)(TC + halo) * ps::DT_CG * sizeof(float);
-    const int which = (d.P == 3 ? 3 : 0) + d.pro_mode;
+    int which = (d.P == 3 ? 3 : 0) + d.pro_mode;
+    if (which == 4 && lb4) which = 6;
     bool set_attr = false;
     if (dev >= 0 && dev < 64 && !attr_set[dev][which]) { set_attr = true; attr_set[dev][which] = true; }
     dim3 tgrid((unsigned)ps::cdiv(d.C, ps::DT_CG), (unsigned)ps::cdiv(d.T, TC), (unsigned)d.batch);
@@ -366,6 +376,7 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
       case 2: return ps::launch_tile<0, 2>(dd, TC, smem, tgrid, s, set_attr);
       case 3: return ps::launch_tile<3, 0>(dd, TC, smem, tgrid, s, set_attr);
       case 4: return ps::launch_tile<3, 1>(dd, TC, smem, tgrid, s, set_attr);
+      case 6: return ps::launch_tile<3, 1, 4>(dd, TC, smem, tgrid, s, set_attr);
       default: return ps::launch_tile<3, 2>(dd, TC, smem, tgrid, s, set_attr);
     }
   }

@@ -507,14 +507,24 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
 
 }  // namespace ps
 
+namespace ps {
+int lstm_simt_pack(const float* w_hh_t, int64_t H, int32_t D, void* packed, cudaStream_t s);
+}
+
+// sizes the tensor-core kernel does not serve get the CUDA-core kernel's gate-minor fp32 image instead
+bool ps_lstm_packed_is_simt(int64_t H) { return H >= 1 && H <= 256 && (H < 32 || H > ps::LT_H || H % 32 != 0); }
+
 extern "C" int64_t ps_lstm_packed_bytes(int64_t H, int32_t D) {
-  if (H < 32 || H > ps::LT_H || H % 32 != 0 || (D != 1 && D != 2)) return 0;
+  if (D != 1 && D != 2) return 0;
+  if (ps_lstm_packed_is_simt(H)) return (int64_t)D * H * 4 * H * (int64_t)sizeof(float);
+  if (H < 32 || H > ps::LT_H || H % 32 != 0) return 0;
   return (int64_t)D * 2 * ps::LT_WHI_BYTES;
 }
 
 extern "C" int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void* packed, void* stream) {
   PS_REQUIRE(w_hh_t && packed);
   if (ps_lstm_packed_bytes(H, D) == 0) return PS_ERR_UNSUPPORTED;
+  if (ps_lstm_packed_is_simt(H)) return ps::lstm_simt_pack(w_hh_t, H, D, packed, (cudaStream_t)stream);
   const int64_t n = (int64_t)D * 4 * ps::LT_H * ps::LT_H;
   ps::lstm_pack_kernel<<<(unsigned)ps::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w_hh_t, (int)H, D, reinterpret_cast<uint8_t*>(packed));
   PS_CHECK_LAUNCH("lstm_pack_kernel");

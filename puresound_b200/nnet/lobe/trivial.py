@@ -47,7 +47,7 @@ class SpecAugment(nn.Module):
         self.time_mask = time_mask_length
         self.mask_value = fill_value
         self._bounds = None   # int32[4] on the device: channel band, frame band
-        self._shape = None    # (channels, frames) of the last tensor seen: the band positions depend on the axis lengths
+        self._shape = None    # (channels, frames) of the masked axes last seen: the band positions depend on their lengths
         self._fresh = False
 
     @staticmethod
@@ -79,8 +79,9 @@ class SpecAugment(nn.Module):
         if self.freq_mask < 1 and self.time_mask < 1:
             return x
         capturing = torch.cuda.is_current_stream_capturing()
-        if (self._shape != (Cn, Tn) or not self._fresh) and not capturing:
-            self._shape = (Cn, Tn)
+        key = (Cn if self.freq_mask >= 1 else 0, Tn if self.time_mask >= 1 else 0)  # only the masked axes' lengths enter the draw
+        if (self._shape != key or not self._fresh) and not capturing:
+            self._shape = key
             self.host_prepare(x.device)
         self._fresh = False
         b = self._bounds

@@ -324,6 +324,42 @@ def test_lstm_intra_and_inter_addressing(ops, H, D):
     close(st[1].cpu(), cn, 2e-5)
 
 
+@pytest.mark.parametrize("H,D,N,L", [(12, 2, 37, 9), (40, 1, 300, 6), (256, 1, 70, 5), (256, 2, 1300, 4), (200, 1, 9, 3)])
+def test_lstm_cuda_core_packed_weights(ops, H, D, N, L):
+    """Sizes the tensor-core recurrence does not serve (SkiM's H = 256, small test sizes): ps_lstm_pack_weights builds the
+    gate-minor fp32 image [D][k][unit][4] (one 16-byte weight load per k, prefetched two chunks ahead); 8 or 16 sequences per
+    thread (N = 1300 at H = 256 takes the 16-wide variant); with and without interleaved gx rows, initial / final states.
+    Bit-identical to the unpacked kernel (same fp32 operations in the same order)."""
+    C = 16
+    sd = {}
+    for s in ["", "_reverse"][:D]:
+        sd[f"weight_ih_l0{s}"], sd[f"weight_hh_l0{s}"] = rnd(4 * H, C, seed=1, scale=0.3).cpu(), rnd(4 * H, H, seed=2, scale=0.1).cpu()
+        sd[f"bias_ih_l0{s}"], sd[f"bias_hh_l0{s}"] = rnd(4 * H, seed=3, scale=0.3).cpu(), rnd(4 * H, seed=4, scale=0.3).cpu()
+    sfx = ["", "_reverse"][:D]
+    w_ih = torch.cat([sd[f"weight_ih_l0{s}"] for s in sfx]).to(DEV)
+    b = torch.cat([sd[f"bias_ih_l0{s}"] + sd[f"bias_hh_l0{s}"] for s in sfx]).to(DEV)
+    w_hh_t = torch.stack([sd[f"weight_hh_l0{s}"].t().contiguous() for s in sfx]).to(DEV)
+    pk = ops.lstm_pack_weights(w_hh_t, H, D)
+    assert pk is not None and pk.numel() == D * H * 4 * H * 4
+    x = rnd(N, L, C, seed=5)
+    P = N * L
+    gx, _ = ops.linear(x.view(1, P, C), w_ih, bias=b)
+    gx = gx.view(P, D * 4 * H)
+    h0, c0 = rnd(D, N, H, seed=6), rnd(D, N, H, seed=7)
+    geo = dict(n_seq=N, L=L, H=H, D=D, inner=1, outer_stride=L, inner_stride=0, step_stride=1)
+    ref, (hn, cn) = R.lstm(sd, "", x.cpu(), D == 2, (h0.cpu(), c0.cpu()), fast=True)
+    plain, st0 = ops.lstm(gx, w_hh_t, h0=h0, c0=c0, want_state=True, **geo)
+    out, st = ops.lstm(gx, w_hh_t, h0=h0, c0=c0, want_state=True, w_packed=pk, **geo)
+    close(out.view(N, L, D * H).cpu(), ref, 2e-5)
+    close(st[0].cpu(), hn, 2e-5)
+    close(st[1].cpu(), cn, 2e-5)
+    if not (H == 256 and N > 1184):  # (the 16-wide variant sums in the same order too, but keep the claim to the like-for-like pair)
+        assert torch.equal(out, plain) and torch.equal(st[0], st0[0]) and torch.equal(st[1], st0[1])
+    gxi = gx.view(P, D, 4, H).permute(0, 1, 3, 2).reshape(P, D * 4 * H).contiguous()
+    outi, sti = ops.lstm(gxi, w_hh_t, h0=h0, c0=c0, want_state=True, w_packed=pk, gx_interleaved=True, **geo)
+    assert torch.equal(outi, out) and torch.equal(sti[1], st[1])
+
+
 def test_film_combine_and_transpose(ops):
     sb, xn = rnd(50, 32, seed=1), rnd(50, 16, seed=2)
     close(ops.film_combine(sb, xn), sb[:, :16] * xn + sb[:, 16:])
