@@ -106,11 +106,8 @@ typedef struct {
   float* fin_scale; float* fin_shift; uint32_t* fin_counter;
   /* optional row LayerNorm in the epilogue (ln_eps > 0): Y = residual + LN_M(X W^T + bias) * ln_gamma + ln_beta, the
    * Linear -> nn.LayerNorm -> + of the DPRNN blocks (dprnn.py:161-163,173-175).  Fused into the tcgen05 kernel when
-   * the norm width is 128, otherwise the library runs ps_rownorm after the GEMM (Y must not alias residual in that case).
-   * ln_width (0 = M): the norm runs over groups of ln_width consecutive outputs (M % ln_width == 0); ln_gamma / ln_beta
-   * hold M entries.  With M = 256, ln_width = 128 a GEMM row is TWO consecutive frames through a block-diagonal weight,
-   * so both CTAs of the pair drain accumulators (at M = 128 the peer's half of the 256-channel MMA is zero padding). */
-  const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t ln_width;
+   * M == 128, otherwise the library runs ps_rownorm after the GEMM (Y must not alias residual in that case). */
+  const float* ln_gamma; const float* ln_beta; float ln_eps;
 } ps_gemm_t;
 
 PS_API int ps_gemm(const ps_gemm_t* d, void* stream);

@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("residual", P), ("res_batch_stride", I64), ("res_row_stride", I64),
         ("stats_partials", P), ("W_packed", P),
         ("fin_gamma", P), ("fin_beta", P), ("fin_eps", F32), ("fin_scale", P), ("fin_shift", P), ("fin_counter", P),
-        ("ln_gamma", P), ("ln_beta", P), ("ln_eps", F32), ("ln_width", I32),
+        ("ln_gamma", P), ("ln_beta", P), ("ln_eps", F32),
     ]
 
 

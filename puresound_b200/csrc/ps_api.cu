@@ -79,8 +79,6 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
   if (d.ln_eps > 0.f) {
     // Linear -> LayerNorm (-> + residual): fused epilogue on the CTA-pair kernel, else GEMM then ps_rownorm in place
     PS_REQUIRE(!d.stats_partials && d.epi_act == PS_ACT_NONE && d.y_row_stride == d.M && d.y_batch_stride == d.rows * d.M);
-    const int64_t lw = d.ln_width > 0 ? d.ln_width : d.M;  // norm over groups of lw consecutive outputs
-    PS_REQUIRE(d.M % lw == 0);
     const bool fuse = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::tc_pair() && ps::gemm_tc_eligible(d) &&
                       ps::gemm_pair_ln_eligible(d);
     if (fuse) return ps::gemm_tc_launch(d, s);
@@ -90,11 +88,6 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
     dd.ln_eps = 0.f; dd.ln_gamma = nullptr; dd.ln_beta = nullptr; dd.residual = nullptr;
     const int rc = ps_gemm(&dd, stream);
     if (rc != PS_OK) return rc;
-    if (lw != d.M) {
-      // groups of one row share nothing: [rows, M] is [rows * M / lw, lw]; ps_rownorm takes one gamma / beta per group position,
-      // so the per-group entries must repeat (they do when the groups are consecutive frames through a block-diagonal weight)
-      return ps_rownorm(d.Y, d.residual, d.Y, d.batch * d.rows * (d.M / lw), lw, d.ln_gamma, d.ln_beta, d.ln_eps, PS_ACT_NONE, nullptr, stream);
-    }
     return ps_rownorm(d.Y, d.residual, d.Y, d.batch * d.rows, d.M, d.ln_gamma, d.ln_beta, d.ln_eps, PS_ACT_NONE, nullptr, stream);
   }
   const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);

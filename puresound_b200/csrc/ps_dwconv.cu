@@ -359,8 +359,10 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
   const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
   if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {
     static bool attr_set[64][7] = {};
-    static int lb4 = -1;  // PS_DW_LB4=1: the 64-register build of the gLN-prologue variant (A/B switch)
-    if (lb4 < 0) { const char* e = getenv("PS_DW_LB4"); lb4 = (e && e[0] == '1') ? 1 : 0; }
+    // the gLN-prologue variant runs its 64-register build (four CTAs = 32 warps per SM instead of three: cfg2 step 42.1 ->
+    // 40.2 ms on the same box, run 98); PS_DW_LB4=0 restores the 80-register one for A/B runs
+    static int lb4 = -1;
+    if (lb4 < 0) { const char* e = getenv("PS_DW_LB4"); lb4 = (e && e[0] == '0') ? 0 : 1; }
     int dev = 0;
     cudaGetDevice(&dev);
     const int TC = ps::dt_chunk(d.P, d.dilation);

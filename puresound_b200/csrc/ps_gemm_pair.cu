@@ -665,10 +665,7 @@ static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t
 }
 
 bool gemm_pair_ln_eligible(const ps_gemm_t& d) {
-  // the norm runs over the 128 TMEM lanes of ONE CTA: M = 128 (the peer's half of the MMA is zero padding) or M = 256 with
-  // ln_width = 128 (two frames per GEMM row, one per CTA)
-  const bool shape = (d.M == 128 && (d.ln_width == 0 || d.ln_width == 128)) || (d.M == 256 && d.ln_width == 128);
-  return shape && d.pro_mode == PS_PRO_NONE && d.epi_act == PS_ACT_NONE && !d.stats_partials && !d.bias_batch;
+  return d.M == 128 && d.pro_mode == PS_PRO_NONE && d.epi_act == PS_ACT_NONE && !d.stats_partials && !d.bias_batch;
 }
 
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {

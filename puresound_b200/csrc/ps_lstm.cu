@@ -195,9 +195,12 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   }
-  // 16 sequences per thread when 8 would need more than one wave of CTAs (SkiM segments: 2144 sequences -> 134 CTAs)
+  // 16 sequences per thread when 8 would need more than one wave of CTAs (SkiM segments: 2144 sequences -> 134 CTAs);
+  // 4 when even that leaves most SMs idle (SkiM's memory LSTMs: 32 sequences x 67 steps - a step is then 1024 k-FMA
+  // rounds per warp instead of 2048, on twice as many SMs)
   const bool wide = packed && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
-  const int SPT = wide ? 16 : 8;
+  const bool narrow = packed && !wide && ps::cdiv(d.n_seq, (int64_t)BG * 4) * d.D <= sms;
+  const int SPT = wide ? 16 : (narrow ? 4 : 8);
   const int BS = BG * SPT;
   const int threads = (int)d.H * BG;
   const size_t smem = (size_t)2 * d.H * BS * sizeof(float) + (size_t)BS * sizeof(int64_t);
@@ -214,6 +217,7 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
     }
   }
   if (wide) ps::lstm_kernel<16, true><<<grid, threads, smem, s>>>(d, BG);
+  else if (narrow) ps::lstm_kernel<4, true><<<grid, threads, smem, s>>>(d, BG);
   else if (packed) ps::lstm_kernel<8, true><<<grid, threads, smem, s>>>(d, BG);
   else ps::lstm_kernel<8, false><<<grid, threads, smem, s>>>(d, BG);
   PS_CHECK_LAUNCH("lstm_kernel");

@@ -76,11 +76,9 @@ def dual_path_pass(cache: ParamCache, out: torch.Tensor, rnn: nn.LSTM, proj: nn.
 
 
 def proj_ln_residual(cache: ParamCache, tag: str, h: torch.Tensor, proj: nn.Linear, norm: nn.LayerNorm, residual: torch.Tensor) -> torch.Tensor:
-    """residual + LayerNorm(Linear(h)) on [1, P, *] tensors with the packed / paired operands cached per module."""
+    """residual + LayerNorm(Linear(h)) on [1, P, *] tensors with the packed weight cached per module."""
     pk = cache.get(tag, [proj.weight], lambda: ops.pack_weights(proj.weight, proj.weight.shape[0], proj.weight.shape[1], proj.weight.shape[1]))
-    paired = cache.get(tag + "_pair", [proj.weight, proj.bias, norm.weight, norm.bias],
-                       lambda: ops.paired_ln_weights(proj.weight, proj.bias, norm.weight, norm.bias))
-    return ops.linear_ln_residual(h, proj.weight, proj.bias, norm.weight, norm.bias, norm.eps, residual, w_packed=pk, paired=paired)
+    return ops.linear_ln_residual(h, proj.weight, proj.bias, norm.weight, norm.bias, norm.eps, residual, w_packed=pk)
 
 
 class DPRNN(nn.Module):

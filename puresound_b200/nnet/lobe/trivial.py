@@ -122,7 +122,8 @@ class FiLM(nn.Module):
         w = self._cache.get("sb", [self.cond_scale.weight, self.cond_bias.weight],
                             lambda: torch.cat([self.cond_scale.weight.view(Cn, Cn + E), self.cond_bias.weight.view(Cn, Cn + E)], 0).contiguous())
         eb, _ = ops.gemm(cond.contiguous(), w[:, Cn:], batch=1, rows=N, M=2 * Cn, K=E, x_batch_stride=0, x_row_stride=E, w_row_stride=Cn + E)
-        sb, _ = ops.linear(xn, w, K=Cn, w_row_stride=Cn + E, bias_batch=eb.view(N, 2 * Cn))
+        pk = self._cache.get("sb_pk", [self.cond_scale.weight, self.cond_bias.weight], lambda: ops.pack_weights(w, 2 * Cn, Cn, Cn + E))
+        sb, _ = ops.linear(xn, w, K=Cn, w_row_stride=Cn + E, bias_batch=eb.view(N, 2 * Cn), w_packed=pk)
         return ops.film_combine(sb, xn)
 
     @torch.no_grad()

@@ -37,7 +37,10 @@ def _lstm_weights(cache: ParamCache, tag: str, rnn: nn.LSTM, use_tc: bool = True
         w_ih = torch.cat([getattr(rnn, f"weight_ih_l0{s}") for s in sfx], 0).contiguous()
         b = torch.cat([getattr(rnn, f"bias_ih_l0{s}") + getattr(rnn, f"bias_hh_l0{s}") for s in sfx], 0).contiguous()
         w_hh_t = torch.stack([getattr(rnn, f"weight_hh_l0{s}").t().contiguous() for s in sfx], 0).contiguous()
-        w_hh_pk = ops.lstm_pack_weights(w_hh_t, H, len(sfx)) if use_tc else None
+        # sizes the tensor-core kernel does not serve (H = 256 of the recipes) always take the CUDA-core kernel's packed image;
+        # for the others the tensor-core image only pays from TC_MIN_POSITIONS on
+        tc_size = 32 <= H <= 128 and H % 32 == 0
+        w_hh_pk = ops.lstm_pack_weights(w_hh_t, H, len(sfx)) if (use_tc or not tc_size) else None
         if w_hh_pk is not None:
             D = len(sfx)
             w_ih = w_ih.view(D, 4, H, -1).permute(0, 2, 1, 3).reshape(D * 4 * H, -1).contiguous()

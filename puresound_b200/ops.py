@@ -7,7 +7,6 @@ frames-major ``[batch, rows, channels]`` fp32 contiguous.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -121,8 +120,7 @@ def gemm(
 ):
     """Y[b,r,m] = epi(sum_k pro(X[b,r,k]) W[m,k]); returns (Y [batch, rows, M], stats partials or None) - or, with
     want_stats and fin=(gamma, beta, eps), (Y, FoldedAffine): the producer also finalizes the gLN/gGN statistics.
-    ln=(weight, bias, eps[, width]): Y = residual + LayerNorm(X W^T + bias) over groups of `width` (default M) outputs - fused
-    epilogue on the tcgen05 kernel when the width is 128.
+    ln=(weight, bias, eps): Y = residual + LayerNorm_M(X W^T + bias) (fused epilogue on the tcgen05 kernel when M == 128).
     y_strides / res_strides = (batch stride, row stride) in floats when `out` / `residual` are views into larger buffers
     (`out` is then the tensor whose data_ptr is the first output element)."""
     lib = _lib.load()
@@ -153,7 +151,6 @@ def gemm(
     folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
     if ln is not None:
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(ln[0]), _p(ln[1]), float(ln[2])
-        d.ln_width = int(ln[3]) if len(ln) > 3 else 0
     ev = None
     if gemm_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -188,38 +185,10 @@ def linear(x: Tensor, W: Tensor, K: Optional[int] = None, w_row_stride: Optional
                 w_row_stride=W.stride(0) if w_row_stride is None else w_row_stride, **kw)
 
 
-PAIR_FRAMES_LN = os.environ.get("PS_LN_PAIR", "1") != "0"  # PS_LN_PAIR=0 in the environment restores one frame per GEMM row
-
-
-def paired_ln_weights(W: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor):
-    """Operands of linear_ln_residual's two-frames-per-row form for M = 128: block-diagonal weight [256, 2K] (+ its tcgen05
-    image), and bias / gamma / beta repeated.  Returns None when the shape is not served (build once, cache)."""
-    M, K = W.shape
-    if M != 128 or (2 * K) % 64 != 0:
-        return None
-    W2 = W.new_zeros(2 * M, 2 * K)
-    W2[:M, :K] = W
-    W2[M:, K:] = W
-    pk = pack_weights(W2, 2 * M, 2 * K, 2 * K)
-    if pk is None:
-        return None
-    b2 = None if bias is None else torch.cat([bias, bias]).contiguous()
-    return W2, pk, b2, torch.cat([gamma, gamma]).contiguous(), torch.cat([beta, beta]).contiguous()
-
-
 def linear_ln_residual(x: Tensor, W: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float, residual: Tensor,
-                       w_packed: Optional[Tensor] = None, paired=None) -> Tensor:
+                       w_packed: Optional[Tensor] = None) -> Tensor:
     """residual + LayerNorm(x W^T + bias) for x [1, P, K], W [M, K] (dprnn.py:161-163,173-175; skim.py SegLSTM; dpcrn.py /
-    dparn.py blocks) in one GEMM.  With `paired` (from paired_ln_weights) and an even P, a GEMM row is TWO consecutive frames
-    through the block-diagonal weight: M = 256 fills the CTA pair's MMA with real outputs (at M = 128 the peer CTA's half is
-    zero padding and only the leader's epilogue warps work), the norm runs per 128-output group."""
-    _, P, K = x.shape
-    M = W.shape[0]
-    if paired is not None and PAIR_FRAMES_LN and P % 2 == 0 and force_gemm_backend != GEMM_SIMT:
-        W2, pk2, b2, g2, bt2 = paired
-        y, _ = gemm(x, W2, batch=1, rows=P // 2, M=2 * M, K=2 * K, x_batch_stride=P * K, x_row_stride=2 * K, w_row_stride=2 * K,
-                    bias=b2, w_packed=pk2, ln=(g2, bt2, eps, M), residual=residual.view(1, P // 2, 2 * M))
-        return y.view(1, P, M)
+    dparn.py blocks) in one GEMM (LayerNorm in the epilogue of the tcgen05 kernel when M == 128)."""
     y, _ = linear(x, W, bias=bias, w_packed=w_packed, ln=(gamma, beta, eps), residual=residual)
     return y
 

@@ -185,26 +185,3 @@ def test_tc_ineligible_shapes_are_refused(ops):
     assert ops.pack_weights(rnd(130, 64, seed=3), 130, 64, 64) is None  # channels must come in multiples of 32
     with pytest.raises(NotImplementedError):
         ops.linear(x, w, backend=ops.GEMM_TCGEN05)
-
-
-@pytest.mark.parametrize("P,K", [(666, 256), (4000, 64), (2, 128), (129 * 2, 512)])
-def test_tc_layernorm_two_frames_per_row(ops, P, K):
-    """linear_ln_residual's paired form: a GEMM row is two consecutive frames through a block-diagonal weight (M = 256, norm over
-    each 128-output group = one CTA of the pair), against the one-frame form, the exact-fp32 back end and fp64."""
-    M = 128
-    x, w, bias = rnd(1, P, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1), rnd(M, seed=3)
-    g, bt, res = rnd(M, seed=4) + 1.5, rnd(M, seed=5), rnd(1, P, M, seed=6)
-    paired = ops.paired_ln_weights(w, bias, g, bt)
-    assert paired is not None
-    pk = ops.pack_weights(w, M, K, K)
-    y = ops.linear_ln_residual(x, w, bias, g, bt, 1e-5, res, w_packed=pk, paired=paired)
-    lin = x.double() @ w.double().t() + bias.double()
-    ref = F.layer_norm(lin, (M,), g.double(), bt.double(), 1e-5) + res.double()
-    check(y, ref, 1e-4)
-    y1 = ops.linear_ln_residual(x, w, bias, g, bt, 1e-5, res, w_packed=pk, paired=None)
-    check(y1, ref, 1e-4)
-    # the library's fallback for the grouped norm (GEMM, then the row-norm kernel over [2P, 128])
-    W2, pk2, b2, g2, bt2 = paired
-    y2, _ = ops.gemm(x, W2, batch=1, rows=P // 2, M=256, K=2 * K, x_batch_stride=P * K, x_row_stride=2 * K, w_row_stride=2 * K, bias=b2,
-                     ln=(g2, bt2, 1e-5, 128), residual=res.view(1, P // 2, 256), backend=ops.GEMM_SIMT)
-    check(y2.view(1, P, M), ref, 1e-5)
