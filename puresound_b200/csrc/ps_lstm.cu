@@ -20,26 +20,45 @@ namespace ps {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// SPT: sequences per thread (8 or 16).  kPacked: W_hh comes as the gate-minor image [D][k][unit][4 gates] built by
-// ps_lstm_pack_weights for the sizes the tensor-core kernel does not serve (SkiM's H = 256): ONE 16-byte load per k and
-// thread instead of four 4-byte loads H apart, issued two chunks (16 k) ahead of the FMAs that use them.  The first
-// version of this kernel (4 x LDG.32 per k, 16 loads in flight per thread) ran a step of H = 256 in ~45 us = the L2 latency
-// times 64 dependent rounds; W_hh is 1 MB per direction there and is streamed from L2 by every CTA at every step, so the
-// kernel needs ~64 KB in flight per SM to reach the L2 rate.
-template <int SPT, bool kPacked>
+// SPT: sequences per thread (4, 8 or 16).  kPacked: W_hh comes as the gate-minor image [D][k][unit][4 gates] built by
+// ps_lstm_pack_weights for the sizes the tensor-core kernel does not serve (SkiM's H = 256).  W_hh is 1 MB per direction
+// there and every CTA streams it from L2 at every step; a thread needs one 16-byte weight vector per k, and fetches it with
+// cp.async into a PRIVATE shared-memory ring (no barrier: the thread that copies is the thread that reads) that runs
+// LSTM_RING k ahead and straight across step boundaries, so the L2 latency never reaches the FMA chain and no registers
+// hold weights in flight.  History (run 98/100, H = 256, 2144 sequences x 150 steps): 4 x LDG.32 per k, 16 loads in
+// flight: ~45 us per step-wave pair; LDG.128 prefetched 16 k ahead through registers (254 registers, 2 warps per
+// scheduler stalled on the h loads): 45 us per step at 16 sequences per thread.
+constexpr int LSTM_CK = 4;     // k per cp.async group
+constexpr int LSTM_NCH = 8;    // groups in flight
+constexpr int LSTM_RING = LSTM_CK * LSTM_NCH;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// HC: compile-time hidden size (256: SkiM's recipes; one thread per unit, BG = 1) or 0 = run-time sizes.  With HC every
+// shared-memory address of the k loop is an immediate offset from one induction register: the run-time-size build spent 48
+// of its 112 instructions per k on address arithmetic and `k < H` guards (ncu, run 101), the fixed-size one is 64 FFMA + 5
+// LDS + 1 cp.async.
+template <int SPT, bool kPacked, int HC = 0>
 __global__ void __launch_bounds__(256, 1) lstm_kernel(const ps_lstm_t d, const int BG) {
-  extern __shared__ __align__(16) float hs[];  // [2][H][BS] hidden state, then [BS] int64 position bases
-  const int H = (int)d.H;
-  const int BS = BG * SPT;
-  const int u = threadIdx.x % H;
-  const int g = threadIdx.x / H;
+  extern __shared__ __align__(16) float hs[];  // [2][H][BS] hidden state | [BS] int64 position bases | weight ring (packed)
+  const int H = HC ? HC : (int)d.H;
+  const int BS = HC ? SPT : BG * SPT;
+  const int u = HC ? (int)threadIdx.x : (int)(threadIdx.x % H);
+  const int g = HC ? 0 : (int)(threadIdx.x / H);
   const int dir = blockIdx.y;
+  const int nthr = HC ? HC : (int)blockDim.x;
   const int64_t q0 = (int64_t)blockIdx.x * BS + (int64_t)g * SPT;
   const int64_t G = (int64_t)d.D * 4 * H;   // gx row width
   const int64_t OW = (int64_t)d.D * H;      // out row width
   const float* __restrict__ W = (kPacked ? reinterpret_cast<const float*>(d.w_packed) : d.w_hh_t) + (int64_t)dir * H * 4 * H;
   const bool gxi = d.gx_interleaved != 0;   // gx rows [dir][unit][gate]: the four gates of a unit are one 16-byte load
   int64_t* base_s = reinterpret_cast<int64_t*>(hs + (size_t)2 * H * BS);
+  float4* ring = reinterpret_cast<float4*>(base_s + ((BS + 1) & ~1)) + threadIdx.x;  // this thread's slots: ring[slot * nthr]
 
   float c[SPT];
   unsigned valid = 0;
@@ -55,20 +74,33 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const ps_lstm_t d, const i
   }
   __syncthreads();
 
-  constexpr int UK = 8;  // k per chunk of the weight pipeline
+  // weight stream (packed): chunk n of the whole launch covers k = (n % KC) * CK .. + CK of step n / KC
+  const int KC = (H + LSTM_CK - 1) / LSTM_CK;
+  int64_t to_issue = (int64_t)d.L * KC;  // chunks not yet requested
+  int issue_kc = 0, issue_slot = 0;      // k chunk / ring slot of the next request
+  const float4* wsrc = reinterpret_cast<const float4*>(W) + u;
+  auto issue_chunk = [&]() {
+    if (to_issue > 0) {
+#pragma unroll
+      for (int j = 0; j < LSTM_CK; ++j) {
+        const int k = issue_kc * LSTM_CK + j;
+        if (HC || k < H) cp_async16(ring + (issue_slot * LSTM_CK + j) * nthr, wsrc + (int64_t)k * H);
+      }
+    }
+    cp_async_commit();  // (an empty group past the end keeps the group count in step with the consumer)
+    --to_issue;
+    if (++issue_kc == KC) issue_kc = 0;
+    if (++issue_slot == LSTM_NCH) issue_slot = 0;
+  };
+  if constexpr (kPacked) {
+#pragma unroll 1
+    for (int n = 0; n < LSTM_NCH; ++n) issue_chunk();
+  }
+  int use_slot = 0;  // ring slot of the next chunk to consume
+
   for (int64_t step = 0; step < d.L; ++step) {
     const int64_t t = dir ? d.L - 1 - step : step;
     const int cur = (int)(step & 1);
-    float4 wq[2][UK];  // packed path: weights of the next two chunks, in flight while the current chunk is used
-    if constexpr (kPacked) {
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int j = 0; j < UK; ++j) {
-          const int k = b * UK + j;
-          wq[b][j] = k < H ? __ldg(reinterpret_cast<const float4*>(W) + (int64_t)k * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
     float acc[4][SPT];
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
@@ -104,22 +136,17 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const ps_lstm_t d, const i
     };
     if constexpr (kPacked) {
 #pragma unroll 1
-      for (int k0 = 0; k0 < H; k0 += 2 * UK) {
+      for (int kc = 0; kc < KC; ++kc) {
+        cp_async_wait<LSTM_NCH - 1>();  // the oldest group in flight (this chunk) has landed
+        float4 wc[LSTM_CK];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          float4 wc[UK];
+        for (int j = 0; j < LSTM_CK; ++j) wc[j] = ring[(use_slot * LSTM_CK + j) * nthr];
+        issue_chunk();  // refill the slot just read (same thread, program order)
+        if (++use_slot == LSTM_NCH) use_slot = 0;
 #pragma unroll
-          for (int j = 0; j < UK; ++j) wc[j] = wq[b][j];
-#pragma unroll
-          for (int j = 0; j < UK; ++j) {  // refill this buffer with the chunk two ahead
-            const int k = k0 + (b + 2) * UK + j;
-            wq[b][j] = k < H ? __ldg(reinterpret_cast<const float4*>(W) + (int64_t)k * H + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < UK; ++j) {
-            const int k = k0 + b * UK + j;
-            if (k < H) fma_k(k, wc[j].x, wc[j].y, wc[j].z, wc[j].w);
-          }
+        for (int j = 0; j < LSTM_CK; ++j) {
+          const int k = kc * LSTM_CK + j;
+          if (HC || k < H) fma_k(k, wc[j].x, wc[j].y, wc[j].z, wc[j].w);
         }
       }
     } else {
@@ -143,6 +170,7 @@ __global__ void __launch_bounds__(256, 1) lstm_kernel(const ps_lstm_t d, const i
     }
     __syncthreads();
   }
+  if constexpr (kPacked) cp_async_wait<0>();
   const float* hfin = hs + (int64_t)(d.L & 1) * H * BS + u * BS + g * SPT;  // the buffer the last step wrote
 #pragma unroll
   for (int i = 0; i < SPT; ++i) {
@@ -198,26 +226,41 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
   // 16 sequences per thread when 8 would need more than one wave of CTAs (SkiM segments: 2144 sequences -> 134 CTAs);
   // 4 when even that leaves most SMs idle (SkiM's memory LSTMs: 32 sequences x 67 steps - a step is then 1024 k-FMA
   // rounds per warp instead of 2048, on twice as many SMs)
-  const bool wide = packed && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
+  const bool wide = packed && d.H == 256 && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
   const bool narrow = packed && !wide && ps::cdiv(d.n_seq, (int64_t)BG * 4) * d.D <= sms;
   const int SPT = wide ? 16 : (narrow ? 4 : 8);
   const int BS = BG * SPT;
   const int threads = (int)d.H * BG;
-  const size_t smem = (size_t)2 * d.H * BS * sizeof(float) + (size_t)BS * sizeof(int64_t);
+  const size_t smem = (size_t)2 * d.H * BS * sizeof(float) + (size_t)((BS + 1) & ~1) * sizeof(int64_t) +
+                      (packed ? (size_t)ps::LSTM_RING * threads * sizeof(float4) : 0);  // <= 32 KB + 128 KB at H = 256
   const int64_t nblk = ps::cdiv(d.n_seq, BS);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
-  if (smem > 48 * 1024) {
-    static bool attr[2] = {false, false};
-    if (!attr[wide]) {
-      cudaError_t e = wide ? cudaFuncSetAttribute(ps::lstm_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)
-                           : cudaFuncSetAttribute(packed ? ps::lstm_kernel<8, true> : ps::lstm_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (packed) {
+    static bool attr[64][3] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int vi = wide ? 2 : (narrow ? 0 : 1);
+    if (dev >= 0 && dev < 64 && !attr[dev][vi]) {
+      const int smax = 200 * 1024;
+      cudaError_t e = cudaSuccess;
+      if (wide) e = cudaFuncSetAttribute(ps::lstm_kernel<16, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      else if (narrow) {
+        e = cudaFuncSetAttribute(ps::lstm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ps::lstm_kernel<4, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      } else {
+        e = cudaFuncSetAttribute(ps::lstm_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ps::lstm_kernel<8, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
+      }
       if (e != cudaSuccess) { ps::set_cuda_error(e, "cudaFuncSetAttribute(lstm_kernel)"); return PS_ERR_CUDA; }
-      attr[wide] = true;
+      attr[dev][vi] = true;
     }
   }
-  if (wide) ps::lstm_kernel<16, true><<<grid, threads, smem, s>>>(d, BG);
+  const bool h256 = packed && d.H == 256;  // the fixed-size build (BG == 1)
+  if (wide) ps::lstm_kernel<16, true, 256><<<grid, threads, smem, s>>>(d, BG);
+  else if (narrow && h256) ps::lstm_kernel<4, true, 256><<<grid, threads, smem, s>>>(d, BG);
   else if (narrow) ps::lstm_kernel<4, true><<<grid, threads, smem, s>>>(d, BG);
+  else if (h256) ps::lstm_kernel<8, true, 256><<<grid, threads, smem, s>>>(d, BG);
   else if (packed) ps::lstm_kernel<8, true><<<grid, threads, smem, s>>>(d, BG);
   else ps::lstm_kernel<8, false><<<grid, threads, smem, s>>>(d, BG);
   PS_CHECK_LAUNCH("lstm_kernel");
