@@ -14,6 +14,8 @@
 // ([N*S] sequences over K) and the inter-chunk pass ([N*K] sequences over S) of
 // DPRNN on one [N,S,K,*] tensor, i.e. the permutes of dprnn.py:165-178 are folded
 // into addressing.
+#include <stdlib.h>
+
 #include "ps_common.cuh"
 
 namespace ps {
@@ -24,13 +26,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // ps_lstm_pack_weights for the sizes the tensor-core kernel does not serve (SkiM's H = 256).  W_hh is 1 MB per direction
 // there and every CTA streams it from L2 at every step; a thread needs one 16-byte weight vector per k, and fetches it with
 // cp.async into a PRIVATE shared-memory ring (no barrier: the thread that copies is the thread that reads) that runs
-// LSTM_RING k ahead and straight across step boundaries, so the L2 latency never reaches the FMA chain and no registers
+// 16 - 32 k ahead and straight across step boundaries, so the L2 latency never reaches the FMA chain and no registers
 // hold weights in flight.  History (run 98/100, H = 256, 2144 sequences x 150 steps): 4 x LDG.32 per k, 16 loads in
 // flight: ~45 us per step-wave pair; LDG.128 prefetched 16 k ahead through registers (254 registers, 2 warps per
 // scheduler stalled on the h loads): 45 us per step at 16 sequences per thread.
 constexpr int LSTM_CK = 4;     // k per cp.async group
-constexpr int LSTM_NCH = 8;    // groups in flight
-constexpr int LSTM_RING = LSTM_CK * LSTM_NCH;
+// groups in flight: 8 (32 k, 128 KB at 256 threads) - or 4 in the fixed-size build with <= 8 sequences per thread, which is
+// meant to run TWO CTAs per SM (2 x (16 KB state + 64 KB ring), <= 128 registers): four warps per scheduler instead of two
+__host__ __device__ constexpr int lstm_nch(int SPT, int HC) { return (HC && SPT <= 8) ? 4 : 8; }
+__host__ __device__ constexpr int lstm_minb(int SPT, int HC) { return (HC && SPT <= 8) ? 2 : 1; }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -44,7 +48,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // of its 112 instructions per k on address arithmetic and `k < H` guards (ncu, run 101), the fixed-size one is 64 FFMA + 5
 // LDS + 1 cp.async.
 template <int SPT, bool kPacked, int HC = 0>
-__global__ void __launch_bounds__(256, 1) lstm_kernel(const ps_lstm_t d, const int BG) {
+__global__ void __launch_bounds__(256, lstm_minb(SPT, HC)) lstm_kernel(const ps_lstm_t d, const int BG) {
+  constexpr int LSTM_NCH = lstm_nch(SPT, HC);
   extern __shared__ __align__(16) float hs[];  // [2][H][BS] hidden state | [BS] int64 position bases | weight ring (packed)
   const int H = HC ? HC : (int)d.H;
   const int BS = HC ? SPT : BG * SPT;
@@ -226,13 +231,16 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
   // 16 sequences per thread when 8 would need more than one wave of CTAs (SkiM segments: 2144 sequences -> 134 CTAs);
   // 4 when even that leaves most SMs idle (SkiM's memory LSTMs: 32 sequences x 67 steps - a step is then 1024 k-FMA
   // rounds per warp instead of 2048, on twice as many SMs)
-  const bool wide = packed && d.H == 256 && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
+  const bool h256 = packed && d.H == 256;  // the fixed-size build (BG == 1)
+  static int spt16 = -1;  // PS_LSTM_SPT16=1: 16 sequences per thread, one CTA per SM (A/B against 8 per thread, two CTAs per SM)
+  if (spt16 < 0) { const char* e = getenv("PS_LSTM_SPT16"); spt16 = (e && e[0] == '1') ? 1 : 0; }
+  const bool wide = spt16 && h256 && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
   const bool narrow = packed && !wide && ps::cdiv(d.n_seq, (int64_t)BG * 4) * d.D <= sms;
   const int SPT = wide ? 16 : (narrow ? 4 : 8);
   const int BS = BG * SPT;
   const int threads = (int)d.H * BG;
   const size_t smem = (size_t)2 * d.H * BS * sizeof(float) + (size_t)((BS + 1) & ~1) * sizeof(int64_t) +
-                      (packed ? (size_t)ps::LSTM_RING * threads * sizeof(float4) : 0);  // <= 32 KB + 128 KB at H = 256
+                      (packed ? (size_t)ps::LSTM_CK * ps::lstm_nch(SPT, h256 ? 256 : 0) * threads * sizeof(float4) : 0);
   const int64_t nblk = ps::cdiv(d.n_seq, BS);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
@@ -256,7 +264,6 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
       attr[dev][vi] = true;
     }
   }
-  const bool h256 = packed && d.H == 256;  // the fixed-size build (BG == 1)
   if (wide) ps::lstm_kernel<16, true, 256><<<grid, threads, smem, s>>>(d, BG);
   else if (narrow && h256) ps::lstm_kernel<4, true, 256><<<grid, threads, smem, s>>>(d, BG);
   else if (narrow) ps::lstm_kernel<4, true><<<grid, threads, smem, s>>>(d, BG);
