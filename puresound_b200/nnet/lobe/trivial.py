@@ -67,11 +67,13 @@ class SpecAugment(nn.Module):
         Cn, Tn = self._shape
         f0, f1 = self._draw(self.freq_mask, Cn)
         t0, t1 = self._draw(self.time_mask, Tn)
-        vals = torch.tensor([f0, f1, t0, t1], dtype=torch.int32)
+        # pinned staging + asynchronous copy: a pageable source would block the host until the stream drains, which serialises
+        # the serving loop (inference_stream) behind the previous batch's forward; the caching host allocator keeps the pinned
+        # block alive until the copy has run
+        vals = torch.tensor([f0, f1, t0, t1], dtype=torch.int32).pin_memory()
         if self._bounds is None or (device is not None and self._bounds.device != torch.device(device)):
-            self._bounds = vals.to(device if device is not None else "cuda")
-        else:
-            self._bounds.copy_(vals)
+            self._bounds = torch.empty(4, dtype=torch.int32, device=device if device is not None else "cuda")
+        self._bounds.copy_(vals, non_blocking=True)
         self._fresh = True
 
     def _mask(self, x: torch.Tensor, rows: int, cols: int, channel_axis_is_rows: bool) -> torch.Tensor:
