@@ -217,16 +217,19 @@ typedef struct {
   const float* gx; const float* w_hh_t;
   const float* h0; const float* c0;
   float* out; float* hn; float* cn;
-  /* tensor-core path (H <= 128, H % 32 == 0): image built by ps_lstm_pack_weights from w_hh_t, else NULL (exact-fp32 CUDA-core path) */
+  /* image built by ps_lstm_pack_weights from w_hh_t, or NULL (exact-fp32 CUDA-core kernel reading w_hh_t).  H <= 128 with
+   * H % 32 == 0: the tensor-core kernel's resident image; every other H <= 256: the CUDA-core kernel's gate-minor fp32 image
+   * [D][k][unit][4 gates] (one 16-byte weight vector per k and thread, streamed through a cp.async ring; same results). */
   const void* w_packed;
   /* 0: gx rows are [D][4 gates][H] (nn.LSTM order); 1: [D][H][4 gates] (rows of W_ih permuted by the caller so the four
-   * gates of a unit are one 16-byte load) - tensor-core path only */
+   * gates of a unit are one 16-byte load); needs w_packed */
   int32_t gx_interleaved;
 } ps_lstm_t;
 PS_API int ps_lstm(const ps_lstm_t* d, void* stream);
-/* bytes of the packed recurrent-weight image (0 if H is not served by the tensor-core path) */
+/* bytes of the packed recurrent-weight image for this H (0 if H > 256 or D is not 1 / 2) */
 PS_API int64_t ps_lstm_packed_bytes(int64_t H, int32_t D);
-/* w_hh_t [D, H, 4H] -> per direction: W_hh as bf16 hi (shared-memory tile image) | bf16 lo (row-major, goes to TMEM) */
+/* w_hh_t [D, H, 4H] -> per direction: W_hh as bf16 hi (shared-memory tile image) | bf16 lo (row-major, goes to TMEM) for
+ * the tensor-core sizes; the gate-minor fp32 image for the others */
 PS_API int ps_lstm_pack_weights(const float* w_hh_t, int64_t H, int32_t D, void* packed, void* stream);
 
 /* FiLM combine (lobe/trivial.py:163-165): y = sb[:, :C] * xn + sb[:, C:]; sb [rows, 2C] */
