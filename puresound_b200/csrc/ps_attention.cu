@@ -13,24 +13,44 @@
 namespace ps {
 
 // 16-byte shared-memory reads of a key / value row (all lanes of a warp read the same row: one broadcast wavefront per
-// float4 instead of four)
+// float4 instead of four).
+// Packed fp32 FMA of sm_100 (FFMA2, fma.rn.f32x2): the per-key work is 2 x DH FMAs in ~50 issue slots and the kernel is
+// issue-bound (run 88), so both loops run two lanes per instruction: the dot product as an (even, odd) pair of partial sums
+// (a dependent chain of DH / 2 instead of DH), the weighted sum of V as DH / 2 accumulator pairs.
+__device__ __forceinline__ unsigned long long att_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void att_unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void att_ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 template <int DH>
 __device__ __forceinline__ float att_dot(const float (&q)[DH], const float* __restrict__ k) {
-  float s = 0.f;
+  unsigned long long s2 = att_pack2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < DH; c += 4) {
     const float4 k4 = *reinterpret_cast<const float4*>(k + c);
-    s = fmaf(q[c], k4.x, s); s = fmaf(q[c + 1], k4.y, s); s = fmaf(q[c + 2], k4.z, s); s = fmaf(q[c + 3], k4.w, s);
+    att_ffma2(s2, att_pack2(q[c], q[c + 1]), att_pack2(k4.x, k4.y));
+    att_ffma2(s2, att_pack2(q[c + 2], q[c + 3]), att_pack2(k4.z, k4.w));
   }
-  return s;
+  float a, b;
+  att_unpack2(s2, a, b);
+  return a + b;
 }
 template <int DH>
 __device__ __forceinline__ void att_axpy(float (&acc)[DH], float p, const float* __restrict__ v) {
+  const unsigned long long pp = att_pack2(p, p);
 #pragma unroll
   for (int c = 0; c < DH; c += 4) {
     const float4 v4 = *reinterpret_cast<const float4*>(v + c);
-    acc[c] = fmaf(p, v4.x, acc[c]); acc[c + 1] = fmaf(p, v4.y, acc[c + 1]);
-    acc[c + 2] = fmaf(p, v4.z, acc[c + 2]); acc[c + 3] = fmaf(p, v4.w, acc[c + 3]);
+    unsigned long long a0 = att_pack2(acc[c], acc[c + 1]), a1 = att_pack2(acc[c + 2], acc[c + 3]);
+    att_ffma2(a0, pp, att_pack2(v4.x, v4.y));
+    att_ffma2(a1, pp, att_pack2(v4.z, v4.w));
+    att_unpack2(a0, acc[c], acc[c + 1]);
+    att_unpack2(a1, acc[c + 2], acc[c + 3]);
   }
 }
 

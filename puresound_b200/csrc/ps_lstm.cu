@@ -40,6 +40,19 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// Packed fp32 FMA of sm_100 (FFMA2): (d.lo, d.hi) += (a.lo, a.hi) * (b.lo, b.hi), each half rounded exactly like fmaf.
+// The k loop of the recurrence is issue-bound (ncu run 102: issue slots 68 % busy, fp32 FMA pipe 54 %): two sequences per
+// instruction halve its FMA instruction count.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -123,20 +136,25 @@ __global__ void __launch_bounds__(256, lstm_minb(SPT, HC)) lstm_kernel(const ps_
         for (int gt = 0; gt < 4; ++gt) acc[gt][i] = 0.f;
       }
     }
+    unsigned long long acc2[4][SPT / 2];  // (sequence 2j, sequence 2j + 1) per gate
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+      for (int j = 0; j < SPT / 2; ++j) acc2[gt][j] = pack2(acc[gt][2 * j], acc[gt][2 * j + 1]);
     const float* hcur = hs + (int64_t)cur * H * BS + g * SPT;
     auto fma_k = [&](int k, float w0, float w1, float w2, float w3) {
-      float hv[SPT];
+      unsigned long long hv2[SPT / 2];
 #pragma unroll
       for (int v = 0; v < SPT / 4; ++v) {
         const float4 h4 = *reinterpret_cast<const float4*>(hcur + k * BS + 4 * v);
-        hv[4 * v] = h4.x; hv[4 * v + 1] = h4.y; hv[4 * v + 2] = h4.z; hv[4 * v + 3] = h4.w;
+        hv2[2 * v] = pack2(h4.x, h4.y);
+        hv2[2 * v + 1] = pack2(h4.z, h4.w);
       }
+      const unsigned long long ww[4] = {pack2(w0, w0), pack2(w1, w1), pack2(w2, w2), pack2(w3, w3)};
 #pragma unroll
-      for (int i = 0; i < SPT; ++i) {
-        acc[0][i] = fmaf(w0, hv[i], acc[0][i]);
-        acc[1][i] = fmaf(w1, hv[i], acc[1][i]);
-        acc[2][i] = fmaf(w2, hv[i], acc[2][i]);
-        acc[3][i] = fmaf(w3, hv[i], acc[3][i]);
+      for (int j = 0; j < SPT / 2; ++j) {
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) ffma2(acc2[gt][j], ww[gt], hv2[j]);
       }
     };
     if constexpr (kPacked) {
@@ -162,6 +180,10 @@ __global__ void __launch_bounds__(256, lstm_minb(SPT, HC)) lstm_kernel(const ps_
       }
     }
     float* hnext = hs + (int64_t)(cur ^ 1) * H * BS + u * BS + g * SPT;
+#pragma unroll
+    for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+      for (int j = 0; j < SPT / 2; ++j) unpack2(acc2[gt][j], acc[gt][2 * j], acc[gt][2 * j + 1]);
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
       const float ig = sigmoidf_(acc[0][i]);

@@ -49,6 +49,7 @@ class SpecAugment(nn.Module):
         self._bounds = None   # int32[4] on the device: channel band, frame band
         self._shape = None    # (channels, frames) of the masked axes last seen: the band positions depend on their lengths
         self._fresh = False
+        self._stage, self._stage_i = None, 0
 
     @staticmethod
     def _draw(mask_param: int, axis_len: int):
@@ -67,13 +68,22 @@ class SpecAugment(nn.Module):
         Cn, Tn = self._shape
         f0, f1 = self._draw(self.freq_mask, Cn)
         t0, t1 = self._draw(self.time_mask, Tn)
-        # pinned staging + asynchronous copy: a pageable source would block the host until the stream drains, which serialises
-        # the serving loop (inference_stream) behind the previous batch's forward; the caching host allocator keeps the pinned
-        # block alive until the copy has run
-        vals = torch.tensor([f0, f1, t0, t1], dtype=torch.int32).pin_memory()
-        if self._bounds is None or (device is not None and self._bounds.device != torch.device(device)):
-            self._bounds = torch.empty(4, dtype=torch.int32, device=device if device is not None else "cuda")
-        self._bounds.copy_(vals, non_blocking=True)
+        # asynchronous copy from a small ring of pinned staging slots (an event per slot guards its reuse): a pageable source -
+        # or a fresh pinned allocation, which is a device-wide synchronisation - would stall the serving loop
+        # (inference_stream) behind the previous batch's forward
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if self._bounds is None or self._bounds.device != dev:
+            self._bounds = torch.empty(4, dtype=torch.int32, device=dev)
+            self._stage = [(torch.empty(4, dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+            self._stage_i = 0
+        slot, ev = self._stage[self._stage_i]
+        self._stage_i = (self._stage_i + 1) % len(self._stage)
+        ev.synchronize()  # (returns at once unless four later calls are still queued)
+        slot[0], slot[1], slot[2], slot[3] = f0, f1, t0, t1
+        self._bounds.copy_(slot, non_blocking=True)
+        ev.record(torch.cuda.current_stream(dev))
         self._fresh = True
 
     def _mask(self, x: torch.Tensor, rows: int, cols: int, channel_axis_is_rows: bool) -> torch.Tensor:
