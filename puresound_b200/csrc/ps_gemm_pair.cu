@@ -185,7 +185,10 @@ __device__ __forceinline__ void epi_chunk_ln(float (&v)[PR_CW], float bsum, floa
   }
 }
 
-// PRO: PS_PRO_NONE, PS_PRO_AFFINE (norm affine + PReLU) or PS_PRO_MASK (x * act(x2): mask apply in front of the decoder)
+// PRO: PS_PRO_NONE, PS_PRO_AFFINE (norm affine + PReLU), PS_PRO_MASK (x * act(x2): mask apply in front of the decoder) or
+// PR_PRO_AFFINE_TANH (kernel-internal: the affine followed by tanh - eval BatchNorm + nn.Tanh in front of the second conv of
+// AttentiveStatisticsPooling, lobe/pooling.py:71-86,104-105; its own instantiation so the TCN path's producers are untouched)
+constexpr int PR_PRO_AFFINE_TANH = 4;
 template <int PRO, int NB, bool kLN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
@@ -518,7 +521,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     };
     int64_t staged_b = -1;
     auto stage_affine = [&](int64_t b) {
-      if constexpr (PRO == PS_PRO_AFFINE) {
+      if constexpr (PRO == PS_PRO_AFFINE || PRO == PR_PRO_AFFINE_TANH) {
         if (b != staged_b) {
           asm volatile("bar.sync 2, %0;" ::"n"(PR_PRODUCERS) : "memory");  // every producer is done with the old rows
           const float* pa = d.pro_a + b * d.pro_batch_stride;
@@ -534,7 +537,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     };
     auto process = [&](const XBuf& x, int kb) {
       float sc[8], sh[8];
-      if constexpr (PRO == PS_PRO_AFFINE) {
+      if constexpr (PRO == PS_PRO_AFFINE || PRO == PR_PRO_AFFINE_TANH) {
         const int k0 = kb * 64 + kofs;
         const float4 a0 = *reinterpret_cast<const float4*>(aff_s + k0), a1 = *reinterpret_cast<const float4*>(aff_s + k0 + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(aff_s + K + k0), b1 = *reinterpret_cast<const float4*>(aff_s + K + k0 + 4);
@@ -563,6 +566,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
             u1 = fmaf(u1, sc[i + 1], sh[i + 1]);
             u0 = u0 > 0.f ? u0 : u0 * pslope;
             u1 = u1 > 0.f ? u1 : u1 * pslope;
+          } else if constexpr (PRO == PR_PRO_AFFINE_TANH) {
+            u0 = tanhf(fmaf(u0, sc[i], sh[i]));
+            u1 = tanhf(fmaf(u1, sc[i + 1], sh[i + 1]));
           }
           const __nv_bfloat162 h2 = __floats2bfloat162_rn(u0, u1);
           const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
@@ -670,7 +676,7 @@ bool gemm_pair_ln_eligible(const ps_gemm_t& d) {
 
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   static int sm_count[64] = {0};
-  static bool attr_set[64][5][2] = {};
+  static bool attr_set[64][6][2] = {};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
@@ -678,10 +684,11 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
     e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
   }
-  const int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
+  int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
+  if (pro == PS_PRO_AFFINE && d.pro_act == PS_ACT_TANH) pro = PR_PRO_AFFINE_TANH;
   const int nb = pair_nb(d.M);
   const bool ln = d.ln_eps > 0.f;  // fused LayerNorm epilogue: M == 128, no prologue (checked by gemm_pair_ln_eligible)
-  const int ai = ln ? 4 : pro;
+  const int ai = ln ? 5 : pro;
   const bool set_attr = !attr_set[dev][ai][nb - 1];
   attr_set[dev][ai][nb - 1] = true;
   const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);
@@ -692,10 +699,12 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   if (ln) return launch_pair<PS_PRO_NONE, 1, true>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
   if (nb == 2) {
     if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+    if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
     if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
     return launch_pair<PS_PRO_NONE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
   }
   if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
   if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
   return launch_pair<PS_PRO_NONE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
 }

@@ -527,7 +527,7 @@ bool gemm_tc_eligible(const ps_gemm_t& d) {
   if (d.M % (pair ? 32 : TC_BN) != 0 || (d.K % 64 != 0 && !k32)) return false;
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE || (pair && d.pro_mode == PS_PRO_MASK))) return false;
   if (d.pro_mode == PS_PRO_MASK && (!al16(d.X2) || !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_RELU || d.pro_act == PS_ACT_SIGMOID))) return false;
-  if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU)) return false;
+  if (d.pro_mode == PS_PRO_AFFINE && !(d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU || (pair && d.pro_act == PS_ACT_TANH))) return false;
   if (!(d.epi_act == PS_ACT_NONE || d.epi_act == PS_ACT_RELU || d.epi_act == PS_ACT_PRELU)) return false;
   if ((d.bias && !al16(d.bias)) || (d.bias_batch && !al16(d.bias_batch))) return false;
   if ((d.x_row_stride & 3) || (d.x_batch_stride & 3) || !al16(d.X) || (!pair && d.x_row_stride < d.K)) return false;

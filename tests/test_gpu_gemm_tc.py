@@ -185,3 +185,19 @@ def test_tc_ineligible_shapes_are_refused(ops):
     assert ops.pack_weights(rnd(130, 64, seed=3), 130, 64, 64) is None  # channels must come in multiples of 32
     with pytest.raises(NotImplementedError):
         ops.linear(x, w, backend=ops.GEMM_TCGEN05)
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(2, 300, 256, 128), (1, 747, 512, 128), (3, 130, 128, 64)])
+def test_tc_affine_tanh_prologue(ops, B, Rr, M, K):
+    """Second conv of AttentiveStatisticsPooling (lobe/pooling.py:71-86,104-105): eval-BatchNorm folded to a per-channel affine,
+    then tanh, applied to the operand on load (batch-independent scale / shift)."""
+    x, w, bias = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1), rnd(M, seed=3)
+    sc, sh = rnd(K, seed=4) + 1.5, rnd(K, seed=5)
+    pk = ops.pack_weights(w, M, K, K)
+    assert pk is not None
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_TANH, sc, sh, 0)
+    y, _ = ops.linear(x, w, pro=pro, bias=bias, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    ref = torch.tanh(x.double() * sc.double() + sh.double()) @ w.double().t() + bias.double()
+    check(y, ref)
+    y2, _ = ops.linear(x, w, pro=pro, bias=bias, backend=ops.GEMM_SIMT)
+    check(y2, ref, 1e-5)
