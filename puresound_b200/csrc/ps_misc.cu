@@ -144,38 +144,62 @@ __global__ void __launch_bounds__(256) l2normalize_kernel(const float* __restric
   for (int64_t e = lane; e < E; e += 32) y[r * E + e] = x[r * E + e] / nrm;
 }
 
-// seg[b,q,k,:] from x[b,t,:]
+// seg[b,q,k,:] from x[b,t,:].  VEC = 4: a thread moves 16 bytes and a 256-thread CTA SEG_ROWS rows (the first version ran
+// one CTA of C threads per 512-byte row: 646,400 CTAs at cfg3, 1.1 TB/s).
+constexpr int SEG_ROWS = 32;
+
+template <int VEC>
 __global__ void __launch_bounds__(256) segment_kernel(const float* __restrict__ x, float* __restrict__ seg, int64_t T,
                                                       int64_t C, int64_t K, int64_t S, int overlap) {
-  const int64_t row = blockIdx.x;  // q*K + k
   const int64_t b = blockIdx.y;
-  const int64_t q = row / K, k = row % K;
-  const int64_t t = overlap ? q * (K / 2) + k - K / 2 : row;
-  float* o = seg + (b * S * K + row) * C;
-  if (t >= 0 && t < T) {
-    const float* s = x + (b * T + t) * C;
-    for (int64_t c = threadIdx.x; c < C; c += blockDim.x) o[c] = s[c];
-  } else {
-    for (int64_t c = threadIdx.x; c < C; c += blockDim.x) o[c] = 0.f;
+  const int cv = (int)(C / VEC);                      // vectors per row
+  const int n = SEG_ROWS * cv;                        // vectors this CTA moves
+  const int64_t row0 = (int64_t)blockIdx.x * SEG_ROWS;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t row = row0 + i / cv;  // q*K + k
+    if (row >= S * K) break;
+    const int c = (int)(i % cv) * VEC;
+    const int64_t q = row / K, k = row % K;
+    const int64_t t = overlap ? q * (K / 2) + k - K / 2 : row;
+    float* o = seg + (b * S * K + row) * C + c;
+    const bool in = t >= 0 && t < T;
+    if constexpr (VEC == 4) {
+      *reinterpret_cast<float4*>(o) = in ? __ldg(reinterpret_cast<const float4*>(x + (b * T + t) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      *o = in ? __ldg(x + (b * T + t) * C + c) : 0.f;
+    }
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ seg, float* __restrict__ y, int64_t T,
                                                     int64_t C, int64_t K, int64_t S, int overlap) {
-  const int64_t t = blockIdx.x;
   const int64_t b = blockIdx.y;
+  const int cv = (int)(C / VEC);
+  const int n = SEG_ROWS * cv;
+  const int64_t t0 = (int64_t)blockIdx.x * SEG_ROWS;
   const float* sb = seg + b * S * K * C;
-  float* o = y + (b * T + t) * C;
-  if (overlap) {
-    const int64_t h = K / 2;
-    const int64_t j1 = (t + h) / K, k1 = (t + h) % K;  // even stream, left h dropped
-    const int64_t j2 = t / K, k2 = t % K;              // odd stream
-    const float* p1 = sb + ((2 * j1) * K + k1) * C;
-    const float* p2 = sb + ((2 * j2 + 1) * K + k2) * C;
-    for (int64_t c = threadIdx.x; c < C; c += blockDim.x) o[c] = (p1[c] + p2[c]) / 2.f;
-  } else {
-    const float* p = sb + t * C;
-    for (int64_t c = threadIdx.x; c < C; c += blockDim.x) o[c] = p[c];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t t = t0 + i / cv;
+    if (t >= T) break;
+    const int c = (int)(i % cv) * VEC;
+    float* o = y + (b * T + t) * C + c;
+    if (overlap) {
+      const int64_t h = K / 2;
+      const int64_t j1 = (t + h) / K, k1 = (t + h) % K;  // even stream, left h dropped
+      const int64_t j2 = t / K, k2 = t % K;              // odd stream
+      const float* p1 = sb + ((2 * j1) * K + k1) * C + c;
+      const float* p2 = sb + ((2 * j2 + 1) * K + k2) * C + c;
+      if constexpr (VEC == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p1)), d = __ldg(reinterpret_cast<const float4*>(p2));
+        *reinterpret_cast<float4*>(o) = make_float4((a.x + d.x) / 2.f, (a.y + d.y) / 2.f, (a.z + d.z) / 2.f, (a.w + d.w) / 2.f);
+      } else {
+        *o = (__ldg(p1) + __ldg(p2)) / 2.f;
+      }
+    } else {
+      if constexpr (VEC == 4) *reinterpret_cast<float4*>(o) = __ldg(reinterpret_cast<const float4*>(sb + t * C + c));
+      else *o = __ldg(sb + t * C + c);
+    }
   }
 }
 
@@ -273,8 +297,10 @@ extern "C" int ps_segment(const float* x, float* seg, int64_t batch, int64_t T, 
   PS_REQUIRE(x && seg && batch > 0 && T > 0 && C > 0 && K > 0 && S > 0);
   if (overlap) PS_REQUIRE(K % 2 == 0);
   if (batch > 65535) return PS_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)(S * K), (unsigned)batch);
-  ps::segment_kernel<<<grid, (C >= 256 ? 256 : 128), 0, (cudaStream_t)stream>>>(x, seg, T, C, K, S, overlap);
+  dim3 grid((unsigned)cdiv(S * K, ps::SEG_ROWS), (unsigned)batch);
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(seg)) & 15) == 0;
+  if (vec) ps::segment_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(x, seg, T, C, K, S, overlap);
+  else ps::segment_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, seg, T, C, K, S, overlap);
   PS_CHECK_LAUNCH("segment_kernel");
   return PS_OK;
 }
@@ -285,8 +311,10 @@ extern "C" int ps_merge(const float* seg, float* y, int64_t batch, int64_t T, in
   if (overlap) PS_REQUIRE(K % 2 == 0 && 2 * ((T - 1 + K / 2) / K) < S && 2 * ((T - 1) / K) + 1 < S);
   else PS_REQUIRE(T <= S * K);
   if (batch > 65535) return PS_ERR_UNSUPPORTED;
-  dim3 grid((unsigned)T, (unsigned)batch);
-  ps::merge_kernel<<<grid, (C >= 256 ? 256 : 128), 0, (cudaStream_t)stream>>>(seg, y, T, C, K, S, overlap);
+  dim3 grid((unsigned)cdiv(T, ps::SEG_ROWS), (unsigned)batch);
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(seg)) & 15) == 0;
+  if (vec) ps::merge_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(seg, y, T, C, K, S, overlap);
+  else ps::merge_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seg, y, T, C, K, S, overlap);
   PS_CHECK_LAUNCH("merge_kernel");
   return PS_OK;
 }
