@@ -251,29 +251,49 @@ class SoTaskWrapModule(nn.Module):
         cur = torch.cuda.current_stream(dev)
         h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
+        # two persistent device staging slots per input (re-made when a batch changes shape), each guarded by the event of
+        # the forward that last read it: no allocation on the copy stream in steady state (blocks freed across streams cannot
+        # be reused until their events complete, so per-batch allocations there end in synchronous cudaMalloc calls)
+        slots = [{"bufs": [None, None], "free": None} for _ in range(2)]
+        state = {"n": 0}
+
         def upload(item):
             noisy, enroll = item if isinstance(item, (tuple, list)) else (item, None)
+            slot = slots[state["n"] % 2]
+            state["n"] += 1
+            xs = []
+            for j, t in enumerate((noisy, enroll)):
+                if t is None:
+                    xs.append(None)
+                    continue
+                buf = slot["bufs"][j]
+                if buf is None or buf.shape != t.shape:
+                    buf = slot["bufs"][j] = torch.empty(t.shape, dtype=torch.float32, device=dev)
+                    h2d.wait_stream(cur)  # the new block may still be in use by work queued on the compute stream
+                xs.append(buf)
             with torch.cuda.stream(h2d):
-                xs = [None if t is None else t.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous() for t in (noisy, enroll)]
+                if slot["free"] is not None:
+                    h2d.wait_event(slot["free"])
+                for buf, t in zip(xs, (noisy, enroll)):
+                    if buf is not None:
+                        buf.copy_(t, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(h2d)
-            return xs[0], xs[1], ev
+            return xs[0], xs[1], ev, slot
 
         it = iter(batches)
         pending = deque()
         nxt = next(it, None)
         up = upload(nxt) if nxt is not None else None
         while up is not None:
-            xn, xe, ev = up
+            xn, xe, ev, slot = up
             nxt = next(it, None)
             up = upload(nxt) if nxt is not None else None  # the next batch's copy runs under this batch's forward
             cur.wait_event(ev)
-            for t in (xn, xe):
-                if t is not None:
-                    t.record_stream(cur)
             y = self._run(xn, xe)
             done = torch.cuda.Event()
             done.record(cur)
+            slot["free"] = done
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
                 out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
