@@ -236,12 +236,15 @@ class SoTaskWrapModule(nn.Module):
         return self._to_host(y) if on_host else y
 
     @torch.no_grad()
-    def inference_stream(self, batches, depth: int = 2):
+    def inference_stream(self, batches, depth: int = 2, reuse_host_buffers: bool = False):
         """Serving loop over HOST batches: yields the enhanced waveform (pinned host tensor) of every item of `batches` - a
         `noisy` tensor or a `(noisy, enroll)` pair, as `inference` takes them - in order.  Three streams: the host-to-device
         copy of batch i+1 and the device-to-host copy of result i-1 overlap the forward of batch i, so a long run costs
         max(copy, compute) per batch instead of their sum; `depth` results may be in flight before the first is yielded.
-        Every batch is computed exactly as `inference` computes it (same kernels, same CUDA-graph replay)."""
+        Every batch is computed exactly as `inference` computes it (same kernels, same CUDA-graph replay).
+        `reuse_host_buffers=True` takes the results from a ring of depth + 2 pinned buffers instead of a fresh pinned tensor
+        per batch (no host allocation in steady state): a yielded tensor is then only valid until depth + 1 further results
+        have been yielded - for consumers that use each result before asking for the next ones."""
         from collections import deque
 
         ops.require_device()
@@ -255,7 +258,17 @@ class SoTaskWrapModule(nn.Module):
         # the forward that last read it: no allocation on the copy stream in steady state (blocks freed across streams cannot
         # be reused until their events complete, so per-batch allocations there end in synchronous cudaMalloc calls)
         slots = [{"bufs": [None, None], "free": None} for _ in range(2)]
-        state = {"n": 0}
+        state = {"n": 0, "o": 0}
+        host_ring = [None] * (depth + 2)
+
+        def host_buffer(shape, dtype):
+            if not reuse_host_buffers:
+                return torch.empty(shape, dtype=dtype, pin_memory=True)
+            i = state["o"] % len(host_ring)
+            state["o"] += 1
+            if host_ring[i] is None or host_ring[i].shape != shape:
+                host_ring[i] = torch.empty(shape, dtype=dtype, pin_memory=True)
+            return host_ring[i]
 
         def upload(item):
             noisy, enroll = item if isinstance(item, (tuple, list)) else (item, None)
@@ -296,7 +309,7 @@ class SoTaskWrapModule(nn.Module):
             slot["free"] = done
             with torch.cuda.stream(d2h):
                 d2h.wait_event(done)
-                out = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+                out = host_buffer(y.shape, y.dtype)
                 out.copy_(y, non_blocking=True)
                 y.record_stream(d2h)
                 fin = torch.cuda.Event()

@@ -92,6 +92,9 @@ def test_inference_stream_equals_inference(model):
         assert not y.is_cuda and y.is_pinned()
         assert torch.equal(y, model.inference(x)), f"batch {i}"
     assert list(model.inference_stream([])) == []
+    # results from the ring of pinned buffers: each one is valid when it is yielded
+    for i, (x, y) in enumerate(zip(xs, model.inference_stream(xs, depth=1, reuse_host_buffers=True))):
+        assert torch.equal(y, ys[i]), f"ring batch {i}"
     # batches of changing shape in one stream (the staging slots are re-made, the graph cache holds two shapes)
     mixed = [testing.noisy_speech(2 if i % 3 else 1, 16000 if i % 2 else 24000, seed=70 + i)[0] for i in range(6)]
     for i, (x, y) in enumerate(zip(mixed, model.inference_stream(mixed))):
