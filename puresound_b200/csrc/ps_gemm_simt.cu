@@ -16,6 +16,8 @@
 // affine + activation, cLN row-norm, or mask product; compile-time selected) is applied on the global->register leg
 // so shared memory already holds the transformed operand; the epilogue adds bias / per-item bias / activation /
 // residual and emits one Welford partial (count, mean, M2) per CTA (big tile only: the slot layout is 128 x 128).
+#include <stdlib.h>
+
 #include "ps_common.cuh"
 
 namespace ps {
@@ -425,6 +427,89 @@ static int thin_launch(const ps_gemm_t& d, cudaStream_t s) {
   return PS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// A handful of rows (batch * rows <= 8) against many output channels: the per-hop 1x1 convs of a single stream (cfg5 at
+// S = 1: 72 GEMVs of 512 x 512 per 10 ms hop) and the heads applied to pooled embeddings.  The 32 x 64 latency tile ran such
+// a product on 8 CTAs with 32 synchronised k-slabs (~13 us); here the transformed operand rows sit in shared memory, a WARP
+// owns one output channel (its weight row is one coalesced 16-byte-per-lane stream), and 8 channels share a CTA: 64 CTAs,
+// four load rounds per warp at K = 512.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FEW_MAXR = 8;
+constexpr int FEW_MAXSMEM = 48 * 1024;
+
+template <int PRO>
+__global__ void __launch_bounds__(256) few_rows_kernel(const ps_gemm_t d, const int R) {
+  extern __shared__ __align__(16) float xs[];  // [R][K], prologue applied
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = (int)d.K;
+  XLoadCtx ctx;
+  ctx.mean = 0.f; ctx.rstd = 1.f;
+  ctx.slope = (d.pro_slope != nullptr) ? __ldg(d.pro_slope) : 0.f;
+  for (int i = tid; i < R * K; i += 256) {
+    const int g = i / K, k = i - g * K;
+    const int64_t b = g / d.rows, r = g % d.rows;
+    const int64_t off = b * d.x_batch_stride + r * d.x_row_stride + k;
+    const float x2 = (PRO == PS_PRO_MASK) ? __ldg(d.X2 + off) : 0.f;
+    xs[i] = pro_apply<PRO>(d, __ldg(d.X + off), x2, b, k, ctx);
+  }
+  __syncthreads();
+  const int64_t m = (int64_t)blockIdx.x * 8 + warp;
+  if (m >= d.M) return;
+  float acc[FEW_MAXR];
+#pragma unroll
+  for (int g = 0; g < FEW_MAXR; ++g) acc[g] = 0.f;
+  const float* wr = d.W + m * d.w_row_stride;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+    for (int g = 0; g < FEW_MAXR; ++g) {
+      if (g < R) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + g * K + k);
+        acc[g] = fmaf(x4.x, w4.x, acc[g]); acc[g] = fmaf(x4.y, w4.y, acc[g]);
+        acc[g] = fmaf(x4.z, w4.z, acc[g]); acc[g] = fmaf(x4.w, w4.w, acc[g]);
+      }
+    }
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int g = 0; g < FEW_MAXR; ++g) {
+    if (g < R) {
+      const float v = warp_sum(acc[g]);
+      if (lane == g) mine = v;
+    }
+  }
+  if (lane < R) {
+    const int64_t b = lane / d.rows, r = lane % d.rows;
+    float v = mine;
+    if (d.bias) v += __ldg(d.bias + m);
+    if (d.bias_batch) v += __ldg(d.bias_batch + b * d.M + m);
+    v = apply_act(v, d.epi_act, d.epi_slope ? __ldg(d.epi_slope) : 0.f);
+    if (d.residual) v += __ldg(d.residual + b * d.res_batch_stride + r * d.res_row_stride + m);
+    d.Y[b * d.y_batch_stride + r * d.y_row_stride + m] = v;
+  }
+}
+
+static bool few_rows_eligible(const ps_gemm_t& d, int x_vec, int w_vec) {
+  const int64_t R = d.batch * d.rows;
+  if (R > FEW_MAXR || !x_vec || !w_vec || d.K % 4 != 0 || R * d.K * (int64_t)sizeof(float) > FEW_MAXSMEM) return false;
+  if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE || d.pro_mode == PS_PRO_MASK)) return false;
+  if (d.stats_partials || d.ln_eps > 0.f || d.M < 32) return false;
+  return getenv("PS_GEMM_NO_FEW_ROWS") == nullptr;  // (A/B switch)
+}
+
+static int few_rows_launch(const ps_gemm_t& d, cudaStream_t s) {
+  const int R = (int)(d.batch * d.rows);
+  const size_t smem = (size_t)R * d.K * sizeof(float);
+  const unsigned blocks = (unsigned)cdiv(d.M, 8);
+  switch (d.pro_mode) {
+    case PS_PRO_AFFINE: few_rows_kernel<PS_PRO_AFFINE><<<blocks, 256, smem, s>>>(d, R); break;
+    case PS_PRO_MASK: few_rows_kernel<PS_PRO_MASK><<<blocks, 256, smem, s>>>(d, R); break;
+    default: few_rows_kernel<PS_PRO_NONE><<<blocks, 256, smem, s>>>(d, R); break;
+  }
+  PS_CHECK_LAUNCH("few_rows_kernel");
+  return PS_OK;
+}
+
 template <int BR, int BC>
 static int launch_shape(const ps_gemm_t& d, cudaStream_t s, int x_vec, int w_vec) {
   const int64_t nrt = cdiv(d.rows, BR), nmt = cdiv(d.M, BC);
@@ -446,6 +531,7 @@ int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s) {
                     (!d.X2 || (reinterpret_cast<uintptr_t>(d.X2) & 15) == 0);
   const int w_vec = ((d.w_row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0);
   if (filterbank_eligible(d)) return filterbank_launch(d, s);
+  if (few_rows_eligible(d, x_vec, w_vec)) return few_rows_launch(d, s);
   if (thin_eligible(d, x_vec)) return thin_launch(d, s);
   // latency shape when the throughput shape would leave most SMs idle (and no statistics are requested: the partial
   // slot layout is defined on 128 x 128 tiles)

@@ -44,6 +44,28 @@ def test_gemm_plain_bias_residual_act(ops, B, Rr, M, K):
     close(y, ref)
 
 
+@pytest.mark.parametrize("B,Rr,M,K", [(1, 1, 512, 512), (1, 3, 320, 512), (2, 4, 100, 64), (1, 8, 512, 320), (8, 1, 192, 1024)])
+@pytest.mark.parametrize("mode", ["none", "affine", "mask"])
+def test_gemm_few_rows_kernel(ops, B, Rr, M, K, mode):
+    """batch * rows <= 8 (a single stream's per-hop 1x1 convs, heads on pooled embeddings): warp-per-output-channel kernel
+    with the operand rows in shared memory; every prologue it takes, bias / per-item bias / activation / residual."""
+    x, w, b, res = rnd(B, Rr, K, seed=1), rnd(M, K, seed=2, scale=0.2), rnd(M, seed=3), rnd(B, Rr, M, seed=4)
+    bb, slope = rnd(B, M, seed=5), torch.tensor([0.2], device=DEV)
+    if mode == "affine":
+        sc, sh = rnd(B, K, seed=6) + 1.5, rnd(B, K, seed=7)
+        pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+        xin = F.prelu(x * sc.unsqueeze(1) + sh.unsqueeze(1), slope)
+    elif mode == "mask":
+        mk = rnd(B, Rr, K, seed=8, scale=2)
+        pro = ops.Prologue(ops.PRO_MASK, ops.ACT_SIGMOID, x2=mk)
+        xin = x * torch.sigmoid(mk)
+    else:
+        pro, xin = ops.NO_PRO, x
+    y, _ = ops.linear(x, w, pro=pro, bias=b, bias_batch=bb, epi_act=ops.ACT_PRELU, epi_slope=slope, residual=res, backend=ops.GEMM_SIMT)
+    ref = F.prelu((xin.double() @ w.double().t() + b.double() + bb.double().unsqueeze(1)).float(), slope) + res
+    close(y, ref, 1e-5)
+
+
 def test_gemm_framed_view_is_conv1d(ops):
     """row stride < K: the waveform read in place as overlapping frames == F.conv1d (encoder.py:50-56)."""
     wav, w = rnd(3, 1000, seed=1), rnd(24, 32, seed=2)
