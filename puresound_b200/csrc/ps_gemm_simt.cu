@@ -428,14 +428,15 @@ static int thin_launch(const ps_gemm_t& d, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// A handful of rows (batch * rows <= 8) against many output channels: the per-hop 1x1 convs of a single stream (cfg5 at
+// A handful of rows (batch * rows <= 32, eight at a time) against many output channels: the per-hop 1x1 convs of a single stream (cfg5 at
 // S = 1: 72 GEMVs of 512 x 512 per 10 ms hop) and the heads applied to pooled embeddings.  The 32 x 64 latency tile ran such
 // a product on 8 CTAs with 32 synchronised k-slabs (~13 us); here the transformed operand rows sit in shared memory, a WARP
 // owns one output channel (its weight row is one coalesced 16-byte-per-lane stream), and 8 channels share a CTA: 64 CTAs,
 // four load rounds per warp at K = 512.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FEW_MAXR = 8;
-constexpr int FEW_MAXSMEM = 48 * 1024;
+constexpr int FEW_MAXR = 8;             // rows per pass over a weight row (accumulators per lane)
+constexpr int FEW_MAXROWS = 32;         // rows per launch: up to four passes, the weight row re-read from L1
+constexpr int FEW_MAXSMEM = 128 * 1024;
 
 template <int PRO>
 __global__ void __launch_bounds__(256) few_rows_kernel(const ps_gemm_t d, const int R) {
@@ -455,43 +456,48 @@ __global__ void __launch_bounds__(256) few_rows_kernel(const ps_gemm_t d, const 
   __syncthreads();
   const int64_t m = (int64_t)blockIdx.x * 8 + warp;
   if (m >= d.M) return;
-  float acc[FEW_MAXR];
-#pragma unroll
-  for (int g = 0; g < FEW_MAXR; ++g) acc[g] = 0.f;
   const float* wr = d.W + m * d.w_row_stride;
-  for (int k = lane * 4; k < K; k += 128) {
-    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+  const float eslope = d.epi_slope ? __ldg(d.epi_slope) : 0.f;
+  float bsum = d.bias ? __ldg(d.bias + m) : 0.f;
+  for (int g0 = 0; g0 < R; g0 += FEW_MAXR) {
+    const int Rg = (R - g0) < FEW_MAXR ? (R - g0) : FEW_MAXR;
+    const float* xg = xs + g0 * K;
+    float acc[FEW_MAXR];
 #pragma unroll
-    for (int g = 0; g < FEW_MAXR; ++g) {
-      if (g < R) {
-        const float4 x4 = *reinterpret_cast<const float4*>(xs + g * K + k);
-        acc[g] = fmaf(x4.x, w4.x, acc[g]); acc[g] = fmaf(x4.y, w4.y, acc[g]);
-        acc[g] = fmaf(x4.z, w4.z, acc[g]); acc[g] = fmaf(x4.w, w4.w, acc[g]);
+    for (int g = 0; g < FEW_MAXR; ++g) acc[g] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+      for (int g = 0; g < FEW_MAXR; ++g) {
+        if (g < Rg) {
+          const float4 x4 = *reinterpret_cast<const float4*>(xg + g * K + k);
+          acc[g] = fmaf(x4.x, w4.x, acc[g]); acc[g] = fmaf(x4.y, w4.y, acc[g]);
+          acc[g] = fmaf(x4.z, w4.z, acc[g]); acc[g] = fmaf(x4.w, w4.w, acc[g]);
+        }
       }
     }
-  }
-  float mine = 0.f;
+    float mine = 0.f;
 #pragma unroll
-  for (int g = 0; g < FEW_MAXR; ++g) {
-    if (g < R) {
-      const float v = warp_sum(acc[g]);
-      if (lane == g) mine = v;
+    for (int g = 0; g < FEW_MAXR; ++g) {
+      if (g < Rg) {
+        const float v = warp_sum(acc[g]);
+        if (lane == g) mine = v;
+      }
     }
-  }
-  if (lane < R) {
-    const int64_t b = lane / d.rows, r = lane % d.rows;
-    float v = mine;
-    if (d.bias) v += __ldg(d.bias + m);
-    if (d.bias_batch) v += __ldg(d.bias_batch + b * d.M + m);
-    v = apply_act(v, d.epi_act, d.epi_slope ? __ldg(d.epi_slope) : 0.f);
-    if (d.residual) v += __ldg(d.residual + b * d.res_batch_stride + r * d.res_row_stride + m);
-    d.Y[b * d.y_batch_stride + r * d.y_row_stride + m] = v;
+    if (lane < Rg) {
+      const int64_t row = g0 + lane, b = row / d.rows, r = row % d.rows;
+      float v = mine + bsum;
+      if (d.bias_batch) v += __ldg(d.bias_batch + b * d.M + m);
+      v = apply_act(v, d.epi_act, eslope);
+      if (d.residual) v += __ldg(d.residual + b * d.res_batch_stride + r * d.res_row_stride + m);
+      d.Y[b * d.y_batch_stride + r * d.y_row_stride + m] = v;
+    }
   }
 }
 
 static bool few_rows_eligible(const ps_gemm_t& d, int x_vec, int w_vec) {
   const int64_t R = d.batch * d.rows;
-  if (R > FEW_MAXR || !x_vec || !w_vec || d.K % 4 != 0 || R * d.K * (int64_t)sizeof(float) > FEW_MAXSMEM) return false;
+  if (R > FEW_MAXROWS || !x_vec || !w_vec || d.K % 4 != 0 || R * d.K * (int64_t)sizeof(float) > FEW_MAXSMEM) return false;
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_AFFINE || d.pro_mode == PS_PRO_MASK)) return false;
   if (d.stats_partials || d.ln_eps > 0.f || d.M < 32) return false;
   return getenv("PS_GEMM_NO_FEW_ROWS") == nullptr;  // (A/B switch)
@@ -501,6 +507,18 @@ static int few_rows_launch(const ps_gemm_t& d, cudaStream_t s) {
   const int R = (int)(d.batch * d.rows);
   const size_t smem = (size_t)R * d.K * sizeof(float);
   const unsigned blocks = (unsigned)cdiv(d.M, 8);
+  if (smem > 48 * 1024) {
+    static bool attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
+      if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(few_rows_kernel)"); return PS_ERR_CUDA; }
+      attr[dev] = true;
+    }
+  }
   switch (d.pro_mode) {
     case PS_PRO_AFFINE: few_rows_kernel<PS_PRO_AFFINE><<<blocks, 256, smem, s>>>(d, R); break;
     case PS_PRO_MASK: few_rows_kernel<PS_PRO_MASK><<<blocks, 256, smem, s>>>(d, R); break;

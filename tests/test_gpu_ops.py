@@ -44,10 +44,11 @@ def test_gemm_plain_bias_residual_act(ops, B, Rr, M, K):
     close(y, ref)
 
 
-@pytest.mark.parametrize("B,Rr,M,K", [(1, 1, 512, 512), (1, 3, 320, 512), (2, 4, 100, 64), (1, 8, 512, 320), (8, 1, 192, 1024)])
+@pytest.mark.parametrize("B,Rr,M,K", [(1, 1, 512, 512), (1, 3, 320, 512), (2, 4, 100, 64), (1, 8, 512, 320), (8, 1, 192, 1024), (1, 19, 512, 512),
+                                       (4, 8, 256, 512), (1, 32, 512, 1024)])
 @pytest.mark.parametrize("mode", ["none", "affine", "mask"])
 def test_gemm_few_rows_kernel(ops, B, Rr, M, K, mode):
-    """batch * rows <= 8 (a single stream's per-hop 1x1 convs, heads on pooled embeddings): warp-per-output-channel kernel
+    """batch * rows <= 32, eight per pass (a few streams' per-hop 1x1 convs, heads on pooled embeddings): warp-per-output-channel kernel
     with the operand rows in shared memory; every prologue it takes, bias / per-item bias / activation / residual."""
     x, w, b, res = rnd(B, Rr, K, seed=1), rnd(M, K, seed=2, scale=0.2), rnd(M, seed=3), rnd(B, Rr, M, seed=4)
     bb, slope = rnd(B, M, seed=5), torch.tensor([0.2], device=DEV)
