@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -rfE --tb=short -p no:cacheprovider > gpurun_out/r118_pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/r118_pytest_gpu.log
+tail -3 gpurun_out/r118_pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r118_smoke.log 2>&1; tail -1 gpurun_out/r118_smoke.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r118_bench_cfg2.log 2>&1; tail -1 gpurun_out/r118_bench_cfg2.log | cut -c1-220
+echo done
