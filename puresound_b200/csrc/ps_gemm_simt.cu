@@ -24,6 +24,16 @@ namespace ps {
 
 constexpr int BK = 16, NT = 256;
 
+__device__ __forceinline__ unsigned long long simt_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void simt_unpack2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void simt_ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+
 struct XLoadCtx {
   float mean, rstd, slope;
 };
@@ -131,11 +141,12 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
   };
 
   const int ty = tid >> 4, tx = tid & 15;
-  float acc[TR][TCc];
+  static_assert(TCc % 2 == 0, "column pairs");
+  unsigned long long acc2[TR][TCc / 2];  // (column j, column j + 1) pairs
 #pragma unroll
   for (int i = 0; i < TR; ++i)
 #pragma unroll
-    for (int j = 0; j < TCc; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TCc / 2; ++j) acc2[i][j] = simt_pack2(0.f, 0.f);
 
   const int64_t nkt = (d.K + BK - 1) / BK;
   load_g(0);
@@ -161,10 +172,14 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
         const float4 t = *reinterpret_cast<const float4*>(&Ws[k][g * 64 + tx * 4]);
         w[g * 4] = t.x; w[g * 4 + 1] = t.y; w[g * 4 + 2] = t.z; w[g * 4 + 3] = t.w;
       }
+      // packed fp32 FMA (sm_100 FFMA2): two adjacent output columns per instruction, the row operand as a broadcast
+      // scalar; each half rounds like fmaf, so results are unchanged
 #pragma unroll
-      for (int i = 0; i < TR; ++i)
+      for (int i = 0; i < TR; ++i) {
+        const unsigned long long aa = simt_pack2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < TCc; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int j = 0; j < TCc; j += 2) simt_ffma2(acc2[i][j / 2], aa, simt_pack2(w[j], w[j + 1]));
+      }
     }
     __syncthreads();
     if (kt + 1 < nkt) {
@@ -174,6 +189,11 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const ps_gemm_t d, const 
   }
 
   // ---- epilogue ----
+  float acc[TR][TCc];
+#pragma unroll
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TCc / 2; ++j) simt_unpack2(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
   const float eslope = (d.epi_slope != nullptr) ? __ldg(d.epi_slope) : 0.f;
   WfAcc st;
   st.init();
