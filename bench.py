@@ -223,23 +223,48 @@ def streaming_bench(args, rank, world, local_rank):
 
 
 def cpu_reference_run(workload: str, sample_batch: int, steps: int, warmup: int, threads: int):
-    """The reference's CPU forward of the path (oracle port: same ATen calls as puresound's nn.Modules)."""
-    from oracle import describe as D
-    from oracle import separator_ref as R
-
+    """The reference's own CPU forward of the path: the UNMODIFIED reference installed in baseline/_ref
+    (`SoTaskWrapModule.inference`, puresound/nnet/base_nn.py:690-722, built from the reference's classes by
+    baseline/ref_models.py with the same seeded weights as the B200 arm) on all host threads.  Where baseline/_ref is
+    absent (never on a box the snapshot was pushed from the authoring container) the oracle port is timed instead.
+    Returns (audio seconds per step, step times, kind)."""
     torch.set_num_threads(threads)
-    m = build_model(workload)
-    sd, cfg = m.state_dict(), D.describe(m)
-    mix, enr = build_inputs(workload, 0, sample_batch)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_models
+
+    cfg, _, L, Le, _ = WORKLOADS[workload]
+    if workload == "cfg5":
+        L = 4 * SR  # the reference has no frame-by-frame Conv-TasNet: its arithmetic for cfg5 is the offline causal forward
+    from puresound_b200 import testing
+
+    mix, _ = testing.noisy_speech(sample_batch, L, seed=1234)
+    enr = testing.noisy_speech(sample_batch, Le, seed=4321)[0] if Le else None
+    if ref_models.available():
+        m = ref_models.build(cfg)
+        kind = "reference"
+
+        def run():
+            with torch.no_grad():
+                return m.inference(mix, enr) if enr is not None else m.inference(mix)
+    else:
+        from oracle import describe as D
+        from oracle import separator_ref as R
+
+        om = build_model(workload)
+        sd, dcfg = om.state_dict(), D.describe(om)
+        kind = "port"
+
+        def run():
+            return R.inference(sd, dcfg, mix, enr)
     for _ in range(warmup):
-        R.inference(sd, cfg, mix, enr)
+        run()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        R.inference(sd, cfg, mix, enr)
+        y = run()
         times.append(time.perf_counter() - t0)
-    audio_s = sample_batch * mix.shape[1] / SR
-    return audio_s, times
+    assert torch.isfinite(y).all()
+    return sample_batch * L / SR, times, kind
 
 
 def main():
@@ -267,19 +292,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        if args.workload == "cfg5":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference has no streaming Conv-TasNet (SURVEY.md section 0.3); see cfg2"}))
-            return 0
-        steps, warm = max(1, args.steps), max(1, min(args.warmup, 1))
-        audio_s, times = cpu_reference_run(args.workload, sample_batch, steps, warm, cores)
+        steps, warm = max(1, args.steps), max(1, args.warmup)
+        audio_s, times, kind = cpu_reference_run(args.workload, sample_batch, steps, warm, cores)
         t = sum(times) / len(times)
         v = audio_s / t
-        sample = f"{sample_batch} x {L / SR:.0f} s utterances of the {batch}-utterance batch per step, {cores} torch threads"
+        if args.workload == "cfg5":
+            sample = f"offline causal forward of {sample_batch} x 4 s utterances per step (the reference has no frame-by-frame Conv-TasNet), {cores} torch threads"
+        else:
+            sample = f"{sample_batch} x {L / SR:.0f} s utterances of the {batch}-utterance batch per step, {cores} torch threads"
+        what = "unmodified reference (baseline/_ref), SoTaskWrapModule.inference on CPU" if kind == "reference" else "oracle port (baseline/_ref absent)"
         print(json.dumps({
             "impl": "reference", "metric": "audio-sec/sec", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": warm, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+            "warmup": warm, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": SCALING_OF.get(args.scaling, "weak"), "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "sample": sample, "what": what},
+            "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return 0
@@ -372,7 +398,7 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
         assert n_out == args.steps
-    assert os.environ.get("PS_PAIR_DBG") or torch.isfinite(yh).all()  # (PS_PAIR_DBG: kernel bottleneck experiments, garbage results)
+    assert torch.isfinite(yh).all()
 
     value = world * audio_s_rank * args.steps / (ms / 1e3)
     e2e_value = world * audio_s_rank * args.steps / (e2e_ms / 1e3)

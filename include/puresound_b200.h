@@ -12,9 +12,12 @@
  *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated;
  *   - activations are "frames-major": [batch, rows(frames), channels], channel
  *     index fastest (the reference's [N, C, T] transposed; ps_transpose converts);
- *   - no allocation, no host synchronisation, no global mutable state: callers
- *     pass outputs/scratch and a cudaStream_t (as void*); re-entrant across
- *     streams and devices;
+ *   - no allocation and no host synchronisation: callers pass outputs/scratch
+ *     and a cudaStream_t (as void*).  Re-entrant across host threads, streams
+ *     and devices: the only process-wide state is a set of std::atomic caches
+ *     of idempotent facts (SM count per device, "dynamic shared-memory limit
+ *     raised for kernel X on device D", A/B switches read from the environment),
+ *     each stored only after the call it stands for succeeded;
  *   - return value: 0 on success, negative ps_status otherwise
  *     (ps_error_string() gives text; the Python host maps them to the
  *     reference's exception types).

@@ -147,12 +147,10 @@ __global__ void __launch_bounds__(256) attention_seq_kernel(const float* __restr
 template <int DH>
 static int attention_seq_launch(const float* qkv, float* out, int64_t batch, int64_t L, int64_t E, int heads, int causal, float scale,
                                 size_t smem, cudaStream_t s) {
-  static bool attr_set = false;  // per instantiation; setting it again on another device is harmless (same value)
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_seq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(attention_seq_kernel)"); return PS_ERR_CUDA; }
-    attr_set = true;
-  }
+  static SmemOnce<1> once;  // per instantiation and device
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = once.ensure(dev, 0, attention_seq_kernel<DH>, 200 * 1024, "cudaFuncSetAttribute(attention_seq_kernel)")) return rc;
   attention_seq_kernel<DH><<<(unsigned)batch, 256, smem, s>>>(qkv, out, (int)L, (int)E, heads, causal, scale);
   return PS_OK;
 }

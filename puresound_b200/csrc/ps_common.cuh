@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "../../include/puresound_b200.h"
 
@@ -29,6 +32,60 @@ void set_cuda_error(cudaError_t e, const char* where);
   } while (0)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- host-side caches of the launchers ------------------------------------------------------------------------
+// The C-ABI promises re-entrancy across host threads, streams and devices.  The launchers keep three kinds of cached
+// facts, all process-wide, monotonic and idempotent (a lost race only repeats an idempotent call): the SM count of a
+// device, "this kernel's dynamic shared-memory limit has been raised on this device", and integer A/B switches read
+// from the environment.  All are std::atomic; a "done" flag is stored only AFTER the call it stands for succeeded.
+constexpr int PS_MAX_DEVICES = 64;
+
+inline int current_device(int* dev) {
+  cudaError_t e = cudaGetDevice(dev);
+  if (e != cudaSuccess || *dev < 0 || *dev >= PS_MAX_DEVICES) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+inline int sm_count_of(int dev, int* out) {
+  static std::atomic<int> cache[PS_MAX_DEVICES];
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || v <= 0) { set_cuda_error(e, "cudaDeviceGetAttribute(multiProcessorCount)"); return PS_ERR_CUDA; }
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  *out = v;
+  return PS_OK;
+}
+
+// one flag per (device, kernel variant)
+template <int N>
+struct SmemOnce {
+  std::atomic<bool> done[PS_MAX_DEVICES][N];
+  template <typename Fn>
+  int ensure(int dev, int variant, Fn* fn, int bytes, const char* where) {
+    std::atomic<bool>& f = done[dev][variant];
+    if (f.load(std::memory_order_acquire)) return PS_OK;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_cuda_error(e, where); return PS_ERR_CUDA; }
+    f.store(true, std::memory_order_release);
+    return PS_OK;
+  }
+};
+
+// integer switch read once from the environment (A/B runs only; product defaults never depend on it being set)
+struct EnvInt {
+  std::atomic<int> v{INT32_MIN};
+  int get(const char* name, int dflt) {
+    int x = v.load(std::memory_order_relaxed);
+    if (x == INT32_MIN) {
+      const char* e = getenv(name);
+      x = e ? atoi(e) : dflt;
+      v.store(x, std::memory_order_relaxed);
+    }
+    return x;
+  }
+};
 
 // if-chain with the hot cases first (PReLU, none): a switch here becomes an indirect branch (BRX) per element
 // once it is inlined into unrolled loops, which measured 4x more instructions in the GEMM producers

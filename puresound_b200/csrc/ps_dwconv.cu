@@ -152,8 +152,8 @@ constexpr int DT_THREADS = 256;
 constexpr int DT_CG = 32;  // channels per CTA: one 128-byte row segment
 
 static inline int dt_chunk(int P, int dilation) {
-  static int forced = -1;  // PS_DW_TC: frames per CTA for A/B runs (the statistics slot count assumes >= 256)
-  if (forced < 0) { const char* e = getenv("PS_DW_TC"); forced = e ? atoi(e) : 0; }
+  static EnvInt env;  // PS_DW_TC: frames per CTA for A/B runs (the statistics slot count assumes >= 256)
+  const int forced = env.get("PS_DW_TC", 0);
   if (forced >= 256) return forced;
   return ((P - 1) * dilation <= 128) ? 256 : 512;
 }
@@ -310,11 +310,11 @@ __global__ void __launch_bounds__(DT_THREADS, MINB) dwconv_tile_kernel(const ps_
 }
 
 template <int PT, int PRO, int MINB = 1>
-static int launch_tile(const ps_dwconv_t& dd, int TC, size_t smem, dim3 grid, cudaStream_t s, bool set_attr) {
-  if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_tile_kernel<PT, PRO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(dwconv_tile_kernel)"); return PS_ERR_CUDA; }
-  }
+static int launch_tile(const ps_dwconv_t& dd, int TC, size_t smem, dim3 grid, cudaStream_t s) {
+  static SmemOnce<1> once;  // per instantiation and device
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = once.ensure(dev, 0, dwconv_tile_kernel<PT, PRO, MINB>, 200 * 1024, "cudaFuncSetAttribute(dwconv_tile_kernel)")) return rc;
   dwconv_tile_kernel<PT, PRO, MINB><<<grid, DT_THREADS, smem, s>>>(dd, TC);
   PS_CHECK_LAUNCH("dwconv_tile_kernel");
   return PS_OK;
@@ -358,28 +358,23 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
   const int halo = (d.P - 1) * d.dilation;
   const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
   if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {
-    static bool attr_set[64][7] = {};
     // the gLN-prologue variant runs its 64-register build (four CTAs = 32 warps per SM instead of three: cfg2 step 42.1 ->
     // 40.2 ms on the same box, run 98); PS_DW_LB4=0 restores the 80-register one for A/B runs
-    static int lb4 = -1;
-    if (lb4 < 0) { const char* e = getenv("PS_DW_LB4"); lb4 = (e && e[0] == '0') ? 0 : 1; }
-    int dev = 0;
-    cudaGetDevice(&dev);
+    static ps::EnvInt lb4_env;
+    const int lb4 = lb4_env.get("PS_DW_LB4", 1);
     const int TC = ps::dt_chunk(d.P, d.dilation);
     const size_t smem = (size_t)(TC + halo) * ps::DT_CG * sizeof(float);
     int which = (d.P == 3 ? 3 : 0) + d.pro_mode;
     if (which == 4 && lb4) which = 6;
-    bool set_attr = false;
-    if (dev >= 0 && dev < 64 && !attr_set[dev][which]) { set_attr = true; attr_set[dev][which] = true; }
     dim3 tgrid((unsigned)ps::cdiv(d.C, ps::DT_CG), (unsigned)ps::cdiv(d.T, TC), (unsigned)d.batch);
     switch (which) {
-      case 0: return ps::launch_tile<0, 0>(dd, TC, smem, tgrid, s, set_attr);
-      case 1: return ps::launch_tile<0, 1>(dd, TC, smem, tgrid, s, set_attr);
-      case 2: return ps::launch_tile<0, 2>(dd, TC, smem, tgrid, s, set_attr);
-      case 3: return ps::launch_tile<3, 0>(dd, TC, smem, tgrid, s, set_attr);
-      case 4: return ps::launch_tile<3, 1>(dd, TC, smem, tgrid, s, set_attr);
-      case 6: return ps::launch_tile<3, 1, 4>(dd, TC, smem, tgrid, s, set_attr);
-      default: return ps::launch_tile<3, 2>(dd, TC, smem, tgrid, s, set_attr);
+      case 0: return ps::launch_tile<0, 0>(dd, TC, smem, tgrid, s);
+      case 1: return ps::launch_tile<0, 1>(dd, TC, smem, tgrid, s);
+      case 2: return ps::launch_tile<0, 2>(dd, TC, smem, tgrid, s);
+      case 3: return ps::launch_tile<3, 0>(dd, TC, smem, tgrid, s);
+      case 4: return ps::launch_tile<3, 1>(dd, TC, smem, tgrid, s);
+      case 6: return ps::launch_tile<3, 1, 4>(dd, TC, smem, tgrid, s);
+      default: return ps::launch_tile<3, 2>(dd, TC, smem, tgrid, s);
     }
   }
   dim3 grid((unsigned)ps::cdiv(d.T, ps::DW_TT), (unsigned)ps::cdiv(d.C, g.chan_per_block), (unsigned)d.batch);

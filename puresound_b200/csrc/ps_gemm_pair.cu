@@ -29,6 +29,14 @@
 
 #include "ps_tc_ptx.cuh"
 
+// Bottleneck experiments (PS_PAIR_DBG: remove one stream of work at a time; results are garbage) exist only in builds with
+// -DPS_EXPERIMENTS; the release library has no such switch and no mutable state.
+#ifdef PS_EXPERIMENTS
+#define PR_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define PR_DBG(bit) false
+#endif
+
 namespace ps {
 
 constexpr int PR_FRAMES = 128;      // frames per pair tile (MMA N)
@@ -244,9 +252,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kWBytes);
-          if (dbg & 1) {  // experiment: no weight traffic (results are garbage)
+          if (PR_DBG(1)) {  // experiment: no weight traffic (results are garbage)
             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"((uint32_t)Cfg::kWBytes) : "memory");
-          } else if (dbg & 32) {  // experiment: four smaller copies
+          } else if (PR_DBG(32)) {  // experiment: four smaller copies
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               bulk_g2s(base + s * STAGE + 2 * PR_XPART + i * (Cfg::kWBytes / 4), src + (size_t)kb * Cfg::kWBytes + i * (Cfg::kWBytes / 4), Cfg::kWBytes / 4, bar_full + 8 * s);
@@ -369,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
           const float* rp = rb ? rb + (int64_t)(c * PR_CW) * rstride + mb * 256 : nullptr;
           const bool first = cnt[mb] == 0.f;
           cnt[mb] += (float)(nj < PR_CW ? nj : PR_CW);
-          if (dbg & 4) continue;
+          if (PR_DBG(4)) continue;
           if constexpr (kLN) {
             float2* part_s = reinterpret_cast<float2*>(fin_s);  // [2 groups][4 quarters][16 frames]; then [2][16] (mean, rstd)
             float2* stat_s = part_s + 2 * 4 * 16;
@@ -488,8 +496,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       if (c.t < n_tiles) {
         const PairTile tc = pr_tile(c.t, n_rt, n_nh);
         c.b = tc.b;
-        c.row_base = (int64_t)((dbg & 64) ? 0 : tc.rt) * PR_FRAMES + rank * PR_FR_CTA + r0;
-        c.x0 = d.X + ((dbg & 64) ? 0 : tc.b) * d.x_batch_stride + kofs;  // (64: experiment, every tile reads tile 0)
+        c.row_base = (int64_t)(PR_DBG(64) ? 0 : tc.rt) * PR_FRAMES + rank * PR_FR_CTA + r0;
+        c.x0 = d.X + (PR_DBG(64) ? 0 : tc.b) * d.x_batch_stride + kofs;  // (64: experiment, every tile reads tile 0)
       }
     };
     auto advance = [&](Cur& c) {
@@ -503,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     const int64_t x2_delta = (PRO == PS_PRO_MASK) ? (d.X2 - d.X) : 0;  // the mask has the strides of X
     const int mask_act = d.pro_act;
     auto issue = [&](XBuf& x, const Cur& c) {
-      if (dbg & 2) return;  // experiment: no activation loads
+      if (PR_DBG(2)) return;  // experiment: no activation loads
       const float* xb = c.x0 + c.kb * 64;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -549,7 +557,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       uint8_t* x_hi = sm + my_s * STAGE;
       uint8_t* x_lo = x_hi + PR_XPART;
 #pragma unroll
-      for (int p = 0; p < 2 && !(dbg & 8); ++p) {
+      for (int p = 0; p < 2 && !PR_DBG(8); ++p) {
         const int r = p * 32 + r0;
         float v[8] = {x.v[p][0].x, x.v[p][0].y, x.v[p][0].z, x.v[p][0].w, x.v[p][1].x, x.v[p][1].y, x.v[p][1].z, x.v[p][1].w};
         if constexpr (PRO == PS_PRO_MASK) {
@@ -658,13 +666,15 @@ int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* pack
 }
 
 template <int PRO, int NB, bool kLN = false>
-static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
-  if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<PRO, NB, kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<NB>::kSmem);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_pair_kernel)"); return PS_ERR_CUDA; }
-  }
-  static int dbg = -1;  // PS_PAIR_DBG: bottleneck experiments only (1 no weight copies, 2 no activation loads, 4 no epilogue, 8 no transform)
-  if (dbg < 0) { const char* e = getenv("PS_PAIR_DBG"); dbg = e ? atoi(e) : 0; }
+static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles) {
+  static SmemOnce<1> once;  // per instantiation and device
+  if (int rc = once.ensure(dev, 0, gemm_pair_kernel<PRO, NB, kLN>, PairCfg<NB>::kSmem, "cudaFuncSetAttribute(gemm_pair_kernel)")) return rc;
+#ifdef PS_EXPERIMENTS
+  static EnvInt dbg_e;
+  const int dbg = dbg_e.get("PS_PAIR_DBG", 0);
+#else
+  const int dbg = 0;
+#endif
   gemm_pair_kernel<PRO, NB, kLN><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
   PS_CHECK_LAUNCH("gemm_pair_kernel");
   return PS_OK;
@@ -675,38 +685,29 @@ bool gemm_pair_ln_eligible(const ps_gemm_t& d) {
 }
 
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
-  static int sm_count[64] = {0};
-  static bool attr_set[64][6][2] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
-  if (sm_count[dev] == 0) {
-    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
-  }
+  int dev = 0, sms = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = sm_count_of(dev, &sms)) return rc;
   int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
   if (pro == PS_PRO_AFFINE && d.pro_act == PS_ACT_TANH) pro = PR_PRO_AFFINE_TANH;
   const int nb = pair_nb(d.M);
   const bool ln = d.ln_eps > 0.f;  // fused LayerNorm epilogue: M == 128, no prologue (checked by gemm_pair_ln_eligible)
-  const int ai = ln ? 5 : pro;
-  const bool set_attr = !attr_set[dev][ai][nb - 1];
-  attr_set[dev][ai][nb - 1] = true;
   const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
-  const int64_t max_pairs = sm_count[dev] / 2;
+  const int64_t max_pairs = sms / 2;
   const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
-  if (ln) return launch_pair<PS_PRO_NONE, 1, true>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  if (ln) return launch_pair<PS_PRO_NONE, 1, true>(d, s, dev, grid, n_rt, n_nh, n_tiles);
   if (nb == 2) {
-    if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-    if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-    if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-    return launch_pair<PS_PRO_NONE, 2>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+    if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    return launch_pair<PS_PRO_NONE, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
   }
-  if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-  if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-  if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-  return launch_pair<PS_PRO_NONE, 1>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+  if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 1>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  return launch_pair<PS_PRO_NONE, 1>(d, s, dev, grid, n_rt, n_nh, n_tiles);
 }
 
 }  // namespace ps

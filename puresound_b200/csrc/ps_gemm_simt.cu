@@ -528,16 +528,12 @@ static int few_rows_launch(const ps_gemm_t& d, cudaStream_t s) {
   const size_t smem = (size_t)R * d.K * sizeof(float);
   const unsigned blocks = (unsigned)cdiv(d.M, 8);
   if (smem > 48 * 1024) {
-    static bool attr[64] = {};
+    static SmemOnce<3> once;
     int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(few_rows_kernel<PS_PRO_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_MAXSMEM);
-      if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(few_rows_kernel)"); return PS_ERR_CUDA; }
-      attr[dev] = true;
-    }
+    if (int rc = current_device(&dev)) return rc;
+    if (int rc = once.ensure(dev, 0, few_rows_kernel<PS_PRO_NONE>, FEW_MAXSMEM, "cudaFuncSetAttribute(few_rows_kernel)")) return rc;
+    if (int rc = once.ensure(dev, 1, few_rows_kernel<PS_PRO_AFFINE>, FEW_MAXSMEM, "cudaFuncSetAttribute(few_rows_kernel)")) return rc;
+    if (int rc = once.ensure(dev, 2, few_rows_kernel<PS_PRO_MASK>, FEW_MAXSMEM, "cudaFuncSetAttribute(few_rows_kernel)")) return rc;
   }
   switch (d.pro_mode) {
     case PS_PRO_AFFINE: few_rows_kernel<PS_PRO_AFFINE><<<blocks, 256, smem, s>>>(d, R); break;

@@ -496,12 +496,8 @@ static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) 
 
 // stage geometry, fixed per process (the packed weight image depends on it): PS_TC_BK=64|32
 int tc_bk() {
-  static int bk = 0;
-  if (bk == 0) {
-    const char* e = getenv("PS_TC_BK");
-    bk = (e && atoi(e) == 64) ? 64 : 32;
-  }
-  return bk;
+  static EnvInt env;
+  return env.get("PS_TC_BK", 32) == 64 ? 64 : 32;
 }
 
 // which tcgen05 kernel serves eligible shapes, fixed per process (the packed weight image depends on it):
@@ -509,12 +505,14 @@ int tc_bk() {
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s);
 int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s);
 bool tc_pair() {
-  static int mode = -1;
-  if (mode < 0) {
+  static std::atomic<int> mode{-1};
+  int m = mode.load(std::memory_order_relaxed);
+  if (m < 0) {
     const char* e = getenv("PS_TC_KERNEL");
-    mode = (e && e[0] == 's') ? 0 : 1;
+    m = (e && e[0] == 's') ? 0 : 1;
+    mode.store(m, std::memory_order_relaxed);
   }
-  return mode == 1;
+  return m == 1;
 }
 
 bool gemm_tc_eligible(const ps_gemm_t& d) {
@@ -539,11 +537,9 @@ bool gemm_tc_eligible(const ps_gemm_t& d) {
 }
 
 template <bool kAffine, int BK>
-static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, bool set_attr) {
-  if (set_attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kAffine, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BK>::kSmem);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(gemm_tc_kernel)"); return PS_ERR_CUDA; }
-  }
+static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles) {
+  static SmemOnce<1> once;  // per instantiation and device
+  if (int rc = once.ensure(dev, 0, gemm_tc_kernel<kAffine, BK>, TcCfg<BK>::kSmem, "cudaFuncSetAttribute(gemm_tc_kernel)")) return rc;
   gemm_tc_kernel<kAffine, BK><<<(unsigned)grid, TC_THREADS, TcCfg<BK>::kSmem, s>>>(d, n_rt, n_nh, n_tiles);
   PS_CHECK_LAUNCH("gemm_tc_kernel");
   return PS_OK;
@@ -551,25 +547,17 @@ static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int64_t grid, int6
 
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
   if (tc_pair()) return gemm_pair_launch(d, s);
-  static int sm_count[64] = {0};
-  static bool attr_set[64][2] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
-  if (sm_count[dev] == 0) {
-    e = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
-  }
+  int dev = 0, sms = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = sm_count_of(dev, &sms)) return rc;
   const bool affine = d.pro_mode == PS_PRO_AFFINE;
-  const bool set_attr = !attr_set[dev][affine];
-  attr_set[dev][affine] = true;
   const int64_t n_rt = cdiv(d.rows, TC_BM), n_nh = d.M / TC_BN;
   const int64_t n_tiles = d.batch * n_rt * n_nh;
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
-  const int64_t grid = n_tiles < sm_count[dev] ? n_tiles : sm_count[dev];
+  const int64_t grid = n_tiles < sms ? n_tiles : sms;
   if (tc_bk() == 64)
-    return affine ? launch_variant<true, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_variant<false, 64>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
-  return affine ? launch_variant<true, 32>(d, s, grid, n_rt, n_nh, n_tiles, set_attr) : launch_variant<false, 32>(d, s, grid, n_rt, n_nh, n_tiles, set_attr);
+    return affine ? launch_variant<true, 64>(d, s, dev, grid, n_rt, n_nh, n_tiles) : launch_variant<false, 64>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  return affine ? launch_variant<true, 32>(d, s, dev, grid, n_rt, n_nh, n_tiles) : launch_variant<false, 32>(d, s, dev, grid, n_rt, n_nh, n_tiles);
 }
 
 }  // namespace ps

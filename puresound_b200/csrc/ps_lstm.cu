@@ -245,17 +245,15 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
   // kernel's image, which this one must not read)
   const bool packed = d.w_packed != nullptr && ps_lstm_packed_is_simt(d.H) && (reinterpret_cast<uintptr_t>(d.w_packed) & 15) == 0;
   if (d.gx_interleaved) PS_REQUIRE((reinterpret_cast<uintptr_t>(d.gx) & 15) == 0);
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
+  int dev = 0, sms = 0;
+  if (int rc = ps::current_device(&dev)) return rc;
+  if (int rc = ps::sm_count_of(dev, &sms)) return rc;
   // 16 sequences per thread when 8 would need more than one wave of CTAs (SkiM segments: 2144 sequences -> 134 CTAs);
   // 4 when even that leaves most SMs idle (SkiM's memory LSTMs: 32 sequences x 67 steps - a step is then 1024 k-FMA
   // rounds per warp instead of 2048, on twice as many SMs)
   const bool h256 = packed && d.H == 256;  // the fixed-size build (BG == 1)
-  static int spt16 = -1;  // PS_LSTM_SPT16=1: 16 sequences per thread, one CTA per SM (A/B against 8 per thread, two CTAs per SM)
-  if (spt16 < 0) { const char* e = getenv("PS_LSTM_SPT16"); spt16 = (e && e[0] == '1') ? 1 : 0; }
+  static ps::EnvInt spt16_env;  // PS_LSTM_SPT16=1: 16 sequences per thread, one CTA per SM (A/B against 8 per thread, two CTAs per SM)
+  const int spt16 = spt16_env.get("PS_LSTM_SPT16", 0) == 1;
   const bool wide = spt16 && h256 && ps::cdiv(d.n_seq, (int64_t)BG * 8) * d.D > sms;
   const bool narrow = packed && !wide && ps::cdiv(d.n_seq, (int64_t)BG * 4) * d.D <= sms;
   const int SPT = wide ? 16 : (narrow ? 4 : 8);
@@ -267,24 +265,19 @@ extern "C" int ps_lstm(const ps_lstm_t* dp, void* stream) {
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);
   if (packed) {
-    static bool attr[64][3] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int vi = wide ? 2 : (narrow ? 0 : 1);
-    if (dev >= 0 && dev < 64 && !attr[dev][vi]) {
-      const int smax = 200 * 1024;
-      cudaError_t e = cudaSuccess;
-      if (wide) e = cudaFuncSetAttribute(ps::lstm_kernel<16, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      else if (narrow) {
-        e = cudaFuncSetAttribute(ps::lstm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ps::lstm_kernel<4, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      } else {
-        e = cudaFuncSetAttribute(ps::lstm_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ps::lstm_kernel<8, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smax);
-      }
-      if (e != cudaSuccess) { ps::set_cuda_error(e, "cudaFuncSetAttribute(lstm_kernel)"); return PS_ERR_CUDA; }
-      attr[dev][vi] = true;
+    static ps::SmemOnce<5> once;
+    const int smax = 200 * 1024;
+    const char* where = "cudaFuncSetAttribute(lstm_kernel)";
+    int rc = PS_OK;
+    if (wide) rc = once.ensure(dev, 0, ps::lstm_kernel<16, true, 256>, smax, where);
+    else if (narrow) {
+      rc = once.ensure(dev, 1, ps::lstm_kernel<4, true>, smax, where);
+      if (rc == PS_OK) rc = once.ensure(dev, 2, ps::lstm_kernel<4, true, 256>, smax, where);
+    } else {
+      rc = once.ensure(dev, 3, ps::lstm_kernel<8, true>, smax, where);
+      if (rc == PS_OK) rc = once.ensure(dev, 4, ps::lstm_kernel<8, true, 256>, smax, where);
     }
+    if (rc != PS_OK) return rc;
   }
   if (wide) ps::lstm_kernel<16, true, 256><<<grid, threads, smem, s>>>(d, BG);
   else if (narrow && h256) ps::lstm_kernel<4, true, 256><<<grid, threads, smem, s>>>(d, BG);

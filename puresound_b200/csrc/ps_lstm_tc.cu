@@ -29,6 +29,12 @@
 
 #include "ps_tc_ptx.cuh"
 
+#ifdef PS_EXPERIMENTS
+#define LT_DBG(bit) ((dbg & (bit)) != 0)
+#else
+#define LT_DBG(bit) false
+#endif
+
 namespace ps {
 
 constexpr int LT_H = 128, LT_N = 64;           // hidden units, sequences per CTA
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
           const uint32_t hs = base + LT_WHI_BYTES + (uint32_t)(hf * LT_NH * 64);  // rows [32*hf, 32*hf+32) of every h tile
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (dbg & 1) break;  // experiment: gate phase alone (PS_LSTM_DBG=1, results are garbage)
+            if (LT_DBG(1)) break;  // experiment: gate phase alone (PS_LSTM_DBG=1, results are garbage)
             const uint32_t dd = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N + hf * LT_NH);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {  // k16 steps over K = 128
@@ -444,8 +450,9 @@ __global__ void lstm_pack_kernel(const float* __restrict__ w_hh_t, int H, int D,
 }
 
 bool lstm_tc_eligible(const ps_lstm_t& d) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("PS_LSTM"); off = (e && e[0] == 's') ? 1 : 0; }  // PS_LSTM=simt forces the fp32 kernel
+  static std::atomic<int> off_c{-1};  // PS_LSTM=simt forces the fp32 kernel
+  int off = off_c.load(std::memory_order_relaxed);
+  if (off < 0) { const char* e = getenv("PS_LSTM"); off = (e && e[0] == 's') ? 1 : 0; off_c.store(off, std::memory_order_relaxed); }
   // the kernel keeps 32-bit row indices: the last position touched must stay below 2^31
   const int64_t last_pos = ((d.n_seq - 1) / d.inner) * d.outer_stride + (d.inner - 1) * d.inner_stride + (d.L - 1) * d.step_stride;
   if (last_pos >= 2147483647LL || d.outer_stride < 0 || d.inner_stride < 0 || d.step_stride < 0) return false;
@@ -454,29 +461,21 @@ bool lstm_tc_eligible(const ps_lstm_t& d) {
 }
 
 int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64) { set_cuda_error(e, "cudaGetDevice"); return PS_ERR_CUDA; }
-  if (!attr_set[dev]) {
-    e = cudaFuncSetAttribute(lstm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaFuncSetAttribute(lstm_tc_kernel)"); return PS_ERR_CUDA; }
-    attr_set[dev] = true;
-  }
+  static SmemOnce<4> once;
+  int dev = 0, n_sm = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (int rc = sm_count_of(dev, &n_sm)) return rc;
+  const char* where = "cudaFuncSetAttribute(lstm_tc_kernel)";
+  if (int rc = once.ensure(dev, 0, lstm_tc_kernel<false, false>, LT_SMEM, where)) return rc;
+  if (int rc = once.ensure(dev, 1, lstm_tc_kernel<false, true>, LT_SMEM, where)) return rc;
+  if (int rc = once.ensure(dev, 2, lstm_tc_kernel<true, false>, LT_SMEM, where)) return rc;
+  if (int rc = once.ensure(dev, 3, lstm_tc_kernel<true, true>, LT_SMEM, where)) return rc;
   // Sequences per CTA = 8 * spq.  A step costs about the same up to 32 sequences (the 192 MMAs of a step are the floor) and
   // grows with the number of 4-sequence chunks per warp beyond (measured on B200, H = 128: 3.7 / 4.7 / 5.1 us for
   // <= 32 / 48 / 64 sequences, profiles/r01_s3_lstm_notes.md); the launch takes ceil(CTAs / SMs) waves of L such steps.
   // Pick the cheapest, larger CTAs on a tie.
-  static int n_sm[64] = {};
-  if (!n_sm[dev]) {
-    e = cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) { set_cuda_error(e, "cudaDeviceGetAttribute"); return PS_ERR_CUDA; }
-  }
-  static int spq_env = -1;
-  if (spq_env < 0) { const char* ev = getenv("PS_LSTM_SPQ"); spq_env = ev ? atoi(ev) : 0; }
+  static EnvInt spq_e;
+  const int spq_env = spq_e.get("PS_LSTM_SPQ", 0);
   int spq = 8;
   if (spq_env >= 1 && spq_env <= 8) {
     spq = spq_env;
@@ -484,13 +483,17 @@ int lstm_tc_launch(const ps_lstm_t& d, cudaStream_t s) {
     static const int step_cost[9] = {0, 37, 37, 37, 37, 47, 47, 51, 51};
     int64_t best = 0;
     for (int c = 8; c >= 1; --c) {
-      const int64_t waves = cdiv(cdiv(d.n_seq, 8 * c) * d.D, n_sm[dev]);
+      const int64_t waves = cdiv(cdiv(d.n_seq, 8 * c) * d.D, n_sm);
       const int64_t cost = waves * step_cost[c];
       if (c == 8 || cost < best) { best = cost; spq = c; }
     }
   }
-  static int dbg = -1;
-  if (dbg < 0) { const char* ev = getenv("PS_LSTM_DBG"); dbg = ev ? atoi(ev) : 0; }
+#ifdef PS_EXPERIMENTS
+  static EnvInt dbg_e;  // bottleneck experiments (results are garbage): compiled out of the release build
+  const int dbg = dbg_e.get("PS_LSTM_DBG", 0);
+#else
+  const int dbg = 0;
+#endif
   const int64_t nblk = cdiv(d.n_seq, 8 * spq);
   if (nblk > 2147483647LL) return PS_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nblk, (unsigned)d.D);

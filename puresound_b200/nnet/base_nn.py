@@ -177,6 +177,15 @@ class SoTaskWrapModule(nn.Module):
         for m in self._host_hooks:
             m.host_prepare(device)
 
+    def _mode_signature(self):
+        """train/eval flags of all sub-modules and the dropout probabilities, folded to one hashable value."""
+        h = 0
+        for i, m in enumerate(self.modules()):
+            h = (h * 1000003 + (2 * i + 1) * int(m.training)) & 0xFFFFFFFFFFFF
+            if isinstance(m, nn.Dropout):
+                h = (h * 1000003 + hash(float(m.p))) & 0xFFFFFFFFFFFF
+        return h
+
     def _param_signature(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
@@ -190,7 +199,11 @@ class SoTaskWrapModule(nn.Module):
         if not self.use_cuda_graph:
             return self._inference_cl(noisy, enroll, constrain)
         sig = self._param_signature()
-        key = (tuple(noisy.shape), None if enroll is None else tuple(enroll.shape), constrain, noisy.device.index)
+        # everything a replay would otherwise silently ignore is part of the key: shapes, device, the mask / output
+        # constraints and the train/eval mode of every sub-module (train-mode BatchNorm / dropout must keep raising)
+        key = (tuple(noisy.shape), None if enroll is None else tuple(enroll.shape), constrain, noisy.device.index,
+               str(self.mask_constraint).lower(), str(self.output_constraint).lower(), self.f_type, self.mask_type,
+               self.drop_first_bin, self._mode_signature())
         ent = self._graphs.get(key)
         if ent is not None and ent["sig"] != sig:
             self._graphs.clear()
@@ -208,6 +221,9 @@ class SoTaskWrapModule(nn.Module):
             with torch.cuda.graph(g):
                 ent["out"] = self._inference_cl(ent["in"], ent["enroll"], constrain)
             ent["graph"] = g
+            # device tensors the captured kernels read by raw pointer but that live in module-level caches (the iSTFT
+            # window-sum-square tables): referenced here so a cache eviction cannot free them under a live graph
+            ent["keep"] = [list(m._wsum.values()) for m in self.modules() if hasattr(m, "_wsum")]
         else:
             ent["in"].copy_(noisy, non_blocking=True)
             if enroll is not None:

@@ -182,6 +182,9 @@ class GatedTCN(nn.Module):
         width = H + (E if concat else 0)
         rows_in = T + 2 * p
         L_out = rows_in - (self.kernel - 1) * self.dilation
+        if L_out < T or (not self.causal and L_out != T):
+            # odd (kernel-1)*dilation without causal trim: the reference fails on `x + res` (conv_tasnet.py:213) - fail as loudly
+            raise RuntimeError(f"The size of tensor a ({L_out}) must match the size of tensor b ({T}) at non-singleton dimension 2")
         xp = torch.zeros(N, rows_in, width, device=x.device, dtype=torch.float32)
         inner = xp.view(-1)[p * width:]  # first un-padded row
         ops.linear(x, self.in_conv.weight.view(H, C), out=inner, y_strides=(rows_in * width, width),

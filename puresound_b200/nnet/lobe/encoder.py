@@ -325,7 +325,11 @@ class ConvEncDec(nn.Module):
             out_len = self.n_fft + self.hop_length * (T - 1)
             stack = w2.unsqueeze(-1).repeat(1, T).unsqueeze(0)
             ws = torch.nn.functional.fold(stack, (1, out_len), kernel_size=(1, self.n_fft), stride=self.hop_length).flatten()
-            self._wsum = {key: ws.to(device)}
+            # insert, never replace: a captured CUDA graph bakes in the device pointer of the entry it was captured with
+            # (SoTaskWrapModule keeps several shape slots alive), so an entry must stay allocated while the module lives
+            if len(self._wsum) >= 64:
+                self._wsum.pop(next(iter(self._wsum)))
+            self._wsum[key] = ws.to(device)
         return self._wsum[key]
 
     def decode_cl(self, feats: torch.Tensor, drop_first_bin: bool, constraint: int = 0) -> torch.Tensor:

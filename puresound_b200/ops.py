@@ -20,8 +20,30 @@ Tensor = torch.Tensor
 
 #: kernels launched through this module since the last reset (bench.py's gpu_launches)
 launch_count = 0
-#: when a list, every ps_gemm launch appends (start_event, end_event, (batch*rows, M, K)) — bench.py's live roofline timing
-gemm_events = None
+#: when a list, every ps_gemm / ps_lstm / ps_dwconv launch appends (kind, start_event, end_event, shape) - bench.py's live
+#: per-kernel roofline timing (CUDA events on the launching stream); shape = (rows, M, K) for "gemm",
+#: (n_seq, L, H, D, K_in) for "lstm" (K_in > 0 when the input projection is fused), (batch, T, C) for "dwconv"
+kernel_events = None
+
+
+class _Timed:
+    """Context manager: bracket one launch with a CUDA-event pair when bench.py asked for per-kernel timing."""
+
+    __slots__ = ("kind", "shape", "ev")
+
+    def __init__(self, kind, shape):
+        self.kind, self.shape, self.ev = kind, shape, None
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *a):
+        if self.ev is not None:
+            self.ev[1].record()
+            kernel_events.append((self.kind, self.ev[0], self.ev[1], self.shape))
 #: force a GEMM back end for every call (tests / A-B runs); None = per-call choice
 force_gemm_backend: Optional[int] = None
 
@@ -84,29 +106,21 @@ class FoldedAffine:
     """gLN / gGN folded to the per-item per-channel affine a consumer prologue applies: scale, shift [B, C]."""
     scale: Tensor
     shift: Tensor
-
-
-_fin_counters = {}
-
-
-def _fin_counter(device, batch: int) -> Tensor:
-    """[>= batch] uint32 zeros, one per device: the producer kernels count finished tiles per item in it and leave it zero."""
-    c = _fin_counters.get(device)
-    if c is None or c.numel() < batch:
-        c = torch.zeros(max(batch, 4096), device=device, dtype=torch.int32)
-        _fin_counters[device] = c
-    return c
+    counter: Optional[Tensor] = None    # the producer's per-item tile counter (kept alive with the result)
 
 
 def _set_fin(d, fin, batch: int, Cn: int, device):
-    """fin = (gamma, beta, eps): ask the producer kernel to also emit the folded norm affine (fused ps_stats_finalize)."""
+    """fin = (gamma, beta, eps): ask the producer kernel to also emit the folded norm affine (fused ps_stats_finalize).
+    The per-item tile counter is allocated (zeroed) per call and kept alive by the returned FoldedAffine: no buffer is
+    shared between launches, streams or captured graphs."""
     gamma, beta, eps = fin
     scale = torch.empty(batch, Cn, device=device, dtype=torch.float32)
     shift = torch.empty_like(scale)
+    counter = torch.zeros(batch, device=device, dtype=torch.int32)
     d.fin_gamma, d.fin_beta, d.fin_eps = _p(gamma), _p(beta), float(eps)
     d.fin_scale, d.fin_shift = scale.data_ptr(), shift.data_ptr()
-    d.fin_counter = _fin_counter(device, batch).data_ptr()
-    return FoldedAffine(scale, shift)
+    d.fin_counter = counter.data_ptr()
+    return FoldedAffine(scale, shift, counter)
 
 
 def gemm(
@@ -151,14 +165,8 @@ def gemm(
     folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
     if ln is not None:
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(ln[0]), _p(ln[1]), float(ln[2])
-    ev = None
-    if gemm_events is not None:
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record()
-    _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
-    if ev is not None:
-        ev[1].record()
-        gemm_events.append((ev[0], ev[1], (batch * rows, M, K)))
+    with _Timed("gemm", (batch * rows, M, K)):
+        _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
     _launched()
     return Y, (folded if folded is not None else partials)
 
@@ -254,7 +262,8 @@ def dwconv(x: Tensor, w: Tensor, bias: Optional[Tensor], P: int, dilation: int, 
     d.pro_rowstats, d.pro_slope = _p(pro.rowstats), _p(pro.slope)
     d.stats_partials = _p(partials)
     folded = _set_fin(d, fin, B, Cn, x.device) if (want_stats and fin is not None) else None
-    _lib.check(lib.ps_dwconv(C.byref(d), _stream()), "ps_dwconv")
+    with _Timed("dwconv", (B, T, Cn)):
+        _lib.check(lib.ps_dwconv(C.byref(d), _stream()), "ps_dwconv")
     _launched()
     return y, (folded if folded is not None else partials)
 
@@ -368,7 +377,8 @@ def lstm(gx: Tensor, w_hh_t: Tensor, *, n_seq: int, L: int, H: int, D: int, inne
     d.out, d.hn, d.cn = out.data_ptr(), _p(hn), _p(cn)
     d.w_packed = _p(w_packed)
     d.gx_interleaved = 1 if (gx_interleaved and w_packed is not None) else 0
-    _lib.check(lib.ps_lstm(C.byref(d), _stream()), "ps_lstm")
+    with _Timed("lstm", (n_seq, L, H, D, 0)):
+        _lib.check(lib.ps_lstm(C.byref(d), _stream()), "ps_lstm")
     _launched()
     return out, ((hn, cn) if want_state else None)
 

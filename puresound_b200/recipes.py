@@ -137,6 +137,14 @@ def baseline_config(name: str, verbose: bool = False) -> SoTaskWrapModule:
             ConvTasNet(512, 0, False, tcn_kernel=3, tcn_dim=512, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8,
                        tcn_with_embed=[0] * 8, tcn_norm="gLN", dconv_norm="gGN", causal=False, tcn_layer="normal"),
             mask_constraint="ReLU", verbose=verbose)
+    if name == "cfg1b":
+        # the reading of BASELINE's (N=512, B=128, H=512) that honours B - a 128-wide residual stream
+        # (reference constructor conv_tasnet.py:239-254 with input_dim=128) around 512-wide blocks; 9,583,688 parameters
+        return SoTaskWrapModule(
+            FreeEncDec(32, 128, 16),
+            ConvTasNet(128, 0, False, tcn_kernel=3, tcn_dim=512, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8,
+                       tcn_with_embed=[0] * 8, tcn_norm="gLN", dconv_norm="gGN", causal=False, tcn_layer="normal"),
+            mask_constraint="ReLU", verbose=verbose)
     if name == "cfg3":
         return SoTaskWrapModule(
             FreeEncDec(32, 128, 16, output_active=True),

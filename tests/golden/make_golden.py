@@ -293,6 +293,42 @@ def full_pins():
         json.dump(pins, fh)
 
 
+@torch.no_grad()
+def round2_pins():
+    """Round-2 additions: the benched shape itself - cfg2 = the cfg1 model at batch 64 (items 0 / 31 / 63 kept) -
+    and cfg-1b (the B=128 reading, FreeEncDec(32,16,128) + ConvTasNet(128,...,tcn_dim=512), conv_tasnet.py:239-254)."""
+    pins = {}
+    stride = 997
+
+    def cfg1b():
+        return quiet(
+            SoTaskWrapModule,
+            encoder=FreeEncDec(32, 128, 16),
+            masker=ConvTasNet(128, 0, False, tcn_kernel=3, tcn_dim=512, repeat_tcn=3, tcn_dilated_basic=2, per_tcn_stack=8, tcn_with_embed=[0] * 8, tcn_norm="gLN", dconv_norm="gGN", causal=False, tcn_layer="normal"),
+            mask_constraint="ReLU",
+            verbose=False,
+        )
+
+    for name, build, n, keep in (("cfg1b", cfg1b, 2, [0, 1]), ("cfg2_b64", full_cfgs()["cfg1"][0], 64, [0, 31, 63])):
+        torch.manual_seed(0)
+        m = build().eval()
+        T.perturb_(m, seed=1)
+        mix, _ = T.noisy_speech(n, 64000, seed=1234)
+        y = m.inference(mix)
+        pins[name] = {
+            "params": sum(p.numel() for p in m.parameters()),
+            "state_checksum": T.state_checksum(m.state_dict()),
+            "batch": n, "length": 64000, "enroll_length": None, "input_seed": 1234, "enroll_seed": 4321, "stride": stride,
+            "out_len": y.shape[-1], "items": keep,
+            "out_abs_mean": float(y[keep].abs().mean()),
+            "out_clamped_frac": float((y[keep].abs() >= 1).float().mean()),
+            "samples": [[float(v) for v in y[i, ::stride]] for i in keep],
+        }
+        print(name, pins[name]["params"], pins[name]["state_checksum"], pins[name]["out_abs_mean"], pins[name]["out_clamped_frac"])
+    with open(os.path.join(HERE, "round2_pins.json"), "w") as fh:
+        json.dump(pins, fh)
+
+
 def _ref_init_model(name):
     spec = importlib.util.spec_from_file_location("ref_tse_model", os.path.join(REF, "egs/tse/model.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -672,6 +708,8 @@ if __name__ == "__main__":
         small_cases()
     if which in ("all", "full"):
         full_pins()
+    if which in ("all", "round2"):
+        round2_pins()
     if which in ("all", "skim"):
         skim_cases()
     if which in ("all", "real"):

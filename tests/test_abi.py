@@ -64,3 +64,24 @@ def test_argument_validation_without_gpu(lib):
         _lib.check(-1, "x")
     with pytest.raises(NotImplementedError):
         _lib.check(-2, "x")
+
+
+def test_integration_doc_struct_mirror_matches_library(lib):
+    """The ps_gemm_t ctypes mirror printed in INTEGRATION.md (what a reference maintainer would paste) has the size and
+    the field order of the real descriptor - a short struct would make the kernel read past it."""
+    from puresound_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = text[text.index("class ps_gemm_t(C.Structure)"):]
+    body = body[body.index("_fields_ = ["):body.index("]\n") + 1]
+    ns = {"C": ctypes}
+    exec(body.strip(), ns)  # noqa: S102  (a literal list of (name, ctype) pairs from our own document)
+    doc_fields = ns["_fields_"]
+
+    class Mirror(ctypes.Structure):
+        _fields_ = doc_fields
+
+    assert ctypes.sizeof(Mirror) == lib.ps_struct_size(0)
+    assert [n for n, _ in doc_fields] == [n for n, _ in _lib.GemmDesc._fields_]
+    for (n, t), (_, t2) in zip(doc_fields, _lib.GemmDesc._fields_):
+        assert ctypes.sizeof(t) == ctypes.sizeof(t2), n

@@ -64,6 +64,42 @@ def test_full_size_parity(name, backend):
     assert float((s_ours - s_ref).abs().max()) <= SISNR_TOL_DB
 
 
+@pytest.mark.parametrize("name", ["cfg2_b64", "cfg1b"])
+def test_benched_shape_parity(name):
+    """The benched cfg2 shape itself - the cfg1 model at batch 64 (255,936 GEMM rows, per-item gLN slots up to b = 63) - and
+    cfg-1b.  The GPU runs the WHOLE batch; the recorded items (0 / 31 / 63) are compared with the reference's own samples
+    (tests/golden/round2_pins.json) and with the oracle run on those items on the host (items never mix in eval mode)."""
+    from test_oracle_full_pins import load_pin
+
+    pin = load_pin(name)
+    torch.manual_seed(0)
+    m = recipes.baseline_config("cfg1b" if name == "cfg1b" else "cfg2").eval()
+    testing.perturb_(m, seed=1)
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, clean = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    items = pin["items"]
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    m = m.to("cuda")
+    for call in range(3):  # eager, capture, CUDA-graph replay (what bench.py times)
+        y = m.inference(mix)
+    pre = m.inference_pre_constraint(mix)
+    assert y.shape == (pin["batch"], pin["out_len"]) and torch.isfinite(y).all()
+    err_pin = (y[items][:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item()
+    y_ref = R.inference(sd, cfg, mix[items])
+    pre_ref = R.inference(sd, cfg, mix[items], pre_clamp=True)
+    err = (y[items] - y_ref).abs().max().item()
+    err_pre = ((pre[items] - pre_ref).abs() / pre_ref.abs().clamp(min=1.0)).max().item()
+    L = y.shape[-1]
+    d_sisnr = float((R.si_snr(y[items], clean[items][:, :L]) - R.si_snr(y_ref, clean[items][:, :L])).abs().max())
+    # every other item: the sharded result of the same batch must agree with itself item by item (batch-size independence)
+    alone = m.inference(mix[5:6])
+    err_alone = (alone - y[5:6]).abs().max().item()
+    print(f"{name}: items {items} max|dy|={err:.3e} (vs reference samples {err_pin:.3e}) pre-clamp={err_pre:.3e} dSI-SNR={d_sisnr:.2e} dB, "
+          f"item 5 alone vs in batch {err_alone:.3e}")
+    assert err_pin <= WAVE_TOL and err <= WAVE_TOL and err_pre <= WAVE_TOL and d_sisnr <= SISNR_TOL_DB
+    assert err_alone <= 1e-4
+
+
 @pytest.mark.parametrize("tag", ["speech_cfg1", "speech_cfg3", "speech_cfg4", "speech_veve", "white_a1_cfg1"])
 def test_real_speech_and_full_scale_noise(tag):
     """SURVEY.md 8d inputs (iii) — the reference's own two-speaker speech fixture (int16 samples carried in the golden file)

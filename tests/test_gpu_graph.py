@@ -105,3 +105,50 @@ def test_inference_stream_equals_inference(model):
     pairs = [(testing.noisy_speech(1, 16000, seed=40 + s)[0], testing.noisy_speech(1, 24000, seed=50 + s)[0]) for s in range(4)]
     for (x, e), y in zip(pairs, tse.inference_stream(pairs, depth=1)):
         assert torch.equal(y, tse.inference(x, e))
+
+
+def test_stft_model_alternating_lengths_replays_the_right_window_table():
+    """ConvEncDec caches the iSTFT window-sum-square table per frame count and a captured graph reads it by raw pointer:
+    two input lengths alternating (both graphs alive) must each keep their own table (the cache used to be
+    replaced, freeing the table under the other graph)."""
+    from puresound_b200 import recipes, testing
+
+    torch.manual_seed(0)
+    m = recipes.baseline_config("cfg4").eval()
+    testing.perturb_(m, seed=1)
+    m = m.to("cuda")
+    m.use_cuda_graph = True
+    enr = testing.noisy_speech(1, 24000, seed=3)[0].cuda()
+    xa = [testing.noisy_speech(1, 16000, seed=60 + i)[0].cuda() for i in range(4)]
+    xb = [testing.noisy_speech(1, 20480, seed=80 + i)[0].cuda() for i in range(4)]
+    for i in range(4):  # A eager, B eager, A capture, B capture, A replay, B replay, ...
+        for x in (xa[i], xb[i]):
+            y = m.inference(x, enr)
+            junk = torch.full((1, y.shape[1]), 7.0, device="cuda")  # same size class as a freed table would be
+            g, m.use_cuda_graph = m.use_cuda_graph, False
+            want = m.inference(x, enr)
+            m.use_cuda_graph = g
+            assert torch.equal(y, want), f"round {i}, L={x.shape[1]}"
+            del junk
+    assert len(m._graphs) == 2
+
+
+def test_mode_or_constraint_change_is_not_replayed(model):
+    """A captured graph is keyed on the train/eval flags and the mask / output constraints: changing them after capture
+    must not replay the old forward."""
+    from puresound_b200 import testing
+
+    model.use_cuda_graph = True
+    model.eval()
+    x = testing.noisy_speech(1, 16000, seed=12)[0].cuda()
+    for _ in range(3):
+        y0 = model.inference(x)
+    old = model.mask_constraint
+    try:
+        model.mask_constraint = "sigmoid"
+        y1 = model.inference(x)
+        assert not torch.equal(y0, y1)
+        assert torch.equal(y1, _eager(model, x))
+    finally:
+        model.mask_constraint = old
+    assert torch.equal(model.inference(x), y0)

@@ -74,3 +74,30 @@ def test_two_ranks_shard_without_collective(tmp_path):
                          mask_constraint="ReLU", verbose=False).eval()
     full = R.inference(m.state_dict(), D.describe(m), testing.white(5, 800, seed=3))
     assert torch.allclose(torch.cat([p["y"] for p in parts]), full, atol=1e-6)
+
+
+def test_sharded_separator_split_and_gather_order():
+    """ShardedSeparator's host logic with stub per-device runners (no GPU): contiguous slices, uneven batches, fewer items
+    than devices, outputs gathered in item order, enroll sliced with its mixture."""
+    from puresound_b200.sharding import ShardedSeparator
+
+    seen = []
+
+    def make(g):
+        def run(noisy, enroll, out):
+            seen.append((g, noisy.shape[0]))
+            out.copy_(noisy * (1 if enroll is None else 2) + (0 if enroll is None else enroll[:, :1]))
+            return None
+        return run
+
+    sep = ShardedSeparator(runners=[make(g) for g in range(4)])
+    x = torch.arange(7 * 5, dtype=torch.float32).view(7, 5)
+    assert torch.equal(sep.inference(x), x)
+    assert seen == [(0, 2), (1, 2), (2, 2), (3, 1)]
+    e = torch.arange(7, dtype=torch.float32).view(7, 1).repeat(1, 3)
+    assert torch.equal(sep.inference(x, e), 2 * x + e[:, :1])
+    seen.clear()
+    assert torch.equal(sep.inference(x[:2]), x[:2])
+    assert seen == [(0, 1), (1, 1)]
+    with pytest.raises(ValueError):
+        sep.inference(x, e[:3])

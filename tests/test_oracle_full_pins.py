@@ -15,9 +15,28 @@ from puresound_b200 import recipes, testing
 
 
 def load_pin(name):
-    """full_size_pins.json (the BASELINE configs) or gated_pins.json (cfg4 with GatedTCN blocks)."""
-    with open(os.path.join(GOLDEN, "gated_pins.json" if name == "cfg4_gated" else "full_size_pins.json")) as fh:
+    """full_size_pins.json (the BASELINE configs), gated_pins.json (cfg4 with GatedTCN blocks) or
+    round2_pins.json (cfg-1b and the benched cfg2 shape: the cfg1 model at batch 64, items 0 / 31 / 63 recorded)."""
+    f = {"cfg4_gated": "gated_pins.json", "cfg1b": "round2_pins.json", "cfg2_b64": "round2_pins.json"}.get(name, "full_size_pins.json")
+    with open(os.path.join(GOLDEN, f)) as fh:
         return json.load(fh)[name]
+
+
+@pytest.mark.parametrize("name", ["cfg1b", "cfg2_b64"])
+def test_oracle_matches_reference_round2_pins(name):
+    """cfg-1b and cfg2 itself: the reference ran the whole 64-utterance batch; items never mix in eval
+    mode, so the oracle is checked on the recorded items only (0 / 31 / 63 of the same seeded batch)."""
+    pin = load_pin(name)
+    torch.manual_seed(0)
+    m = recipes.baseline_config("cfg1b" if name == "cfg1b" else "cfg2").eval()
+    testing.perturb_(m, seed=1)
+    assert m.overall_parameters == pin["params"]
+    assert testing.state_checksum(m.state_dict()) == pytest.approx(pin["state_checksum"], rel=1e-12)
+    mix, _ = testing.noisy_speech(pin["batch"], pin["length"], seed=pin["input_seed"])
+    y = R.inference(m.state_dict(), D.describe(m), mix[pin["items"]])
+    assert y.shape[-1] == pin["out_len"]
+    assert (y[:, :: pin["stride"]] - torch.tensor(pin["samples"])).abs().max().item() <= 2e-5
+    assert abs(float(y.abs().mean()) - pin["out_abs_mean"]) <= 1e-6
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5_offline", "veve_dprnn_v0_causal", "cfg4_gated"])
