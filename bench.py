@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """Headline benchmark: audio-seconds per second of the separator forward on N B200s.
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2] [--impl ours|reference] [--scaling auto|strong|weak]
 
 A *step* is one pass of the hot path over one batch of synthetic 16 kHz audio.
 The workload is BASELINE.json configs[1] (cfg2: Conv-TasNet N=512,H=512,P=3,X=8,R=3,
-batch 64 x 4 s) per GPU; utterances are independent, so ranks shard them with no
-data-path collective (weak scaling: 64 utterances on every rank).  One JSON line is
-printed by rank 0 (see README / DESIGN.md for the keys).
+ONE batch of 64 x 4 s).  Utterances are independent, so ranks shard them with no
+data-path collective.  With N > 1 ranks the headline `value` is STRONG scaling - the
+same 64-utterance batch cut into contiguous slices of 64/N per rank (BASELINE configs[1],
+SURVEY.md 8e) - and the weak-scaling figure (64 utterances on every rank) is measured in
+the same run and reported under the `weak` key.  cfg5 (streams per GPU) is weak by
+definition.  One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
 
-`--impl reference` times the reference's CPU forward of the same path on the host
-cores: the oracle port (oracle/separator_ref.py, which issues the same ATen calls
-the reference does) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, installed by
+__graft_entry__.build()) - its SoTaskWrapModule.inference on the host cores - on a
+bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -30,10 +33,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SR = 16000
+SCALING_OF = {"strong": "strong", "weak": "weak"}
 WORKLOADS = {
     # name: (config, batch per GPU, samples, enroll samples, description)
     "cfg1": ("cfg1", 1, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) 1 x 4 s @16 kHz"),
-    "cfg2": ("cfg2", 64, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) batch 64 x 4 s @16 kHz per GPU"),
+    # the reading of (N=512, B=128, H=512) that honours B (128-wide residual stream, 512-wide blocks)
+    "cfg1b": ("cfg1b", 64, 64000, None, "Conv-TasNet NS cfg-1b (encoder/residual width B=128, H=512, P=3, X=8, R=3) batch 64 x 4 s @16 kHz"),
+    "cfg2": ("cfg2", 64, 64000, None, "Conv-TasNet NS (N=512,H=512,P=3,X=8,R=3) batch 64 x 4 s @16 kHz"),
     "cfg3": ("cfg3", 32, 160000, None, "DPRNN-LSTM (chunk 100, 6 blocks, H=128 bi) batch 32 x 10 s @16 kHz per GPU"),
     "cfg4": ("cfg4", 64, 64000, 96000, "TSE: STFT 512/128 + TCN (H=256, dvec 192) + speaker net, 64 x (4 s mix + 6 s enroll) per GPU"),
     # widening row: cfg4 with GatedTCN blocks as in the reference's tse_unet_tcn recipes
@@ -103,11 +109,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_inputs(workload: str, rank: int, batch=None):
+def build_inputs(workload: str, rank: int, batch=None, span=None):
+    """Seeded synthetic noisy speech.  span=(a, b): rows [a, b) of the ONE global batch (strong scaling: every rank derives
+    its slice from the same seeded batch); otherwise a per-rank batch (weak scaling)."""
     from puresound_b200 import testing
 
     cfg, n, L, Le, _ = WORKLOADS[workload]
     n = batch or n
+    if span is not None:
+        mix, _ = testing.noisy_speech(n, L, seed=1234)
+        enr = testing.noisy_speech(n, Le, seed=4321)[0] if Le else None
+        a, b = span
+        return mix[a:b].contiguous(), (enr[a:b].contiguous() if enr is not None else None)
     mix, _ = testing.noisy_speech(n, L, seed=1234 + rank)
     enr = testing.noisy_speech(n, Le, seed=4321 + rank)[0] if Le else None
     return mix, enr
@@ -122,31 +135,68 @@ def build_model(workload: str):
     return m
 
 
-def gemm_flops_bytes(model, workload):
-    """Algorithmic FLOPs (2*MAC) and fp32 bytes of ONE launch of the dominant kernel: a 1x1-conv GEMM of the
-    TCN stack, [batch*T, K] x [M, K]^T (reads X and W once, writes Y once; +residual for out_conv)."""
-    _, n, L, _, _ = WORKLOADS[workload]
-    enc = model.encoder
-    T = (L - enc.win_length) // enc.hop_length + 1
-    mk = model.masker
-    if not hasattr(mk, "tcn_dim"):
-        return None
-    M, K = mk.tcn_dim, mk.input_dim
-    rows = n * T
-    return {"flops": 2.0 * rows * M * K, "bytes": 4.0 * (rows * K + rows * M + M * K), "rows": rows, "M": M, "K": K}
-
-
-def ncu_traffic(kernel: str, fb):
+def ncu_traffic(kernel: str, shape):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/traffic.json names the report it was read from); None when the workload's shape differs."""
+    capture (profiles/traffic.json names the report it was read from); None when no capture of this shape is committed."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as fh:
-        t = json.load(fh).get(kernel)
-    if not t or [t["rows"], t["M"], t["K"]] != [fb["rows"], fb["M"], fb["K"]]:
-        return None
-    return t["dram_bytes_per_launch"]
+        table = json.load(fh)
+    for key, t in table.items():
+        if key.split("@")[0] == kernel and list(t.get("shape", [t.get("rows"), t.get("M"), t.get("K")])) == list(shape):
+            return t["dram_bytes_per_launch"]
+    return None
+
+
+def kernel_rooflines(events, eager_ms, hbm_peak, tf_peak, peak_kind):
+    """Group the live CUDA-event pairs of the eager pass by (kernel kind, shape) and put each group against the roofline
+    that bounds it.  Algorithmic work per launch (DESIGN.md section 4 / SURVEY.md 8d):
+      gemm   [rows, K] x [M, K]^T : 2*rows*M*K FLOP (3 tensor passes are ISSUED for the 3xBF16 split; frac counts useful
+                                    FLOPs, so 1/3 is its ceiling), bytes 4*(rows*K + rows*M + M*K)
+      lstm   n_seq x L x D, H (+ fused input projection K_in): 2*4H*(H + K_in) FLOP per step, sequence and direction (3 passes)
+      dwconv [B, T, C]            : 2*4*B*T*C bytes (one read, one write)
+    Returns the groups sorted by their share of the step; the first is the dominant kernel."""
+    groups = {}
+    for kind, a, b, shape in events:
+        groups.setdefault((kind, tuple(shape)), []).append(a.elapsed_time(b))
+    out = []
+    for (kind, shape), durs in groups.items():
+        avg_ms = sum(durs) / len(durs)
+        r = {"kernel": None, "shape": list(shape), "avg_launch_ms": avg_ms, "launches_timed": len(durs), "share_of_step": sum(durs) / eager_ms}
+        if kind == "gemm":
+            rows, M, K = shape
+            flops, nbytes = 2.0 * rows * M * K, 4.0 * (rows * K + rows * M + M * K)
+            t_tensor, t_hbm = 3 * flops / (tf_peak * 1e12), nbytes / (hbm_peak * 1e9)
+            r["kernel"] = "ps_gemm (1x1 conv / linear, %d x %d x %d)" % (rows, M, K)
+            if t_tensor >= t_hbm:  # tensor-bound shape
+                ach = flops / (avg_ms / 1e3) / 1e12
+                r.update({"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "tensor_passes": 3,
+                          "issued_frac": 3 * ach / tf_peak, "algorithmic_bytes": nbytes, "hbm_frac_if_memory_bound": nbytes / (avg_ms / 1e3) / 1e9 / hbm_peak})
+            else:
+                ach = nbytes / (avg_ms / 1e3) / 1e9
+                r.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes": nbytes})
+            r["traffic"] = ncu_traffic("gemm", shape)
+        elif kind == "lstm":
+            n_seq, L, H, D, K_in = shape
+            flops = 2.0 * 4 * H * (H + K_in) * n_seq * L * D
+            ach = flops / (avg_ms / 1e3) / 1e12
+            r.update({"kernel": "ps_lstm (recurrence%s, %d seq x %d steps x %d dir, H=%d)" % (" + input projection" if K_in else "", n_seq, L, D, H),
+                      "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "tensor_passes": 3,
+                      "issued_frac": 3 * ach / tf_peak, "step_latency_us": 1e3 * avg_ms / L,
+                      "note": "a recurrence: L dependent steps per launch, so latency per step (step_latency_us) bounds it before the tensor peak does",
+                      "traffic": ncu_traffic("lstm", shape)})
+        elif kind == "dwconv":
+            B, T, Cn = shape
+            nbytes = 2.0 * 4 * B * T * Cn
+            ach = nbytes / (avg_ms / 1e3) / 1e9
+            r.update({"kernel": "ps_dwconv (dilated depthwise conv + norm/PReLU prologue + Welford partials, %d x %d x %d)" % (B, T, Cn),
+                      "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes": nbytes,
+                      "traffic": ncu_traffic("dwconv", shape)})
+        r["peak_source"] = f"{peak_kind} ({'bf16 sustained' if r.get('bound') == 'tensor' else 'copy bandwidth'})"
+        out.append(r)
+    out.sort(key=lambda r: -r["share_of_step"])
+    return out
 
 
 def streaming_bench(args, rank, world, local_rank):
@@ -205,6 +255,24 @@ def streaming_bench(args, rank, world, local_rank):
     ms = sharding.max_over_ranks(sum(lat256) / len(lat256), dev)
     e2e_ms = sharding.max_over_ranks(e2e256, dev)
     audio_s = S * hop / SR
+    # roofline of a hop: every weight is read once per hop (all S streams share it) and every stream
+    # touches (P-1) taps + one new slot of each block's dilation-history ring - memory traffic that has to move whatever
+    # the kernel structure is; the GEMM FLOPs (2 * 19.24 MMAC per stream-hop) are 3 passes of 9.85 GFLOP = 21 us of tensor time
+    hbm_peak, tf_peak, peak_kind = peaks()
+    w_bytes = 4 * sum(p.numel() for p in m.parameters())
+    blocks = [b for st in m.masker.tcn_list for b in st]
+    state_bytes = 4 * S * sum(b.kernel * b.hid_channels for b in blocks)
+    hop_bytes = float(w_bytes + state_bytes)
+    roof = {"bound": "hbm", "kernel": f"one hop of {S} streams = CUDA-graph replay of {launches // steps} kernels (encoder, 24 TCN blocks, decoder)",
+            "achieved": hop_bytes / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hop_bytes / (ms / 1e3) / 1e9 / hbm_peak,
+            "traffic": None, "algorithmic_bytes": hop_bytes, "weights_bytes": w_bytes, "state_bytes": state_bytes,
+            "peak_source": f"{peak_kind} (copy bandwidth)", "avg_launch_ms": ms, "launches_timed": steps,
+            "note": "latency-bound: a hop is a chain of dependent small kernels; frac is the hop's unavoidable bytes against the HBM peak"}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        a_s, times, kind = cpu_reference_run("cfg5", 4, 2, 1, os.cpu_count() or 1)
+        cpu = {"value": a_s / min(times), "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": kind,
+               "sample": "offline causal forward of 4 x 4 s utterances (the reference has no frame-by-frame Conv-TasNet), best of 2 after 1 warm-up"}
     if rank == 0:
         pct = lambda v, q: v[min(len(v) - 1, int(q * len(v)))]
         print(json.dumps({
@@ -217,7 +285,7 @@ def streaming_bench(args, rank, world, local_rank):
             "clocks": clk.summary(),
             "e2e": {"value": world * audio_s / (e2e_ms / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": S * hop * 4, "d2h_bytes_per_step": S * hop * 4,
                     "ms_per_step": e2e_ms},
-            "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }))
     return 0
 
@@ -276,6 +344,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="utterances in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="N > 1: strong = ONE batch cut into slices (BASELINE configs[1]); weak = a full batch on every rank; auto = strong, with the weak figure under the `weak` key")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement of a strong-scaling run")
     ap.add_argument("--gemm-backend", default="auto", choices=["auto", "simt"],
                     help="auto: tcgen05 3xBF16 GEMM where eligible, exact-fp32 CUDA-core GEMM elsewhere; simt: CUDA-core everywhere")
     args = ap.parse_args()
@@ -285,7 +356,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg_name, batch, L, Le, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "ns_dparn_v0": 4, "cfg5": 1,
+    sample_batch = args.cpu_sample_batch or {"cfg1": 1, "cfg1b": 8, "cfg2": 4, "cfg3": 2, "cfg4": 8, "cfg4_gated": 4, "tse_unet_tcn_v0": 2, "ns_dpcrn_v0": 4, "ns_dparn_v0": 4, "cfg5": 4,
                                                 "tse_skim_v0_causal": 2, "tse_skim_v2_causal": 2}[args.workload]
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -314,7 +385,7 @@ def main():
         return streaming_bench(args, rank, world, local_rank)
 
     # ------------------------------------------------------------------ our arm (B200)
-    from puresound_b200 import ops
+    from puresound_b200 import ops, sharding
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -322,23 +393,16 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL carries no data of the path: it times it (a barrier around the timed region, one scalar MAX of the device time)
         dist.init_process_group("nccl", device_id=dev)
     ops.require_device()
     if args.gemm_backend != "auto":
         ops.force_gemm_backend = ops.GEMM_SIMT
 
+    scaling = args.scaling if args.scaling != "auto" else ("strong" if world > 1 else "weak")
+    if scaling == "strong" and batch < world:
+        scaling = "weak"  # nothing to split (cfg1: one utterance)
     model = build_model(args.workload).to(dev)
-    mix_h, enr_h = build_inputs(args.workload, rank)
-    mix_h = mix_h.pin_memory()
-    enr_h = enr_h.pin_memory() if enr_h is not None else None
-    mix_d = mix_h.to(dev)
-    enr_d = enr_h.to(dev) if enr_h is not None else None
-    audio_s_rank = batch * L / SR
-
-    def step_resident():
-        return model.inference(mix_d, enr_d)  # public API, device tensors in and out (CUDA-graph replay after two calls)
-
-    from puresound_b200 import sharding
 
     def barrier():
         sharding.barrier(dev)
@@ -346,33 +410,51 @@ def main():
     def max_over_ranks(ms: float) -> float:
         return sharding.max_over_ranks(ms, dev)
 
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            y = step_resident()
-        barrier()
-        # ---- value: inputs resident in HBM, device-timed; the public API replays its captured CUDA graph ----
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local_rank) as clk:
-            e0.record()
-            for _ in range(args.steps):
-                y = step_resident()
-            e1.record()
+    def timed_resident(mix_d, enr_d, steps, warm):
+        """K device-timed replays of the public API on resident inputs; returns (ms for the K steps, clock summary, last result)."""
+        with torch.no_grad():
+            for _ in range(warm):
+                y = model.inference(mix_d, enr_d)
             barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        # ---- roofline pass: the same K steps launched eagerly (no graph) with a CUDA-event pair around every GEMM on
-        #      the launching stream, which also counts the kernels of a step ----
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local_rank) as clk:
+                e0.record()
+                for _ in range(steps):
+                    y = model.inference(mix_d, enr_d)  # public API, device tensors in and out (CUDA-graph replay)
+                e1.record()
+                barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), clk.summary(), y
+
+    # the rank's share of the job
+    if scaling == "strong":
+        a, b = sharding.shard_slice(batch, rank, world)
+        mix_h, enr_h = build_inputs(args.workload, rank, span=(a, b))
+        job_audio_s = batch * L / SR           # ONE batch for the whole job
+    else:
+        mix_h, enr_h = build_inputs(args.workload, rank)
+        job_audio_s = world * batch * L / SR   # a full batch per rank
+    mix_h = mix_h.pin_memory()
+    enr_h = enr_h.pin_memory() if enr_h is not None else None
+    mix_d = mix_h.to(dev)
+    enr_d = enr_h.to(dev) if enr_h is not None else None
+    warm = max(args.warmup, 3)
+
+    ms, clocks, y = timed_resident(mix_d, enr_d, args.steps, warm)
+    with torch.no_grad():
+        # ---- roofline pass: the same K steps launched eagerly (no graph) with a CUDA-event pair around every GEMM / LSTM /
+        #      depthwise-conv launch on the launching stream, which also counts the kernels of a step ----
         graphed, model.use_cuda_graph = model.use_cuda_graph, False
-        ops.gemm_events = []
+        ops.kernel_events = []
         launches0 = ops.launch_count
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
         for _ in range(args.steps):
-            y = step_resident()
+            y = model.inference(mix_d, enr_d)
         r1.record()
         barrier()
         launches = ops.launch_count - launches0
         eager_ms = r0.elapsed_time(r1)
-        gemm_ev, ops.gemm_events = ops.gemm_events, None
+        events, ops.kernel_events = ops.kernel_events, None
         model.use_cuda_graph = graphed
         # ---- e2e: the public API with HOST buffers; H2D of the inputs and D2H of the result inside the timed region ----
         for _ in range(2):
@@ -400,49 +482,56 @@ def main():
         assert n_out == args.steps
     assert torch.isfinite(yh).all()
 
-    value = world * audio_s_rank * args.steps / (ms / 1e3)
-    e2e_value = world * audio_s_rank * args.steps / (e2e_ms / 1e3)
+    value = job_audio_s * args.steps / (ms / 1e3)
+    e2e_value = job_audio_s * args.steps / (e2e_ms / 1e3)
     h2d = mix_h.numel() * 4 + (enr_h.numel() * 4 if enr_h is not None else 0)
     d2h = yh.numel() * 4
 
+    # ---- weak-scaling figure beside the strong one (N > 1): a full batch on every rank, same timing rules ----
+    weak = None
+    if world > 1 and scaling == "strong" and not args.no_weak:
+        wm, we = build_inputs(args.workload, rank)
+        wm_d, we_d = wm.to(dev), (we.to(dev) if we is not None else None)
+        wms, _, _ = timed_resident(wm_d, we_d, args.steps, warm)
+        weak = {"value": world * batch * L / SR * args.steps / (wms / 1e3), "unit": "audio-s/s", "ms_per_step": wms / args.steps,
+                "batch_per_rank": batch, "scaling": "weak"}
+        del wm_d, we_d
+
     hbm_peak, tf_peak, peak_kind = peaks()
+    roofs = kernel_rooflines(events, eager_ms, hbm_peak, tf_peak, peak_kind) if events else []
     roof = None
-    fb = gemm_flops_bytes(model, args.workload)
-    if fb is not None and gemm_ev:
-        # dominant kernel = the dense 1x1-conv GEMM of the TCN blocks (same shape for pointwise / out_conv when C == H)
-        durs = [a.elapsed_time(b) for (a, b, shape) in gemm_ev if shape == (fb["rows"], fb["M"], fb["K"])]
-        if durs:
-            avg_ms = sum(durs) / len(durs)
-            achieved = fb["flops"] / (avg_ms / 1e3) / 1e12
-            roof = {"bound": "tensor", "kernel": "ps_gemm (1x1 conv, %d x %d x %d)" % (fb["rows"], fb["M"], fb["K"]),
-                    "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": ncu_traffic("gemm_pair_kernel" if os.environ.get("PS_TC_KERNEL", "pair")[0] != "s" else "gemm_tc_kernel", fb),
-                    "peak_source": f"{peak_kind} bf16 sustained", "avg_launch_ms": avg_ms, "launches_timed": len(durs),
-                    "share_of_step": sum(durs) / eager_ms, "eager_ms_per_step": eager_ms / args.steps,
-                    "tensor_passes": 3, "issued_frac": 3 * achieved / tf_peak,
-                    "algorithmic_bytes": fb["bytes"], "hbm_frac_if_memory_bound": fb["bytes"] / (avg_ms / 1e3) / 1e9 / hbm_peak,
-                    "note": "3xBF16 split: useful FLOPs / measured bf16 peak (three tensor passes are issued, so 1/3 is the ceiling of frac); "
-                            "the step runs at the 1000 W power cap (see clocks.reasons)"}
+    if roofs:
+        roof = dict(roofs[0])
+        roof["eager_ms_per_step"] = eager_ms / args.steps
+        if roof.get("bound") == "tensor":
+            roof["note"] = ("3xBF16 split: useful FLOPs / measured bf16 peak (three tensor passes are issued, so 1/3 is the ceiling of frac); "
+                            "the step runs at the 1000 W power cap (see clocks.reasons)" + ("; " + roof["note"] if roof.get("note") else ""))
+        roof["other_kernels"] = [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "launches_timed", "share_of_step") if k in r}
+                                 for r in roofs[1:4]]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        audio_s, times = cpu_reference_run(args.workload, sample_batch, 2, 1, cores)
-        cpu = {"value": audio_s / min(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
+        audio_s, times, kind = cpu_reference_run(args.workload, sample_batch, 2, 1, cores)
+        cpu = {"value": audio_s / min(times), "unit": "audio-s/s", "cores": cores, "kind": kind,
                "sample": f"{sample_batch} x {L / SR:.0f} s utterances of the {batch}-utterance batch, best of 2 after 1 warm-up"}
 
     if rank == 0:
+        per_rank = mix_h.shape[0]
         print(json.dumps({
-            "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "l2": "activations (524 MB per tensor at cfg2) exceed the 126 MB L2",
                                             "gemm_backend": args.gemm_backend, "accumulate": "fp32",
+                                            "sharding": (f"one batch of {batch} utterances cut into contiguous slices, {per_rank} on rank 0; no data-path collective "
+                                                         "(NCCL only for the timing barrier and the MAX of the device time)") if scaling == "strong"
+                                            else f"{batch} utterances on every rank; no data-path collective (NCCL only for the timing barrier and the MAX of the device time)",
                                             "timed_region": "model.inference(device tensors): CUDA-graph replay of the whole forward",
-                                            "roofline_pass": "the same K steps re-run eagerly with a CUDA-event pair around every GEMM launch"},
-            "clocks": clk.summary(), "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                           "ms_per_step": e2e_ms / args.steps, "api": "model.inference_stream(host batches, reuse_host_buffers=True): H2D / forward / D2H on three streams, results in a ring of pinned buffers",
-                                           "sequential_api_ms_per_step": e2e_seq_ms / args.steps,
-                                           "sequential_api_value": world * audio_s_rank * args.steps / (e2e_seq_ms / 1e3)},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                                            "roofline_pass": "the same K steps re-run eagerly with a CUDA-event pair around every GEMM / LSTM / depthwise-conv launch"},
+            "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                      "ms_per_step": e2e_ms / args.steps, "api": "model.inference_stream(host batches, reuse_host_buffers=True): H2D / forward / D2H on three streams, results in a ring of pinned buffers",
+                                      "sequential_api_ms_per_step": e2e_seq_ms / args.steps,
+                                      "sequential_api_value": job_audio_s * args.steps / (e2e_seq_ms / 1e3)},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "weak": weak,
         }))
     if dist is not None:
         dist.destroy_process_group()

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpuresound_b200.so")
+# PS_B200_LIB: path of another build of the same library (profiling runs load the -DPS_EXPERIMENTS build this way)
+LIB_PATH = os.environ.get("PS_B200_LIB") or os.path.join(HERE, "libpuresound_b200.so")
 
 P = C.c_void_p
 I64 = C.c_int64
@@ -94,6 +95,7 @@ SIGNATURES = {
     "ps_struct_size": (I64, [C.c_int]),
     "ps_gemm": (C.c_int, [C.POINTER(GemmDesc), P]),
     "ps_gemm_stats_slots": (I64, [I64, I64]),
+    "ps_gemm_path": (I32, [C.POINTER(GemmDesc)]),
     "ps_gemm_packed_bytes": (I64, [I64, I64]),
     "ps_gemm_pack_weights": (C.c_int, [P, I64, I64, I64, P, P]),
     "ps_stats_finalize": (C.c_int, [P, I64, I64, P, P, F32, I64, P, P, P, P]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpuresound_b200.so")
-SOURCES = ["ps_api.cu", "ps_gemm_simt.cu", "ps_gemm_tc.cu", "ps_gemm_pair.cu", "ps_norm.cu", "ps_dwconv.cu", "ps_misc.cu", "ps_gated.cu", "ps_attention.cu", "ps_sdr.cu", "ps_lstm.cu", "ps_lstm_tc.cu", "ps_stream.cu"]
+SOURCES = ["ps_api.cu", "ps_gemm_simt.cu", "ps_gemm_tc.cu", "ps_gemm_pair.cu", "ps_gemm_wide.cu", "ps_norm.cu", "ps_dwconv.cu", "ps_misc.cu", "ps_gated.cu", "ps_attention.cu", "ps_sdr.cu", "ps_lstm.cu", "ps_lstm_tc.cu", "ps_stream.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
@@ -40,17 +40,25 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True builds libpuresound_b200_exp.so with -DPS_EXPERIMENTS (the bottleneck switches of the GEMM / LSTM
+    kernels: results are garbage) next to the release library; it is only ever loaded through PS_B200_LIB (profiling runs)."""
+    global OBJ, LIB
+    if experiments:
+        OBJ, LIB = os.path.join(HERE, "build_exp"), os.path.join(HERE, "libpuresound_b200_exp.so")
+    else:
+        OBJ, LIB = os.path.join(HERE, "build"), os.path.join(HERE, "libpuresound_b200.so")
+    flags = NVCC_FLAGS + (["-DPS_EXPERIMENTS"] if experiments else [])
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
-    dig = _digest()
+    dig = _digest() + ("exp" if experiments else "")
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -72,4 +80,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

@@ -62,6 +62,23 @@ extern "C" int64_t ps_gemm_stats_slots(int64_t rows, int64_t M) {
   return ps::cdiv(rows, 128) * ps::cdiv(M, 128);
 }
 
+namespace ps {
+bool gemm_wide_eligible(const ps_gemm_t& d, int sms);
+}
+
+extern "C" int ps_gemm_path(const ps_gemm_t* dp) {
+  PS_REQUIRE(dp != nullptr);
+  const ps_gemm_t& d = *dp;
+  const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);
+  if (d.ln_eps > 0.f && !(tc && ps::tc_pair() && ps::gemm_pair_ln_eligible(d))) return 0;
+  if (!tc) return 0;
+  if (!ps::tc_pair()) return 1;
+  int dev = 0, sms = 0;
+  if (int rc = ps::current_device(&dev)) return rc;
+  if (int rc = ps::sm_count_of(dev, &sms)) return rc;
+  return ps::gemm_wide_eligible(d, sms) ? 3 : 2;
+}
+
 extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
   PS_REQUIRE(dp != nullptr);
   const ps_gemm_t& d = *dp;

@@ -45,11 +45,18 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
   return ok != 0;
 }
 // bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU
+#ifndef PS_MBAR_HINT_NS
+#define PS_MBAR_HINT_NS 2000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+#if PS_MBAR_HINT_NS > 0
+  while (!mbar_try_wait_hint(bar, parity, (uint32_t)PS_MBAR_HINT_NS)) {
+#else
+  while (!mbar_try_wait(bar, parity)) {
+#endif
     if ((++spins & 255u) == 1u) {  // watchdog arithmetic once per 256 polls
       const long long now = clock64();
       if (t0 == 0) t0 = now;

@@ -26,6 +26,13 @@ launch_count = 0
 kernel_events = None
 
 
+#: when a list, every ps_gemm call appends ((rows, M, K), path) with path = ps_gemm_path(): 0 exact-fp32 CUDA cores,
+#: 1 single-CTA tcgen05, 2 CTA-pair tcgen05 (128-frame tiles), 3 wide CTA-pair tcgen05 (256-frame tiles)
+path_log = None
+GEMM_PATH_NAMES = {0: "gemm_simt_kernel (fp32 CUDA cores)", 1: "gemm_tc_kernel (tcgen05, one CTA)", 2: "gemm_pair_kernel (tcgen05 cta_group::2, 128-frame tiles)",
+                   3: "gemm_wide_kernel (tcgen05 cta_group::2, 256-frame tiles)"}
+
+
 class _Timed:
     """Context manager: bracket one launch with a CUDA-event pair when bench.py asked for per-kernel timing."""
 
@@ -165,6 +172,8 @@ def gemm(
     folded = _set_fin(d, fin, batch, M, X.device) if (want_stats and fin is not None) else None
     if ln is not None:
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(ln[0]), _p(ln[1]), float(ln[2])
+    if path_log is not None:
+        path_log.append(((batch * rows, M, K), int(lib.ps_gemm_path(C.byref(d)))))
     with _Timed("gemm", (batch * rows, M, K)):
         _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
     _launched()

@@ -16,6 +16,16 @@ once in a CUDA graph and replayed (``StreamingSeparator(use_graph=True)``).
 Per block and hop: GEMM(W_in) -> one fused kernel (norm1+PReLU, ring push, causal
 dilated depthwise taps from the ring, norm2+PReLU) -> GEMM(W_pw) -> [cLN+PReLU row
 kernel | bN1d folded into the next GEMM's prologue] -> GEMM(W_out)+residual.
+
+Speaker conditioning (the only causal Conv-TasNet recipe upstream is a TSE model,
+``td_tse_conv_tasnet_v0_causal``, egs/tse/model.py:142-182; embed concat at
+conv_tasnet.py:78-83; streaming signature ``step_frame(x, embed)``,
+skim_inference.py:177): the embedding of a stream does not change from frame to
+frame, so ``cat(x, repeat(e))`` through ``W_in`` is folded ONCE - at
+``set_embedding`` / the first ``step_frame`` that sees a new embedding - into a
+per-stream bias ``W_in[:, C:] e`` per conditioned block (what the offline path does
+per item, nnet/conv_tasnet.py), kept in a static buffer the hop graph reads through
+the GEMM's residual input.
 """
 from __future__ import annotations
 
@@ -66,27 +76,68 @@ class StreamingConvTasNet(ConvTasNet):
                     folded.append([ops.bn_fold(n.weight, n.bias, n.running_mean, n.running_var, n.eps) for n in norms])
                 else:
                     folded.append(None)
-        self._state = {"S": n_streams, "rings": rings, "folded": folded, "step": torch.zeros(1, dtype=torch.int64, device=dev)}
+        # per-stream embedding bias of the conditioned blocks (filled by set_embedding), static so a captured hop reads it
+        ebias = [torch.zeros(n_streams, blk.hid_channels, device=dev) if blk.emb_dim else None for stack in self.tcn_list for blk in stack]
+        self._state = {"S": n_streams, "rings": rings, "folded": folded, "step": torch.zeros(1, dtype=torch.int64, device=dev),
+                       "ebias": ebias, "embed_sig": None}
         self.frames_counter = 0
 
+    @classmethod
+    def from_offline(cls, masker: ConvTasNet) -> "StreamingConvTasNet":
+        """Streaming view of an offline causal ``ConvTasNet`` (e.g. the masker of ``td_tse_conv_tasnet_v0_causal``): same
+        blocks, shared parameters and packed-weight caches."""
+        if isinstance(masker, cls):
+            return masker
+        if masker.tcn_layer.lower() != "normal":
+            raise NotImplementedError("streaming serves tcn_layer='normal' blocks")
+        new = cls(**masker.get_args)
+        new.tcn_list = masker.tcn_list
+        return new
+
+    @torch.no_grad()
+    def set_embedding(self, embed: torch.Tensor):
+        """embed [S, E] (or [S, E, 1]): one speaker embedding per stream.  Folds it into the per-stream bias of every
+        conditioned block (L2-normalised first when embed_norm, conv_tasnet.py:348-349); a captured hop graph sees the new
+        values on its next replay."""
+        st = self._state
+        if st is None:
+            raise RuntimeError("call init_status(n_streams) first")
+        if not any(self.tcn_with_embed):
+            raise ValueError("this masker has no conditioned block (tcn_with_embed is all zeros)")
+        e = embed.reshape(embed.shape[0], -1).to(device=st["step"].device, dtype=torch.float32).contiguous()
+        if e.shape != (st["S"], self.embed_dim):
+            raise ValueError(f"expected an embedding of shape {(st['S'], self.embed_dim)}, got {tuple(e.shape)}")
+        if self.embed_norm:
+            e = ops.l2normalize(e)
+        j = 0
+        for stack in self.tcn_list:
+            for blk in stack:
+                if blk.emb_dim:
+                    Cc, H, E = blk.in_channels, blk.hid_channels, blk.emb_dim
+                    w_in = blk.in_conv[0].weight.view(H, Cc + E)
+                    ops.gemm(e, w_in[:, Cc:], batch=1, rows=e.shape[0], M=H, K=E, x_batch_stride=0, x_row_stride=E, w_row_stride=Cc + E,
+                             out=st["ebias"][j])
+                j += 1
+        st["embed_sig"] = (embed.data_ptr(), embed._version, tuple(embed.shape))
+
     # ------------------------------------------------------------------ one hop
-    def _block_step(self, blk, j: int, x: torch.Tensor, embed_bias: Optional[torch.Tensor]) -> torch.Tensor:
+    def _block_step(self, blk, j: int, x: torch.Tensor) -> torch.Tensor:
         st = self._state
         S = st["S"]
         Cc, H, E = blk.in_channels, blk.hid_channels, blk.emb_dim
         dsc = blk.dconv[0]
         n1, n2, n3 = blk.in_conv[1], dsc.depthwise[1], dsc.pointwise[1]
         kind = 0 if self.tcn_norm == "cLN" else 1
-        if embed_bias is not None or E != 0:
-            raise NotImplementedError("conditioned streaming blocks are a 'next' row (SURVEY.md 8f)")
         xin = x.view(1, S, Cc)
+        ebias = st["ebias"][j]  # [S, H] per-stream W_in[:, C:] e of a conditioned block: rides the GEMM's residual input
         # with enough concurrent streams a hop is a [S x 512 x 512] GEMM worth the tensor cores (3xBF16, as offline);
         # few streams keep the exact-fp32 latency tile (the CTA-pair kernel has ~10 us of fixed cost)
         tc = S >= self.TC_MIN_STREAMS
         pk_in = blk._packed("in", blk.in_conv[0].weight, H, Cc, Cc + E) if tc else None
         pk_pw = blk._packed("pw", dsc.pointwise[0].weight, H, H, H) if tc else None
         pk_out = blk._packed("out", blk.out_conv.weight, Cc, H, H) if tc else None
-        u1, _ = ops.linear(xin, blk.in_conv[0].weight.view(H, Cc), K=Cc, w_row_stride=Cc, w_packed=pk_in)
+        u1, _ = ops.linear(xin, blk.in_conv[0].weight.view(H, Cc + E), K=Cc, w_row_stride=Cc + E, w_packed=pk_in,
+                           residual=None if ebias is None else ebias.view(1, S, H))
         u2 = torch.empty(S, H, device=x.device, dtype=torch.float32)
         d = _lib.StreamDwDesc()
         d.streams, d.C, d.P, d.dilation = S, H, blk.kernel, blk.dilation
@@ -121,14 +172,20 @@ class StreamingConvTasNet(ConvTasNet):
         """x [S, C] (one frame per stream) -> mask logits [S, C]; advances every stream by one frame."""
         if self._state is None:
             raise RuntimeError("call init_status(n_streams) first")
-        if embed is not None or any(self.tcn_with_embed):
-            raise NotImplementedError("speaker-conditioned streaming is a 'next' row (SURVEY.md 8f)")
         if x.shape[0] != self._state["S"]:
             raise ValueError(f"expected {self._state['S']} streams, got {x.shape[0]}")
+        if any(self.tcn_with_embed):
+            if embed is not None:
+                if self._state["embed_sig"] != (embed.data_ptr(), embed._version, tuple(embed.shape)):
+                    self.set_embedding(embed)  # a new embedding tensor: fold it once (not per frame)
+            elif self._state["embed_sig"] is None:
+                raise ValueError("this masker is speaker-conditioned: pass embed or call set_embedding(embed) first")
+        elif embed is not None:
+            raise ValueError("this masker was built without conditioned blocks")
         j = 0
         for stack in self.tcn_list:
             for blk in stack:
-                x = self._block_step(blk, j, x, None)
+                x = self._block_step(blk, j, x)
                 j += 1
         _lib.check(_lib.load().ps_stream_advance(self._state["step"].data_ptr(), torch.cuda.current_stream().cuda_stream), "ps_stream_advance")
         ops._launched()
@@ -154,13 +211,15 @@ class StreamingSeparator(nn.Module):
 
     def __init__(self, model: nn.Module, use_graph: bool = True):
         super().__init__()
-        if not isinstance(model.encoder, FreeEncDec) or not isinstance(model.masker, StreamingConvTasNet):
-            raise NotImplementedError("StreamingSeparator needs FreeEncDec + StreamingConvTasNet")
-        if model.speaker_net is not None or model.embedding_free_tse:
-            raise NotImplementedError("speaker-conditioned streaming is a 'next' row (SURVEY.md 8f)")
+        if not isinstance(model.encoder, FreeEncDec) or not isinstance(model.masker, ConvTasNet):
+            raise NotImplementedError("StreamingSeparator needs FreeEncDec + a causal ConvTasNet")
+        if model.embedding_free_tse:
+            raise NotImplementedError("embedding-free TSE streams through the DPRNN / SkiM wrappers")
         if model.mask_type.lower() != "real" or model.f_type.lower() != "real":
             raise NotImplementedError
         self.model = model
+        # an offline causal masker (td_tse_conv_tasnet_v0_causal from recipes.init_model) gets its streaming view here
+        self.masker = StreamingConvTasNet.from_offline(model.masker)
         self.use_graph = use_graph
         self._mask_act = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}[model.mask_constraint.lower()]
         self._constraint = {"linear": 1, "sigmoid": 2}[model.output_constraint.lower()]
@@ -175,14 +234,27 @@ class StreamingSeparator(nn.Module):
         return self.model.encoder.win_length
 
     @torch.no_grad()
-    def init_status(self, n_streams: int = 1):
+    def init_status(self, n_streams: int = 1, enroll: Optional[torch.Tensor] = None, embed: Optional[torch.Tensor] = None):
+        """(Re)start n_streams streams.  For a TSE model pass either the enrollment waveforms `enroll` [S, Le] (the speaker
+        net runs once here: SoTaskWrapModule.inference_tse_embedding, base_nn.py:724-738) or ready embeddings `embed` [S, E]."""
         ops.require_device()
         enc = self.model.encoder
         dev = next(self.model.parameters()).device
         if enc.win_length % enc.hop_length != 0:
             raise NotImplementedError("streaming needs win_length to be a multiple of hop_length")
         S, win, hop = n_streams, enc.win_length, enc.hop_length
-        self.model.masker.init_status(S)
+        self.masker.init_status(S)
+        conditioned = any(self.masker.tcn_with_embed)
+        if conditioned:
+            if embed is None:
+                if enroll is None or self.model.speaker_net is None:
+                    raise ValueError("a speaker-conditioned model needs init_status(n_streams, enroll=...) or embed=...")
+                if enroll.shape[0] != S:
+                    raise ValueError(f"expected {S} enrollment utterances, got {enroll.shape[0]}")
+                embed = self.model.inference_tse_embedding(enroll.to(dev)).squeeze(-1)
+            self.masker.set_embedding(embed)
+        elif enroll is not None or embed is not None:
+            raise ValueError("this model has no conditioned block")
         self._st = {
             "S": S, "chunks": 0, "prime": win // hop - 1,
             "hist": torch.zeros(S, max(win - hop, 1), device=dev), "frame": torch.zeros(S, win, device=dev),
@@ -207,7 +279,7 @@ class StreamingSeparator(nn.Module):
         S, win, hop = st["S"], self.win, self.hop
         Nf = enc.encoder.out_channels
         feats, _ = ops.linear(st["frame"].view(1, S, win), enc.encoder.weight.view(Nf, win), epi_act=ACT_RELU if enc.output_active else ACT_NONE)
-        mask = self.model.masker.step_frame_cl(feats.view(S, Nf))
+        mask = self.masker.step_frame_cl(feats.view(S, Nf))
         fr, _ = ops.linear(feats, self._w_dec_t, pro=Prologue(PRO_MASK, self._mask_act, x2=mask.view(1, S, Nf)))
         lib = _lib.load()
         _lib.check(lib.ps_stream_ola(fr.data_ptr(), st["acc"].data_ptr(), st["out"].data_ptr(), S, win, hop, self._constraint,

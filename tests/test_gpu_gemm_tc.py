@@ -201,3 +201,54 @@ def test_tc_affine_tanh_prologue(ops, B, Rr, M, K):
     check(y, ref)
     y2, _ = ops.linear(x, w, pro=pro, bias=bias, backend=ops.GEMM_SIMT)
     check(y2, ref, 1e-5)
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(2, 10000, 512, 512), (40, 517, 512, 64), (3, 7000, 512, 192), (64, 300, 1024, 128), (1, 19000, 512, 256)])
+def test_tc_wide_tiles(ops, B, Rr, M, K):
+    """gemm_wide_kernel (256-frame tiles, MMA N = 256, per-block accumulator hand-over with the skewed MMA order at the tile
+    boundaries): chosen for M % 512 == 0 once there is a full wave of tiles.  K = 64 (fewer stages than the skew holds), 192,
+    128 (exactly the ring), 256, 512; ragged last tiles; M = 1024 (two channel groups); affine + PReLU prologue, bias,
+    per-item bias, residual, Welford partials - against fp64 and the exact-fp32 back end."""
+    x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
+    sc, sh, slope = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4), torch.tensor([0.2], device=DEV)
+    bias, bb, res = rnd(M, seed=5), rnd(B, M, seed=6), rnd(B, Rr, M, seed=7)
+    pk = ops.pack_weights(w, M, K, K)
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+    ops.path_log = []
+    y, part = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    y0, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05)  # no prologue, no epilogue extras, no statistics
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [3, 3], paths
+    for b0 in range(0, B, 8):
+        sl = slice(b0, b0 + 8)
+        xin = F.prelu((x[sl] * sc[sl].unsqueeze(1) + sh[sl].unsqueeze(1)), slope).double()
+        ref = xin @ w.double().t() + bias.double() + bb[sl].double().unsqueeze(1) + res[sl].double()
+        check(y[sl], ref)
+        check(y0[sl], x[sl].double() @ w.double().t())
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, M)
+    yd = y.double()
+    mu, rstd = yd.mean(dim=(1, 2)), 1 / torch.sqrt(yd.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
+    assert (shift[:, 0].double() + mu * rstd).abs().max() <= 5e-5
+    y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
+    check(y, y2.double())
+
+
+def test_tc_wide_slopes_and_nonfinite(ops):
+    """PReLU slopes outside (0, 1] take the select instead of max(u, slope*u); Inf / NaN inputs stay in their rows and come
+    out non-finite (the reference's look-ahead probe, base_nn.py:740-777, depends on it)."""
+    B, Rr, M, K = 2, 9600, 512, 128
+    x, w = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1)
+    sc, sh = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4)
+    pk = ops.pack_weights(w, M, K, K)
+    for sl in (0.0, 1.0, 1.7, -0.3):
+        slope = torch.tensor([sl], device=DEV)
+        pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+        y, _ = ops.linear(x, w, pro=pro, w_packed=pk, backend=ops.GEMM_TCGEN05)
+        check(y, F.prelu(x * sc.unsqueeze(1) + sh.unsqueeze(1), slope).double() @ w.double().t())
+    x[0, 5000:, :] = float("inf")
+    x[1, :100, 3] = float("nan")
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc.abs() + 0.1, sh, K, None, torch.tensor([0.25], device=DEV))
+    y, _ = ops.linear(x, w, pro=pro, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    assert torch.isfinite(y[0, :5000]).all() and not torch.isfinite(y[0, 5000:]).any()
+    assert not torch.isfinite(y[1, :100]).any() and torch.isfinite(y[1, 100:]).all()

@@ -83,6 +83,75 @@ def test_streaming_many_streams_tensor_core_path():
     assert err <= 1e-3
 
 
+@pytest.mark.parametrize("norm,use_graph", [("cLN", True), ("bN1d", True), ("bN1d", False)])
+def test_streaming_with_speaker_embedding_equals_offline(norm, use_graph):
+    """Speaker-conditioned streaming (reference signature step_frame(x, embed), skim_inference.py:177; embed concat
+    conv_tasnet.py:78-83): a small causal TSE model - conditioned block 0 of each repeat, embed_norm, TCN + ASP speaker
+    net - streamed with one enrollment per stream equals the offline oracle run with the same enrollments; then the
+    embeddings are swapped between streams on the live separator (set_embedding) and the outputs follow."""
+    from puresound_b200.nnet.conv_tasnet import TCN, ConvTasNet
+    from puresound_b200.nnet.lobe.pooling import AttentiveStatisticsPooling
+
+    torch.manual_seed(7)
+    nf, hid, E = 24, 40, 12
+    m = SoTaskWrapModule(
+        FreeEncDec(32, nf, 16),
+        ConvTasNet(nf, E, True, tcn_dim=hid, per_tcn_stack=3, repeat_tcn=2, tcn_with_embed=[1, 0, 0], tcn_norm=norm, dconv_norm=norm, causal=True),
+        speaker_net=torch.nn.ModuleList([TCN(nf, 16, 3, dilation=2 ** i) for i in range(2)] + [AttentiveStatisticsPooling(nf, 8), torch.nn.Conv1d(2 * nf, E, 1, bias=False)]),
+        mask_constraint="ReLU", verbose=False).eval()
+    testing.perturb_(m, seed=8)
+    S, hop, win = 3, 16, 32
+    wav = testing.white(S, hop * 70, amp=0.1, seed=9)
+    enr = testing.white(S, 1600, amp=0.1, seed=10)
+    sd, cfg = {k: v.clone() for k, v in m.state_dict().items()}, D.describe(m)
+    ref = R.inference(sd, cfg, wav, enr)
+    m = m.cuda()
+    sep = StreamingSeparator(m, use_graph=use_graph)
+    sep.init_status(S, enroll=enr)
+
+    def stream(sep):
+        outs = [sep.step_wave(wav[:, j * hop:(j + 1) * hop].cuda()) for j in range(wav.shape[1] // hop)]
+        return torch.cat(outs, dim=1).cpu()[:, (win // hop - 1) * hop:]
+
+    y = stream(sep)
+    n = y.shape[1]
+    err = (y - ref[:, :n]).abs().max().item()
+    assert err <= 2e-5, err
+    assert (m.inference(wav, enr) - ref).abs().max().item() <= 2e-5  # offline engine path of the same model
+    # ready-made embeddings, rolled by one stream: every stream now follows its neighbour's speaker
+    dvec = m.inference_tse_embedding(enr.cuda()).squeeze(-1)
+    ref_rolled = R.inference(sd, cfg, wav, enr.roll(1, 0))
+    sep.init_status(S, embed=dvec.roll(1, 0))
+    y2 = stream(sep)
+    assert (y2 - ref_rolled[:, :n]).abs().max().item() <= 2e-5
+    assert (y2 - y).abs().max().item() > 1e-5  # the conditioning matters (white-noise enrollments give close embeddings)
+    with pytest.raises(ValueError):
+        sep.init_status(S)  # a conditioned model without enrollment
+
+
+def test_streaming_td_tse_conv_tasnet_v0_causal_recipe():
+    """The one causal Conv-TasNet recipe the reference ships (egs/tse/model.py:142-182, bN1d norms, dvec 192 into block 0 of
+    each repeat) built by recipes.init_model as an OFFLINE model and streamed through its streaming view: 2 streams x 0.5 s
+    with a 1.5 s enrollment each against the offline oracle."""
+    from puresound_b200 import recipes
+
+    torch.manual_seed(0)
+    m = recipes.init_model("td_tse_conv_tasnet_v0_causal", verbose=False).eval()
+    testing.perturb_(m, seed=1)
+    wav = testing.noisy_speech(2, 16 * 500, seed=21)[0]
+    enr = testing.noisy_speech(2, 24000, seed=22)[0]
+    ref = R.inference(m.state_dict(), D.describe(m), wav, enr)
+    m = m.cuda()
+    sep = StreamingSeparator(m, use_graph=True)
+    sep.init_status(2, enroll=enr)
+    outs = [sep.step_wave(wav[:, j * 16:(j + 1) * 16].cuda()) for j in range(500)]
+    y = torch.cat(outs, dim=1).cpu()[:, 16:]
+    n = y.shape[1]
+    err = (y - ref[:, :n]).abs().max().item()
+    print(f"td_tse_conv_tasnet_v0_causal streaming vs offline oracle: max|err|={err:.3e} over {n} samples x 2 streams")
+    assert err <= 1e-3
+
+
 @pytest.mark.parametrize("n_streams", [1, 3])
 def test_streaming_skim_equals_offline(n_streams):
     """The reference's own streaming test (test/test_streaming.py:62-116): StreamingSkiM offline forward == step_chunk ==
