@@ -686,11 +686,14 @@ bool gemm_pair_ln_eligible(const ps_gemm_t& d) {
 
 bool gemm_wide_eligible(const ps_gemm_t& d, int sms);
 int gemm_wide_launch(const ps_gemm_t& d, cudaStream_t s, int dev, int sms);
+bool gemm_wide_tma_eligible(const ps_gemm_t& d, int sms);
+int gemm_wide_tma_launch(const ps_gemm_t& d, cudaStream_t s, int dev, int sms);
 
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (int rc = current_device(&dev)) return rc;
   if (int rc = sm_count_of(dev, &sms)) return rc;
+  if (gemm_wide_tma_eligible(d, sms)) return gemm_wide_tma_launch(d, s, dev, sms);  // PS_TC_WIDE=2: TMA-fed variant (A/B)
   if (gemm_wide_eligible(d, sms)) return gemm_wide_launch(d, s, dev, sms);  // 256-frame tiles (ps_gemm_wide.cu)
   int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
   if (pro == PS_PRO_AFFINE && d.pro_act == PS_ACT_TANH) pro = PR_PRO_AFFINE_TANH;
