@@ -322,11 +322,18 @@ static int launch_tile(const ps_dwconv_t& dd, int TC, size_t smem, dim3 grid, cu
 
 }  // namespace ps
 
+namespace ps {
+bool dwconv_tma_eligible(const ps_dwconv_t& d);
+int dwconv_tma_launch(const ps_dwconv_t& d, cudaStream_t s);
+int64_t dwconv_tma_slots(int64_t T, int64_t C);
+}
+
 extern "C" int64_t ps_dwconv_stats_slots(int64_t T, int64_t C) {
   if (T <= 0 || C <= 0) return 0;
   ps::DwGeom g = ps::dw_geom(C);
   const int64_t a = ps::cdiv(T, ps::DW_TT) * ps::cdiv(C, g.chan_per_block);  // streaming kernel
-  const int64_t t = ps::cdiv(T, 256) * ps::cdiv(C, ps::DT_CG);               // tiled kernel (its largest grid)
+  int64_t t = ps::cdiv(T, 256) * ps::cdiv(C, ps::DT_CG);                     // tiled kernel (its largest grid)
+  if (C % 32 == 0 && ps::dwconv_tma_slots(T, C) > t) t = ps::dwconv_tma_slots(T, C);  // TMA sliding-window kernel
   return a > t ? a : t;
 }
 
@@ -355,6 +362,7 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
     cudaError_t e = cudaMemsetAsync(d.stats_partials, 0, (size_t)d.batch * dd.stats_slots * 3 * sizeof(float), s);
     if (e != cudaSuccess) { ps::set_cuda_error(e, "cudaMemsetAsync(stats_partials)"); return PS_ERR_CUDA; }
   }
+  if (ps::dwconv_tma_eligible(dd)) return ps::dwconv_tma_launch(dd, s);  // TMA-fed sliding window (ps_dwconv_tma.cu)
   const int halo = (d.P - 1) * d.dilation;
   const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
   if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {

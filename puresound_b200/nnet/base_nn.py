@@ -218,7 +218,15 @@ class SoTaskWrapModule(nn.Module):
             ent["in"] = noisy.clone()
             ent["enroll"] = None if enroll is None else enroll.clone()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # an explicit capture stream ON THE INPUT'S DEVICE: torch.cuda.graph's default capture stream is one class-wide
+            # stream created on whichever device captured first, so a replica on another GPU (ShardedSeparator) would
+            # capture on a foreign device's stream ("operation not permitted when stream is capturing")
+            if not hasattr(self, "_cap_streams"):
+                self._cap_streams = {}
+            cs = self._cap_streams.get(noisy.device.index)
+            if cs is None:
+                cs = self._cap_streams[noisy.device.index] = torch.cuda.Stream(noisy.device)
+            with torch.cuda.device(noisy.device), torch.cuda.graph(g, stream=cs):
                 ent["out"] = self._inference_cl(ent["in"], ent["enroll"], constrain)
             ent["graph"] = g
             # device tensors the captured kernels read by raw pointer but that live in module-level caches (the iSTFT

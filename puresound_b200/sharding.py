@@ -70,12 +70,15 @@ class ShardedSeparator:
             raise RuntimeError("ShardedSeparator needs at least one CUDA device (no CPU fallback)")
         self.devices = [torch.device("cuda", d) if isinstance(d, int) else torch.device(d) for d in devices]
         self.replicas = []
-        saved, model._graphs = model._graphs, OrderedDict()  # captured graphs belong to the source model's device
+        saved, model._graphs = model._graphs, OrderedDict()  # captured graphs / capture streams belong to the source's device
+        saved_cs = model.__dict__.pop("_cap_streams", None)
         try:
             for dev in self.devices:
                 self.replicas.append(copy.deepcopy(model).to(dev).eval())
         finally:
             model._graphs = saved
+            if saved_cs is not None:
+                model._cap_streams = saved_cs
         self.streams = [torch.cuda.Stream(dev) for dev in self.devices]
         self.runners = [self._device_runner(g) for g in range(len(self.devices))]
 

@@ -308,7 +308,8 @@ class StreamingSeparator(nn.Module):
             if st["graph"] is None:
                 # capture the fixed kernel chain of one hop (capture records, it does not execute) ...
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                dev = st["out"].device
+                with torch.cuda.device(dev), torch.cuda.graph(g, stream=torch.cuda.Stream(dev)):  # capture stream on OUR device
                     self._compute()
                 st["graph"] = g
             st["graph"].replay()  # ... and replay it for this and every later hop

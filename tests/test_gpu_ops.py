@@ -158,7 +158,11 @@ def test_dwconv(ops, C, T, P, d, causal, mode):
     sc_ref, sh_ref = ops.stats_finalize(part, gamma, beta, 1e-8, C)
     for _ in range(2):
         y2, fa = ops.dwconv(x, w, b, P, d, causal, pro, want_stats=True, fin=(gamma, beta, 1e-8))
-        assert torch.equal(y2, y) and torch.equal(fa.scale, sc_ref) and torch.equal(fa.shift, sh_ref)
+        # (shapes the TMA sliding-window kernel serves take the tiled kernel when the finalize is fused: same taps in the
+        # same order, but another partition of the statistics partials - equal to rounding, not bit for bit)
+        assert torch.equal(y2, y)
+        close(fa.scale, sc_ref, 1e-6)
+        close(fa.shift, sh_ref, 1e-5)
 
 
 def test_rownorm_layernorm_residual(ops):
@@ -407,3 +411,43 @@ def test_nan_inf_propagate(ops):
 def test_host_tensors_are_rejected(ops):
     with pytest.raises(TypeError):
         ops.linear(torch.zeros(1, 4, 4), torch.zeros(4, 4))
+
+
+@pytest.mark.parametrize("B,C,T,d,causal,mode", [
+    (2, 64, 3999, 1, False, "affine"), (2, 64, 3999, 128, False, "affine"), (3, 512, 1000, 16, False, "affine"), (2, 32, 700, 64, True, "affine"),
+    (1, 512, 3999, 32, False, "affine"), (2, 96, 64, 2, False, "none"), (5, 128, 777, 160, True, "none"), (64, 32, 500, 8, False, "affine")])
+def test_dwconv_tma_sliding_window(ops, B, C, T, d, causal, mode):
+    """dwconv_tma_kernel (P = 3, C % 32 == 0): rows enter a shared-memory ring by tensor-map TMA, are normalised + PReLU'd in
+    place once and serve their three taps from the ring.  Runs shorter than / equal to / longer than the item, the largest
+    dilations of the TCN stack (halo up to 320 frames, 7-8 ring slots), causal and centred padding (zero AFTER the prologue),
+    several runs per item (halo re-read where runs meet), against F.conv1d; the statistics of the whole item from the per-run
+    partials; and bit-equality with dwconv_tile_kernel's taps order is NOT required (only the 1e-5 tolerance)."""
+    P = 3
+    x, w, b = rnd(B, T, C, seed=1, scale=2), rnd(C, P, seed=2), rnd(C, seed=3)
+    slope = torch.tensor([0.25], device=DEV)
+    if mode == "none":
+        pro, xin = ops.NO_PRO, x
+    else:
+        sc, sh = rnd(B, C, seed=4) + 1.5, rnd(B, C, seed=5)
+        pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, C, None, slope)
+        xin = F.prelu(x * sc.unsqueeze(1) + sh.unsqueeze(1), slope)
+    y, part = ops.dwconv(x, w, b, P, d, causal, pro, want_stats=True)
+    pad = (P - 1) * d if causal else ((P - 1) // 2) * d
+    ref = F.conv1d(xin.transpose(1, 2), w.unsqueeze(1), b, dilation=d, padding=pad, groups=C)
+    if causal:
+        ref = ref[..., :-pad]
+    ref = ref.transpose(1, 2)
+    close(y, ref)
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, C)
+    mu = ref.mean(dim=(1, 2))
+    rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    close(scale[:, 0], rstd)
+    close(shift[:, 0], -mu * rstd, 2e-5)
+    # NaN / Inf stay where the taps reach (the reference's look-ahead probe, base_nn.py:740-777)
+    x2 = x.clone()
+    x2[0, T // 2:, :] = float("inf")
+    y2, _ = ops.dwconv(x2, w, b, P, d, causal, pro)
+    reach = 0 if causal else d
+    first_bad = max(T // 2 - reach, 0)
+    assert torch.isfinite(y2[0, :first_bad]).all() and not torch.isfinite(y2[0, T // 2:]).any()
+    assert torch.equal(y2[1:], y[1:])
