@@ -63,7 +63,7 @@ PS_API const char* ps_last_cuda_error(void); /* thread-local text of the last CU
 PS_API int ps_version(void);
 /* 1 if the current device is compute capability 10.x, else 0 (negative on error) */
 PS_API int ps_device_ok(void);
-/* sizeof() of the descriptor structs, so FFI hosts can verify their mirror: 0 ps_gemm_t, 1 ps_dwconv_t, 2 ps_lstm_t, 3 ps_stream_dw_t */
+/* sizeof() of the descriptor structs, so FFI hosts can verify their mirror: 0 ps_gemm_t, 1 ps_dwconv_t, 2 ps_lstm_t, 3 ps_stream_dw_t, 4 ps_gated_t, 5 ps_stream_hop_block_t, 6 ps_stream_hop_t */
 PS_API int64_t ps_struct_size(int which);
 
 /* --------------------------------------------------------------------------
@@ -298,6 +298,46 @@ PS_API int ps_stream_push(const float* chunk, float* hist, float* frame, int64_t
 /* overlap-add emit: acc[s,:] += frame[s,:]; out[s,:hop] = constrain(acc[s,:hop]); acc <- shift left by hop */
 PS_API int ps_stream_ola(const float* frame, float* acc, float* out, int64_t streams, int64_t win, int64_t hop, int32_t constraint, void* stream);
 PS_API int ps_stream_advance(int64_t* step, void* stream);
+
+/* --------------------------------------------------------------------------
+ * One hop of every concurrent stream of a causal Conv-TasNet as ONE persistent cooperative kernel (round 2): frame
+ * assembly, encoder, every TCN block (1x1 conv, per-frame norm + PReLU, dilation-history ring + causal depthwise taps,
+ * 1x1 conv, 1x1 conv + residual), mask + decoder, overlap-add emit - phases of one grid (one CTA per SM) separated by
+ * grid barriers, exact fp32.  Same state and arithmetic as the ps_stream_* chain above + ps_gemm (API pattern:
+ * StreamingSkiM.step_frame, streaming/skim_inference.py:176-218; arithmetic: conv_tasnet.py:11-90, lobe/cnn.py:58-79,
+ * lobe/norm.py:37-50, lobe/encoder.py:50-94).  norm_kind 0: cLN (n*_a / n*_b = gamma / beta), 1: eval-BatchNorm folded to
+ * a per-channel affine (n*_a / n*_b = scale / shift).  All pointers are device pointers; `blocks` is a device array.
+ * -------------------------------------------------------------------------- */
+typedef struct {
+  const float* w_in; int64_t w_in_ld;   /* [H, >= C]: the first C columns of in_conv (speaker columns are folded) */
+  const float* ebias;                   /* [streams, H] per-stream speaker bias W_in[:, C:] e, or NULL           */
+  const float* n1_a; const float* n1_b; const float* slope1;
+  const float* dw_w; const float* dw_b; /* depthwise taps [H, P], bias [H] or NULL                                */
+  const float* n2_a; const float* n2_b; const float* slope2;
+  const float* w_pw; const float* b_pw; /* [H, H], [H] or NULL                                                    */
+  const float* n3_a; const float* n3_b; const float* slope3;
+  const float* w_out; const float* b_out; /* [C, H], [C] or NULL                                                  */
+  float* ring;                          /* [streams, (P-1)*dilation + 1, H] dilation history                     */
+  int32_t P, dilation;
+  /* optional bf16 split of the three 1x1-conv weights for the tensor-core path (many streams): [M][K] hi then [M][K] lo
+   * bf16 (hi = bf16(w), lo = bf16(w - hi)); NULL = exact-fp32 FFMA path */
+  const uint16_t* w_in_p; const uint16_t* w_pw_p; const uint16_t* w_out_p;
+} ps_stream_hop_block_t;
+
+typedef struct {
+  int64_t streams;
+  int32_t C, H, win, hop, n_blocks, norm_kind, enc_relu, mask_act, constraint; float eps;
+  const float* w_enc;                   /* [C, win]                                                               */
+  const float* w_dec_t;                 /* [win, C] (the ConvTranspose1d weight transposed)                       */
+  const ps_stream_hop_block_t* blocks;  /* device array [n_blocks]                                                */
+  const float* chunk;                   /* [streams, hop] new samples                                             */
+  float* hist; float* frame; float* frame_out; float* acc; float* out; /* [S,win-hop] [S,win] [S,win] [S,win] [S,hop] */
+  int64_t* step;                        /* frames processed so far (advanced by the kernel)                       */
+  float* feats; float* x; float* u1; float* u2; float* u3; /* scratch [S,C] [S,C] [S,H] [S,H] [S,H]                */
+  uint32_t* barrier;                    /* 2 words, zero before the first launch, owned by the kernel afterwards  */
+  const uint16_t* w_enc_p; const uint16_t* w_dec_p; /* optional bf16 splits of w_enc / w_dec_t (see the block struct)   */
+} ps_stream_hop_t;
+PS_API int ps_stream_hop(const ps_stream_hop_t* d, void* stream);
 
 #ifdef __cplusplus
 }

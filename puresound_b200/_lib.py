@@ -84,7 +84,35 @@ class GatedDesc(C.Structure):
     ]
 
 
-STRUCTS = {0: GemmDesc, 1: DwconvDesc, 2: LstmDesc, 3: StreamDwDesc, 4: GatedDesc}
+class StreamHopBlock(C.Structure):
+    _fields_ = [
+        ("w_in", P), ("w_in_ld", I64), ("ebias", P),
+        ("n1_a", P), ("n1_b", P), ("slope1", P),
+        ("dw_w", P), ("dw_b", P),
+        ("n2_a", P), ("n2_b", P), ("slope2", P),
+        ("w_pw", P), ("b_pw", P),
+        ("n3_a", P), ("n3_b", P), ("slope3", P),
+        ("w_out", P), ("b_out", P),
+        ("ring", P), ("P", I32), ("dilation", I32),
+        ("w_in_p", P), ("w_pw_p", P), ("w_out_p", P),
+    ]
+
+
+class StreamHopDesc(C.Structure):
+    _fields_ = [
+        ("streams", I64),
+        ("C", I32), ("H", I32), ("win", I32), ("hop", I32), ("n_blocks", I32), ("norm_kind", I32), ("enc_relu", I32), ("mask_act", I32),
+        ("constraint", I32), ("eps", F32),
+        ("w_enc", P), ("w_dec_t", P), ("blocks", P), ("chunk", P),
+        ("hist", P), ("frame", P), ("frame_out", P), ("acc", P), ("out", P),
+        ("step", P),
+        ("feats", P), ("x", P), ("u1", P), ("u2", P), ("u3", P),
+        ("barrier", P),
+        ("w_enc_p", P), ("w_dec_p", P),
+    ]
+
+
+STRUCTS = {0: GemmDesc, 1: DwconvDesc, 2: LstmDesc, 3: StreamDwDesc, 4: GatedDesc, 5: StreamHopBlock, 6: StreamHopDesc}
 
 # name -> (restype, argtypes); must list every symbol include/puresound_b200.h declares
 SIGNATURES = {
@@ -125,6 +153,7 @@ SIGNATURES = {
     "ps_stream_push": (C.c_int, [P, P, P, I64, I64, I64, P]),
     "ps_stream_ola": (C.c_int, [P, P, P, I64, I64, I64, I32, P]),
     "ps_stream_advance": (C.c_int, [P, P]),
+    "ps_stream_hop": (C.c_int, [C.POINTER(StreamHopDesc), P]),
 }
 
 _lib = None

@@ -53,6 +53,8 @@ extern "C" int64_t ps_struct_size(int which) {
     case 2: return (int64_t)sizeof(ps_lstm_t);
     case 3: return (int64_t)sizeof(ps_stream_dw_t);
     case 4: return (int64_t)sizeof(ps_gated_t);
+    case 5: return (int64_t)sizeof(ps_stream_hop_block_t);
+    case 6: return (int64_t)sizeof(ps_stream_hop_t);
     default: return -1;
   }
 }

@@ -30,6 +30,7 @@ the GEMM's residual input.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -200,6 +201,8 @@ class StreamingConvTasNet(ConvTasNet):
 
 
 class StreamingSeparator(nn.Module):
+    HOP_MMA_MIN_STREAMS = 32  # concurrent streams from which the hop kernel's GEMM phases run on the tensor cores
+
     """Waveform-in / waveform-out streaming around a task wrapper whose encoder is a ``FreeEncDec`` and whose
     masker is a ``StreamingConvTasNet`` (caller pattern: egs/tse/demo/utils.py:78-118).
 
@@ -209,7 +212,9 @@ class StreamingSeparator(nn.Module):
     ``SoTaskWrapModule.inference`` on the whole signal, delayed by ``win - hop`` samples of priming.
     """
 
-    def __init__(self, model: nn.Module, use_graph: bool = True):
+    def __init__(self, model: nn.Module, use_graph: bool = True, use_hop_kernel: bool = True):
+        """use_hop_kernel: run a hop as ONE persistent cooperative kernel (ps_stream_hop: every phase of the stack behind grid
+        barriers, exact fp32) instead of the chain of ~125 kernels (A/B: use_hop_kernel=False)."""
         super().__init__()
         if not isinstance(model.encoder, FreeEncDec) or not isinstance(model.masker, ConvTasNet):
             raise NotImplementedError("StreamingSeparator needs FreeEncDec + a causal ConvTasNet")
@@ -221,6 +226,7 @@ class StreamingSeparator(nn.Module):
         # an offline causal masker (td_tse_conv_tasnet_v0_causal from recipes.init_model) gets its streaming view here
         self.masker = StreamingConvTasNet.from_offline(model.masker)
         self.use_graph = use_graph
+        self.use_hop_kernel = use_hop_kernel and os.environ.get("PS_STREAM_HOP", "1") != "0"
         self._mask_act = {"linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}[model.mask_constraint.lower()]
         self._constraint = {"linear": 1, "sigmoid": 2}[model.output_constraint.lower()]
         self._st = None
@@ -264,6 +270,74 @@ class StreamingSeparator(nn.Module):
         # decoder weight transposed once (cache) before any graph capture
         Nf = enc.decoder.in_channels
         self._w_dec_t = enc._cache.get("dec_t", [enc.decoder.weight], lambda: enc.decoder.weight.view(Nf, win).t().contiguous())
+        self._hop = self._build_hop_descriptor() if self.use_hop_kernel else None
+
+    def _build_hop_descriptor(self):
+        """Descriptor of the persistent hop kernel (ps_stream_hop): per-block pointer table on the device + scratch rows.
+        Returns None when the model is outside what that kernel serves (the kernel chain is used then)."""
+        st, mst = self._st, self.masker._state
+        enc, mk = self.model.encoder, self.masker
+        S, win, hop = st["S"], self.win, self.hop
+        Cc, H = mk.input_dim, mk.tcn_dim
+        blocks = [b for stack in mk.tcn_list for b in stack]
+        if Cc % 4 or H % 4 or win % 4 or H > 2048 or enc.encoder.out_channels != Cc:
+            return None
+        dev = st["out"].device
+        kind = 0 if mk.tcn_norm == "cLN" else 1
+        arr = (_lib.StreamHopBlock * len(blocks))()
+        keep = []
+        # From HOP_MMA_MIN_STREAMS concurrent streams on, the GEMM phases run on the tensor cores (mma.sync, 3xBF16 split,
+        # ~2^-17 per product like the offline GEMMs); below, exact-fp32 FFMA.  The split of every weight is made once here.
+        mma = S >= self.HOP_MMA_MIN_STREAMS and Cc % 16 == 0 and H % 16 == 0 and win % 16 == 0
+
+        def split(w2d: torch.Tensor):
+            if not mma:
+                return None
+            hi = w2d.detach().to(torch.bfloat16)
+            lo = (w2d.detach() - hi.float()).to(torch.bfloat16)
+            pk = torch.cat([hi, lo], 0).contiguous()
+            keep.append(pk)
+            return pk.data_ptr()
+
+        for j, blk in enumerate(blocks):
+            dsc = blk.dconv[0]
+            n1, n2, n3 = blk.in_conv[1], dsc.depthwise[1], dsc.pointwise[1]
+            e = arr[j]
+            e.w_in, e.w_in_ld = blk.in_conv[0].weight.data_ptr(), blk.in_channels + blk.emb_dim
+            e.ebias = ops._p(mst["ebias"][j])
+            if kind == 0:
+                trip = [(n.gamma, n.beta) for n in (n1, n2, n3)]
+            else:
+                trip = mst["folded"][j]
+            (e.n1_a, e.n1_b), (e.n2_a, e.n2_b), (e.n3_a, e.n3_b) = [(a.data_ptr(), b.data_ptr()) for a, b in trip]
+            e.slope1, e.slope2, e.slope3 = (prelu_slope(blk.in_conv[2]).data_ptr(), prelu_slope(dsc.depthwise[2]).data_ptr(),
+                                            prelu_slope(dsc.pointwise[2]).data_ptr())
+            dw, pw = dsc.depthwise[0], dsc.pointwise[0]
+            e.dw_w, e.dw_b = dw.weight.data_ptr(), ops._p(dw.bias)
+            e.w_pw, e.b_pw = pw.weight.data_ptr(), ops._p(pw.bias)
+            e.w_out, e.b_out = blk.out_conv.weight.data_ptr(), ops._p(blk.out_conv.bias)
+            e.ring, e.P, e.dilation = mst["rings"][j].data_ptr(), blk.kernel, blk.dilation
+            e.w_in_p = split(blk.in_conv[0].weight.view(H, blk.in_channels + blk.emb_dim)[:, :Cc])
+            e.w_pw_p = split(pw.weight.view(H, H))
+            e.w_out_p = split(blk.out_conv.weight.view(Cc, H))
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        scratch = {k: torch.zeros(S, n, device=dev) for k, n in (("feats", Cc), ("x", Cc), ("u1", H), ("u2", H), ("u3", H), ("frame_out", win))}
+        barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        d = _lib.StreamHopDesc()
+        d.streams, d.C, d.H, d.win, d.hop, d.n_blocks = S, Cc, H, win, hop, len(blocks)
+        d.norm_kind, d.enc_relu, d.mask_act, d.constraint = kind, int(bool(enc.output_active)), self._mask_act, self._constraint
+        d.eps = float(blocks[0].in_conv[1].eps) if kind == 0 else 0.0
+        d.w_enc, d.w_dec_t, d.blocks = enc.encoder.weight.data_ptr(), self._w_dec_t.data_ptr(), table.data_ptr()
+        d.chunk, d.hist, d.frame, d.frame_out = st["chunk"].data_ptr(), st["hist"].data_ptr(), st["frame"].data_ptr(), scratch["frame_out"].data_ptr()
+        d.acc, d.out, d.step = st["acc"].data_ptr(), st["out"].data_ptr(), mst["step"].data_ptr()
+        d.feats, d.x, d.u1, d.u2, d.u3 = (scratch[k].data_ptr() for k in ("feats", "x", "u1", "u2", "u3"))
+        d.barrier = barrier.data_ptr()
+        d.w_enc_p, d.w_dec_p = split(enc.encoder.weight.view(Cc, win)), split(self._w_dec_t)
+        return {"desc": d, "keep": (table, scratch, barrier, keep)}
+
+    def _hop_kernel(self):
+        _lib.check(_lib.load().ps_stream_hop(C.byref(self._hop["desc"]), torch.cuda.current_stream().cuda_stream), "ps_stream_hop")
+        ops._launched()
 
     def _push(self):
         st = self._st
@@ -271,6 +345,10 @@ class StreamingSeparator(nn.Module):
         _lib.check(lib.ps_stream_push(st["chunk"].data_ptr(), st["hist"].data_ptr(), st["frame"].data_ptr(), st["S"], self.win, self.hop,
                                       torch.cuda.current_stream().cuda_stream), "ps_stream_push")
         ops._launched()
+
+    def _push_and_compute(self):
+        self._push()
+        self._compute()
 
     def _compute(self):
         """encoder GEMM -> masker step -> mask-apply + decoder GEMM -> overlap-add emit, all on static buffers."""
@@ -296,21 +374,23 @@ class StreamingSeparator(nn.Module):
             raise ValueError(f"expected a chunk of shape {(st['S'], self.hop)}, got {tuple(chunk.shape)}")
         on_host = not chunk.is_cuda
         st["chunk"].copy_(chunk, non_blocking=True)
-        self._push()
         st["chunks"] += 1
+        hopk = self._hop is not None
         if st["chunks"] <= st["prime"]:
+            self._push()
             out = torch.zeros_like(st["out"])  # the first complete window has not arrived yet
             return out.cpu() if on_host else out
+        step = self._hop_kernel if hopk else self._push_and_compute  # (the hop kernel assembles the frame itself)
         first = st["chunks"] == st["prime"] + 1
         if not self.use_graph or first:
-            self._compute()  # the first hop runs eagerly: it loads the kernels and fills the weight caches
+            step()  # the first hop runs eagerly: it loads the kernels and fills the weight caches
         else:
             if st["graph"] is None:
                 # capture the fixed kernel chain of one hop (capture records, it does not execute) ...
                 g = torch.cuda.CUDAGraph()
                 dev = st["out"].device
                 with torch.cuda.device(dev), torch.cuda.graph(g, stream=torch.cuda.Stream(dev)):  # capture stream on OUR device
-                    self._compute()
+                    step()
                 st["graph"] = g
             st["graph"].replay()  # ... and replay it for this and every later hop
         out = st["out"].clone()

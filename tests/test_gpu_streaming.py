@@ -23,10 +23,11 @@ def build(norm, win, hop, nf, hid, X, Rp, seed):
     return m
 
 
-def run_stream(m, wav, use_graph):
+def run_stream(m, wav, use_graph, use_hop_kernel=True):
     S, L = wav.shape
-    sep = StreamingSeparator(m, use_graph=use_graph)
+    sep = StreamingSeparator(m, use_graph=use_graph, use_hop_kernel=use_hop_kernel)
     sep.init_status(S)
+    assert (sep._hop is not None) == use_hop_kernel
     hop, win = sep.hop, sep.win
     outs = []
     for j in range(L // hop):
@@ -37,11 +38,13 @@ def run_stream(m, wav, use_graph):
 
 @pytest.mark.parametrize("norm,win,hop", [("cLN", 32, 16), ("bN1d", 32, 16), ("cLN", 48, 16)])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_streaming_equals_offline_small(norm, win, hop, use_graph):
+@pytest.mark.parametrize("hop_kernel", [True, False])
+def test_streaming_equals_offline_small(norm, win, hop, use_graph, hop_kernel):
+    """hop_kernel=True: the persistent cooperative kernel (ps_stream_hop, one launch per hop); False: the kernel chain."""
     m = build(norm, win, hop, 24, 40, 4, 2, seed=3)
     wav = testing.white(3, hop * 90, amp=0.1, seed=5)
     ref = R.inference(m.state_dict(), D.describe(m), wav)
-    y = run_stream(m.cuda(), wav, use_graph)
+    y = run_stream(m.cuda(), wav, use_graph, hop_kernel)
     n = y.shape[1]
     assert n >= ref.shape[1] - win
     err = (y - ref[:, :n]).abs().max().item()
@@ -206,3 +209,26 @@ def test_streaming_guards():
     sep.init_status(2)
     with pytest.raises(ValueError):
         sep.step_wave(torch.zeros(1, 16))
+
+
+@pytest.mark.parametrize("S", [1, 5, 40, 200, 256])
+def test_hop_kernel_stream_counts_and_launches(S):
+    """ps_stream_hop at stream counts that exercise every tile shape of its GEMM phases (1 x 4 ... 16 x 64 channel slabs, ragged
+    last row group), full cfg-5 width, against the kernel chain on the same inputs (both exact fp32: 2e-5) - and ONE launch per
+    hop instead of ~125."""
+    from puresound_b200 import ops
+
+    m = build("cLN", 320, 160, 512, 512, 3, 1, seed=4).cuda()
+    wav = testing.white(S, 160 * 8, amp=0.1, seed=6)
+    outs = {}
+    for hopk in (True, False):
+        sep = StreamingSeparator(m, use_graph=False, use_hop_kernel=hopk)
+        sep.init_status(S)
+        ys, n0 = [], None
+        for j in range(8):
+            if j == 7:
+                n0 = ops.launch_count
+            ys.append(sep.step_wave(wav[:, j * 160:(j + 1) * 160].cuda()))
+        outs[hopk] = (torch.cat(ys, dim=1).cpu(), ops.launch_count - n0)
+    assert (outs[True][0] - outs[False][0]).abs().max().item() <= (2e-5 if S < 32 else 2e-4)  # (tensor-core phases from 32 streams on)
+    assert outs[True][1] == 1 and outs[False][1] > 10, (outs[True][1], outs[False][1])
