@@ -13,6 +13,11 @@ void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+bool pdl_enabled() {
+  static EnvInt env;
+  return env.get("PS_PDL", 0) != 0;
+}
+
 int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s);
 bool gemm_tc_eligible(const ps_gemm_t& d);
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s);

@@ -73,6 +73,41 @@ struct SmemOnce {
   }
 };
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The separator forward is 170-650 short kernels in stream order (replayed from a CUDA graph); at batch 1 a kernel's launch
+// latency, barrier / TMEM setup and first loads were longer than its work.  Kernels on the hot path (GEMMs, depthwise conv,
+// statistics merge, overlap-add) are launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+//   * call pdl_trigger() at entry: the NEXT kernel of the stream may be scheduled on SMs that are idle or become free,
+//   * call pdl_wait() after their on-chip prologue and BEFORE their first access to global memory that another kernel of
+//     the stream writes or reads: it returns when every earlier kernel has completed and flushed (griddepcontrol.wait is
+//     transitive through the chain), so from there on plain stream order holds - only the prologue overlaps.
+// A kernel launched this way after one that never triggers simply starts when that one ends.  Stream capture records the
+// programmatic edges in the graph.  MEASURED (round 2, run 14, CUDA-graph replay): no gain - cfg1 2.02 -> 2.12 ms, cfg4 6.13 ->
+// 6.07 ms, cfg2 37.7 -> 37.8 ms: graph replay already issues the nodes back to back and the kernels' cost at batch 1 is
+// inside them (weight stream per tile), not between them.  So the attribute is OFF by default; PS_PDL=1 turns it on.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+struct EnvInt;
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // integer switch read once from the environment (A/B runs only; product defaults never depend on it being set)
 struct EnvInt {
   std::atomic<int> v{INT32_MIN};

@@ -357,12 +357,12 @@ extern "C" int ps_dwconv(const ps_dwconv_t* dp, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   ps_dwconv_t dd = d;
   dd.stats_slots = ps_dwconv_stats_slots(d.T, d.C);
+  if (ps::dwconv_tma_eligible(dd)) return ps::dwconv_tma_launch(dd, s);  // TMA-fed sliding window (ps_dwconv_tma.cu); zeroes its own unused slots
   if (d.stats_partials) {
     // both kernels fill a prefix of the slot array; the rest must read as empty (count 0) partials
     cudaError_t e = cudaMemsetAsync(d.stats_partials, 0, (size_t)d.batch * dd.stats_slots * 3 * sizeof(float), s);
     if (e != cudaSuccess) { ps::set_cuda_error(e, "cudaMemsetAsync(stats_partials)"); return PS_ERR_CUDA; }
   }
-  if (ps::dwconv_tma_eligible(dd)) return ps::dwconv_tma_launch(dd, s);  // TMA-fed sliding window (ps_dwconv_tma.cu)
   const int halo = (d.P - 1) * d.dilation;
   const bool act_ok = d.pro_mode == PS_PRO_NONE || d.pro_act == PS_ACT_PRELU || d.pro_act == PS_ACT_NONE;
   if (g.vec == 4 && halo <= 1024 && act_ok && d.T < (1 << 30) && !getenv("PS_DWCONV_STREAMING")) {

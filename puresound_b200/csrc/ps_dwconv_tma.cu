@@ -48,13 +48,22 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
   const int tb = (ta + rows_per_cta) < T ? (ta + rows_per_cta) : T;
   const uint32_t ring_u = smem_u32(ring), bar_u = smem_u32(full_bar);
 
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) mbar_init(bar_u + 8 * s, 1);
     fence_barrier_init();
     tma_prefetch_desc(&xmap);
   }
   __syncthreads();
-  if (ta >= T) return;  // (empty run: its statistics slot was zeroed by the launcher)
+  pdl_wait();  // the producer of x and the statistics merge that made pro_a / pro_b are complete
+  // statistics slots no run of this launch writes must read as empty partials (count 0): the first CTA of every item zeroes
+  // them (the launcher used to memset the whole array, a graph node that cut the programmatic launch chain)
+  if (d.stats_partials && cg == 0 && split == 0) {
+    const int64_t used = (int64_t)gridDim.x * gridDim.y;
+    float* sp = d.stats_partials + b * d.stats_slots * 3;
+    for (int64_t i = used * 3 + tid; i < d.stats_slots * 3; i += DM_THREADS) sp[i] = 0.f;
+  }
+  if (ta >= T) return;  // (cannot happen: the grid has ceil(T / rows_per_cta) runs)
 
   const int n_out = (tb - ta + DM_CH - 1) / DM_CH;  // output chunks of this run
   const int total_in = n_out + HC;                  // input chunks: rows [ta - halo_l, ...)
@@ -210,8 +219,8 @@ template <int PRO>
 static int launch_dm(const ps_dwconv_t& d, const CUtensorMap& xmap, int rows, int nslots, int HC, dim3 grid, cudaStream_t s, int dev) {
   static SmemOnce<1> once;
   if (int rc = once.ensure(dev, 0, dwconv_tma_kernel<PRO>, DM_MAXSLOTS * DM_CHUNK_BYTES, "cudaFuncSetAttribute(dwconv_tma_kernel)")) return rc;
-  dwconv_tma_kernel<PRO><<<grid, DM_THREADS, (size_t)nslots * DM_CHUNK_BYTES, s>>>(d, xmap, rows, nslots, HC);
-  PS_CHECK_LAUNCH("dwconv_tma_kernel");
+  cudaError_t le = launch_pdl(dwconv_tma_kernel<PRO>, grid, dim3(DM_THREADS), (size_t)nslots * DM_CHUNK_BYTES, s, d, xmap, rows, nslots, HC);
+  if (le != cudaSuccess) { set_cuda_error(le, "dwconv_tma_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }
 

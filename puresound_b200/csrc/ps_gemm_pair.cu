@@ -233,11 +233,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     }
     fence_barrier_init();
   }
+  pdl_trigger();  // (PS_PDL=1) the next kernel of the stream may start its prologue on SMs this grid leaves idle / frees
   if (warp == 1) tmem_alloc_pair(smem_u32((const void*)tmem_ptr_s), 512);
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  pdl_wait();  // every earlier kernel of the stream is complete: operands, folded norms, residual are in place
 
   if (warp == 0) {
     // ===================== weight loader =====================
@@ -675,8 +677,8 @@ static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid
 #else
   const int dbg = 0;
 #endif
-  gemm_pair_kernel<PRO, NB, kLN><<<(unsigned)grid, PR_THREADS, PairCfg<NB>::kSmem, s>>>(d, n_rt, n_nh, n_tiles, dbg);
-  PS_CHECK_LAUNCH("gemm_pair_kernel");
+  cudaError_t le = launch_pdl(gemm_pair_kernel<PRO, NB, kLN>, dim3((unsigned)grid), dim3(PR_THREADS), PairCfg<NB>::kSmem, s, d, n_rt, n_nh, n_tiles, dbg);
+  if (le != cudaSuccess) { set_cuda_error(le, "gemm_pair_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }
 

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) ola_kernel(const float* __restrict__ fram
                                                   int64_t out_len) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t b = blockIdx.y;
+  pdl_trigger();
+  pdl_wait();  // the synthesis GEMM's frames are complete
   if (j >= out_len) return;
   int64_t t_hi = j / hop;
   if (t_hi > T - 1) t_hi = T - 1;
@@ -240,7 +242,8 @@ extern "C" int ps_ola(const float* frames, int64_t batch, int64_t T, int64_t win
   if (batch > 65535) return PS_ERR_UNSUPPORTED;
   const int64_t out_len = (T - 1) * hop + win;
   dim3 grid((unsigned)cdiv(out_len, 256), (unsigned)batch);
-  ps::ola_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, T, win, hop, wsum, constraint, y, out_len);
+  cudaError_t le = ps::launch_pdl(ps::ola_kernel, grid, dim3(256), 0, (cudaStream_t)stream, frames, T, win, hop, wsum, (int)constraint, y, out_len);
+  if (le != cudaSuccess) { ps::set_cuda_error(le, "ola_kernel"); return PS_ERR_CUDA; }
   PS_CHECK_LAUNCH("ola_kernel");
   return PS_OK;
 }

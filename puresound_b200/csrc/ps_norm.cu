@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) stats_finalize_kernel(const float* __rest
                                                              float* __restrict__ meanvar) {
   __shared__ double sn[256], sm[256], s2[256];
   const int64_t b = blockIdx.x;
+  pdl_trigger();
+  pdl_wait();  // the producer kernel's partials are complete and visible
   stats_finalize_item<0>(partials + b * slots * 3, slots, gamma, beta, eps, C, scale + b * C, shift + b * C,
                          meanvar ? meanvar + b * 2 : nullptr, (int)threadIdx.x, sn, sm, s2);
 }
@@ -128,9 +130,9 @@ extern "C" int ps_stats_finalize(const float* partials, int64_t batch, int64_t s
                                  const float* beta, float eps, int64_t C, float* scale, float* shift, float* meanvar,
                                  void* stream) {
   PS_REQUIRE(partials && scale && shift && batch > 0 && slots > 0 && C > 0);
-  ps::stats_finalize_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(partials, slots, gamma, beta, eps, C,
-                                                                               scale, shift, meanvar);
-  PS_CHECK_LAUNCH("stats_finalize_kernel");
+  cudaError_t le = ps::launch_pdl(ps::stats_finalize_kernel, dim3((unsigned)batch), dim3(256), 0, (cudaStream_t)stream, partials, slots, gamma, beta, eps, C,
+                                  scale, shift, meanvar);
+  if (le != cudaSuccess) { ps::set_cuda_error(le, "stats_finalize_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }
 
