@@ -56,10 +56,17 @@ constexpr int PR_MAXK = 1024;
 constexpr int PR_AFF_BYTES = 2 * PR_MAXK * 4;
 constexpr int PR_CW = 16;           // frames (TMEM columns) per epilogue chunk
 
-template <int NB>
+// SUB = 32-k sub-tiles per shared-memory stage.  A stage hand-over (producers -> full -> relay -> MMA issue -> commit -> empty ->
+// producers) has a round trip of ~1.9 us whatever it carries (profiles/r02_gemm_notes.md): with one 256-channel block (NB = 1:
+// M = 32 ... 256, the DPRNN projections, the U-Net shell, the decoder) a 32-k stage is only 8 KB of fp32 operand per CTA, and
+// that hand-over rate - not HBM, not the tensor pipe - capped those launches at ~2.5 TB/s of operand reads.  NB = 1 has the
+// shared memory for 64-k stages (SUB = 2: 48 KB x 4), which halves the hand-overs per byte.
+template <int NB, int SUB = 1>
 struct PairCfg {
-  static constexpr int kStageBytes = 2 * PR_XPART + 2 * NB * PR_WBLK;       // NB=2: 40 KB, NB=1: 24 KB
-  static constexpr int kWBytes = 2 * NB * PR_WBLK;                          // weight bytes per stage per CTA
+  static constexpr int kWBytes = 2 * NB * PR_WBLK;                          // weight bytes per 32-k sub-tile per CTA
+  static constexpr int kXBytes = 2 * PR_XPART;                              // operand bytes (hi + lo) per sub-tile per CTA
+  static constexpr int kStageBytes = SUB * (kXBytes + kWBytes);             // NB=2: 40 KB, NB=1: 24 KB (SUB=2: 48 KB)
+  static constexpr int kWOff = SUB * kXBytes;                               // stage layout: [X sub 0 .. X sub SUB-1 | W sub 0 .. ]
   static constexpr int kAccCols = NB * PR_FRAMES;                           // TMEM columns of one accumulator set
   static constexpr int kFinBytes = 3 * 256 * 8;                             // fp64 scratch of the fused statistics finalize
   static constexpr int kSmem = PR_STAGES * kStageBytes + PR_AFF_BYTES + 1024 /*align*/ + 512 /*barriers, scratch*/ + kFinBytes;
@@ -197,10 +204,10 @@ __device__ __forceinline__ void epi_chunk_ln(float (&v)[PR_CW], float bsum, floa
 // PR_PRO_AFFINE_TANH (kernel-internal: the affine followed by tanh - eval BatchNorm + nn.Tanh in front of the second conv of
 // AttentiveStatisticsPooling, lobe/pooling.py:71-86,104-105; its own instantiation so the TCN path's producers are untouched)
 constexpr int PR_PRO_AFFINE_TANH = 4;
-template <int PRO, int NB, bool kLN = false>
+template <int PRO, int NB, bool kLN = false, int SUB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
-  using Cfg = PairCfg<NB>;
+  using Cfg = PairCfg<NB, SUB>;
   constexpr int STAGE = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -219,11 +226,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
   const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int KB = (int)(d.K / PR_BK);
+  const int KB = (int)(d.K / (PR_BK * SUB));  // stages per tile
 
   if (tid == 0) {
     for (int s = 0; s < PR_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, PR_PRODUCERS / 64 + 1);  // the 4 producer warps of this stage + the weight copy
+      mbar_init(bar_full + 8 * s, PR_PRODUCERS / (SUB == 2 ? 32 : 64) + 1);  // the producer warps of this stage (4, or all 8 at SUB = 2) + the weight copy
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_pfull + 8 * s, 1);
     }
@@ -249,19 +256,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.W_packed);
     for (int64_t t = pair; t < n_tiles; t += n_pairs) {
       const PairTile tc = pr_tile(t, n_rt, n_nh);
-      const uint8_t* src = wp + (size_t)(tc.nh * 2 + rank) * KB * Cfg::kWBytes;
+      constexpr uint32_t WST = SUB * Cfg::kWBytes;  // the SUB sub-tiles of a stage are adjacent in the packed image
+      const uint8_t* src = wp + (size_t)(tc.nh * 2 + rank) * KB * WST;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kWBytes);
+          mbar_arrive_expect_tx(bar_full + 8 * s, WST);
           if (PR_DBG(1)) {  // experiment: no weight traffic (results are garbage)
-            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"((uint32_t)Cfg::kWBytes) : "memory");
-          } else if (PR_DBG(32)) {  // experiment: four smaller copies
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              bulk_g2s(base + s * STAGE + 2 * PR_XPART + i * (Cfg::kWBytes / 4), src + (size_t)kb * Cfg::kWBytes + i * (Cfg::kWBytes / 4), Cfg::kWBytes / 4, bar_full + 8 * s);
+            asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(WST) : "memory");
           } else
-            bulk_g2s(base + s * STAGE + 2 * PR_XPART, src + (size_t)kb * Cfg::kWBytes, Cfg::kWBytes, bar_full + 8 * s);
+            bulk_g2s(base + s * STAGE + Cfg::kWOff, src + (size_t)kb * WST, WST, bar_full + 8 * s);
         }
         __syncwarp();
         if (++s == PR_STAGES) { s = 0; ph ^= 1; }
@@ -284,20 +288,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
           mbar_wait(bar_pfull + 8 * s, ph);  // the peer's stage (relayed)
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sa = base + s * STAGE;
-            const uint64_t x_hi = pr_desc(sa), x_lo = pr_desc(sa + PR_XPART);
 #pragma unroll
-            for (int mb = 0; mb < NB; ++mb) {
-              const uint64_t w_hi = pr_desc(sa + 2 * PR_XPART + mb * PR_WBLK);
-              const uint64_t w_lo = pr_desc(sa + 2 * PR_XPART + (NB + mb) * PR_WBLK);
+            for (int sub = 0; sub < SUB; ++sub) {
+              const uint32_t sa = base + s * STAGE;
+              const uint32_t xa = sa + sub * Cfg::kXBytes, wa = sa + Cfg::kWOff + sub * Cfg::kWBytes;
+              const uint64_t x_hi = pr_desc(xa), x_lo = pr_desc(xa + PR_XPART);
 #pragma unroll
-              for (int k = 0; k < PR_BK / 16; ++k) {
-                const uint64_t ko = (uint64_t)((k * 32) >> 4);
-                const uint32_t dd = tmem_d + (uint32_t)(mb * PR_FRAMES);
-                // small cross terms first, the dominant hi*hi last
-                umma_bf16_pair(dd, w_lo + ko, x_hi + ko, PR_IDESC, (kb | k) != 0);
-                umma_bf16_pair(dd, w_hi + ko, x_lo + ko, PR_IDESC, 1);
-                umma_bf16_pair(dd, w_hi + ko, x_hi + ko, PR_IDESC, 1);
+              for (int mb = 0; mb < NB; ++mb) {
+                const uint64_t w_hi = pr_desc(wa + mb * PR_WBLK);
+                const uint64_t w_lo = pr_desc(wa + (NB + mb) * PR_WBLK);
+#pragma unroll
+                for (int k = 0; k < PR_BK / 16; ++k) {
+                  const uint64_t ko = (uint64_t)((k * 32) >> 4);
+                  const uint32_t dd = tmem_d + (uint32_t)(mb * PR_FRAMES);
+                  // small cross terms first, the dominant hi*hi last
+                  umma_bf16_pair(dd, w_lo + ko, x_hi + ko, PR_IDESC, (kb | sub | k) != 0);
+                  umma_bf16_pair(dd, w_hi + ko, x_lo + ko, PR_IDESC, 1);
+                  umma_bf16_pair(dd, w_hi + ko, x_hi + ko, PR_IDESC, 1);
+                }
               }
             }
             umma_commit_pair(bar_empty + 8 * s);                  // frees this stage in both CTAs when the MMAs retire
@@ -479,7 +487,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
     const int K = (int)d.K;
     const int64_t t_step = k32 ? 2 * n_pairs : n_pairs;
     const float pslope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;  // AFFINE w/o act = slope 1
-    int s = half;  // this thread's stage: half 0 walks stages 0,2,4,.., half 1 walks 1,3,5,.. (mod the ring depth)
+    // this thread's stage: half 0 walks stages 0,2,4,.., half 1 walks 1,3,5,.. (mod the ring depth); at SUB = 2 a stage is
+    // 64 k, so both halves fill the SAME stage (sub-tile = half) and walk 0,1,2,..
+    int s = SUB == 2 ? 0 : half;
     uint32_t ph = 0;
 
     struct XBuf {
@@ -556,7 +566,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       }
       const int my_s = s;
       mbar_wait(bar_empty + 8 * my_s, ph ^ 1);
-      uint8_t* x_hi = sm + my_s * STAGE;
+      uint8_t* x_hi = sm + my_s * STAGE + (SUB == 2 ? half * Cfg::kXBytes : 0);
       uint8_t* x_lo = x_hi + PR_XPART;
 #pragma unroll
       for (int p = 0; p < 2 && !PR_DBG(8); ++p) {
@@ -595,7 +605,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor cores of both SMs (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * my_s);  // one arrival per warp (a warp lies entirely in one half)
-      s += 2;
+      s += SUB == 2 ? 1 : 2;
       if (s >= PR_STAGES) { s -= PR_STAGES; ph ^= 1; }
     };
 
@@ -667,17 +677,17 @@ int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* pack
   return PS_OK;
 }
 
-template <int PRO, int NB, bool kLN = false>
+template <int PRO, int NB, bool kLN = false, int SUB = 1>
 static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles) {
   static SmemOnce<1> once;  // per instantiation and device
-  if (int rc = once.ensure(dev, 0, gemm_pair_kernel<PRO, NB, kLN>, PairCfg<NB>::kSmem, "cudaFuncSetAttribute(gemm_pair_kernel)")) return rc;
+  if (int rc = once.ensure(dev, 0, gemm_pair_kernel<PRO, NB, kLN, SUB>, PairCfg<NB, SUB>::kSmem, "cudaFuncSetAttribute(gemm_pair_kernel)")) return rc;
 #ifdef PS_EXPERIMENTS
   static EnvInt dbg_e;
   const int dbg = dbg_e.get("PS_PAIR_DBG", 0);
 #else
   const int dbg = 0;
 #endif
-  cudaError_t le = launch_pdl(gemm_pair_kernel<PRO, NB, kLN>, dim3((unsigned)grid), dim3(PR_THREADS), PairCfg<NB>::kSmem, s, d, n_rt, n_nh, n_tiles, dbg);
+  cudaError_t le = launch_pdl(gemm_pair_kernel<PRO, NB, kLN, SUB>, dim3((unsigned)grid), dim3(PR_THREADS), PairCfg<NB, SUB>::kSmem, s, d, n_rt, n_nh, n_tiles, dbg);
   if (le != cudaSuccess) { set_cuda_error(le, "gemm_pair_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }
@@ -706,7 +716,18 @@ int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
   const int64_t max_pairs = sms / 2;
   const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+  // one 256-channel block and K a multiple of 64: 64-k stages (SUB = 2), half the stage hand-overs per operand byte.
+  // PS_PAIR_SUB=1 keeps 32-k stages (A/B).
+  static EnvInt sub_env;
+  const bool sub2 = nb == 1 && d.K % 64 == 0 && sub_env.get("PS_PAIR_SUB", 2) == 2;
+  // (the LayerNorm-epilogue variant keeps 32-k stages: measured slower with 64-k ones, cfg3 projection 0.495 -> 0.538 ms)
   if (ln) return launch_pair<PS_PRO_NONE, 1, true>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  if (sub2) {
+    if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+    return launch_pair<PS_PRO_NONE, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
+  }
   if (nb == 2) {
     if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);
     if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles);

@@ -11,6 +11,7 @@ output constraint fused.  Training (``forward(**kw)`` -> loss) is out of scope.
 """
 from __future__ import annotations
 
+import gc
 import os
 from collections import OrderedDict
 from typing import Optional, Tuple
@@ -177,17 +178,28 @@ class SoTaskWrapModule(nn.Module):
         for m in self._host_hooks:
             m.host_prepare(device)
 
+    def _sig_lists(self):
+        """Tensors / modules the two signatures walk, collected once: walking the module tree on every call cost 1.9 ms of
+        host time per inference() at cfg2's 386 tensors / 417 modules - as long as a whole batch-1 forward, and 8 x that in
+        the single-process ShardedSeparator.  (.to() / load_state_dict keep the Parameter objects, so the lists stay valid;
+        a model whose sub-modules are replaced after its first inference() must be re-wrapped.)"""
+        c = self.__dict__.get("_sig_cache")
+        if c is None:
+            # SUB-modules only: a list holding `self` would be a reference cycle, the model would then be freed by the cyclic
+            # collector at some later allocation - possibly in the middle of ANOTHER model's stream capture, where destroying
+            # this one's CUDA graphs / streams invalidates that capture (seen as cudaErrorStreamCaptureInvalidated in the tests)
+            mods = [m for m in self.modules() if m is not self]
+            c = (list(self.parameters()) + list(self.buffers()), mods, [m for m in mods if isinstance(m, nn.Dropout)])
+            self.__dict__["_sig_cache"] = c
+        return c
+
     def _mode_signature(self):
         """train/eval flags of all sub-modules and the dropout probabilities, folded to one hashable value."""
-        h = 0
-        for i, m in enumerate(self.modules()):
-            h = (h * 1000003 + (2 * i + 1) * int(m.training)) & 0xFFFFFFFFFFFF
-            if isinstance(m, nn.Dropout):
-                h = (h * 1000003 + hash(float(m.p))) & 0xFFFFFFFFFFFF
-        return h
+        _, mods, drops = self._sig_lists()
+        return (self.training, tuple(m.training for m in mods), tuple(float(m.p) for m in drops))
 
     def _param_signature(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return tuple([(t.data_ptr(), t._version) for t in self._sig_lists()[0]])
 
     def _run(self, noisy: torch.Tensor, enroll: Optional[torch.Tensor], constrain: bool = True) -> torch.Tensor:
         """_inference_cl through a captured CUDA graph.  A forward is 170-650 small launches; at batch 1 (cfg1) and for
@@ -226,8 +238,18 @@ class SoTaskWrapModule(nn.Module):
             cs = self._cap_streams.get(noisy.device.index)
             if cs is None:
                 cs = self._cap_streams[noisy.device.index] = torch.cuda.Stream(noisy.device)
-            with torch.cuda.device(noisy.device), torch.cuda.graph(g, stream=cs):
-                ent["out"] = self._inference_cl(ent["in"], ent["enroll"], constrain)
+            # no cyclic garbage collection while the stream captures: a dead model of the caller's (reference cycles are
+            # enough) that owns CUDA graphs would be finalised wherever the collector happens to run, and destroying a
+            # graph inside a capture invalidates it (cudaErrorStreamCaptureInvalidated); torch.cuda.graph no longer
+            # collects before capturing
+            gc_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.device(noisy.device), torch.cuda.graph(g, stream=cs):
+                    ent["out"] = self._inference_cl(ent["in"], ent["enroll"], constrain)
+            finally:
+                if gc_on:
+                    gc.enable()
             ent["graph"] = g
             # device tensors the captured kernels read by raw pointer but that live in module-level caches (the iSTFT
             # window-sum-square tables): referenced here so a cache eviction cannot free them under a live graph

@@ -72,6 +72,7 @@ class ShardedSeparator:
         self.replicas = []
         saved, model._graphs = model._graphs, OrderedDict()  # captured graphs / capture streams belong to the source's device
         saved_cs = model.__dict__.pop("_cap_streams", None)
+        model.__dict__.pop("_sig_cache", None)  # (lists of the source's tensors / modules: rebuilt per replica)
         try:
             for dev in self.devices:
                 self.replicas.append(copy.deepcopy(model).to(dev).eval())
