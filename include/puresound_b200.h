@@ -115,8 +115,8 @@ typedef struct {
 
 PS_API int ps_gemm(const ps_gemm_t* d, void* stream);
 /* which kernel ps_gemm would run for this descriptor on the current device (no launch): 0 exact-fp32 CUDA cores,
- * 1 single-CTA tcgen05, 2 CTA-pair tcgen05 (128-frame tiles), 3 wide CTA-pair tcgen05 (256-frame tiles); negative ps_status
- * on error.  For tests, profiles and bench labels. */
+ * 1 single-CTA tcgen05, 2 CTA-pair tcgen05 (128-frame tiles), 3 wide CTA-pair tcgen05 (256-frame tiles), 4 few-channel
+ * tcgen05 (M <= 128: frames on the MMA's M side, weights resident in shared memory); negative ps_status on error.  For tests, profiles and bench labels. */
 PS_API int ps_gemm_path(const ps_gemm_t* d);
 /* number of (count,mean,M2) slots per batch item ps_gemm writes for this shape */
 PS_API int64_t ps_gemm_stats_slots(int64_t rows, int64_t M);

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpuresound_b200.so")
-SOURCES = ["ps_api.cu", "ps_gemm_simt.cu", "ps_gemm_tc.cu", "ps_gemm_pair.cu", "ps_gemm_wide.cu", "ps_gemm_wide_tma.cu", "ps_norm.cu", "ps_dwconv.cu", "ps_dwconv_tma.cu", "ps_misc.cu", "ps_gated.cu", "ps_attention.cu", "ps_sdr.cu", "ps_lstm.cu", "ps_lstm_tc.cu", "ps_stream.cu", "ps_stream_hop.cu"]
+SOURCES = ["ps_api.cu", "ps_gemm_simt.cu", "ps_gemm_tc.cu", "ps_gemm_pair.cu", "ps_gemm_wide.cu", "ps_gemm_wide_tma.cu", "ps_gemm_rows.cu", "ps_norm.cu", "ps_dwconv.cu", "ps_dwconv_tma.cu", "ps_misc.cu", "ps_gated.cu", "ps_attention.cu", "ps_sdr.cu", "ps_lstm.cu", "ps_lstm_tc.cu", "ps_stream.cu", "ps_stream_hop.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -23,6 +23,7 @@ bool gemm_tc_eligible(const ps_gemm_t& d);
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s);
 bool tc_pair();
 bool gemm_pair_ln_eligible(const ps_gemm_t& d);
+bool gemm_rows_eligible(const ps_gemm_t& d);
 
 }  // namespace ps
 
@@ -77,9 +78,10 @@ extern "C" int ps_gemm_path(const ps_gemm_t* dp) {
   PS_REQUIRE(dp != nullptr);
   const ps_gemm_t& d = *dp;
   const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);
-  if (d.ln_eps > 0.f && !(tc && ps::tc_pair() && ps::gemm_pair_ln_eligible(d))) return 0;
+  if (d.ln_eps > 0.f && !(tc && ps::tc_pair() && (ps::gemm_pair_ln_eligible(d) || ps::gemm_rows_eligible(d)))) return 0;
   if (!tc) return 0;
   if (!ps::tc_pair()) return 1;
+  if (ps::gemm_rows_eligible(d)) return 4;
   int dev = 0, sms = 0;
   if (int rc = ps::current_device(&dev)) return rc;
   if (int rc = ps::sm_count_of(dev, &sms)) return rc;
@@ -104,7 +106,7 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
     // Linear -> LayerNorm (-> + residual): fused epilogue on the CTA-pair kernel, else GEMM then ps_rownorm in place
     PS_REQUIRE(!d.stats_partials && d.epi_act == PS_ACT_NONE && d.y_row_stride == d.M && d.y_batch_stride == d.rows * d.M);
     const bool fuse = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::tc_pair() && ps::gemm_tc_eligible(d) &&
-                      ps::gemm_pair_ln_eligible(d);
+                      (ps::gemm_pair_ln_eligible(d) || ps::gemm_rows_eligible(d));
     if (fuse) return ps::gemm_tc_launch(d, s);
     if (d.backend == PS_GEMM_TCGEN05) return PS_ERR_UNSUPPORTED;
     PS_REQUIRE(!d.residual || (d.res_row_stride == d.M && d.res_batch_stride == d.rows * d.M && d.residual != d.Y));
@@ -116,7 +118,8 @@ extern "C" int ps_gemm(const ps_gemm_t* dp, void* stream) {
   }
   const bool tc = (d.backend == PS_GEMM_TCGEN05 || d.backend == PS_GEMM_AUTO) && ps::gemm_tc_eligible(d);
   if (d.backend == PS_GEMM_TCGEN05 && !tc) return PS_ERR_UNSUPPORTED;
-  if (tc && ps::tc_pair()) return ps::gemm_tc_launch(d, s);  // the CTA-pair kernel fuses the statistics finalize
+  // the CTA-pair kernels fuse the statistics finalize (the few-channel kernel of ps_gemm_rows.cu does not)
+  if (tc && ps::tc_pair() && !ps::gemm_rows_eligible(d)) return ps::gemm_tc_launch(d, s);
   // the other kernels leave the finalize to a follow-up launch
   ps_gemm_t dd = d;
   dd.fin_scale = nullptr;

@@ -504,6 +504,11 @@ int tc_bk() {
 // PS_TC_KERNEL=pair (default; CTA-pair kernel of ps_gemm_pair.cu) | single (the one-CTA kernel of this file)
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s);
 int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s);
+// few output channels (M <= 128) with the frames on the MMA's M side and the weights resident (ps_gemm_rows.cu)
+bool gemm_rows_eligible(const ps_gemm_t& d);
+int gemm_rows_launch(const ps_gemm_t& d, const void* wimg, cudaStream_t s);
+int64_t gemm_rows_image_bytes(int64_t M, int64_t K);
+int gemm_rows_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s);
 bool tc_pair() {
   static std::atomic<int> mode{-1};
   int m = mode.load(std::memory_order_relaxed);
@@ -545,8 +550,15 @@ static int launch_variant(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t g
   return PS_OK;
 }
 
+// bytes of the CTA-pair image (channels padded to whole 256-channel blocks); the rows image (ps_gemm_rows.cu), when the
+// shape has one, follows it in the same buffer
+static inline int64_t pair_image_bytes(int64_t M, int64_t K) { return (M + 255) / 256 * 256 * K * 4; }
+
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
-  if (tc_pair()) return gemm_pair_launch(d, s);
+  if (tc_pair()) {
+    if (gemm_rows_eligible(d)) return gemm_rows_launch(d, reinterpret_cast<const uint8_t*>(d.W_packed) + pair_image_bytes(d.M, d.K), s);
+    return gemm_pair_launch(d, s);
+  }
   int dev = 0, sms = 0;
   if (int rc = current_device(&dev)) return rc;
   if (int rc = sm_count_of(dev, &sms)) return rc;
@@ -564,7 +576,10 @@ int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s) {
 
 extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
   if (M <= 0 || K <= 0 || (K % 64 != 0 && !(K == 32 && ps::tc_pair()))) return 0;
-  if (ps::tc_pair()) return M % 32 == 0 ? (M + 255) / 256 * 256 * K * 4 : 0;  // padded to whole 256-channel blocks
+  if (ps::tc_pair()) {  // padded to whole 256-channel blocks (+ the resident image of the few-channel kernel)
+    if (M % 32 != 0) return 0;
+    return (M + 255) / 256 * 256 * K * 4 + (K % 64 == 0 ? ps::gemm_rows_image_bytes(M, K) : 0);
+  }
   if (M % ps::TC_BN != 0) return 0;
   return M * K * 4;  // bf16 hi + bf16 lo
 }
@@ -572,7 +587,12 @@ extern "C" int64_t ps_gemm_packed_bytes(int64_t M, int64_t K) {
 extern "C" int ps_gemm_pack_weights(const float* W, int64_t w_row_stride, int64_t M, int64_t K, void* packed, void* stream) {
   PS_REQUIRE(W && packed && w_row_stride >= K);
   if (ps_gemm_packed_bytes(M, K) == 0) return PS_ERR_UNSUPPORTED;
-  if (ps::tc_pair()) return ps::gemm_pair_pack(W, w_row_stride, M, K, packed, (cudaStream_t)stream);
+  if (ps::tc_pair()) {
+    if (int rc = ps::gemm_pair_pack(W, w_row_stride, M, K, packed, (cudaStream_t)stream)) return rc;
+    if (K % 64 == 0 && ps::gemm_rows_image_bytes(M, K) > 0)
+      return ps::gemm_rows_pack(W, w_row_stride, M, K, reinterpret_cast<uint8_t*>(packed) + (M + 255) / 256 * 256 * K * 4, (cudaStream_t)stream);
+    return PS_OK;
+  }
   const unsigned blocks = (unsigned)ps::cdiv(M * K, 256);
   if (ps::tc_bk() == 64)
     ps::pack_weights_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>(W, w_row_stride, M, K, reinterpret_cast<uint8_t*>(packed));

@@ -27,10 +27,11 @@ kernel_events = None
 
 
 #: when a list, every ps_gemm call appends ((rows, M, K), path) with path = ps_gemm_path(): 0 exact-fp32 CUDA cores,
-#: 1 single-CTA tcgen05, 2 CTA-pair tcgen05 (128-frame tiles), 3 wide CTA-pair tcgen05 (256-frame tiles)
+#: 1 single-CTA tcgen05, 2 CTA-pair tcgen05 (128-frame tiles), 3 wide CTA-pair tcgen05 (256-frame tiles), 4 few-channel tcgen05 (M <= 128)
 path_log = None
 GEMM_PATH_NAMES = {0: "gemm_simt_kernel (fp32 CUDA cores)", 1: "gemm_tc_kernel (tcgen05, one CTA)", 2: "gemm_pair_kernel (tcgen05 cta_group::2, 128-frame tiles)",
-                   3: "gemm_wide_kernel (tcgen05 cta_group::2, 256-frame tiles)"}
+                   3: "gemm_wide_kernel (tcgen05 cta_group::2, 256-frame tiles)",
+                   4: "gemm_rows_kernel (tcgen05, M <= 128 channels on the MMA's N side, weights resident)"}
 
 
 class _Timed:

@@ -252,3 +252,94 @@ def test_tc_wide_slopes_and_nonfinite(ops):
     y, _ = ops.linear(x, w, pro=pro, w_packed=pk, backend=ops.GEMM_TCGEN05)
     assert torch.isfinite(y[0, :5000]).all() and not torch.isfinite(y[0, 5000:]).any()
     assert not torch.isfinite(y[1, :100]).any() and torch.isfinite(y[1, 100:]).all()
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(2, 333, 128, 256), (1, 5000, 32, 512), (3, 129, 64, 512), (5, 77, 96, 64), (1, 40000, 128, 128),
+                                       (64, 300, 64, 192)])
+def test_tc_rows_kernel_few_channels(ops, B, Rr, M, K):
+    """gemm_rows_kernel (ps_gemm_rows.cu): M <= 128 output channels on the MMA's N side, frames on the 128 TMEM lanes, the
+    packed weight matrix resident in shared memory.  BN = 32 / 64 / 128 (M = 96 pads to 128), one and many tiles per CTA,
+    ragged last tiles, folded norm affine + PReLU prologue, bias, per-item bias, PReLU epilogue, residual, Welford partials,
+    the fused-finalize request (served by a follow-up merge) - against fp64 and the exact-fp32 back end."""
+    x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
+    sc, sh, slope = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4), torch.tensor([0.2], device=DEV)
+    bias, bb, res = rnd(M, seed=5), rnd(B, M, seed=6), rnd(B, Rr, M, seed=7)
+    pk = ops.pack_weights(w, M, K, K)
+    assert pk is not None and pk.numel() == 256 * K * 4 + (32 if M <= 32 else 64 if M <= 64 else 128) * K * 4
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+    ops.path_log = []
+    y, part = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    y0, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05, epi_act=ops.ACT_PRELU, epi_slope=slope)
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [4, 4], paths
+    xin = F.prelu((x * sc.unsqueeze(1) + sh.unsqueeze(1)), slope).double()
+    ref = xin @ w.double().t() + bias.double() + bb.double().unsqueeze(1) + res.double()
+    check(y, ref)
+    check(y0, F.prelu(x.double() @ w.double().t(), slope.double()))
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, M)
+    mu, rstd = ref.mean(dim=(1, 2)), 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
+    assert (shift[:, 0].double() + mu * rstd).abs().max() <= 5e-5
+    g, bt = rnd(M, seed=8) + 1.5, rnd(M, seed=9)
+    y3, fold = ops.linear(x, w, bias=bias, want_stats=True, fin=(g, bt, 1e-8), w_packed=pk, backend=ops.GEMM_TCGEN05)
+    ref3 = x.double() @ w.double().t() + bias.double()
+    check(y3, ref3)
+    rstd3 = 1 / torch.sqrt(ref3.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (fold.scale.double() - g.double() * rstd3.unsqueeze(1)).abs().max() <= 1e-5 * (g.abs().max() * rstd3.max()).item()
+    y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
+    check(y, y2.double())
+
+
+@pytest.mark.parametrize("M,K,with_res", [(128, 256, True), (128, 256, False), (64, 128, True), (96, 192, True), (32, 1024, False)])
+def test_tc_rows_kernel_layernorm(ops, M, K, with_res):
+    """Linear -> nn.LayerNorm -> + residual (dprnn.py:161-163,173-175) on the few-channel kernel: an epilogue thread owns one
+    frame (a TMEM lane), so mean and variance over the M channels are thread-local.  In place over the residual as well."""
+    B, Rr = 3, 1333
+    x, w, bias = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.1), rnd(M, seed=3)
+    g, bt, res = rnd(M, seed=4) + 1.5, rnd(M, seed=5), rnd(B, Rr, M, seed=6)
+    pk = ops.pack_weights(w, M, K, K)
+    kw = dict(bias=bias, ln=(g, bt, 1e-5), residual=res if with_res else None)
+    ops.path_log = []
+    y, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05, **kw)
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [4], paths
+    lin = x.double() @ w.double().t() + bias.double()
+    ref = F.layer_norm(lin, (M,), g.double(), bt.double(), 1e-5) + (res.double() if with_res else 0)
+    check(y, ref, 1e-4)
+    if with_res:  # out aliasing the residual (a thread reads exactly the elements it then writes)
+        buf = res.clone()
+        ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05, out=buf, **dict(kw, residual=buf))
+        check(buf, ref, 1e-4)
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "sigmoid"])
+def test_tc_rows_kernel_mask_prologue_and_views(ops, act):
+    """The decoder GEMM (mask apply on load, M = 32) at many tiles per CTA; overlapping operand rows (row stride < K: the
+    U-Net shell's tap windows) and a strided output view; NaN / Inf rows stay local."""
+    B, Rr, M, K = 2, 30000, 32, 512
+    x, mk, w = rnd(B, Rr, K, seed=1, scale=2), rnd(B, Rr, K, seed=2, scale=2), rnd(M, K, seed=3, scale=0.1)
+    code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "sigmoid": ops.ACT_SIGMOID}[act]
+    f = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid}[act]
+    pk = ops.pack_weights(w, M, K, K)
+    ops.path_log = []
+    y, _ = ops.linear(x, w, pro=ops.Prologue(ops.PRO_MASK, code, x2=mk), w_packed=pk, backend=ops.GEMM_TCGEN05)
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [4], paths
+    check(y, (x.double() * f(mk.double())) @ w.double().t())
+    if act != "none":
+        return
+    N, L, win, hop, Mo = 2, 16000, 256, 64, 64
+    wav, w2 = rnd(N, L, seed=4), rnd(Mo, win, seed=5, scale=0.05)
+    T = (L - win) // hop + 1
+    pk2 = ops.pack_weights(w2, Mo, win, win)
+    big = torch.zeros(N, T, 3 * Mo, device=DEV)
+    ops.gemm(wav, w2, batch=N, rows=T, M=Mo, K=win, x_batch_stride=L, x_row_stride=hop, w_row_stride=win, w_packed=pk2,
+             backend=ops.GEMM_TCGEN05, out=big[:, :, Mo:], y_strides=(T * 3 * Mo, 3 * Mo))
+    check(big[:, :, Mo:2 * Mo], wav.unfold(1, win, hop).double() @ w2.double().t())
+    assert big[:, :, :Mo].abs().max() == 0 and big[:, :, 2 * Mo:].abs().max() == 0
+    xn = rnd(1, 1000, 128, seed=6)
+    xn[0, 500:, :] = float("inf")
+    xn[0, :10, 7] = float("nan")
+    w3 = rnd(128, 128, seed=7, scale=0.1)
+    yn, _ = ops.linear(xn, w3, w_packed=ops.pack_weights(w3, 128, 128, 128), backend=ops.GEMM_TCGEN05)
+    assert not torch.isfinite(yn[0, :10]).any() and torch.isfinite(yn[0, 10:500]).all() and not torch.isfinite(yn[0, 500:]).any()
