@@ -72,6 +72,7 @@ extern "C" int64_t ps_gemm_stats_slots(int64_t rows, int64_t M) {
 
 namespace ps {
 bool gemm_wide_eligible(const ps_gemm_t& d, int sms);
+bool gemm_pair_few_tiles(const ps_gemm_t& d, int sms);
 }
 
 extern "C" int ps_gemm_path(const ps_gemm_t* dp) {
@@ -85,6 +86,7 @@ extern "C" int ps_gemm_path(const ps_gemm_t* dp) {
   int dev = 0, sms = 0;
   if (int rc = ps::current_device(&dev)) return rc;
   if (int rc = ps::sm_count_of(dev, &sms)) return rc;
+  if (ps::gemm_pair_few_tiles(d, sms)) return 2;
   return ps::gemm_wide_eligible(d, sms) ? 3 : 2;
 }
 

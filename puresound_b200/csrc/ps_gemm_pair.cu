@@ -206,7 +206,7 @@ __device__ __forceinline__ void epi_chunk_ln(float (&v)[PR_CW], float bsum, floa
 constexpr int PR_PRO_AFFINE_TANH = 4;
 template <int PRO, int NB, bool kLN = false, int SUB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
-    gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg) {
+    gemm_pair_kernel(const ps_gemm_t d, const int64_t n_rt, const int64_t n_nh, const int64_t n_tiles, const int dbg, const int w_from2) {
   using Cfg = PairCfg<NB, SUB>;
   constexpr int STAGE = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -258,12 +258,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PR_THREADS, 1)
       const PairTile tc = pr_tile(t, n_rt, n_nh);
       constexpr uint32_t WST = SUB * Cfg::kWBytes;  // the SUB sub-tiles of a stage are adjacent in the packed image
       const uint8_t* src = wp + (size_t)(tc.nh * 2 + rank) * KB * WST;
+      // w_from2 (NB = 1 only): the image is the TWO-block one of a 512-channel group - per 32-k stage
+      // [hi block 0 | hi block 1 | lo block 0 | lo block 1] - and this tile is block nh & 1 of group nh >> 1: the hi and lo
+      // parts of every sub-tile are fetched as two 8 KB copies
+      const uint8_t* src2 = wp + (size_t)((tc.nh >> 1) * 2 + rank) * (KB * SUB) * (4 * PR_WBLK) + (size_t)(tc.nh & 1) * PR_WBLK;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * s, WST);
           if (PR_DBG(1)) {  // experiment: no weight traffic (results are garbage)
             asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(WST) : "memory");
+          } else if (NB == 1 && w_from2) {
+#pragma unroll
+            for (int sub = 0; sub < SUB; ++sub) {
+              const uint8_t* g = src2 + (size_t)(kb * SUB + sub) * (4 * PR_WBLK);
+              const uint32_t dst = base + s * STAGE + Cfg::kWOff + sub * Cfg::kWBytes;
+              bulk_g2s(dst, g, PR_WBLK, bar_full + 8 * s);
+              bulk_g2s(dst + PR_WBLK, g + 2 * PR_WBLK, PR_WBLK, bar_full + 8 * s);
+            }
           } else
             bulk_g2s(base + s * STAGE + Cfg::kWOff, src + (size_t)kb * WST, WST, bar_full + 8 * s);
         }
@@ -678,7 +690,7 @@ int gemm_pair_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* pack
 }
 
 template <int PRO, int NB, bool kLN = false, int SUB = 1>
-static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles) {
+static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_nh, int64_t n_tiles, int w_from2 = 0) {
   static SmemOnce<1> once;  // per instantiation and device
   if (int rc = once.ensure(dev, 0, gemm_pair_kernel<PRO, NB, kLN, SUB>, PairCfg<NB, SUB>::kSmem, "cudaFuncSetAttribute(gemm_pair_kernel)")) return rc;
 #ifdef PS_EXPERIMENTS
@@ -687,7 +699,7 @@ static int launch_pair(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid
 #else
   const int dbg = 0;
 #endif
-  cudaError_t le = launch_pdl(gemm_pair_kernel<PRO, NB, kLN, SUB>, dim3((unsigned)grid), dim3(PR_THREADS), PairCfg<NB, SUB>::kSmem, s, d, n_rt, n_nh, n_tiles, dbg);
+  cudaError_t le = launch_pdl(gemm_pair_kernel<PRO, NB, kLN, SUB>, dim3((unsigned)grid), dim3(PR_THREADS), PairCfg<NB, SUB>::kSmem, s, d, n_rt, n_nh, n_tiles, dbg, w_from2);
   if (le != cudaSuccess) { set_cuda_error(le, "gemm_pair_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }
@@ -701,14 +713,45 @@ int gemm_wide_launch(const ps_gemm_t& d, cudaStream_t s, int dev, int sms);
 bool gemm_wide_tma_eligible(const ps_gemm_t& d, int sms);
 int gemm_wide_tma_launch(const ps_gemm_t& d, cudaStream_t s, int dev, int sms);
 
+// see gemm_pair_launch: a 512-channel layer with so few tiles that one-block tiles with 64-k stages win
+bool gemm_pair_few_tiles(const ps_gemm_t& d, int sms) {
+  static EnvInt from2_env;
+  // measured (run 29, isolated launches, 74 CTA pairs): 16 ... 64 tiles of 256 frames (batch 1 ... 4 x 4 s) 0.016-0.043 ms
+  // against 0.021-0.040; at 128 tiles (1.7 per pair: batch 8, or the 64 x 497-frame TSE batch) the 256-frame kernel wins
+  // without a residual (0.054 against 0.057-0.064 ms) and loses with one (0.074 / 0.060 against 0.070 / 0.051 ms); from 3
+  // tiles per pair on it wins everywhere.  In the step: cfg1 2.03 -> 1.52 ms, cfg4 5.27 -> 5.00 ms.
+  const int thr = from2_env.get("PS_PAIR_FROM2", 10) * (d.residual ? 2 : 1);
+  if (thr <= 0 || pair_nb(d.M) != 2 || d.K % 64 != 0 || d.ln_eps > 0.f) return false;
+  const int64_t wide_tiles = d.batch * cdiv(d.rows, 256) * cdiv(d.M, 512);
+  return wide_tiles * 10 < (int64_t)thr * (sms / 2);
+}
+
 int gemm_pair_launch(const ps_gemm_t& d, cudaStream_t s) {
   int dev = 0, sms = 0;
   if (int rc = current_device(&dev)) return rc;
   if (int rc = sm_count_of(dev, &sms)) return rc;
   if (gemm_wide_tma_eligible(d, sms)) return gemm_wide_tma_launch(d, s, dev, sms);  // PS_TC_WIDE=2: TMA-fed variant (A/B)
-  if (gemm_wide_eligible(d, sms)) return gemm_wide_launch(d, s, dev, sms);  // 256-frame tiles (ps_gemm_wide.cu)
   int pro = d.pro_mode;  // NONE (0), AFFINE (1) or MASK (3): checked by gemm_tc_eligible
   if (pro == PS_PRO_AFFINE && d.pro_act == PS_ACT_TANH) pro = PR_PRO_AFFINE_TANH;
+  // FEW tiles of a 512-channel layer (batch 1, the 497-frame items of the TSE model, a batch shard of 8 utterances): what
+  // a launch costs there is the chain of stage hand-overs of ONE tile (profiles/r02_gemm_notes.md section 5), so the tile is
+  // cut to one 256-channel block with 64-k stages - half the hand-overs per tile and twice the CTA pairs at work - reading
+  // the hi / lo parts out of the two-block image.  PS_PAIR_FROM2 = number of 256-frame tiles per CTA pair, in tenths,
+  // below which this path is taken (default 10, doubled for launches with a residual; 0 = never).
+  if (gemm_pair_few_tiles(d, sms)) {
+    {
+      const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256);
+      const int64_t n_tiles = d.batch * n_rt * n_nh;
+      if (n_tiles >= (1LL << 31)) return PS_ERR_UNSUPPORTED;
+      const int64_t max_pairs = sms / 2;
+      const int64_t grid = 2 * (n_tiles < max_pairs ? n_tiles : max_pairs);
+      if (pro == PS_PRO_AFFINE) return launch_pair<PS_PRO_AFFINE, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles, 1);
+      if (pro == PR_PRO_AFFINE_TANH) return launch_pair<PR_PRO_AFFINE_TANH, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles, 1);
+      if (pro == PS_PRO_MASK) return launch_pair<PS_PRO_MASK, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles, 1);
+      return launch_pair<PS_PRO_NONE, 1, false, 2>(d, s, dev, grid, n_rt, n_nh, n_tiles, 1);
+    }
+  }
+  if (gemm_wide_eligible(d, sms)) return gemm_wide_launch(d, s, dev, sms);  // 256-frame tiles (ps_gemm_wide.cu)
   const int nb = pair_nb(d.M);
   const bool ln = d.ln_eps > 0.f;  // fused LayerNorm epilogue: M == 128, no prologue (checked by gemm_pair_ln_eligible)
   const int64_t n_rt = cdiv(d.rows, PR_FRAMES), n_nh = cdiv(d.M, 256 * nb);

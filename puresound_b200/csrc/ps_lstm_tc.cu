@@ -323,6 +323,34 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
     char* outu = reinterpret_cast<char*>(d.out + (int64_t)dir * Hr + u);
     const int64_t stepg = d.step_stride * (int64_t)Gb, stepo = d.step_stride * (int64_t)OWb;
     const uint32_t* rows = reinterpret_cast<const uint32_t*>(row_s) + wq * SPH;  // unsigned: row * width is one IMAD.WIDE.U32
+    // gx of a chunk travels in one of two register buffers and is requested TWO chunks ahead of its use, across the step
+    // boundary: the first two chunks of step t + 1 are requested while the last two of step t are computed, so every
+    // load has a chunk of cell updates plus a barrier wait to land (ncu, run 27: with the first chunk requested just
+    // before the wait on the tensor core and the others one chunk ahead, the first FFMA on a loaded value held 16 % of
+    // the kernel's stall samples)
+    float gxa[4][CH], gxb[4][CH];
+    auto load_gx = [&](float(&gx)[4][CH], const char* gxt, int half, int j0) {
+      const uint4 r4 = *reinterpret_cast<const uint4*>(rows + half * LT_NH + j0);
+      const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const float* p = reinterpret_cast<const float*>(gxt + (uint64_t)r[j] * Gb);
+        if constexpr (gxi) {
+          const float4 v4 = __ldg(reinterpret_cast<const float4*>(p));
+          gx[0][j] = v4.x; gx[1][j] = v4.y; gx[2][j] = v4.z; gx[3][j] = v4.w;
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * Hr);
+        }
+      }
+    };
+    const int64_t dstep = dir ? -stepg : stepg;
+    if (live && d.L > 0) {
+      const char* g0 = gxu + (dir ? d.L - 1 : 0) * stepg;
+      load_gx(gxa, g0, 0, 0);
+      if constexpr (kCh2) load_gx(gxb, g0, 0, CH);
+      else load_gx(gxb, g0, 1, 0);
+    }
     for (int64_t step = 0; step < d.L; ++step) {
       const int64_t t = dir ? d.L - 1 - step : step;
       const char* gxt = gxu + t * stepg;
@@ -337,29 +365,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
         }
         continue;
       }
-      // next step's gx lines -> L2 (lanes 0-7 / 8-15 cover the slots of half A / B; 4 gates x 128 B per warp quarter)
-      if (step + 1 < d.L && lane < 16 && (lane & 7) < spq) {
-        const char* pn = gxt + (dir ? -stepg : stepg) + (uint64_t)rows[(lane >> 3) * LT_NH + (lane & 7)] * Gb - (gxi ? 4 * u : u) * 4 +
+      // the lines of step t + 2 -> L2 (lanes 0-7 / 8-15 cover the slots of half A / B; 4 gates x 128 B per warp quarter)
+      if (step + 2 < d.L && lane < 16 && (lane & 7) < spq) {
+        const char* pn = gxt + 2 * dstep + (uint64_t)rows[(lane >> 3) * LT_NH + (lane & 7)] * Gb - (gxi ? 4 * u : u) * 4 +
                          (kGxi ? q * 512 : q * 128);
 #pragma unroll
         for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + g * (kGxi ? 128 : Hr * 4)));
       }
-      float gxa[4][CH], gxb[4][CH];
-      auto load_gx = [&](float(&gx)[4][CH], int half, int j0) {
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rows + half * LT_NH + j0);
-        const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          const float* p = reinterpret_cast<const float*>(gxt + (uint64_t)r[j] * Gb);
-          if constexpr (gxi) {
-            const float4 v4 = __ldg(reinterpret_cast<const float4*>(p));
-            gx[0][j] = v4.x; gx[1][j] = v4.y; gx[2][j] = v4.z; gx[3][j] = v4.w;
-          } else {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) gx[g][j] = __ldg(p + g * Hr);
-          }
-        }
-      };
       auto chunk = [&](const float(&gx)[4][CH], int half, int j0) {
         float a[4][CH];
         const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + LT_ACC_COL + (uint32_t)(half * LT_NH + wq * SPH + j0);
@@ -382,29 +394,31 @@ __global__ void __launch_bounds__(LT_THREADS, 1) lstm_tc_kernel(const ps_lstm_t 
 #pragma unroll
         for (int j = 0; j < CH; j += 2) store_h2(h[j], h[j + 1], half, j0 + j);
       };
-      // gx of a chunk is requested one chunk ahead (the first one before the wait on the tensor core)
       const uint32_t par = (uint32_t)(step & 1);
-      load_gx(gxa, 0, 0);
+      const bool more = step + 1 < d.L;
+      const char* gxn = gxt + dstep;  // next step's rows (only dereferenced when there is a next step)
       mbar_wait(bar_mma, par);
       tc_fence_after();
       if constexpr (kCh2) {
-        load_gx(gxb, 0, CH);
         chunk(gxa, 0, 0);
-        load_gx(gxa, 1, 0);
+        load_gx(gxa, gxt, 1, 0);
         chunk(gxb, 0, CH);
+        load_gx(gxb, gxt, 1, CH);
         release_half(0);
         mbar_wait(bar_mma + 8, par);
         tc_fence_after();
-        load_gx(gxb, 1, CH);
         chunk(gxa, 1, 0);
+        if (more) load_gx(gxa, gxn, 0, 0);
         chunk(gxb, 1, CH);
+        if (more) load_gx(gxb, gxn, 0, CH);
       } else {
-        load_gx(gxb, 1, 0);
         chunk(gxa, 0, 0);
+        if (more) load_gx(gxa, gxn, 0, 0);
         release_half(0);
         mbar_wait(bar_mma + 8, par);
         tc_fence_after();
         chunk(gxb, 1, 0);
+        if (more) load_gx(gxb, gxn, 1, 0);
       }
       release_half(1);
     }

@@ -218,7 +218,9 @@ def test_tc_wide_tiles(ops, B, Rr, M, K):
     y, part = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
     y0, _ = ops.linear(x, w, w_packed=pk, backend=ops.GEMM_TCGEN05)  # no prologue, no epilogue extras, no statistics
     paths, ops.path_log = ops.path_log, None
-    assert [p for _, p in paths] == [3, 3], paths
+    # the call without a residual has at least one 256-frame tile per CTA pair -> gemm_wide_kernel; with a residual, launches
+    # below two tiles per pair go to one-block tiles with 64-k stages (gemm_pair_few_tiles), the largest shape stays wide
+    assert paths[1][1] == 3 and paths[0][1] == (3 if B * ((Rr + 255) // 256) * (M // 512) >= 148 else 2), paths
     for b0 in range(0, B, 8):
         sl = slice(b0, b0 + 8)
         xin = F.prelu((x[sl] * sc[sl].unsqueeze(1) + sh[sl].unsqueeze(1)), slope).double()
@@ -232,6 +234,30 @@ def test_tc_wide_tiles(ops, B, Rr, M, K):
     assert (shift[:, 0].double() + mu * rstd).abs().max() <= 5e-5
     y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
     check(y, y2.double())
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(1, 3999, 512, 512), (3, 497, 512, 256), (1, 640, 1024, 64), (2, 900, 384, 128)])
+def test_tc_few_tiles_one_block_from_two_block_image(ops, B, Rr, M, K):
+    """512-channel layers with fewer than one 256-frame tile per CTA pair (batch 1, the TSE model's 497-frame items): one
+    256-channel block per tile with 64-k stages, the hi / lo parts fetched out of the two-block packed image (w_from2);
+    M = 384 pads its second block.  Prologue, bias, per-item bias, residual, statistics and the fused finalize."""
+    x, w = rnd(B, Rr, K, seed=1, scale=3), rnd(M, K, seed=2, scale=0.05)
+    sc, sh, slope = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4), torch.tensor([0.2], device=DEV)
+    bias, bb, res = rnd(M, seed=5), rnd(B, M, seed=6), rnd(B, Rr, M, seed=7)
+    g, bt = rnd(M, seed=8) + 1.5, rnd(M, seed=9)
+    pk = ops.pack_weights(w, M, K, K)
+    pro = ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope)
+    ops.path_log = []
+    y, fold = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, want_stats=True, fin=(g, bt, 1e-8), w_packed=pk,
+                         backend=ops.GEMM_TCGEN05)
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [2], paths
+    ref = F.prelu((x * sc.unsqueeze(1) + sh.unsqueeze(1)), slope).double() @ w.double().t() + bias.double() + bb.double().unsqueeze(1) + res.double()
+    check(y, ref)
+    rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (fold.scale.double() - g.double() * rstd.unsqueeze(1)).abs().max() <= 1e-5 * (g.abs().max() * rstd.max()).item()
+    mu = ref.mean(dim=(1, 2))
+    assert (fold.shift.double() - (bt.double() - (mu * rstd).unsqueeze(1) * g.double())).abs().max() <= 1e-4
 
 
 def test_tc_wide_slopes_and_nonfinite(ops):
