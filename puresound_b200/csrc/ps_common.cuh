@@ -205,8 +205,12 @@ __device__ __forceinline__ Wf wf_block_reduce(Wf v, Wf* smem) {
 }
 
 // ---- gLN / gGN statistics merge of ONE batch item by a group of 256 threads (tid in [0,256)) -----------------
-// Chan-merge of the (count, mean, M2) partials in a fixed order in fp64 -> folded per-channel affine
-//   scale[c] = gamma[c] * rstd,  shift[c] = beta[c] - mean * rstd * gamma[c].
+// The (count, mean, M2) partials are turned into raw moments and summed in fp64 in a fixed order,
+//   S0 = sum n_i,  S1 = sum n_i mean_i,  S2 = sum (M2_i + n_i mean_i^2),   mean = S1 / S0,  var = (S2 - S1^2 / S0) / S0,
+// -> folded per-channel affine  scale[c] = gamma[c] * rstd,  shift[c] = beta[c] - mean * rstd * gamma[c].
+// (fp64 additions of fp32 inputs: the cancellation in var leaves 53 - log2(1 + mean^2 / var) bits, far beyond the fp32
+// result.  The first version Chan-merged pairwise with two fp64 DIVISIONS per merge through an 8-level barrier tree: 5.7 us
+// per launch, 20 % of a batch-1 Conv-TasNet forward - run 31.)
 // BAR = barrier id the 256 threads share (0 = the whole 256-thread CTA).  Partials are read with ld.cg: they may have
 // been written by other CTAs of the same launch (fused finalize), so a stale L1 line must not be used.
 // Used by stats_finalize_kernel and, fused, by the CTA that completes an item's last tile in the producer kernels.
@@ -214,35 +218,31 @@ template <int BAR>
 __device__ __forceinline__ void stats_finalize_item(const float* p, int64_t slots, const float* gamma, const float* beta, float eps,
                                                     int64_t C, float* scale_b, float* shift_b, float* meanvar_b, int tid,
                                                     double* sn, double* sm, double* s2) {
-  double n = 0.0, mean = 0.0, m2 = 0.0;
+  double n = 0.0, a1 = 0.0, a2 = 0.0;
   for (int64_t i = tid; i < slots; i += 256) {
     const double bn = __ldcg(p + i * 3), bm = __ldcg(p + i * 3 + 1), b2 = __ldcg(p + i * 3 + 2);
     if (bn > 0.0) {
-      const double nn = n + bn, dlt = bm - mean;
-      mean += dlt * (bn / nn);
-      m2 += b2 + dlt * dlt * n * (bn / nn);
-      n = nn;
+      const double t = bn * bm;
+      n += bn;
+      a1 += t;
+      a2 += b2 + t * bm;
     }
   }
-  sn[tid] = n; sm[tid] = mean; s2[tid] = m2;
+  // xor butterfly: both lanes of a pair add the same two values, so every lane ends with the same bits
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((tid & 31) == 0) { sn[tid >> 5] = n; sm[tid >> 5] = a1; s2[tid >> 5] = a2; }
   asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");
-  for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) {
-      double an = sn[tid], am = sm[tid], a2 = s2[tid];
-      const double bn = sn[tid + o], bm = sm[tid + o], b2 = s2[tid + o];
-      if (bn > 0.0) {
-        const double nn = an + bn, dlt = bm - am;
-        am += dlt * (bn / nn);
-        a2 += b2 + dlt * dlt * an * (bn / nn);
-        an = nn;
-      }
-      sn[tid] = an; sm[tid] = am; s2[tid] = a2;
-    }
-    asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");
-  }
-  const double cnt = sn[0];
-  const double mu = sm[0];
-  const double var = cnt > 0.0 ? s2[0] / cnt : 0.0;
+  double cnt = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { cnt += sn[w]; t1 += sm[w]; t2 += s2[w]; }  // fixed order, every thread the same
+  const double mu = cnt > 0.0 ? t1 / cnt : 0.0;
+  double var = cnt > 0.0 ? (t2 - t1 * mu) / cnt : 0.0;
+  var = var > 0.0 ? var : 0.0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   const float muf = (float)mu;
   for (int64_t c = tid; c < C; c += 256) {

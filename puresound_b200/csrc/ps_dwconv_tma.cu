@@ -173,10 +173,30 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
       mine.m2 = fmaxf(ssq - ssum * md, 0.f);
     }
     Wf tot = wf_block_reduce(mine, red);
+    __shared__ int fin_last;
     if (tid == 0) {
       const int64_t slot = (int64_t)split * gridDim.x + cg;
       float* o = d.stats_partials + (b * d.stats_slots + slot) * 3;
       o[0] = tot.n; o[1] = tot.mean; o[2] = tot.m2;
+      if (d.fin_scale) {
+        // fused gLN / gGN finalize (few-frame launches, where a separate merge launch costs as much as this kernel): the
+        // CTA that writes an item's last partial merges them all, in slot order (see ps_gemm_pair.cu).  The zeroed tail
+        // slots were written by this item's first CTA before the barrier inside wf_block_reduce, i.e. before ITS count.
+        __threadfence();
+        const unsigned int total = gridDim.x * gridDim.y;
+        fin_last = (atomicAdd(d.fin_counter + b, 1u) + 1u == total) ? 1 : 0;
+      }
+    }
+    if (d.fin_scale) {
+      static_assert(DM_THREADS == 256, "the fused finalize runs on a 256-thread CTA");
+      __shared__ double fin_s[3 * 256];
+      __syncthreads();
+      if (fin_last) {
+        __threadfence();
+        stats_finalize_item<0>(d.stats_partials + b * d.stats_slots * 3, d.stats_slots, d.fin_gamma, d.fin_beta, d.fin_eps, d.C,
+                               d.fin_scale + b * d.C, d.fin_shift + b * d.C, nullptr, tid, fin_s, fin_s + 256, fin_s + 512);
+        if (tid == 0) d.fin_counter[b] = 0;
+      }
     }
   }
 }
@@ -190,7 +210,6 @@ bool dwconv_tma_eligible(const ps_dwconv_t& d) {
   const int halo = 2 * d.dilation;
   const int HC = (halo + DM_CH - 1) / DM_CH;
   if (HC + 3 > DM_MAXSLOTS) return false;
-  if (d.fin_scale) return false;
   if (d.T >= (1LL << 30) || d.batch >= (1LL << 31) || d.T * d.C * 4 >= (1LL << 40)) return false;
   if ((reinterpret_cast<uintptr_t>(d.x) | reinterpret_cast<uintptr_t>(d.y)) & 15) return false;
   if (d.pro_mode == PS_PRO_AFFINE && (((reinterpret_cast<uintptr_t>(d.pro_a) | reinterpret_cast<uintptr_t>(d.pro_b)) & 15) || (d.pro_batch_stride & 3))) return false;
