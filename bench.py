@@ -153,20 +153,23 @@ def kernel_rooflines(events, eager_ms, hbm_peak, tf_peak, peak_kind):
     """Group the live CUDA-event pairs of the eager pass by (kernel kind, shape) and put each group against the roofline
     that bounds it.  Algorithmic work per launch (DESIGN.md section 4 / SURVEY.md 8d):
       gemm   [rows, K] x [M, K]^T : 2*rows*M*K FLOP (3 tensor passes are ISSUED for the 3xBF16 split; frac counts useful
-                                    FLOPs, so 1/3 is its ceiling), bytes 4*(rows*K + rows*M + M*K)
+                                    FLOPs, so 1/3 is its ceiling), bytes 4*(rows*K + rows*M + M*K) + the residual / mask
+                                    operand reads of the launches that have one (mean over the group)
       lstm   n_seq x L x D, H (+ fused input projection K_in): 2*4H*(H + K_in) FLOP per step, sequence and direction (3 passes)
       dwconv [B, T, C]            : 2*4*B*T*C bytes (one read, one write)
     Returns the groups sorted by their share of the step; the first is the dominant kernel."""
-    groups = {}
-    for kind, a, b, shape in events:
+    groups, extras = {}, {}
+    for kind, a, b, shape, extra in events:
         groups.setdefault((kind, tuple(shape)), []).append(a.elapsed_time(b))
+        extras[(kind, tuple(shape))] = extras.get((kind, tuple(shape)), 0.0) + float(extra)
     out = []
     for (kind, shape), durs in groups.items():
         avg_ms = sum(durs) / len(durs)
+        extra_bytes = extras[(kind, shape)] / len(durs)  # mean per launch: residual / mask operand reads of the group's GEMMs
         r = {"kernel": None, "shape": list(shape), "avg_launch_ms": avg_ms, "launches_timed": len(durs), "share_of_step": sum(durs) / eager_ms}
         if kind == "gemm":
             rows, M, K = shape
-            flops, nbytes = 2.0 * rows * M * K, 4.0 * (rows * K + rows * M + M * K)
+            flops, nbytes = 2.0 * rows * M * K, 4.0 * (rows * K + rows * M + M * K) + extra_bytes
             t_tensor, t_hbm = 3 * flops / (tf_peak * 1e12), nbytes / (hbm_peak * 1e9)
             r["kernel"] = "ps_gemm (1x1 conv / linear, %d x %d x %d)" % (rows, M, K)
             if t_tensor >= t_hbm:  # tensor-bound shape

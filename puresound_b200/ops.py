@@ -22,7 +22,8 @@ Tensor = torch.Tensor
 launch_count = 0
 #: when a list, every ps_gemm / ps_lstm / ps_dwconv launch appends (kind, start_event, end_event, shape) - bench.py's live
 #: per-kernel roofline timing (CUDA events on the launching stream); shape = (rows, M, K) for "gemm",
-#: (n_seq, L, H, D, K_in) for "lstm" (K_in > 0 when the input projection is fused), (batch, T, C) for "dwconv"
+#: (n_seq, L, H, D, K_in) for "lstm" (K_in > 0 when the input projection is fused), (batch, T, C) for "dwconv"; a fifth
+#: element carries the launch's algorithmic bytes beyond the shape (residual / mask operand of a GEMM)
 kernel_events = None
 
 
@@ -37,10 +38,11 @@ GEMM_PATH_NAMES = {0: "gemm_simt_kernel (fp32 CUDA cores)", 1: "gemm_tc_kernel (
 class _Timed:
     """Context manager: bracket one launch with a CUDA-event pair when bench.py asked for per-kernel timing."""
 
-    __slots__ = ("kind", "shape", "ev")
+    __slots__ = ("kind", "shape", "ev", "extra_bytes")
 
-    def __init__(self, kind, shape):
-        self.kind, self.shape, self.ev = kind, shape, None
+    def __init__(self, kind, shape, extra_bytes=0):
+        # extra_bytes: algorithmic HBM bytes of this launch beyond what the shape implies (a GEMM's residual / mask operand)
+        self.kind, self.shape, self.ev, self.extra_bytes = kind, shape, None, extra_bytes
 
     def __enter__(self):
         if kernel_events is not None:
@@ -51,7 +53,7 @@ class _Timed:
     def __exit__(self, *a):
         if self.ev is not None:
             self.ev[1].record()
-            kernel_events.append((self.kind, self.ev[0], self.ev[1], self.shape))
+            kernel_events.append((self.kind, self.ev[0], self.ev[1], self.shape, self.extra_bytes))
 #: force a GEMM back end for every call (tests / A-B runs); None = per-call choice
 force_gemm_backend: Optional[int] = None
 
@@ -175,7 +177,8 @@ def gemm(
         d.ln_gamma, d.ln_beta, d.ln_eps = _p(ln[0]), _p(ln[1]), float(ln[2])
     if path_log is not None:
         path_log.append(((batch * rows, M, K), int(lib.ps_gemm_path(C.byref(d)))))
-    with _Timed("gemm", (batch * rows, M, K)):
+    extra = 4 * batch * rows * ((M if residual is not None else 0) + (K if pro.x2 is not None else 0))
+    with _Timed("gemm", (batch * rows, M, K), extra):
         _lib.check(lib.ps_gemm(C.byref(d), _stream()), "ps_gemm")
     _launched()
     return Y, (folded if folded is not None else partials)

@@ -53,6 +53,12 @@ class ShardedSeparator:
     One host thread issues the work of all devices back to back (after the first two calls per shape a forward is one
     graph replay, ~0.1 ms of host time), then waits for every device: wall time = the slowest slice, not the sum.
 
+    Results equal the single-device forward of the whole batch bit for bit as long as a slice and the whole batch are
+    served by the same kernel variants (an item's tiles, statistics slots and merge order do not depend on its
+    neighbours); the 1x1-conv GEMM picks its tile shape by the number of tiles of a launch (ps_gemm_pair.cu:
+    gemm_pair_few_tiles), so a slice of 8 utterances and a batch of 64 can differ in the last bits of the 3xBF16 sums -
+    measured (run 17) at 4 and 8 devices, inside the parity tolerances of tests/test_gpu_full.py.
+
     ``ShardedSeparator(model, devices)`` replicates ``model`` (an engine ``SoTaskWrapModule``); ``runners=`` swaps the
     per-device callables for tests of the split / gather logic on a box without GPUs."""
 
