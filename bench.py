@@ -67,16 +67,22 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+
+    nvidia-smi needs ~0.1-0.3 s to deliver its first sample, so the sampler is started BEFORE the warm-up (start()) and only
+    the samples received between window_open() and window_close() are summarised.  A timed region shorter than a sampling
+    period (8 ranks x 20 steps of 5.5 ms) can still end with no sample: the caller then keeps the same load running under
+    the open window until two samples have arrived (timed_resident), and the summary says so (`extended`)."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t_open, self.t_close, self.extended = None, None, False
 
-    def __enter__(self):
+    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -86,9 +92,19 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def __exit__(self, *a):
+    def window_open(self):
+        self.t_open = time.perf_counter()
+
+    def window_close(self):
+        self.t_close = time.perf_counter()
+
+    def in_window(self):
+        t1 = self.t_close if self.t_close is not None else float("inf")
+        return [r for t, r in list(self.rows) if self.t_open is not None and self.t_open <= t <= t1 and len(r) >= 8]
+
+    def stop(self):
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -96,17 +112,30 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
+    # context-manager form: the window is the body
+    def __enter__(self):
+        self.start()
+        self.window_open()
+        return self
+
+    def __exit__(self, *a):
+        self.window_close()
+        self.stop()
+
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = self.in_window()
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if self.extended:
+            out["extended"] = "the timed region was shorter than the sampling period: the same steps kept running (untimed) until two samples had arrived"
+        return out
 
 
 def build_inputs(workload: str, rank: int, batch=None, span=None):
@@ -429,18 +458,30 @@ def main():
 
     def timed_resident(mix_d, enr_d, steps, warm):
         """K device-timed replays of the public API on resident inputs; returns (ms for the K steps, clock summary, last result)."""
+        clk = ClockSampler(local_rank).start()  # (nvidia-smi delivers its first sample after ~0.2 s: started before the warm-up)
         with torch.no_grad():
             for _ in range(warm):
                 y = model.inference(mix_d, enr_d)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with ClockSampler(local_rank) as clk:
-                e0.record()
-                for _ in range(steps):
-                    y = model.inference(mix_d, enr_d)  # public API, device tensors in and out (CUDA-graph replay)
-                e1.record()
-                barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), clk.summary(), y
+            clk.window_open()
+            e0.record()
+            for _ in range(steps):
+                y = model.inference(mix_d, enr_d)  # public API, device tensors in and out (CUDA-graph replay)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            # a region shorter than the sampling period: keep the same load running (untimed) until two samples arrived
+            t_give_up = time.perf_counter() + 1.5
+            while len(clk.in_window()) < 2 and clk.proc is not None and time.perf_counter() < t_give_up:
+                clk.extended = True
+                for _ in range(max(1, steps // 4)):
+                    y = model.inference(mix_d, enr_d)
+                torch.cuda.synchronize(dev)
+            clk.window_close()
+            clk.stop()
+            barrier()
+        return max_over_ranks(ms), clk.summary(), y
 
     # the rank's share of the job
     if scaling == "strong":

@@ -26,7 +26,8 @@ namespace ps {
 
 constexpr int RW_BM = 128;                       // frames per tile (MMA M = TMEM lanes)
 constexpr int RW_BK = 32;                        // k per shared-memory stage (64-byte swizzle rows)
-constexpr int RW_STAGES = 4;                     // operand ring depth
+constexpr int RW_STAGES = 4;                     // operand ring depth with the weights resident
+constexpr int RW_STAGES_WS = 6;                  // ring depth with the weights streamed (a stage then also carries a weight block)
 constexpr int RW_APART = RW_BM * RW_BK * 2;      // 8 KB: operand hi (or lo) of one stage
 constexpr int RW_STAGE = 2 * RW_APART;           // 16 KB
 constexpr int RW_PRODUCERS = 256, RW_EPI = 128;
@@ -38,7 +39,9 @@ constexpr int RW_AFF_BYTES = 2 * RW_MAXK * 4;
 constexpr int RW_VEC_BYTES = 3 * 128 * 4;        // bias | ln gamma | ln beta of the (<= 128) channels
 constexpr int RW_WMAX = 128 * 1024;              // resident weight image: BN * K * 4 bytes
 constexpr int RW_PF_DIST = 4;                    // L2 prefetch distance of the operand stream, in 64-k blocks
-constexpr int RW_TAIL = RW_STAGES * RW_STAGE + RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int RW_MISC = RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int RW_TAIL = RW_STAGES * RW_STAGE + RW_MISC;
+constexpr int RW_KMAX_WS = 4096;                 // streamed weights: any K up to here (the affine prologue still needs K <= RW_MAXK)
 
 __host__ __device__ constexpr uint32_t rw_swz(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
 
@@ -58,7 +61,10 @@ __host__ __device__ constexpr uint32_t rw_tmem_cols(int BN) { return BN <= 32 ? 
 
 // (128 registers is the ceiling at 14 warps: SM sub-partitions 0 and 1 hold four warps each, 4 x 32 x 128 = their 16 K
 // registers; a 144-register build fails to launch.  The affine variant spills 172 B, the mask variant 80 B.)
-template <int PRO, int BN, bool kLN>
+// kWS: the packed weight matrix does not fit next to the operand ring (BN * K * 4 > 128 KB: the U-Net shell's tap windows of
+// 768-1536 floats, out_conv of the 128-channel Conv-TasNet reading) - its 32-k blocks then travel through the ring with the
+// operand stages (one cp.async.bulk per stage from warp 0, L2-resident source), six stages deep.
+template <int PRO, int BN, bool kLN, bool kWS = false>
 __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_t d, const uint8_t* __restrict__ wimg, const int64_t n_rt,
                                                                   const int64_t n_tiles) {
   // D = f32, A = B = bf16, both K-major, M = 128, N = BN
@@ -69,25 +75,27 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   const int K = (int)d.K, KB = K / RW_BK;
-  const uint32_t wbytes = (uint32_t)KB * 2u * WBLK;  // a multiple of 4 KB
+  constexpr int NST = kWS ? RW_STAGES_WS : RW_STAGES;            // ring depth
+  constexpr int STAGE = RW_STAGE + (kWS ? 2 * WBLK : 0);         // operand hi | lo (| weight hi | lo)
+  const uint32_t wbytes = kWS ? 0u : (uint32_t)KB * 2u * WBLK;   // resident image: a multiple of 4 KB
   const uint32_t ring = base + wbytes;
   uint8_t* ring_p = sm + wbytes;
-  float* epi_stage = reinterpret_cast<float*>(ring_p + RW_STAGES * RW_STAGE);
-  float* aff_s = reinterpret_cast<float*>(ring_p + RW_STAGES * RW_STAGE + RW_EPI_STAGE);
-  float* vec_s = reinterpret_cast<float*>(ring_p + RW_STAGES * RW_STAGE + RW_EPI_STAGE + RW_AFF_BYTES);  // bias | gamma | beta
-  const uint32_t bars = ring + RW_STAGES * RW_STAGE + RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES;
-  // barrier map (8 B each): full[0..3] empty[0..3] tfull[0..1] tempty[0..1] w, then the TMEM pointer, then statistics scratch
-  const uint32_t bar_full = bars, bar_empty = bars + 32, bar_tfull = bars + 64, bar_tempty = bars + 80, bar_w = bars + 96;
-  uint8_t* bars_p = ring_p + RW_STAGES * RW_STAGE + RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES;
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(bars_p + 112);
-  Wf* wf_s = reinterpret_cast<Wf*>(bars_p + 128);
+  float* epi_stage = reinterpret_cast<float*>(ring_p + NST * STAGE);
+  float* aff_s = reinterpret_cast<float*>(ring_p + NST * STAGE + RW_EPI_STAGE);
+  float* vec_s = reinterpret_cast<float*>(ring_p + NST * STAGE + RW_EPI_STAGE + RW_AFF_BYTES);  // bias | gamma | beta
+  const uint32_t bars = ring + NST * STAGE + RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES;
+  // barrier map (8 B each): full[0..5] empty[0..5] tfull[0..1] tempty[0..1] w, then the TMEM pointer, then statistics scratch
+  const uint32_t bar_full = bars, bar_empty = bars + 48, bar_tfull = bars + 96, bar_tempty = bars + 112, bar_w = bars + 128;
+  uint8_t* bars_p = ring_p + NST * STAGE + RW_EPI_STAGE + RW_AFF_BYTES + RW_VEC_BYTES;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(bars_p + 144);
+  Wf* wf_s = reinterpret_cast<Wf*>(bars_p + 160);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = (int)d.M;
 
   if (tid == 0) {
-    for (int s = 0; s < RW_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 2 * RW_PRODUCERS / 32);  // one arrival per producer warp and row half (every warp fills a part of every stage)
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_full + 8 * s, 2 * RW_PRODUCERS / 32 + (kWS ? 1 : 0));  // one arrival per producer warp and row half (every warp fills a part of every stage)
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -112,18 +120,35 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
-    // ===================== the weight image, once =====================
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bar_w, wbytes);
-      for (uint32_t o = 0; o < wbytes; o += 4096) bulk_g2s(base + o, wimg + o, 4096, bar_w);
+    if constexpr (!kWS) {
+      // ===================== the weight image, once =====================
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bar_w, wbytes);
+        for (uint32_t o = 0; o < wbytes; o += 4096) bulk_g2s(base + o, wimg + o, 4096, bar_w);
+      }
+      __syncwarp();
+    } else {
+      // ===================== weight blocks through the ring =====================
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_full + 8 * s, 2 * WBLK);
+            bulk_g2s(ring + s * STAGE + RW_STAGE, wimg + (size_t)kb * (2 * WBLK), 2 * WBLK, bar_full + 8 * s);
+          }
+          __syncwarp();
+          if (++s == NST) { s = 0; ph ^= 1; }
+        }
+      }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int s = 0;
     uint32_t ph = 0;
     int64_t it = 0;
-    mbar_wait(bar_w, 0);
+    if constexpr (!kWS) mbar_wait(bar_w, 0);
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int a = (int)(it & 1);
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
         mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = ring + s * RW_STAGE, wa = base + (uint32_t)kb * 2u * WBLK;
+          const uint32_t sa = ring + s * STAGE, wa = kWS ? sa + RW_STAGE : base + (uint32_t)kb * 2u * WBLK;
           const uint64_t a_hi = rw_desc(sa), a_lo = rw_desc(sa + RW_APART);
           const uint64_t b_hi = rw_desc(wa), b_lo = rw_desc(wa + WBLK);
 #pragma unroll
@@ -149,7 +174,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
           if (kb == KB - 1) umma_commit(bar_tfull + 8 * a);  // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++s == RW_STAGES) { s = 0; ph ^= 1; }
+        if (++s == NST) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp < 6) {
@@ -412,7 +437,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
         sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
       }
       const int my_s = s + sub;
-      uint8_t* a_hi = ring_p + my_s * RW_STAGE;
+      uint8_t* a_hi = ring_p + my_s * STAGE;
       uint8_t* a_lo = a_hi + RW_APART;
       auto split_store = [&](const float(&v)[8], int p) {
         const int r = (c.u & 1) * 64 + p * 32 + r0;
@@ -469,7 +494,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) gemm_rows_kernel(const ps_gemm_
       }
       if (c.u & 1) {
         s += 2;
-        if (s == RW_STAGES) { s = 0; ph ^= 1; }
+        if (s == NST) { s = 0; ph ^= 1; }
       }
     };
 
@@ -553,9 +578,11 @@ __global__ void pack_weights_rows_kernel(const float* __restrict__ W, int64_t ld
 int64_t gemm_rows_image_bytes(int64_t M, int64_t K) {
   static EnvInt env;
   if (env.get("PS_GEMM_ROWS", 1) == 0) return 0;
-  if (M < 32 || M > 128 || M % 32 != 0 || K < 64 || K % 64 != 0 || K > RW_MAXK) return 0;
-  const int64_t bytes = (int64_t)rw_bn(M) * K * 4;
-  return bytes <= RW_WMAX ? bytes : 0;
+  if (M < 32 || M > 128 || M % 32 != 0 || K < 64 || K % 64 != 0 || K > RW_KMAX_WS) return 0;
+  const int64_t bytes = (int64_t)rw_bn(M) * K * 4;  // resident when <= 128 KB, else streamed through the operand ring
+  static EnvInt ws_env;
+  if (bytes > RW_WMAX && ws_env.get("PS_GEMM_ROWS_WS", 1) == 0) return 0;  // A/B: streamed-weight shapes back on the CTA-pair kernel
+  return bytes;
 }
 
 int gemm_rows_pack(const float* W, int64_t ldw, int64_t M, int64_t K, void* packed, cudaStream_t s) {
@@ -570,6 +597,7 @@ static inline bool rw_al16(const void* p) { return (reinterpret_cast<uintptr_t>(
 // d has passed gemm_tc_eligible (alignment of X / Y / bias / residual / prologue vectors, activation kinds)
 bool gemm_rows_eligible(const ps_gemm_t& d) {
   if (gemm_rows_image_bytes(d.M, d.K) == 0) return false;
+  if (d.pro_mode == PS_PRO_AFFINE && d.K > RW_MAXK) return false;  // scale | shift rows of an item are staged in shared memory
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_MASK || (d.pro_mode == PS_PRO_AFFINE && (d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU))))
     return false;
   if (d.ln_eps > 0.f && (d.pro_mode != PS_PRO_NONE || d.epi_act != PS_ACT_NONE || d.stats_partials || d.bias_batch)) return false;
@@ -579,10 +607,16 @@ bool gemm_rows_eligible(const ps_gemm_t& d) {
 
 template <int PRO, int BN, bool kLN>
 static int launch_rows(const ps_gemm_t& d, const uint8_t* wimg, cudaStream_t s, int dev, int64_t grid, int64_t n_rt, int64_t n_tiles) {
-  static SmemOnce<1> once;  // per instantiation and device: raised to the largest image once
-  if (int rc = once.ensure(dev, 0, gemm_rows_kernel<PRO, BN, kLN>, RW_WMAX + RW_TAIL, "cudaFuncSetAttribute(gemm_rows_kernel)")) return rc;
-  const int smem = (int)(BN * d.K * 4) + RW_TAIL;
-  gemm_rows_kernel<PRO, BN, kLN><<<(unsigned)grid, RW_THREADS, smem, s>>>(d, wimg, n_rt, n_tiles);
+  static SmemOnce<2> once;  // per instantiation and device: raised to the largest image once
+  if ((int64_t)BN * d.K * 4 <= RW_WMAX) {
+    if (int rc = once.ensure(dev, 0, gemm_rows_kernel<PRO, BN, kLN, false>, RW_WMAX + RW_TAIL, "cudaFuncSetAttribute(gemm_rows_kernel)")) return rc;
+    const int smem = (int)(BN * d.K * 4) + RW_TAIL;
+    gemm_rows_kernel<PRO, BN, kLN, false><<<(unsigned)grid, RW_THREADS, smem, s>>>(d, wimg, n_rt, n_tiles);
+  } else {
+    constexpr int smem = RW_STAGES_WS * (RW_STAGE + 2 * BN * RW_BK * 2) + RW_MISC;
+    if (int rc = once.ensure(dev, 1, gemm_rows_kernel<PRO, BN, kLN, true>, smem, "cudaFuncSetAttribute(gemm_rows_kernel)")) return rc;
+    gemm_rows_kernel<PRO, BN, kLN, true><<<(unsigned)grid, RW_THREADS, smem, s>>>(d, wimg, n_rt, n_tiles);
+  }
   PS_CHECK_LAUNCH("gemm_rows_kernel");
   return PS_OK;
 }

@@ -369,3 +369,36 @@ def test_tc_rows_kernel_mask_prologue_and_views(ops, act):
     w3 = rnd(128, 128, seed=7, scale=0.1)
     yn, _ = ops.linear(xn, w3, w_packed=ops.pack_weights(w3, 128, 128, 128), backend=ops.GEMM_TCGEN05)
     assert not torch.isfinite(yn[0, :10]).any() and torch.isfinite(yn[0, 10:500]).all() and not torch.isfinite(yn[0, 500:]).any()
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(2, 3000, 128, 512), (1, 9000, 64, 1536), (3, 700, 32, 2048), (1, 20000, 128, 768), (2, 333, 96, 1024)])
+def test_tc_rows_kernel_streamed_weights(ops, B, Rr, M, K):
+    """gemm_rows_kernel with a packed weight matrix of more than 128 KB (the U-Net shell's tap windows, out_conv of the
+    128-channel Conv-TasNet reading): the 32-k weight blocks travel through the six-stage ring with the operand.  Plain,
+    affine + PReLU (K <= 1024), mask prologue, bias / per-item bias / residual / statistics, LayerNorm epilogue."""
+    x, w = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.03)
+    bias, bb, res = rnd(M, seed=5), rnd(B, M, seed=6), rnd(B, Rr, M, seed=7)
+    pk = ops.pack_weights(w, M, K, K)
+    ops.path_log = []
+    y, part = ops.linear(x, w, bias=bias, bias_batch=bb, residual=res, want_stats=True, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    mk = rnd(B, Rr, K, seed=8, scale=2)
+    ym, _ = ops.linear(x, w, pro=ops.Prologue(ops.PRO_MASK, ops.ACT_SIGMOID, x2=mk), w_packed=pk, backend=ops.GEMM_TCGEN05)
+    g, bt = rnd(M, seed=9) + 1.5, rnd(M, seed=10)
+    yl, _ = ops.linear(x, w, bias=bias, ln=(g, bt, 1e-5), residual=res, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    paths, ops.path_log = ops.path_log, None
+    assert [p for _, p in paths] == [4, 4, 4], paths
+    ref = x.double() @ w.double().t() + bias.double() + bb.double().unsqueeze(1) + res.double()
+    check(y, ref)
+    scale, shift = ops.stats_finalize(part, None, None, 1e-8, M)
+    rstd = 1 / torch.sqrt(ref.var(dim=(1, 2), unbiased=False) + 1e-8)
+    assert (scale[:, 0].double() - rstd).abs().max() <= 1e-5 * rstd.abs().max()
+    check(ym, (x.double() * torch.sigmoid(mk.double())) @ w.double().t())
+    lin = x.double() @ w.double().t() + bias.double()
+    check(yl, F.layer_norm(lin, (M,), g.double(), bt.double(), 1e-5) + res.double(), 2e-4)
+    if K <= 1024:
+        sc, sh, slope = rnd(B, K, seed=3) + 1.5, rnd(B, K, seed=4), torch.tensor([0.2], device=DEV)
+        ops.path_log = []
+        ya, _ = ops.linear(x, w, pro=ops.Prologue(ops.PRO_AFFINE, ops.ACT_PRELU, sc, sh, K, None, slope), w_packed=pk, backend=ops.GEMM_TCGEN05)
+        paths, ops.path_log = ops.path_log, None
+        assert [p for _, p in paths] == [4], paths
+        check(ya, F.prelu(x * sc.unsqueeze(1) + sh.unsqueeze(1), slope).double() @ w.double().t())
