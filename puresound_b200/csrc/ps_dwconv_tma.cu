@@ -30,6 +30,31 @@ constexpr int DM_THREADS = 256;  // 8 float4 columns x 32 rows
 constexpr int DM_MAXSLOTS = 8;
 constexpr int DM_CHUNK_BYTES = DM_CH * DM_CG * 4;  // 8 KB
 
+// Packed fp32 arithmetic (sm_100: fma / add / mul .f32x2, SASS FFMA2 / FADD2 / FMUL2): two lanes of a float4 per instruction,
+// each half rounded like the scalar operation.  In the cfg2 step the kernel is issue-bound at the power-capped clock (ncu,
+// run 34: issue slots 78 % busy), so halving the FMA-pipe instructions of the taps, the statistics and the prologue is time.
+__device__ __forceinline__ uint64_t dm_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void dm_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t dm_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t dm_add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t dm_mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 template <int PRO>
 __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_t d, const __grid_constant__ CUtensorMap xmap, const int rows_per_cta,
                                                                const int nslots, const int HC) {
@@ -68,18 +93,21 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
   const int n_out = (tb - ta + DM_CH - 1) / DM_CH;  // output chunks of this run
   const int total_in = n_out + HC;                  // input chunks: rows [ta - halo_l, ...)
   const int in_row0 = ta - halo_l;
-  int issued = 0;  // (thread 0) input chunks requested so far
-  auto issue_until = [&](int limit) {  // request chunks [issued, min(limit, total_in)): chunk i -> slot i % nslots
+  // (every ring index below is a running counter with a wrap: `i % nslots` / `i / nslots` with a run-time nslots were two
+  // integer divisions per chunk and thread - the kernel executed 146 instructions per 16-byte output, ncu run 39)
+  int issued = 0, s_is = 0;  // (thread 0) input chunks requested so far, slot of the next request
+  auto issue_until = [&](int limit) {  // request chunks [issued, min(limit, total_in)): chunk i -> slot i mod nslots
     while (issued < limit && issued < total_in) {
-      const int s = issued % nslots;
-      mbar_arrive_expect_tx(bar_u + 8 * s, DM_CHUNK_BYTES);
-      tma_load_3d(ring_u + s * DM_CHUNK_BYTES, &xmap, cg * DM_CG, in_row0 + issued * DM_CH, (int)b, bar_u + 8 * s);
+      mbar_arrive_expect_tx(bar_u + 8 * s_is, DM_CHUNK_BYTES);
+      tma_load_3d(ring_u + s_is * DM_CHUNK_BYTES, &xmap, cg * DM_CG, in_row0 + issued * DM_CH, (int)b, bar_u + 8 * s_is);
       ++issued;
+      s_is = s_is + 1 == nslots ? 0 : s_is + 1;
     }
   };
   if (tid == 0) issue_until(nslots);
 
   const float slope = (d.pro_act == PS_ACT_PRELU && d.pro_slope) ? __ldg(d.pro_slope) : 1.f;
+  const bool slope01 = slope > 0.f && slope <= 1.f;  // PReLU(z) = max(z, slope * z) then: one FMNMX instead of compare + select
   float pa[4] = {1.f, 1.f, 1.f, 1.f}, pb[4] = {0.f, 0.f, 0.f, 0.f}, bias[4] = {0.f, 0.f, 0.f, 0.f}, w[3][4];
   if constexpr (PRO == 1) {
     const float4 a4 = __ldg(reinterpret_cast<const float4*>(d.pro_a + b * d.pro_batch_stride + c0));
@@ -96,36 +124,68 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
 #pragma unroll
     for (int i = 0; i < 4; ++i) w[p][i] = __ldg(d.w + (c0 + i) * 3 + p);
 
-  float piv = 0.f, ssum = 0.f, ssq = 0.f;
+  const uint64_t pa01 = dm_pack(pa[0], pa[1]), pa23 = dm_pack(pa[2], pa[3]), pb01 = dm_pack(pb[0], pb[1]), pb23 = dm_pack(pb[2], pb[3]);
+  const uint64_t bias01 = dm_pack(bias[0], bias[1]), bias23 = dm_pack(bias[2], bias[3]), slope2 = dm_pack(slope, slope);
+  uint64_t w01[3], w23[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) { w01[p] = dm_pack(w[p][0], w[p][1]); w23[p] = dm_pack(w[p][2], w[p][3]); }
+  // tap p of this thread's row h reads ring row r + p * dil counted from the first row of input chunk k: slot offset and
+  // byte offset inside the slot do not depend on k
+  int tap_slot[2][3];
+  uint32_t tap_off[2][3];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const int o = ty + 32 * h + p * dil;
+      tap_slot[h][p] = o >> 6;
+      tap_off[h][p] = (uint32_t)(((o & 63) * DM_CG + tx * 4) * 4);
+    }
+  // statistics: shifted sums about a pivot (this thread's first output), kept as two packed pairs of partial sums
+  float piv = 0.f;
+  uint64_t npiv2 = dm_pack(0.f, 0.f), ssum01 = npiv2, ssum23 = npiv2, ssq01 = npiv2, ssq23 = npiv2;
   int nout = 0;
-  float* yb = d.y + (b * T) * (int64_t)C + c0;
-  int tr = 0;   // input chunks transformed so far
-  int sk = 0;   // slot of input chunk k
+  float* yrow[2];  // output pointer of this thread's two rows of the current chunk
+#pragma unroll
+  for (int h = 0; h < 2; ++h) yrow[h] = d.y + (b * T + ta + ty + 32 * h) * (int64_t)C + c0;
+  int tr = 0, s_tr = 0;  // input chunks transformed so far, slot of the next one
+  uint32_t ph_tr = 0;    // its mbarrier phase
+  int t_in = in_row0 + ty;  // frame of this thread's first row of input chunk tr
+  int sk = 0;               // slot of input chunk k
   for (int k = 0; k < n_out; ++k) {
     // ---- input chunks up to k + HC have landed and carry PReLU(norm(x)), zero outside the item
     while (tr <= k + HC && tr < total_in) {
-      const int s = tr % nslots;
-      mbar_wait(bar_u + 8 * s, (uint32_t)((tr / nslots) & 1));
+      mbar_wait(bar_u + 8 * s_tr, ph_tr);
       if constexpr (PRO == 1) {
-        float* cp = reinterpret_cast<float*>(ring + s * DM_CHUNK_BYTES);
+        float* cp = reinterpret_cast<float*>(ring + s_tr * DM_CHUNK_BYTES) + ty * DM_CG + tx * 4;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int r = ty + 32 * h;
-          const int t = in_row0 + tr * DM_CH + r;
-          float4* q = reinterpret_cast<float4*>(cp + r * DM_CG + tx * 4);
-          const float4 v = *q;
-          float o[4] = {v.x, v.y, v.z, v.w};
-          const bool ok = t >= 0 && t < T;
+          const int t = t_in + 32 * h;
+          float4* q = reinterpret_cast<float4*>(cp + 32 * h * DM_CG);
+          if (t >= 0 && t < T) {
+            const float4 v = *q;
+            uint64_t z01 = dm_fma2(dm_pack(v.x, v.y), pa01, pb01), z23 = dm_fma2(dm_pack(v.z, v.w), pa23, pb23);
+            float o[4], m[4];
+            dm_unpack(z01, o[0], o[1]);
+            dm_unpack(z23, o[2], o[3]);
+            dm_unpack(dm_mul2(z01, slope2), m[0], m[1]);
+            dm_unpack(dm_mul2(z23, slope2), m[2], m[3]);
+            if (slope01) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float z = fmaf(o[i], pa[i], pb[i]);
-            z = z > 0.f ? z : z * slope;
-            o[i] = ok ? z : 0.f;  // zero padding applies AFTER the prologue: the reference pads the activated tensor
+              for (int i = 0; i < 4; ++i) o[i] = fmaxf(o[i], m[i]);  // (a NaN z gives a NaN slope * z: max(NaN, NaN) = NaN)
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = o[i] > 0.f ? o[i] : m[i];
+            }
+            *q = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            *q = make_float4(0.f, 0.f, 0.f, 0.f);  // zero padding applies AFTER the prologue: the reference pads the activated tensor
           }
-          *q = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
       ++tr;
+      t_in += DM_CH;
+      if (++s_tr == nslots) { s_tr = 0; ph_tr ^= 1; }
     }
     __syncthreads();  // transformed rows visible to every thread; every thread is done with the taps of chunk k - 1
     if (tid == 0) {
@@ -133,37 +193,40 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
       issue_until(k + nslots);    // chunks < k are dead: their slots take the chunks up to k + nslots - 1
     }
     // ---- taps of output chunk k from the ring
-    const int t0 = ta + k * DM_CH;
+    const int t0 = ta + k * DM_CH + ty;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int r = ty + 32 * h;
-      const int t = t0 + r;
-      if (t >= tb) continue;
-      float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
+      if (t0 + 32 * h < tb) {
+        uint64_t a01 = bias01, a23 = bias23;
 #pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const int o = r + p * dil;  // row offset from the first row of input chunk k
-        int s = sk + (o >> 6);
-        s = s >= nslots ? s - nslots : s;
-        const float4 u4 = *reinterpret_cast<const float4*>(ring + s * DM_CHUNK_BYTES + ((o & 63) * DM_CG + tx * 4) * 4);
-        acc[0] = fmaf(w[p][0], u4.x, acc[0]);
-        acc[1] = fmaf(w[p][1], u4.y, acc[1]);
-        acc[2] = fmaf(w[p][2], u4.z, acc[2]);
-        acc[3] = fmaf(w[p][3], u4.w, acc[3]);
+        for (int p = 0; p < 3; ++p) {
+          int sl = sk + tap_slot[h][p];
+          sl = sl >= nslots ? sl - nslots : sl;
+          const float4 u4 = *reinterpret_cast<const float4*>(ring + sl * DM_CHUNK_BYTES + tap_off[h][p]);
+          a01 = dm_fma2(w01[p], dm_pack(u4.x, u4.y), a01);
+          a23 = dm_fma2(w23[p], dm_pack(u4.z, u4.w), a23);
+        }
+        float acc[4];
+        dm_unpack(a01, acc[0], acc[1]);
+        dm_unpack(a23, acc[2], acc[3]);
+        *reinterpret_cast<float4*>(yrow[h]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (nout == 0) { piv = acc[0]; npiv2 = dm_pack(-piv, -piv); }
+        ++nout;
+        const uint64_t d01 = dm_add2(a01, npiv2), d23 = dm_add2(a23, npiv2);
+        ssum01 = dm_add2(ssum01, d01);
+        ssum23 = dm_add2(ssum23, d23);
+        ssq01 = dm_fma2(d01, d01, ssq01);
+        ssq23 = dm_fma2(d23, d23, ssq23);
       }
-      *reinterpret_cast<float4*>(yb + (int64_t)t * C) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      if (nout == 0) piv = acc[0];
-      ++nout;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float dv = acc[i] - piv;
-        ssum += dv;
-        ssq = fmaf(dv, dv, ssq);
-      }
+      yrow[h] += (int64_t)DM_CH * C;
     }
     sk = sk + 1 == nslots ? 0 : sk + 1;
   }
   if (d.stats_partials) {
+    float s0, s1, s2, s3, q0, q1, q2, q3;
+    dm_unpack(ssum01, s0, s1); dm_unpack(ssum23, s2, s3);
+    dm_unpack(ssq01, q0, q1); dm_unpack(ssq23, q2, q3);
+    const float ssum = (s0 + s1) + (s2 + s3), ssq = (q0 + q1) + (q2 + q3);
     Wf mine;
     mine.n = (float)(nout * 4);
     mine.mean = 0.f; mine.m2 = 0.f;

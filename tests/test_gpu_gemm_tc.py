@@ -402,3 +402,18 @@ def test_tc_rows_kernel_streamed_weights(ops, B, Rr, M, K):
         paths, ops.path_log = ops.path_log, None
         assert [p for _, p in paths] == [4], paths
         check(ya, F.prelu(x * sc.unsqueeze(1) + sh.unsqueeze(1), slope).double() @ w.double().t())
+
+
+@pytest.mark.parametrize("B,Rr,M,K", [(3, 333, 96, 128), (2, 130, 32, 512), (2, 257, 128, 768), (1, 3999, 512, 512), (3, 497, 384, 128)])
+def test_tc_outputs_stay_inside_their_view(ops, B, Rr, M, K):
+    """Guard bands around a strided output view (compute-sanitizer is not available on the GPU pool): ragged last tiles, channel
+    counts below the MMA width (96 -> 128, 384 -> 512) and the few-tile path must not write a byte outside [B, rows, M] - rows
+    past the end of an item are computed (the operand re-reads the last row) but never stored."""
+    x, w, bias = rnd(B, Rr, K, seed=1, scale=2), rnd(M, K, seed=2, scale=0.05), rnd(M, seed=3)
+    pk = ops.pack_weights(w, M, K, K)
+    sentinel = 12345.0
+    big = torch.full((B, Rr + 3, M + 32), sentinel, device=DEV)
+    ops.gemm(x, w, batch=B, rows=Rr, M=M, K=K, x_batch_stride=Rr * K, x_row_stride=K, w_row_stride=K, bias=bias, w_packed=pk,
+             backend=ops.GEMM_TCGEN05, out=big, y_strides=((Rr + 3) * (M + 32), M + 32))
+    check(big[:, :Rr, :M], x.double() @ w.double().t() + bias.double())
+    assert (big[:, Rr:, :] == sentinel).all() and (big[:, :, M:] == sentinel).all()
