@@ -316,6 +316,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WD_THREADS, 1)
         mbar_wait_relaxed(bar_tfull + 8 * mb, aph);
         tc_fence_after();
         float pv = 0.f, sm1 = 0.f, sq1 = 0.f, cn = 0.f;
+        if (rb && !want_stats && epi_act == PS_ACT_NONE && nvalid == WD_FRAMES && !WD_DBG(4) && !(dbg & 0x100)) {
+          // out_conv of a full tile (bias + residual, no activation, no statistics): the residual of chunk i + 1 is
+          // requested BEFORE chunk i is read from TMEM, added and stored, so its (L2) latency passes behind that work
+          // instead of being waited for once per chunk (the generic loop below issues a chunk's 16 loads and uses them at once)
+          float r[WD_CW], rn[WD_CW];
+          int c = g * 2;
+          {
+            const float* p = rb + (int64_t)(c * WD_CW) * rstride + mb * 256;
+#pragma unroll
+            for (int j = 0; j < WD_CW; ++j) { r[j] = __ldg(p); p += rstride; }
+          }
+#pragma unroll 1
+          while (c < NCH) {
+            const int c2 = c + ((c & 1) ? (G - 1) * 2 + 1 : 1);
+            if (c2 < NCH) {
+              const float* p = rb + (int64_t)(c2 * WD_CW) * rstride + mb * 256;
+#pragma unroll
+              for (int j = 0; j < WD_CW; ++j) { rn[j] = __ldg(p); p += rstride; }
+            }
+            float v[WD_CW];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mb * WD_FRAMES + c * WD_CW), v);
+            float* yp = yb + (int64_t)(c * WD_CW) * ystride + mb * 256;
+#pragma unroll
+            for (int j = 0; j < WD_CW; ++j) {
+              *yp = v[j] + bsum + r[j];
+              yp += ystride;
+            }
+#pragma unroll
+            for (int j = 0; j < WD_CW; ++j) r[j] = rn[j];
+            c = c2;
+          }
+        } else
         // real loops (not unrolled): the chunk body exists once per variant, which keeps the kernel inside the
         // instruction cache
 #pragma unroll 1
@@ -563,10 +595,12 @@ static int launch_wide(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid
   if (int rc = once.ensure(dev, 0, gemm_wide_kernel<PRO>, WD_SMEM, "cudaFuncSetAttribute(gemm_wide_kernel)")) return rc;
 #ifdef PS_EXPERIMENTS
   static EnvInt dbg_e;
-  const int dbg = dbg_e.get("PS_WIDE_DBG", 0);
+  int dbg = dbg_e.get("PS_WIDE_DBG", 0);
 #else
-  const int dbg = 0;
+  int dbg = 0;
 #endif
+  static EnvInt respf_e;  // A/B: PS_WIDE_RESPF=0 keeps the generic epilogue for the out_conv form (bit 0x100 of dbg)
+  if (respf_e.get("PS_WIDE_RESPF", 1) == 0) dbg |= 0x100;
   cudaError_t le = launch_pdl(gemm_wide_kernel<PRO>, dim3((unsigned)grid), dim3(WD_THREADS), WD_SMEM, s, d, n_rt, n_nh, n_tiles, dbg);
   if (le != cudaSuccess) { set_cuda_error(le, "gemm_wide_kernel"); return PS_ERR_CUDA; }
   return PS_OK;

@@ -234,6 +234,10 @@ def test_tc_wide_tiles(ops, B, Rr, M, K):
     assert (shift[:, 0].double() + mu * rstd).abs().max() <= 5e-5
     y2, _ = ops.linear(x, w, pro=pro, bias=bias, bias_batch=bb, residual=res, backend=ops.GEMM_SIMT)
     check(y, y2.double())
+    # out_conv form (bias + residual, no statistics): full tiles take the epilogue that requests the residual one chunk ahead
+    y4, _ = ops.linear(x, w, pro=pro, bias=bias, residual=res, w_packed=pk, backend=ops.GEMM_TCGEN05)
+    y5, _ = ops.linear(x, w, pro=pro, bias=bias, residual=res, backend=ops.GEMM_SIMT)
+    check(y4, y5.double())
 
 
 @pytest.mark.parametrize("B,Rr,M,K", [(1, 3999, 512, 512), (3, 497, 512, 256), (1, 640, 1024, 64), (2, 900, 384, 128)])
