@@ -18,6 +18,13 @@ bool pdl_enabled() {
   return env.get("PS_PDL", 0) != 0;
 }
 
+bool order_reversed() {
+  static EnvInt env;
+  static std::atomic<unsigned> flip{0};
+  if (env.get("PS_ORDER_ALT", 0) == 0) return false;
+  return (flip.fetch_add(1, std::memory_order_relaxed) & 1u) != 0;
+}
+
 int gemm_simt_launch(const ps_gemm_t& d, cudaStream_t s);
 bool gemm_tc_eligible(const ps_gemm_t& d);
 int gemm_tc_launch(const ps_gemm_t& d, cudaStream_t s);

@@ -122,6 +122,11 @@ struct EnvInt {
   }
 };
 
+// EXPERIMENT (PS_ORDER_ALT=1): consecutive big launches of a stream walk their tensors in alternating directions, so that a
+// kernel starts with the part of its input the previous kernel wrote LAST - the part most likely still in the 126 MB L2
+// (a [64, 3999, 512] tensor is 524 MB).  One process-wide toggle, flipped by every launch that honours it.
+bool order_reversed();
+
 // if-chain with the hot cases first (PReLU, none): a switch here becomes an indirect branch (BRX) per element
 // once it is inlined into unrolled loops, which measured 4x more instructions in the GEMM producers
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {

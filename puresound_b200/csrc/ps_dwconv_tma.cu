@@ -57,13 +57,14 @@ __device__ __forceinline__ uint64_t dm_mul2(uint64_t a, uint64_t b) {
 
 template <int PRO>
 __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_t d, const __grid_constant__ CUtensorMap xmap, const int rows_per_cta,
-                                                               const int nslots, const int HC) {
+                                                               const int nslots, const int HC, const int rev) {
   extern __shared__ __align__(128) uint8_t ring[];  // [nslots][64 rows][32 channels] fp32
   __shared__ __align__(8) uint64_t full_bar[DM_MAXSLOTS];
   __shared__ Wf red[DM_THREADS / 32];
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  const int cg = blockIdx.x, split = blockIdx.y;
-  const int64_t b = blockIdx.z;
+  // rev: the launch walks items and runs from the last to the first (CTAs are dispatched in blockIdx order)
+  const int cg = blockIdx.x, split = rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+  const int64_t b = rev ? (int64_t)(gridDim.z - 1 - blockIdx.z) : (int64_t)blockIdx.z;
   const int T = (int)d.T, C = (int)d.C;
   const int c0 = cg * DM_CG + tx * 4;
   const int dil = d.dilation;
@@ -301,7 +302,7 @@ template <int PRO>
 static int launch_dm(const ps_dwconv_t& d, const CUtensorMap& xmap, int rows, int nslots, int HC, dim3 grid, cudaStream_t s, int dev) {
   static SmemOnce<1> once;
   if (int rc = once.ensure(dev, 0, dwconv_tma_kernel<PRO>, DM_MAXSLOTS * DM_CHUNK_BYTES, "cudaFuncSetAttribute(dwconv_tma_kernel)")) return rc;
-  cudaError_t le = launch_pdl(dwconv_tma_kernel<PRO>, grid, dim3(DM_THREADS), (size_t)nslots * DM_CHUNK_BYTES, s, d, xmap, rows, nslots, HC);
+  cudaError_t le = launch_pdl(dwconv_tma_kernel<PRO>, grid, dim3(DM_THREADS), (size_t)nslots * DM_CHUNK_BYTES, s, d, xmap, rows, nslots, HC, order_reversed() ? 1 : 0);
   if (le != cudaSuccess) { set_cuda_error(le, "dwconv_tma_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
 }

@@ -180,7 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WD_THREADS, 1)
     uint32_t gs = 0;  // stages issued so far (ring position = gs & 3, phase = (gs >> 2) & 1)
     const uint8_t* wp = reinterpret_cast<const uint8_t*>(d.W_packed);
     for (int64_t t = pair; t < n_tiles; t += n_pairs) {
-      const WideTile tc = wd_tile(t, n_rt, n_nh);
+      const WideTile tc = wd_tile((dbg & 0x200) ? n_tiles - 1 - t : t, n_rt, n_nh);
       const uint8_t* src = wp + (size_t)(tc.nh * 2 + rank) * KB * WD_WBYTES;
       for (int kb = 0; kb < KB; ++kb, ++gs) {
         const uint32_t s = gs & (WD_STAGES - 1), ph = (gs >> 2) & 1u;
@@ -288,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WD_THREADS, 1)
     const bool want_stats = d.stats_partials != nullptr;
     int64_t it = 0;
     for (int64_t t = pair; t < n_tiles; t += n_pairs, ++it) {
-      const WideTile tc = wd_tile(t, n_rt, n_nh);
+      const WideTile tc = wd_tile((dbg & 0x200) ? n_tiles - 1 - t : t, n_rt, n_nh);
       const uint32_t aph = (uint32_t)(it & 1);
       const int64_t frame0 = (int64_t)tc.rt * WD_FRAMES;
       const int nvalid = (int)((d.rows - frame0) < WD_FRAMES ? (d.rows - frame0) : WD_FRAMES);
@@ -447,7 +447,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WD_THREADS, 1)
     const int64_t last_row = d.rows - 1;
     auto decode = [&](Cur& c) {
       if (c.t < n_tiles) {
-        const WideTile tc = wd_tile(c.t, n_rt, n_nh);
+        const WideTile tc = wd_tile((dbg & 0x200) ? n_tiles - 1 - c.t : c.t, n_rt, n_nh);
         c.b = tc.b;
         c.row_base = (int64_t)tc.rt * WD_FRAMES + rank * WD_FR_CTA + r0;
         c.x0 = d.X + tc.b * d.x_batch_stride + kofs;
@@ -601,6 +601,7 @@ static int launch_wide(const ps_gemm_t& d, cudaStream_t s, int dev, int64_t grid
 #endif
   static EnvInt respf_e;  // A/B: PS_WIDE_RESPF=0 keeps the generic epilogue for the out_conv form (bit 0x100 of dbg)
   if (respf_e.get("PS_WIDE_RESPF", 1) == 0) dbg |= 0x100;
+  if (order_reversed()) dbg |= 0x200;  // walk the tiles from the last to the first (see ps_common.cuh: order_reversed)
   cudaError_t le = launch_pdl(gemm_wide_kernel<PRO>, dim3((unsigned)grid), dim3(WD_THREADS), WD_SMEM, s, d, n_rt, n_nh, n_tiles, dbg);
   if (le != cudaSuccess) { set_cuda_error(le, "gemm_wide_kernel"); return PS_ERR_CUDA; }
   return PS_OK;
