@@ -597,6 +597,7 @@ static inline bool rw_al16(const void* p) { return (reinterpret_cast<uintptr_t>(
 // d has passed gemm_tc_eligible (alignment of X / Y / bias / residual / prologue vectors, activation kinds)
 bool gemm_rows_eligible(const ps_gemm_t& d) {
   if (gemm_rows_image_bytes(d.M, d.K) == 0) return false;
+  if (d.rows >= (1LL << 30) || d.batch * cdiv(d.rows, RW_BM) >= (1LL << 30)) return false;  // 32-bit cursors in the producers
   if (d.pro_mode == PS_PRO_AFFINE && d.K > RW_MAXK) return false;  // scale | shift rows of an item are staged in shared memory
   if (!(d.pro_mode == PS_PRO_NONE || d.pro_mode == PS_PRO_MASK || (d.pro_mode == PS_PRO_AFFINE && (d.pro_act == PS_ACT_NONE || d.pro_act == PS_ACT_PRELU))))
     return false;

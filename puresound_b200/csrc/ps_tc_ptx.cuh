@@ -66,11 +66,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // same, for waiters that are not on the critical path (epilogue waiting for an accumulator, the weight loader waiting
 // for a free stage): back off between polls so the spin does not eat the issue slots the producer warps need
+#ifndef PS_RELAXED_SLEEP_NS
+#define PS_RELAXED_SLEEP_NS 64
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
+    __nanosleep(PS_RELAXED_SLEEP_NS);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
