@@ -18,6 +18,8 @@
 //     stores go through a per-warp shared-memory transpose so that a warp instruction writes 4 rows x 128 B.
 // Warps: 0 = weight copy (once), 1 = MMA issuer (+ TMEM allocation), 2-5 = epilogue (one per TMEM lane quarter),
 // 6-13 = activation producers (fp32 global -> prologue transform -> bf16 hi / lo -> swizzled UMMA tile).
+// (Tried and dropped, run 49: one 256-wide tile for 129 ... 256 channels - slower than the CTA-pair kernel with 64-k stages on
+// every shape of the TSE / SkiM models: 31808 x 256 x 256 0.039 -> 0.042 ms, 191968 x 256 x 256 0.123 -> 0.149 ms, cfg4 4.86 -> 5.35 ms.)
 // Prologues: none, folded norm affine + PReLU, mask product x * act(x2) (mask apply in front of the decoder,
 // base_nn.py:41-79).  Epilogues: bias, per-item bias, ReLU / PReLU, residual, Welford partials; or the row LayerNorm.
 #include "ps_tc_ptx.cuh"
