@@ -130,18 +130,16 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
   uint64_t w01[3], w23[3];
 #pragma unroll
   for (int p = 0; p < 3; ++p) { w01[p] = dm_pack(w[p][0], w[p][1]); w23[p] = dm_pack(w[p][2], w[p][3]); }
-  // tap p of this thread's row h reads ring row r + p * dil counted from the first row of input chunk k: slot offset and
-  // byte offset inside the slot do not depend on k
-  int tap_slot[2][3];
-  uint32_t tap_off[2][3];
+  // The ring is [nslots * 64 rows][32 channels] contiguous: tap p of this thread's row h reads ring row
+  // (64 sk + ty + 32 h + p dil) mod (64 nslots).  Byte offsets that do not depend on the chunk are kept in registers (made
+  // opaque: the compiler otherwise re-derives them from ty, tx, dil in every iteration - ~25 integer instructions per row).
+  uint32_t tapb[3];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      const int o = ty + 32 * h + p * dil;
-      tap_slot[h][p] = o >> 6;
-      tap_off[h][p] = (uint32_t)(((o & 63) * DM_CG + tx * 4) * 4);
-    }
+  for (int p = 0; p < 3; ++p) {
+    tapb[p] = (uint32_t)(((ty + p * dil) * DM_CG + tx * 4) * 4);
+    asm volatile("" : "+r"(tapb[p]));
+  }
+  const uint32_t ring_bytes = (uint32_t)nslots * DM_CHUNK_BYTES;
   // statistics: shifted sums about a pivot (this thread's first output), kept as two packed pairs of partial sums
   float piv = 0.f;
   uint64_t npiv2 = dm_pack(0.f, 0.f), ssum01 = npiv2, ssum23 = npiv2, ssq01 = npiv2, ssq23 = npiv2;
@@ -195,15 +193,16 @@ __global__ void __launch_bounds__(DM_THREADS) dwconv_tma_kernel(const ps_dwconv_
     }
     // ---- taps of output chunk k from the ring
     const int t0 = ta + k * DM_CH + ty;
+    const uint32_t skb = (uint32_t)sk * DM_CHUNK_BYTES;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (t0 + 32 * h < tb) {
         uint64_t a01 = bias01, a23 = bias23;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
-          int sl = sk + tap_slot[h][p];
-          sl = sl >= nslots ? sl - nslots : sl;
-          const float4 u4 = *reinterpret_cast<const float4*>(ring + sl * DM_CHUNK_BYTES + tap_off[h][p]);
+          uint32_t off = skb + tapb[p] + (uint32_t)(h * 32 * DM_CG * 4);  // < 2 * ring_bytes: the halo is at most nslots - 3 chunks
+          off = off >= ring_bytes ? off - ring_bytes : off;
+          const float4 u4 = *reinterpret_cast<const float4*>(ring + off);
           a01 = dm_fma2(w01[p], dm_pack(u4.x, u4.y), a01);
           a23 = dm_fma2(w23[p], dm_pack(u4.z, u4.w), a23);
         }
