@@ -185,7 +185,11 @@ class GatedTCN(nn.Module):
         if L_out < T or (not self.causal and L_out != T):
             # odd (kernel-1)*dilation without causal trim: the reference fails on `x + res` (conv_tasnet.py:213) - fail as loudly
             raise RuntimeError(f"The size of tensor a ({L_out}) must match the size of tensor b ({T}) at non-singleton dimension 2")
-        xp = torch.zeros(N, rows_in, width, device=x.device, dtype=torch.float32)
+        # only the pad rows are zeroed: the un-padded rows are written in full below (in_conv, the embedding columns) - a
+        # zero-fill of the whole [N, T + 2p, width] buffer per block was 9 % of the gated TSE step
+        xp = torch.empty(N, rows_in, width, device=x.device, dtype=torch.float32)
+        xp[:, :p].zero_()
+        xp[:, p + T:].zero_()
         inner = xp.view(-1)[p * width:]  # first un-padded row
         ops.linear(x, self.in_conv.weight.view(H, C), out=inner, y_strides=(rows_in * width, width),
                    w_packed=self._cache.get("in", [self.in_conv.weight], lambda: ops.pack_weights(self.in_conv.weight.view(H, C), H, C, C)))
@@ -198,7 +202,9 @@ class GatedTCN(nn.Module):
                                   lambda: torch.cat([self.cond_scale.weight.view(H, E), self.cond_bias.weight.view(H, E)], 0).contiguous())
             sb, _ = ops.gemm(embed.contiguous(), wsb, batch=1, rows=N, M=2 * H, K=E, x_batch_stride=0, x_row_stride=E, w_row_stride=E)
             sb = sb.view(N, 2 * H)
-            right_in = torch.zeros(N, rows_in, H, device=x.device, dtype=torch.float32)
+            right_in = torch.empty(N, rows_in, H, device=x.device, dtype=torch.float32)
+            right_in[:, :p].zero_()
+            right_in[:, p + T:].zero_()
             film = ops.Prologue(ops.PRO_AFFINE, ops.ACT_NONE, sb[:, :H], sb[:, H:], 2 * H)
             ops.gated(inner, film, batch=N, rows=T, C_=H, a_strides=(rows_in * width, width),
                       out=right_in.view(-1)[p * H:], y_strides=(rows_in * H, H))
