@@ -132,3 +132,37 @@ def test_spec_augment_draws_like_torchaudio():
     assert (s, e) == (int(v0.long()), int(v0.long()) + int(v.long())) and torch.equal(torch.rand(1), nxt)
     torch.manual_seed(11)
     assert SpecAugment._draw(0, 80) == (0, 0) and torch.equal(torch.rand(1), v / 10)  # no mask, no draw
+
+
+def test_bench_clock_sampler_window_and_roofline_bytes():
+    """bench.py host logic that needs no GPU: only the clock samples received inside the timed window are summarised (the
+    sampler runs from before the warm-up), and a GEMM group's algorithmic bytes include the residual / mask operand reads of
+    its launches."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    clk = bench.ClockSampler(0)
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "990.0", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+    clk.rows = [(1.0, row(1965, False)), (2.0, row(1550, True)), (2.5, row(1560, True)), (3.5, row(1965, False))]
+    clk.t_open, clk.t_close = 1.5, 3.0
+    s = clk.summary()
+    assert s["samples"] == 2 and s["sm_mhz"] == 1555.0 and s["sm_max_mhz"] == 1965.0 and s["reasons"] == ["sw_power_cap"]
+    assert "extended" not in s
+    clk.extended = True
+    assert "extended" in clk.summary()
+
+    class Ev:  # stands in for a CUDA event pair: elapsed_time in ms
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    rows, M, K = 1000, 128, 256
+    events = [("gemm", Ev(0.0), Ev(0.5), (rows, M, K), 4 * rows * M), ("gemm", Ev(1.0), Ev(1.5), (rows, M, K), 0)]
+    (g,) = bench.kernel_rooflines(events, 2.0, 6549.8, 1392.7, "measured")
+    assert g["launches_timed"] == 2 and abs(g["avg_launch_ms"] - 0.5) < 1e-9
+    assert g["algorithmic_bytes"] == 4.0 * (rows * K + rows * M + M * K) + 2 * rows * M  # mean residual bytes of the two launches
