@@ -49,7 +49,32 @@ __global__ void __launch_bounds__(256) gated_kernel(const GatedSide A, const Gat
                                                     int64_t yms, int64_t yrs, int64_t batch, int64_t mid, int64_t rows, int C4) {
   const float sa = A.slope_p ? __ldg(A.slope_p) : 0.f;
   const float sb = (B.x && B.slope_p) ? __ldg(B.slope_p) : 0.f;
-  const int64_t total = batch * mid * rows * C4;
+  const int64_t n_rows = batch * mid * rows;
+  if (C4 <= (int)blockDim.x && n_rows < (1LL << 31)) {
+    // Fast path: a thread keeps its column and walks rows - the (column, row-in-CTA) split is computed once, a row index is
+    // taken apart with two 32-bit divisions.  The generic loop below pays six 64-bit divisions / remainders per 16-byte
+    // element: as the transform copy of the U-Net shells (tap buffers of tse_unet_tcn / DPCRN / DPARN) it was 20-28 % of
+    // those recipes' steps, issue-bound (run 53).
+    const uint32_t rpb = blockDim.x / (uint32_t)C4;  // rows per CTA pass
+    const uint32_t rl = threadIdx.x / (uint32_t)C4;
+    const int c = (int)(threadIdx.x - rl * (uint32_t)C4) * V;
+    if (rl >= rpb) return;
+    const uint32_t nr = (uint32_t)n_rows, rows32 = (uint32_t)rows, mid32 = (uint32_t)mid;
+    for (uint32_t R = blockIdx.x * rpb + rl; R < nr; R += gridDim.x * rpb) {
+      const uint32_t bm = R / rows32, r = R - bm * rows32;
+      const uint32_t b = bm / mid32, m = bm - b * mid32;
+      float4 v = gated_load<V>(A, sa, b, m, mid, r, rows, c);
+      if (B.x) {
+        const float4 g = gated_load<V>(B, sb, b, m, mid, r, rows, c);
+        v.x *= gated_sigmoid(g.x); v.y *= gated_sigmoid(g.y); v.z *= gated_sigmoid(g.z); v.w *= gated_sigmoid(g.w);
+      }
+      float* yp = y + (int64_t)b * ybs + (int64_t)m * yms + (int64_t)r * yrs + c;
+      if constexpr (V == 4) *reinterpret_cast<float4*>(yp) = v;
+      else *yp = v.x;
+    }
+    return;
+  }
+  const int64_t total = n_rows * C4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * V;
     const int64_t br = i / C4, r = br % rows, bm = br / rows, m = bm % mid, b = bm / mid;
@@ -93,7 +118,8 @@ extern "C" int ps_gated(const ps_gated_t* dp, void* stream) {
                    (d.y_mid_stride & 3) == 0 && (d.y_row_stride & 3) == 0 && ps::gated_side_vec(A) && (!d.b || ps::gated_side_vec(B));
   const int64_t cols = vec ? d.C / 4 : d.C;
   const int64_t total = d.batch * mid * d.rows * cols;
-  int64_t blocks = ps::cdiv(total, 256);
+  // fast path (cols <= 256): a CTA pass covers 256 / cols rows; else one element per thread and pass
+  int64_t blocks = cols <= 256 ? ps::cdiv(d.batch * mid * d.rows, 256 / cols) : ps::cdiv(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 CTAs of 256 threads per SM
   if (vec)
     ps::gated_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(A, B, d.y, d.y_batch_stride, d.y_mid_stride, d.y_row_stride, d.batch, mid, d.rows, (int)cols);
