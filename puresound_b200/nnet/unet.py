@@ -23,6 +23,8 @@ The bottleneck is the engine's ``TCN`` / ``GatedTCN`` stack on ``[N, T, C*F']``.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -158,14 +160,40 @@ class Unet(nn.Module):
         x, T_alloc, t_off, T = src
         Fp, W = dst.shape[1], dst.shape[2]
         F_, C_ = x.shape[1], x.shape[2]
+        d4 = dst.view(N, T_dst, Fp, W)
         for j, sh in enumerate(shifts):
             t0, t1 = max(0, -sh), min(T_dst, T - sh)  # destination frames with a source frame
+            c0 = j * slot_width + col
+            # the buffer comes uninitialised (_tap_buffer zeroes only its padding rows): the frames of this slot that have
+            # no source frame - the time padding at the edges of every item - are zeroed here, the rest is written below
             if t1 <= t0:
+                d4[:, :, f_lo:f_lo + F_, c0:c0 + C_].zero_()
                 continue
+            if t0 > 0:
+                d4[:, :t0, f_lo:f_lo + F_, c0:c0 + C_].zero_()
+            if t1 < T_dst:
+                d4[:, t1:, f_lo:f_lo + F_, c0:c0 + C_].zero_()
             a = x.view(-1)[(t_off + t0 + sh) * F_ * C_:]
             y = dst.view(-1)[(t0 * Fp + f_lo) * W + j * slot_width + col:]
             ops.gated(a, ops.NO_PRO, batch=N, mid=t1 - t0, rows=F_, C_=C_, a_strides=(T_alloc * F_ * C_, F_ * C_, C_),
                       out=y, y_strides=(T_dst * Fp * W, Fp * W, W))
+
+    @staticmethod
+    def _tap_buffer(N: int, T: int, Fp: int, W: int, f_lo: int, F_: int, device) -> torch.Tensor:
+        """[N*T + 1, Fp, W] tap buffer (+1 frame of slack: the last window positions read past the end) with only its PADDING
+        zeroed - the frequency rows outside [f_lo, f_lo + F) and the slack frame; every other element is written by _stack.
+        (A zero-fill of the whole buffer per layer was 7 % of a tse_unet_tcn_v0 forward, run 53.  PS_UNET_POISON=1 fills the
+        buffer with NaN first: any element neither zeroed nor written then shows up in the output - used by the tests.)"""
+        buf = torch.empty(N * T + 1, Fp, W, device=device, dtype=torch.float32)
+        if os.environ.get("PS_UNET_POISON") == "1":
+            buf.fill_(float("nan"))
+        b4 = buf[:N * T].view(N, T, Fp, W)
+        if f_lo > 0:
+            b4[:, :, :f_lo].zero_()
+        if f_lo + F_ < Fp:
+            b4[:, :, f_lo + F_:].zero_()
+        buf[N * T:].zero_()
+        return buf
 
     def _down(self, i: int, x: torch.Tensor, N: int, T: int):
         """Activated layer input x [N*T, F, C] -> raw conv output as (tensor, T, R, F', C'): one flat framed GEMM per item over
@@ -188,7 +216,7 @@ class Unet(nn.Module):
         step = P * s
         Fp = -(-(F_ + 2 * pf) // step) * step   # frequency rows per frame, a multiple of the row step so windows are equidistant
         W = kt * C_
-        buf = torch.zeros(N * T + 1, Fp, W, device=x.device, dtype=torch.float32)  # +1 frame: the last window positions read past the end
+        buf = self._tap_buffer(N, T, Fp, W, pf, F_, x.device)
         self._stack(buf[:N * T], T, (x, T, 0, T), N, C_, 0, [j - left for j in range(kt)], pf)
         rows_w = kf + (P - 1) * s
         R = Fp // step
@@ -235,7 +263,7 @@ class Unet(nn.Module):
         W = tk * Cin
         Rb = F_ + pad_lo + pad_hi
         To = T + tk - 1  # output frame t_o = t_i + kt: slot kt holds input frame t_o - kt
-        buf = torch.zeros(N * To + 1, Rb, W, device=x.device, dtype=torch.float32)  # +1 frame of slack for the last windows
+        buf = self._tap_buffer(N, To, Rb, W, pad_lo, F_, x.device)
         shifts = [-j for j in range(tk)]
         self._stack(buf[:N * To], To, xs, N, Cin, 0, shifts, pad_lo)
         self._stack(buf[:N * To], To, (skip, T, 0, T), N, Cin, C_, shifts, pad_lo)
