@@ -164,9 +164,11 @@ def build_model(workload: str):
     return m
 
 
-def ncu_traffic(kernel: str, shape):
+def ncu_traffic(kernel: str, shape, residual_frac: float = 0.0):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-    capture (profiles/traffic.json names the report it was read from); None when no capture of this shape is committed."""
+    capture (profiles/traffic.json names the report it was read from); None when no capture of this shape is committed.
+    residual_frac: share of the group's launches that read a residual - the figure is then the mean of the captured launch
+    without and with one (like the group's algorithmic bytes)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
@@ -174,7 +176,10 @@ def ncu_traffic(kernel: str, shape):
         table = json.load(fh)
     for key, t in table.items():
         if key.split("@")[0] == kernel and list(t.get("shape", [t.get("rows"), t.get("M"), t.get("K")])) == list(shape):
-            return t["dram_bytes_per_launch"]
+            base, with_res = t["dram_bytes_per_launch"], t.get("dram_bytes_per_launch_with_residual")
+            if residual_frac > 0.0 and with_res:
+                return (1.0 - residual_frac) * base + residual_frac * with_res
+            return base
     return None
 
 
@@ -208,7 +213,7 @@ def kernel_rooflines(events, eager_ms, hbm_peak, tf_peak, peak_kind):
             else:
                 ach = nbytes / (avg_ms / 1e3) / 1e9
                 r.update({"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "algorithmic_bytes": nbytes})
-            r["traffic"] = ncu_traffic("gemm", shape)
+            r["traffic"] = ncu_traffic("gemm", shape, min(1.0, extra_bytes / (4.0 * rows * M)))
         elif kind == "lstm":
             n_seq, L, H, D, K_in = shape
             flops = 2.0 * 4 * H * (H + K_in) * n_seq * L * D
