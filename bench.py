@@ -569,7 +569,7 @@ def main():
         if roof.get("bound") == "tensor":
             roof["note"] = ("3xBF16 split: useful FLOPs / measured bf16 peak (three tensor passes are issued, so 1/3 is the ceiling of frac); "
                             "the step runs at the 1000 W power cap (see clocks.reasons)" + ("; " + roof["note"] if roof.get("note") else ""))
-        roof["other_kernels"] = [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "launches_timed", "share_of_step") if k in r}
+        roof["other_kernels"] = [{k: r[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "launches_timed", "share_of_step", "algorithmic_bytes", "traffic", "step_latency_us") if k in r}
                                  for r in roofs[1:4]]
 
     cpu = None
